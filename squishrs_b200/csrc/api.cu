@@ -1,0 +1,162 @@
+// Context, error plumbing, pinned staging and the fused batch entry points of the C ABI.
+#include <stdarg.h>
+#include <stdlib.h>
+#include "common.cuh"
+
+int32_t sq_xxh3_init(sq_ctx *ctx);
+
+static thread_local char g_create_err[512] = "";
+
+int32_t sq_set_error(sq_ctx *ctx, int32_t code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(ctx ? ctx->err : g_create_err, 512, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int32_t sq_ensure(sq_ctx *ctx, void **p, size_t *cap, size_t need) {
+    if (*cap >= need) return SQ_OK;
+    if (*p) { SQ_CUDA(ctx, cudaDeviceSynchronize()); SQ_CUDA(ctx, cudaFree(*p)); *p = nullptr; *cap = 0; }
+    size_t want = need + need / 8 + 4096;
+    SQ_CUDA(ctx, cudaMalloc(p, want));
+    *cap = want;
+    return SQ_OK;
+}
+
+extern "C" int32_t sq_abi_version(void) { return 1; }
+extern "C" int32_t sq_kernel_launches(sq_ctx *ctx, uint64_t *out) {
+    if (!ctx || !out) return SQ_ERR_INVALID_ARG;
+    *out = ctx->launches;
+    return SQ_OK;
+}
+
+extern "C" const char *sq_strerror(int32_t s) {
+    switch (s) {  // display strings of AppError (reference src/util/errors.rs:7-65)
+    case SQ_OK: return "ok";
+    case SQ_ERR_IO: return "I/O error";
+    case SQ_ERR_READ_DIR: return "Failed to read directory";
+    case SQ_ERR_READ_ENTRY: return "Failed to read entry";
+    case SQ_ERR_WRITER: return "Error writing to squish";
+    case SQ_ERR_READER: return "Error reading from squish";
+    case SQ_ERR_FLUSH: return "Failed to flush archive writer";
+    case SQ_ERR_COMPRESSION: return "Compression error";
+    case SQ_ERR_ARCHIVE: return "Archive format error";
+    case SQ_ERR_ENCODER: return "Zstd encoder error";
+    case SQ_ERR_LOCK_POISONED: return "Mutex poisoned";
+    case SQ_ERR_SENDER: return "Error sending to writer thread";
+    case SQ_ERR_CREATE_DIR: return "Error creating directory";
+    case SQ_ERR_CREATE_FILE: return "Error creating file";
+    case SQ_ERR_FILE_NOT_EXIST: return "Specified file does not exist";
+    case SQ_ERR_ILLEGAL_UTF8: return "Illegal UTF8 detected";
+    case SQ_ERR_MISSING_CHUNK: return "Missing Chunk for File";
+    case SQ_ERR_INVALID_CHUNK_SIZE: return "Invalid chunk size";
+    case SQ_ERR_CAP_THREADS: return "Unable to Cap Maximum Threads";
+    case SQ_ERR_INVALID_TIMESTAMP: return "Invalid timestamp in squish";
+    case SQ_ERR_OTHER: return "Unknown error";
+    case SQ_ERR_NO_DEVICE: return "No CUDA device (this library has no CPU fallback)";
+    case SQ_ERR_CUDA: return "CUDA runtime error";
+    case SQ_ERR_INVALID_ARG: return "Invalid argument";
+    case SQ_ERR_CAPACITY: return "Output capacity exceeded";
+    default: return "Unknown status";
+    }
+}
+
+extern "C" const char *sq_last_error(const sq_ctx *ctx) { return ctx ? ctx->err : g_create_err; }
+
+extern "C" int32_t sq_create(const sq_config *cfg, sq_ctx **out) {
+    if (!out) return SQ_ERR_INVALID_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return sq_set_error(nullptr, SQ_ERR_NO_DEVICE, "no CUDA device available (%s); libsquish_b200 has no CPU fallback",
+                            e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    int dev = cfg ? cfg->device : 0;
+    if (dev < 0 || dev >= ndev) return sq_set_error(nullptr, SQ_ERR_INVALID_ARG, "device %d out of range (%d devices)", dev, ndev);
+    sq_ctx *ctx = (sq_ctx *)calloc(1, sizeof(sq_ctx));
+    if (!ctx) return SQ_ERR_OTHER;
+    ctx->device = dev;
+    ctx->chunk_size = cfg && cfg->chunk_size ? cfg->chunk_size : SQ_CHUNK_SIZE;
+    ctx->max_batch = cfg && cfg->max_batch_chunks ? cfg->max_batch_chunks : 4096;
+    ctx->dedup_capacity = cfg && cfg->dedup_capacity ? cfg->dedup_capacity : (1ull << 20);
+    int32_t rc = SQ_OK;
+    auto fail = [&](int32_t code) { snprintf(g_create_err, sizeof g_create_err, "%s", ctx->err); sq_destroy(ctx); return code; };
+    if (ctx->chunk_size > SQ_CHUNK_SIZE) { sq_set_error(ctx, SQ_ERR_INVALID_CHUNK_SIZE, "chunk_size %u > %u", ctx->chunk_size, SQ_CHUNK_SIZE); return fail(SQ_ERR_INVALID_CHUNK_SIZE); }
+    if (cudaSetDevice(dev) != cudaSuccess) { sq_set_error(ctx, SQ_ERR_CUDA, "cudaSetDevice(%d) failed", dev); return fail(SQ_ERR_CUDA); }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) { sq_set_error(ctx, SQ_ERR_CUDA, "cudaGetDeviceProperties failed"); return fail(SQ_ERR_CUDA); }
+    if (prop.major < 10) { sq_set_error(ctx, SQ_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", dev, prop.major, prop.minor); return fail(SQ_ERR_NO_DEVICE); }
+    ctx->sm_count = prop.multiProcessorCount;
+    auto init = [&]() -> int32_t {
+        SQ_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        SQ_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        SQ_CUDA(ctx, cudaMalloc(&ctx->d_work_counter, 64 * sizeof(uint32_t)));
+        SQ_CUDA(ctx, cudaMemset(ctx->d_work_counter, 0, 64 * sizeof(uint32_t)));
+        int32_t r = sq_xxh3_init(ctx);
+        if (r) return r;
+        return sq_dedup_create(ctx);
+    };
+    rc = init();
+    if (rc) return fail(rc);
+    *out = ctx;
+    return SQ_OK;
+}
+
+extern "C" void sq_destroy(sq_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    sq_dedup_destroy(ctx);
+    sq_enc_destroy(ctx);
+    sq_dec_destroy(ctx);
+    if (ctx->d_work_counter) cudaFree(ctx->d_work_counter);
+    if (ctx->d_stage_in) cudaFree(ctx->d_stage_in);
+    if (ctx->d_stage_out) cudaFree(ctx->d_stage_out);
+    if (ctx->d_stage_meta) cudaFree(ctx->d_stage_meta);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    free(ctx);
+}
+
+extern "C" int32_t sq_synchronize(sq_ctx *ctx, void *stream) {
+    if (!ctx) return SQ_ERR_INVALID_ARG;
+    SQ_CUDA(ctx, cudaStreamSynchronize(sq_stream(ctx, stream)));
+    return SQ_OK;
+}
+
+extern "C" int32_t sq_host_alloc(sq_ctx *ctx, size_t bytes, void **out) {
+    if (!ctx || !out) return SQ_ERR_INVALID_ARG;
+    SQ_CUDA(ctx, cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+    return SQ_OK;
+}
+extern "C" int32_t sq_host_free(sq_ctx *ctx, void *p) {
+    if (!ctx) return SQ_ERR_INVALID_ARG;
+    if (p) SQ_CUDA(ctx, cudaFreeHost(p));
+    return SQ_OK;
+}
+extern "C" void sq_free(void *p) { free(p); }
+
+// ---- host convenience for K1 ---------------------------------------------------------
+extern "C" int32_t sq_digest_host(sq_ctx *ctx, const void *h_data, size_t data_len, const sq_span *h_spans, uint32_t n,
+                                  uint8_t *h_digests) {
+    if (!ctx) return SQ_ERR_INVALID_ARG;
+    if (n == 0) return SQ_OK;
+    if (!h_spans || !h_digests || (!h_data && data_len)) return sq_set_error(ctx, SQ_ERR_INVALID_ARG, "sq_digest_host: null pointer");
+    for (uint32_t i = 0; i < n; i++)
+        if (h_spans[i].off + h_spans[i].len > data_len || h_spans[i].len > ctx->chunk_size)
+            return sq_set_error(ctx, SQ_ERR_INVALID_CHUNK_SIZE, "span %u [%llu,+%u) outside the batch or larger than a chunk", i,
+                                (unsigned long long)h_spans[i].off, h_spans[i].len);
+    int32_t rc;
+    if ((rc = sq_ensure(ctx, &ctx->d_stage_in, &ctx->stage_in_cap, data_len + 64))) return rc;
+    size_t meta = (size_t)n * (sizeof(sq_span) + 16);
+    if ((rc = sq_ensure(ctx, &ctx->d_stage_meta, &ctx->stage_meta_cap, meta))) return rc;
+    sq_span *d_spans = (sq_span *)ctx->d_stage_meta;
+    uint8_t *d_dig = (uint8_t *)ctx->d_stage_meta + (size_t)n * sizeof(sq_span);
+    SQ_CUDA(ctx, cudaMemcpyAsync(ctx->d_stage_in, h_data, data_len, cudaMemcpyHostToDevice, ctx->stream));
+    SQ_CUDA(ctx, cudaMemcpyAsync(d_spans, h_spans, (size_t)n * sizeof(sq_span), cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = sq_digest_device(ctx, ctx->d_stage_in, d_spans, n, d_dig, ctx->stream))) return rc;
+    SQ_CUDA(ctx, cudaMemcpyAsync(h_digests, d_dig, (size_t)n * 16, cudaMemcpyDeviceToHost, ctx->stream));
+    SQ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SQ_OK;
+}

@@ -1,0 +1,60 @@
+// Shared internals of libsquish_b200: context, error plumbing, small device helpers.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include "../../include/squish_b200.h"
+
+#if defined(__CUDACC__)
+#define SQ_HD __host__ __device__ __forceinline__
+#else
+#define SQ_HD inline
+#endif
+
+struct sq_dedup_table;  // dedup.cu
+struct sq_enc_scratch;  // zstd_enc.cu
+struct sq_dec_scratch;  // zstd_dec.cu
+
+struct sq_ctx {
+    int device;
+    int sm_count;
+    uint32_t chunk_size;
+    uint32_t max_batch;
+    uint64_t dedup_capacity;
+    cudaStream_t stream;      // the context's own stream
+    cudaStream_t copy_stream; // second stream for double-buffered uploads
+    char err[512];
+    uint64_t launches;        // kernels launched through this context (bench: gpu_launches)
+    // K1
+    uint32_t *d_work_counter; // persistent-warp work queue heads (a few u32)
+    // K2
+    sq_dedup_table *dedup;
+    // K3 / K4 scratch (lazily sized)
+    sq_enc_scratch *enc;
+    sq_dec_scratch *dec;
+    // staging for the *_host entry points (lazily grown)
+    void *d_stage_in; size_t stage_in_cap;
+    void *d_stage_out; size_t stage_out_cap;
+    void *d_stage_meta; size_t stage_meta_cap;
+};
+
+int32_t sq_set_error(sq_ctx *ctx, int32_t code, const char *fmt, ...);
+int32_t sq_ensure(sq_ctx *ctx, void **p, size_t *cap, size_t need);
+
+#define SQ_CUDA(ctx, call)                                                                       \
+    do {                                                                                         \
+        cudaError_t e__ = (call);                                                                \
+        if (e__ != cudaSuccess)                                                                  \
+            return sq_set_error((ctx), SQ_ERR_CUDA, "%s failed: %s (%s:%d)", #call,              \
+                                cudaGetErrorString(e__), __FILE__, __LINE__);                    \
+    } while (0)
+
+#define SQ_LAUNCHED(ctx, k) ((ctx)->launches += (k))
+static inline cudaStream_t sq_stream(sq_ctx *ctx, void *s) { return s ? (cudaStream_t)s : ctx->stream; }
+
+// entry points implemented per translation unit
+int32_t sq_dedup_create(sq_ctx *ctx);
+void sq_dedup_destroy(sq_ctx *ctx);
+void sq_enc_destroy(sq_ctx *ctx);
+void sq_dec_destroy(sq_ctx *ctx);

@@ -1,0 +1,120 @@
+// Fused batch entry points: ChunkStore::insert for a whole batch (reference src/util/chunk.rs:80-100)
+// = K1 digest -> K2 dedup -> K3 encode of the winners, and read_chunks for a batch
+// (src/archive/reader.rs:259-314) = K4 decode.  Host variants add the H2D / D2H copies.
+#include "common.cuh"
+
+extern "C" int32_t sq_encode_status(sq_ctx *ctx);
+
+namespace {
+__global__ void pack_results_kernel(const uint4 *__restrict__ digests, const uint8_t *__restrict__ is_new,
+                                    const uint64_t *__restrict__ frame_off, const uint32_t *__restrict__ frame_len, uint32_t n,
+                                    sq_chunk_result *__restrict__ res) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    sq_chunk_result r;
+    *reinterpret_cast<uint4 *>(r.digest) = digests[i];
+    r.is_new = is_new[i];
+    r.frame_off = r.is_new ? frame_off[i] : 0;
+    r.frame_len = r.is_new ? frame_len[i] : 0;
+    r.reserved[0] = r.reserved[1] = r.reserved[2] = 0;
+    res[i] = r;
+}
+}  // namespace
+
+// per-batch metadata scratch layout inside ctx->d_stage_meta (device)
+struct pack_meta {
+    uint8_t *digests; uint8_t *is_new; uint64_t *frame_off; uint32_t *frame_len; uint64_t *total;
+    sq_span *spans; sq_chunk_result *results; sq_frame *frames; sq_frame_result *fres;
+};
+static int32_t meta_layout(sq_ctx *ctx, uint32_t n, pack_meta *m) {
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+    size_t o_dig = take((size_t)n * 16), o_new = take(n), o_fo = take((size_t)n * 8), o_fl = take((size_t)n * 4), o_tot = take(8),
+           o_sp = take((size_t)n * sizeof(sq_span)), o_res = take((size_t)n * sizeof(sq_chunk_result)),
+           o_fr = take((size_t)n * sizeof(sq_frame)), o_frs = take((size_t)n * sizeof(sq_frame_result));
+    int32_t rc = sq_ensure(ctx, &ctx->d_stage_meta, &ctx->stage_meta_cap, off);
+    if (rc) return rc;
+    uint8_t *b = (uint8_t *)ctx->d_stage_meta;
+    m->digests = b + o_dig; m->is_new = b + o_new; m->frame_off = (uint64_t *)(b + o_fo); m->frame_len = (uint32_t *)(b + o_fl);
+    m->total = (uint64_t *)(b + o_tot); m->spans = (sq_span *)(b + o_sp); m->results = (sq_chunk_result *)(b + o_res);
+    m->frames = (sq_frame *)(b + o_fr); m->fres = (sq_frame_result *)(b + o_frs);
+    return SQ_OK;
+}
+
+extern "C" int32_t sq_pack_device(sq_ctx *ctx, const void *d_data, const sq_span *d_spans, uint32_t n, uint64_t gidx_base,
+                                  sq_chunk_result *d_results, void *d_out, uint64_t out_capacity, uint64_t *out_used, void *stream) {
+    if (!ctx) return SQ_ERR_INVALID_ARG;
+    if (n == 0) { if (out_used) *out_used = 0; return SQ_OK; }
+    if (!d_data || !d_spans || !d_results || !d_out) return sq_set_error(ctx, SQ_ERR_INVALID_ARG, "sq_pack_device: null pointer");
+    pack_meta m;
+    int32_t rc = meta_layout(ctx, n, &m);
+    if (rc) return rc;
+    cudaStream_t st = sq_stream(ctx, stream);
+    if ((rc = sq_digest_device(ctx, d_data, d_spans, n, m.digests, st))) return rc;
+    if ((rc = sq_dedup_insert_device(ctx, m.digests, nullptr, gidx_base, n, m.is_new, st))) return rc;
+    if ((rc = sq_encode_device(ctx, d_data, d_spans, m.is_new, n, d_out, out_capacity, m.frame_off, m.frame_len, m.total, st))) return rc;
+    pack_results_kernel<<<(n + 127) / 128, 128, 0, st>>>((const uint4 *)m.digests, m.is_new, m.frame_off, m.frame_len, n, d_results);
+    SQ_LAUNCHED(ctx, 1);
+    SQ_CUDA(ctx, cudaGetLastError());
+    if (out_used) {
+        SQ_CUDA(ctx, cudaMemcpyAsync(out_used, m.total, 8, cudaMemcpyDeviceToHost, st));
+        SQ_CUDA(ctx, cudaStreamSynchronize(st));
+        if ((rc = sq_encode_status(ctx))) return rc;
+    }
+    return SQ_OK;
+}
+
+extern "C" int32_t sq_pack_host(sq_ctx *ctx, const void *h_data, size_t data_len, const sq_span *h_spans, uint32_t n,
+                                uint64_t gidx_base, sq_chunk_result *h_results, void *h_out, uint64_t out_capacity, uint64_t *out_used) {
+    if (!ctx) return SQ_ERR_INVALID_ARG;
+    if (n == 0) { if (out_used) *out_used = 0; return SQ_OK; }
+    if (!h_spans || !h_results || !h_out || (!h_data && data_len)) return sq_set_error(ctx, SQ_ERR_INVALID_ARG, "sq_pack_host: null pointer");
+    uint64_t bound = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        if (h_spans[i].off + h_spans[i].len > data_len || h_spans[i].len > ctx->chunk_size || h_spans[i].len == 0)
+            return sq_set_error(ctx, SQ_ERR_INVALID_CHUNK_SIZE, "span %u [%llu,+%u) invalid", i, (unsigned long long)h_spans[i].off, h_spans[i].len);
+        bound += sq_encode_bound(h_spans[i].len);
+    }
+    int32_t rc;
+    if ((rc = sq_ensure(ctx, &ctx->d_stage_in, &ctx->stage_in_cap, data_len + 64))) return rc;
+    if ((rc = sq_ensure(ctx, &ctx->d_stage_out, &ctx->stage_out_cap, bound))) return rc;
+    pack_meta m;
+    if ((rc = meta_layout(ctx, n, &m))) return rc;
+    cudaStream_t st = ctx->stream;
+    SQ_CUDA(ctx, cudaMemcpyAsync(ctx->d_stage_in, h_data, data_len, cudaMemcpyHostToDevice, st));
+    SQ_CUDA(ctx, cudaMemcpyAsync(m.spans, h_spans, (size_t)n * sizeof(sq_span), cudaMemcpyHostToDevice, st));
+    uint64_t used = 0;
+    if ((rc = sq_pack_device(ctx, ctx->d_stage_in, m.spans, n, gidx_base, m.results, ctx->d_stage_out, bound, &used, st))) return rc;
+    if (used > out_capacity) return sq_set_error(ctx, SQ_ERR_CAPACITY, "pack output needs %llu bytes, caller gave %llu", (unsigned long long)used, (unsigned long long)out_capacity);
+    SQ_CUDA(ctx, cudaMemcpyAsync(h_results, m.results, (size_t)n * sizeof(sq_chunk_result), cudaMemcpyDeviceToHost, st));
+    if (used) SQ_CUDA(ctx, cudaMemcpyAsync(h_out, ctx->d_stage_out, used, cudaMemcpyDeviceToHost, st));
+    SQ_CUDA(ctx, cudaStreamSynchronize(st));
+    if (out_used) *out_used = used;
+    return SQ_OK;
+}
+
+extern "C" int32_t sq_unpack_host(sq_ctx *ctx, const void *h_comp, size_t comp_len, const sq_frame *h_frames, uint32_t n, void *h_out,
+                                  size_t out_len, sq_frame_result *h_results) {
+    if (!ctx) return SQ_ERR_INVALID_ARG;
+    if (n == 0) return SQ_OK;
+    if (!h_comp || !h_frames || !h_results || (!h_out && out_len)) return sq_set_error(ctx, SQ_ERR_INVALID_ARG, "sq_unpack_host: null pointer");
+    for (uint32_t i = 0; i < n; i++) {
+        if (h_frames[i].src_off + h_frames[i].src_len > comp_len)
+            return sq_set_error(ctx, SQ_ERR_READER, "frame %u payload outside the compressed buffer", i);
+        if (h_frames[i].dst_off + h_frames[i].capacity > out_len)
+            return sq_set_error(ctx, SQ_ERR_CAPACITY, "frame %u capacity outside the output buffer", i);
+    }
+    int32_t rc;
+    if ((rc = sq_ensure(ctx, &ctx->d_stage_in, &ctx->stage_in_cap, comp_len + 64))) return rc;
+    if ((rc = sq_ensure(ctx, &ctx->d_stage_out, &ctx->stage_out_cap, out_len + 64))) return rc;
+    pack_meta m;
+    if ((rc = meta_layout(ctx, n, &m))) return rc;
+    cudaStream_t st = ctx->stream;
+    SQ_CUDA(ctx, cudaMemcpyAsync(ctx->d_stage_in, h_comp, comp_len, cudaMemcpyHostToDevice, st));
+    SQ_CUDA(ctx, cudaMemcpyAsync(m.frames, h_frames, (size_t)n * sizeof(sq_frame), cudaMemcpyHostToDevice, st));
+    if ((rc = sq_decode_device(ctx, ctx->d_stage_in, m.frames, n, ctx->d_stage_out, m.fres, st))) return rc;
+    SQ_CUDA(ctx, cudaMemcpyAsync(h_results, m.fres, (size_t)n * sizeof(sq_frame_result), cudaMemcpyDeviceToHost, st));
+    SQ_CUDA(ctx, cudaMemcpyAsync(h_out, ctx->d_stage_out, out_len, cudaMemcpyDeviceToHost, st));
+    SQ_CUDA(ctx, cudaStreamSynchronize(st));
+    return SQ_OK;
+}

@@ -1,0 +1,232 @@
+// K3 — zstd frame encoder for sm_100a.
+//
+// Replaces zstd::bulk::compress(chunk, 12) (reference src/util/chunk.rs:89-90): one standard
+// zstd frame per selected chunk -- single segment, frame content size present, no checksum,
+// no dictionary id (the shape libzstd's one-shot API emits).
+//
+// Stages (all on the caller's stream):
+//   plan      per chunk: block count / frame header size                       (enc_plan_kernel)
+//   compress  per 128 KiB block: LZ parse + entropy coding into block scratch  (see zstd_enc_lz.cuh)
+//   size      per chunk: frame length from the block bodies                    (enc_size_kernel)
+//   place     exclusive scan of frame lengths over the batch -> frame offsets  (enc_scan_kernel)
+//   emit      per block: write header + body (or raw fallback) into d_out      (enc_emit_kernel)
+#include "common.cuh"
+
+#define SQ_BLOCK_MAX (128u * 1024u)  // zstd Block_Maximum_Size
+#define SQ_MAX_BLOCKS 16u            // 2 MiB / 128 KiB
+
+struct sq_block_info {   // one per (chunk, block)
+    uint32_t body_len;   // bytes of compressed body in scratch (type 2) / 1 (type 1) / block_len (type 0)
+    uint32_t type;       // 0 raw, 1 RLE, 2 compressed
+};
+
+struct sq_enc_scratch {
+    sq_block_info *blocks;   // [max_batch * SQ_MAX_BLOCKS]
+    uint32_t *frame_len;     // [max_batch]
+    uint8_t *bodies;         // compressed block bodies, stride SQ_BLOCK_MAX per (chunk, block) of the current wave
+    size_t bodies_cap;
+    uint32_t cap_chunks;
+    uint32_t *status;        // [0] != 0 => capacity overflow
+};
+
+namespace {
+
+__host__ __device__ inline uint32_t frame_header_len(uint32_t len) { return 4 + 1 + (len <= 255 ? 1 : len <= 65791 ? 2 : 4); }
+__host__ __device__ inline uint32_t n_blocks(uint32_t len) { return len == 0 ? 1 : (len + SQ_BLOCK_MAX - 1) / SQ_BLOCK_MAX; }
+
+// v0 "compress": every block raw.  The LZ/entropy stages overwrite blocks[] where they win.
+__global__ void enc_plan_kernel(const sq_span *__restrict__ spans, const uint8_t *__restrict__ select, uint32_t n,
+                                sq_block_info *__restrict__ blocks) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * SQ_MAX_BLOCKS) return;
+    uint32_t c = t / SQ_MAX_BLOCKS, b = t % SQ_MAX_BLOCKS;
+    uint32_t len = spans[c].len, nb = n_blocks(len);
+    sq_block_info bi = {0, 0};
+    if ((!select || select[c]) && b < nb) {
+        uint32_t blen = min(SQ_BLOCK_MAX, len - b * SQ_BLOCK_MAX);
+        bi.body_len = blen;
+        bi.type = 0;
+    }
+    blocks[t] = bi;
+}
+
+__global__ void enc_size_kernel(const sq_span *__restrict__ spans, const uint8_t *__restrict__ select, uint32_t n,
+                                const sq_block_info *__restrict__ blocks, uint32_t *__restrict__ frame_len) {
+    uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    uint32_t fl = 0;
+    if (!select || select[c]) {
+        uint32_t len = spans[c].len, nb = n_blocks(len);
+        fl = frame_header_len(len);
+        for (uint32_t b = 0; b < nb; b++) fl += 3 + blocks[c * SQ_MAX_BLOCKS + b].body_len;
+    }
+    frame_len[c] = fl;
+}
+
+// single-CTA exclusive scan (n <= a few 100k): 1024 threads, serial over tiles
+__global__ void __launch_bounds__(1024) enc_scan_kernel(const uint32_t *__restrict__ frame_len, uint32_t n, uint64_t out_capacity,
+                                                         uint64_t *__restrict__ frame_off, uint32_t *__restrict__ frame_len_out,
+                                                         uint64_t *__restrict__ total, uint32_t *__restrict__ status) {
+    __shared__ uint64_t warp_sums[32];
+    __shared__ uint64_t carry;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < n; base += 1024) {
+        uint32_t i = base + threadIdx.x;
+        uint64_t v = i < n ? frame_len[i] : 0, x = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { uint64_t y = __shfl_up_sync(0xffffffffu, x, d); if (lane >= d) x += y; }
+        if (lane == 31) warp_sums[w] = x;
+        __syncthreads();
+        if (w == 0) {
+            uint64_t s = warp_sums[lane], z = s;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { uint64_t y = __shfl_up_sync(0xffffffffu, z, d); if (lane >= d) z += y; }
+            warp_sums[lane] = z - s;  // exclusive
+        }
+        __syncthreads();
+        uint64_t excl = carry + warp_sums[w] + x - v;
+        if (i < n) { frame_off[i] = excl; frame_len_out[i] = (uint32_t)v; }
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        *total = carry;
+        if (carry > out_capacity) atomicExch(status, 1u);
+    }
+}
+
+// Cooperative byte copy by one CTA to an arbitrarily aligned destination.
+__device__ void cta_copy(uint8_t *__restrict__ dst, const uint8_t *__restrict__ src, uint32_t n) {
+    // head: until dst is 16-byte aligned
+    uint32_t head = (uint32_t)((16 - (reinterpret_cast<uintptr_t>(dst) & 15)) & 15);
+    if (head > n) head = n;
+    if (threadIdx.x < head) dst[threadIdx.x] = src[threadIdx.x];
+    dst += head; src += head; n -= head;
+    const uint32_t nvec = n >> 4;
+    const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 3) * 8;
+    const uint32_t *s32 = reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(src) & ~(uintptr_t)3);
+    uint4 *d128 = reinterpret_cast<uint4 *>(dst);
+    if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+        const uint4 *s128 = reinterpret_cast<const uint4 *>(src);
+        for (uint32_t i = threadIdx.x; i < nvec; i += blockDim.x) d128[i] = __ldg(&s128[i]);
+    } else {
+        for (uint32_t i = threadIdx.x; i < nvec; i += blockDim.x) {
+            const uint32_t *p = s32 + 4 * i;
+            uint32_t w0 = __ldg(p), w1 = __ldg(p + 1), w2 = __ldg(p + 2), w3 = __ldg(p + 3);
+            uint4 o;
+            if (sh == 0) { o = make_uint4(w0, w1, w2, w3); }
+            else {
+                uint32_t w4 = __ldg(p + 4);
+                o.x = __funnelshift_r(w0, w1, sh); o.y = __funnelshift_r(w1, w2, sh);
+                o.z = __funnelshift_r(w2, w3, sh); o.w = __funnelshift_r(w3, w4, sh);
+            }
+            d128[i] = o;
+        }
+    }
+    const uint32_t done = nvec << 4, tail = n - done;
+    if (threadIdx.x < tail) dst[done + threadIdx.x] = src[done + threadIdx.x];
+}
+
+// grid = (SQ_MAX_BLOCKS, n): CTA (b, c) writes block b of chunk c; b == 0 also writes the frame header.
+__global__ void __launch_bounds__(256) enc_emit_kernel(const uint8_t *__restrict__ data, const sq_span *__restrict__ spans, uint32_t n,
+                                                        const sq_block_info *__restrict__ blocks, const uint8_t *__restrict__ bodies,
+                                                        const uint64_t *__restrict__ frame_off, const uint32_t *__restrict__ frame_len,
+                                                        uint8_t *__restrict__ out, const uint32_t *__restrict__ status) {
+    const uint32_t c = blockIdx.y, b = blockIdx.x;
+    if (*status) return;            // capacity overflow: write nothing
+    if (frame_len[c] == 0) return;  // not selected
+    const uint32_t len = spans[c].len, nb = n_blocks(len);
+    if (b >= nb) return;
+    uint8_t *f = out + frame_off[c];
+    uint32_t hl = frame_header_len(len);
+    if (b == 0 && threadIdx.x == 0) {
+        f[0] = 0x28; f[1] = 0xB5; f[2] = 0x2F; f[3] = 0xFD;  // magic 0xFD2FB528 LE
+        if (len <= 255) { f[4] = 0x20; f[5] = (uint8_t)len; }
+        else if (len <= 65791) { f[4] = 0x60; uint32_t v = len - 256; f[5] = (uint8_t)v; f[6] = (uint8_t)(v >> 8); }
+        else { f[4] = 0xA0; f[5] = (uint8_t)len; f[6] = (uint8_t)(len >> 8); f[7] = (uint8_t)(len >> 16); f[8] = (uint8_t)(len >> 24); }
+    }
+    uint32_t pos = hl;
+    for (uint32_t k = 0; k < b; k++) pos += 3 + blocks[c * SQ_MAX_BLOCKS + k].body_len;
+    const sq_block_info bi = blocks[c * SQ_MAX_BLOCKS + b];
+    const uint32_t blen = len == 0 ? 0 : min(SQ_BLOCK_MAX, len - b * SQ_BLOCK_MAX);
+    if (threadIdx.x == 0) {
+        // Block_Header: bit0 last, bits1-2 type, bits 3.. size (regenerated size for raw/RLE, body size for compressed)
+        uint32_t h = (b + 1 == nb ? 1u : 0u) | bi.type << 1 | (bi.type == 2 ? bi.body_len : blen) << 3;
+        f[pos] = (uint8_t)h; f[pos + 1] = (uint8_t)(h >> 8); f[pos + 2] = (uint8_t)(h >> 16);
+    }
+    const uint8_t *src = bi.type == 0 ? data + spans[c].off + (uint64_t)b * SQ_BLOCK_MAX
+                                      : bodies + ((uint64_t)c * SQ_MAX_BLOCKS + b) * SQ_BLOCK_MAX;
+    cta_copy(f + pos + 3, src, bi.body_len);
+}
+
+}  // namespace
+
+static int32_t enc_scratch(sq_ctx *ctx, uint32_t n) {
+    if (!ctx->enc) {
+        ctx->enc = new sq_enc_scratch();
+        memset(ctx->enc, 0, sizeof(sq_enc_scratch));
+    }
+    sq_enc_scratch *e = ctx->enc;
+    if (e->cap_chunks < n) {
+        SQ_CUDA(ctx, cudaDeviceSynchronize());
+        cudaFree(e->blocks); cudaFree(e->frame_len); cudaFree(e->status);
+        uint32_t cap = n > ctx->max_batch ? n : ctx->max_batch;
+        SQ_CUDA(ctx, cudaMalloc(&e->blocks, (size_t)cap * SQ_MAX_BLOCKS * sizeof(sq_block_info)));
+        SQ_CUDA(ctx, cudaMalloc(&e->frame_len, (size_t)cap * sizeof(uint32_t)));
+        SQ_CUDA(ctx, cudaMalloc(&e->status, 4 * sizeof(uint32_t)));
+        SQ_CUDA(ctx, cudaMemset(e->status, 0, 4 * sizeof(uint32_t)));
+        e->cap_chunks = cap;
+    }
+    return SQ_OK;
+}
+
+void sq_enc_destroy(sq_ctx *ctx) {
+    sq_enc_scratch *e = ctx->enc;
+    if (!e) return;
+    cudaFree(e->blocks); cudaFree(e->frame_len); cudaFree(e->bodies); cudaFree(e->status);
+    delete e;
+    ctx->enc = nullptr;
+}
+
+extern "C" size_t sq_encode_bound(size_t len) {
+    size_t nb = len == 0 ? 1 : (len + SQ_BLOCK_MAX - 1) / SQ_BLOCK_MAX;
+    return 9 + 3 * nb + len;  // header (<= 9) + raw blocks: the encoder never emits more than this
+}
+
+extern "C" int32_t sq_encode_device(sq_ctx *ctx, const void *d_data, const sq_span *d_spans, const uint8_t *d_select, uint32_t n,
+                                    void *d_out, uint64_t out_capacity, uint64_t *d_frame_off, uint32_t *d_frame_len, uint64_t *d_total,
+                                    void *stream) {
+    if (!ctx) return SQ_ERR_INVALID_ARG;
+    if (n == 0) return SQ_OK;
+    if (!d_data || !d_spans || !d_out || !d_frame_off || !d_frame_len || !d_total)
+        return sq_set_error(ctx, SQ_ERR_INVALID_ARG, "sq_encode_device: null pointer");
+    int32_t rc = enc_scratch(ctx, n);
+    if (rc) return rc;
+    sq_enc_scratch *e = ctx->enc;
+    cudaStream_t st = sq_stream(ctx, stream);
+    const uint32_t nb = n * SQ_MAX_BLOCKS;
+    enc_plan_kernel<<<(nb + 255) / 256, 256, 0, st>>>(d_spans, d_select, n, e->blocks);
+    enc_size_kernel<<<(n + 255) / 256, 256, 0, st>>>(d_spans, d_select, n, e->blocks, e->frame_len);
+    enc_scan_kernel<<<1, 1024, 0, st>>>(e->frame_len, n, out_capacity, d_frame_off, d_frame_len, d_total, e->status);
+    enc_emit_kernel<<<dim3(SQ_MAX_BLOCKS, n), 256, 0, st>>>((const uint8_t *)d_data, d_spans, n, e->blocks, e->bodies, d_frame_off, d_frame_len,
+                                                            (uint8_t *)d_out, e->status);
+    SQ_LAUNCHED(ctx, 4);
+    SQ_CUDA(ctx, cudaGetLastError());
+    return SQ_OK;
+}
+
+// status of the most recent encode on this context (synchronizes): SQ_ERR_CAPACITY if d_out was too small
+extern "C" int32_t sq_encode_status(sq_ctx *ctx) {
+    if (!ctx || !ctx->enc) return SQ_OK;
+    uint32_t s = 0;
+    SQ_CUDA(ctx, cudaDeviceSynchronize());
+    SQ_CUDA(ctx, cudaMemcpy(&s, ctx->enc->status, sizeof s, cudaMemcpyDeviceToHost));
+    if (s) {
+        cudaMemset(ctx->enc->status, 0, sizeof s);
+        return sq_set_error(ctx, SQ_ERR_CAPACITY, "encode output buffer too small");
+    }
+    return SQ_OK;
+}

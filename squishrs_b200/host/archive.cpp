@@ -1,0 +1,521 @@
+// Host side of the packer / unpacker: the reference's archive layer re-done around batched GPU calls.
+//
+//   sq_archive_pack    ArchiveWriter::new + pack      (reference src/archive/writer.rs:66-195,229-329)
+//                      + walk_dir                      (src/fsutil/directory.rs:39-73)
+//                      + chunk record serialisation    (src/fsutil/writer.rs:17-39)
+//   sq_archive_unpack  ArchiveReader::new + unpack     (src/archive/reader.rs:46-118,232-413)
+//   sq_archive_list    ArchiveReader::new + get_summary (src/archive/reader.rs:155-219)
+//
+// The `.squish` byte layout is kept exactly: "squish"+"1.2.0", u64 timestamp,
+// u64 unique-chunk count (patched), chunk records {digest[16], orig_size u64 (always 2 MiB, the
+// reference's quirk writer.rs:255), comp_size u64, frame}, u32 file count, per-file manifest.
+// Differences, all invisible to a reader: chunk records are written in ascending global chunk
+// index (the reference's order is channel-arrival order), files are read by a pool of host threads
+// into pinned batch buffers while the previous batch is on the GPU, and every per-chunk operation
+// (digest, dedup verdict, zstd frame) comes from the CUDA kernels -- never from the CPU.
+#include <dirent.h>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <time.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <atomic>
+#include <string>
+#include <thread>
+#include <unordered_map>
+#include <vector>
+
+#include "../csrc/common.cuh"
+
+namespace {
+
+const char kPrefix[] = "squish";           // header.rs:10
+const char kVersion[] = SQ_FORMAT_VERSION;  // lib.rs:17
+
+double now_s() {
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec + ts.tv_nsec * 1e-9;
+}
+void put32(uint8_t *p, uint32_t v) { memcpy(p, &v, 4); }  // little-endian host
+void put64(uint8_t *p, uint64_t v) { memcpy(p, &v, 8); }
+uint32_t get32(const uint8_t *p) { uint32_t v; memcpy(&v, p, 4); return v; }
+uint64_t get64(const uint8_t *p) { uint64_t v; memcpy(&v, p, 8); return v; }
+
+struct FileItem {
+    std::string disk_path, rel_path;
+    uint64_t size = 0;
+    uint64_t first_chunk = 0;
+    uint32_t n_chunks = 0;
+};
+
+// walk_dir: iterative stack DFS; directories by stat() (follows symlinks), everything else a file
+int32_t walk_dir(sq_ctx *ctx, const std::string &root, std::vector<std::string> *files) {
+    struct stat st;
+    if (stat(root.c_str(), &st) != 0 || !S_ISDIR(st.st_mode))
+        return sq_set_error(ctx, SQ_ERR_READ_DIR, "Failed to read directory %s", root.c_str());
+    std::vector<std::string> stack{root};
+    while (!stack.empty()) {
+        std::string dir = std::move(stack.back());
+        stack.pop_back();
+        DIR *d = opendir(dir.c_str());
+        if (!d) return sq_set_error(ctx, SQ_ERR_READ_DIR, "Failed to read directory %s", dir.c_str());
+        while (dirent *e = readdir(d)) {
+            if (!strcmp(e->d_name, ".") || !strcmp(e->d_name, "..")) continue;
+            std::string p = dir + "/" + e->d_name;
+            if (stat(p.c_str(), &st) == 0 && S_ISDIR(st.st_mode)) stack.push_back(std::move(p));
+            else files->push_back(std::move(p));
+        }
+        closedir(d);
+    }
+    return SQ_OK;
+}
+
+template <class F>
+void parallel_for(size_t n, int threads, F fn) {
+    if (threads < 1) threads = 1;
+    if ((size_t)threads > n) threads = (int)(n ? n : 1);
+    std::atomic<size_t> next{0};
+    std::vector<std::thread> pool;
+    for (int t = 0; t < threads; t++)
+        pool.emplace_back([&] { for (size_t i; (i = next.fetch_add(1)) < n;) fn(i); });
+    for (auto &th : pool) th.join();
+}
+
+struct ChunkRef { uint32_t file; uint32_t len; uint64_t file_off; };
+
+// One pinned batch: chunk payloads at 16-byte aligned offsets + spans.
+struct Batch {
+    uint8_t *pinned = nullptr;
+    size_t cap = 0, used = 0;
+    std::vector<sq_span> spans;
+    uint64_t first_gidx = 0;
+    int32_t err = 0;
+};
+
+bool utf8_ok(const uint8_t *s, size_t n) {  // String::from_utf8 (reader.rs:178,350)
+    size_t i = 0;
+    while (i < n) {
+        uint8_t c = s[i];
+        size_t k;
+        if (c < 0x80) k = 0;
+        else if (c >= 0xC2 && c <= 0xDF) k = 1;
+        else if (c >= 0xE0 && c <= 0xEF) k = 2;
+        else if (c >= 0xF0 && c <= 0xF4) k = 3;
+        else return false;
+        if (i + k >= n + (k ? 0 : 1)) return false;
+        for (size_t j = 1; j <= k; j++) if ((s[i + j] >> 6) != 2) return false;
+        i += k + 1;
+    }
+    return true;
+}
+
+// ---- archive index (ArchiveReader::new) -----------------------------------------------------
+struct Record { const uint8_t *digest; uint64_t orig, comp; const uint8_t *payload; };
+struct Archive {
+    const uint8_t *buf = nullptr; uint64_t size = 0; int fd = -1;
+    uint64_t timestamp = 0, nchunks = 0, file_table_off = 0;
+    uint32_t file_count = 0;
+    char version[16] = {0};
+    std::vector<Record> records;
+    ~Archive() { if (buf && size) munmap((void *)buf, size); if (fd >= 0) close(fd); }
+};
+
+int32_t open_archive(sq_ctx *ctx, const char *path, Archive *a, bool keep_records) {
+    a->fd = open(path, O_RDONLY);
+    if (a->fd < 0) return sq_set_error(ctx, SQ_ERR_FILE_NOT_EXIST, "Specified file does not exist: `%s`", path);  // reader.rs:47-48
+    struct stat st;
+    if (fstat(a->fd, &st)) return sq_set_error(ctx, SQ_ERR_IO, "I/O error: fstat %s", path);
+    a->size = (uint64_t)st.st_size;
+    if (a->size) {
+        void *m = mmap(nullptr, a->size, PROT_READ, MAP_PRIVATE, a->fd, 0);
+        if (m == MAP_FAILED) return sq_set_error(ctx, SQ_ERR_IO, "I/O error: mmap %s", path);
+        a->buf = (const uint8_t *)m;
+    }
+    // verify_header (header.rs:119-163): expected_len is the READER's own magic+version length
+    const size_t hl = 6 + strlen(kVersion);
+    if (a->size < hl) return sq_set_error(ctx, SQ_ERR_IO, "I/O error: failed to fill whole buffer");
+    if (memcmp(a->buf, kPrefix, 6)) return sq_set_error(ctx, SQ_ERR_ARCHIVE, "Archive format error: Invalid archive header: prefix mismatch");
+    memcpy(a->version, a->buf + 6, hl - 6);
+    if (!utf8_ok((const uint8_t *)a->version, hl - 6)) return sq_set_error(ctx, SQ_ERR_ARCHIVE, "Archive format error: Invalid UTF-8 in version string");
+    std::string v(a->version), cur(kVersion);
+    auto major_minor = [](const std::string &s, std::string *mm) {
+        size_t d1 = s.find('.');
+        if (d1 == std::string::npos) return false;
+        size_t d2 = s.find('.', d1 + 1);
+        *mm = s.substr(0, d2);
+        return true;
+    };
+    std::string hmm, cmm;
+    if (!major_minor(v, &hmm)) return sq_set_error(ctx, SQ_ERR_ARCHIVE, "Archive format error: Invalid version format in archive header");
+    major_minor(cur, &cmm);
+    if (hmm != cmm)
+        return sq_set_error(ctx, SQ_ERR_ARCHIVE, "Archive format error: Incompatible version: archive %s vs current %s", hmm.c_str(), cmm.c_str());
+    uint64_t p = hl;
+    if (a->size < p + 16) return sq_set_error(ctx, SQ_ERR_READER, "Error reading from squish: failed to fill whole buffer");
+    a->timestamp = get64(a->buf + p); p += 8;
+    a->nchunks = get64(a->buf + p); p += 8;
+    if (keep_records) a->records.reserve((size_t)std::min<uint64_t>(a->nchunks, 1u << 24));
+    for (uint64_t i = 0; i < a->nchunks; i++) {  // reader.rs:75-96
+        if (a->size < p + 32) return sq_set_error(ctx, SQ_ERR_READER, "Error reading from squish: failed to fill whole buffer");
+        Record r{a->buf + p, get64(a->buf + p + 16), get64(a->buf + p + 24), a->buf + p + 32};
+        p += 32;
+        if (r.comp > a->size - p) return sq_set_error(ctx, SQ_ERR_READER, "Error reading from squish: failed to fill whole buffer");
+        p += r.comp;
+        if (keep_records) a->records.push_back(r);
+    }
+    if (a->size < p + 4) return sq_set_error(ctx, SQ_ERR_READER, "Error reading from squish: failed to fill whole buffer");
+    a->file_count = get32(a->buf + p);
+    a->file_table_off = p + 4;
+    return SQ_OK;
+}
+
+struct ManifestEntry { const uint8_t *path; uint32_t path_len; uint64_t orig_size; uint32_t chunk_count; const uint8_t *hashes; };
+int32_t read_manifest(sq_ctx *ctx, const Archive &a, std::vector<ManifestEntry> *out, uint64_t *total) {
+    uint64_t p = a.file_table_off;
+    *total = 0;
+    for (uint32_t i = 0; i < a.file_count; i++) {
+        ManifestEntry e;
+        if (a.size < p + 4) return sq_set_error(ctx, SQ_ERR_READER, "Error reading from squish: failed to fill whole buffer");
+        e.path_len = get32(a.buf + p); p += 4;
+        if (a.size < p + e.path_len + 12) return sq_set_error(ctx, SQ_ERR_READER, "Error reading from squish: failed to fill whole buffer");
+        e.path = a.buf + p; p += e.path_len;
+        if (!utf8_ok(e.path, e.path_len)) return sq_set_error(ctx, SQ_ERR_ILLEGAL_UTF8, "Illegal UTF8 detected");
+        e.orig_size = get64(a.buf + p); p += 8;
+        e.chunk_count = get32(a.buf + p); p += 4;
+        if (a.size < p + (uint64_t)e.chunk_count * 16) return sq_set_error(ctx, SQ_ERR_READER, "Error reading from squish: failed to fill whole buffer");
+        e.hashes = a.buf + p; p += (uint64_t)e.chunk_count * 16;
+        *total += e.orig_size;
+        out->push_back(e);
+    }
+    return SQ_OK;
+}
+
+// Upper bound of the decoded size of a record payload from its frame headers (all frames must carry
+// a Frame_Content_Size), else `fallback`.  Lets 200k small records avoid 2 MiB of capacity each.
+uint64_t payload_decoded_bound(const uint8_t *p, uint64_t n, uint64_t fallback) {
+    // only the first frame is inspected: a single-frame payload with FCS is what every writer emits
+    if (n < 6 || get32(p) != 0xFD2FB528u) return fallback;
+    uint8_t fhd = p[4];
+    uint32_t fcs_flag = fhd >> 6, single = (fhd >> 5) & 1, did = fhd & 3;
+    uint32_t pos = 5 + (single ? 0 : 1) + (did == 3 ? 4 : did);
+    uint32_t fcs_bytes = fcs_flag == 0 ? (single ? 1 : 0) : fcs_flag == 1 ? 2 : fcs_flag == 2 ? 4 : 8;
+    if (!fcs_bytes || n < pos + fcs_bytes) return fallback;
+    uint64_t fcs = 0;
+    memcpy(&fcs, p + pos, fcs_bytes);
+    if (fcs_flag == 1) fcs += 256;
+    // more than one frame in the payload?  walk blocks to the end of frame 1
+    uint64_t q = pos + fcs_bytes;
+    for (;;) {
+        if (n < q + 3) return fallback;
+        uint32_t bh = p[q] | p[q + 1] << 8 | p[q + 2] << 16;
+        uint32_t type = (bh >> 1) & 3, bsz = bh >> 3;
+        q += 3 + (type == 1 ? 1 : type == 3 ? 0 : bsz);
+        if (type == 3) return fallback;
+        if (bh & 1) break;
+    }
+    if (fhd & 4) q += 4;
+    if (q != n) return fallback;  // trailing frames / garbage: let the decoder decide with the full capacity
+    return std::min<uint64_t>(fcs, fallback);
+}
+
+}  // namespace
+
+extern "C" int32_t sq_archive_list(const char *archive_path, sq_summary *summary, char **listing) {
+    if (!archive_path) return SQ_ERR_INVALID_ARG;
+    Archive a;
+    int32_t rc = open_archive(nullptr, archive_path, &a, false);
+    if (rc) return rc;
+    std::vector<ManifestEntry> man;
+    uint64_t total = 0;
+    if ((rc = read_manifest(nullptr, a, &man, &total))) return rc;
+    if (summary) {
+        memset(summary, 0, sizeof *summary);
+        summary->unique_chunks = a.nchunks;
+        summary->total_original_size = total;
+        summary->archive_size = a.size;
+        summary->timestamp = a.timestamp;
+        summary->compression_ratio = total ? (double)a.size / (double)total * 100.0 : 0.0;  // reader.rs:204-208
+        summary->file_count = a.file_count;
+        snprintf(summary->version, sizeof summary->version, "%s", a.version);
+    }
+    if (listing) {
+        std::string s;
+        for (auto &e : man) { s += std::to_string(e.orig_size); s += ' '; s.append((const char *)e.path, e.path_len); s += '\n'; }
+        char *out = (char *)malloc(s.size() + 1);
+        memcpy(out, s.c_str(), s.size() + 1);
+        *listing = out;
+    }
+    return SQ_OK;
+}
+
+extern "C" int32_t sq_archive_pack(sq_ctx *ctx, const char *input_dir, const char *output_path, int32_t threads, sq_pack_report *report) {
+    if (!ctx || !input_dir || !output_path) return SQ_ERR_INVALID_ARG;
+    const double t0 = now_s();
+    double t_dev = 0;
+    if (threads < 1) threads = 1;
+    std::string root(input_dir);
+    while (root.size() > 1 && (root.back() == '/' || root.back() == '\\')) root.pop_back();  // lib.rs:28
+    std::vector<std::string> paths;
+    int32_t rc = walk_dir(ctx, root, &paths);
+    if (rc) return rc;
+
+    std::vector<FileItem> files(paths.size());
+    std::atomic<int32_t> ferr{0};
+    parallel_for(paths.size(), threads, [&](size_t i) {
+        struct stat st;
+        files[i].disk_path = paths[i];
+        files[i].rel_path = paths[i].substr(root.size() + 1);  // strip_prefix(input_path) (writer.rs:230)
+        if (stat(paths[i].c_str(), &st)) ferr = SQ_ERR_IO; else files[i].size = (uint64_t)st.st_size;
+    });
+    if (ferr) return sq_set_error(ctx, SQ_ERR_IO, "I/O error: stat failed under %s", root.c_str());
+    const uint32_t cs = ctx->chunk_size;
+    std::vector<ChunkRef> chunks;
+    for (size_t i = 0; i < files.size(); i++) {  // chunk rule writer.rs:240-246
+        files[i].first_chunk = chunks.size();
+        for (uint64_t off = 0; off < files[i].size; off += cs)
+            chunks.push_back({(uint32_t)i, (uint32_t)std::min<uint64_t>(cs, files[i].size - off), off});
+        files[i].n_chunks = (uint32_t)(chunks.size() - files[i].first_chunk);
+    }
+    const uint64_t total_chunks = chunks.size();
+    if (total_chunks > ctx->dedup_capacity)
+        return sq_set_error(ctx, SQ_ERR_CAPACITY, "%llu chunks exceed the context's dedup_capacity %llu", (unsigned long long)total_chunks,
+                            (unsigned long long)ctx->dedup_capacity);
+    if ((rc = sq_dedup_reset(ctx))) return rc;  // ChunkStore::new (writer.rs:88)
+
+    FILE *out = fopen(output_path, "wb+");
+    if (!out) return sq_set_error(ctx, SQ_ERR_IO, "I/O error: cannot create %s", output_path);
+    setvbuf(out, nullptr, _IOFBF, 4 << 20);
+    uint8_t pre[32];
+    const size_t hl = 6 + strlen(kVersion);
+    memcpy(pre, kPrefix, 6); memcpy(pre + 6, kVersion, hl - 6);      // write_header (header.rs:35-38)
+    put64(pre + hl, (uint64_t)time(nullptr));                          // write_timestamp (header.rs:55-63)
+    put64(pre + hl + 8, 0);                                            // write_placeholder_u64 (header.rs:192-196)
+    const long count_pos = (long)hl + 8;
+    bool werr = fwrite(pre, 1, hl + 16, out) != hl + 16;
+
+    // batches: up to batch_bytes of chunk payload or max_batch chunks
+    const size_t batch_bytes = 256u << 20;
+    const size_t slot_cap = batch_bytes + (size_t)cs;
+    Batch bufs[2];
+    for (auto &b : bufs) {
+        void *p = nullptr;
+        if ((rc = sq_host_alloc(ctx, slot_cap, &p))) { fclose(out); return rc; }
+        b.pinned = (uint8_t *)p; b.cap = slot_cap;
+    }
+    uint64_t out_cap = sq_encode_bound(cs) * (uint64_t)(batch_bytes / cs + 1) + batch_bytes / 16;
+    void *h_out = nullptr;
+    if ((rc = sq_host_alloc(ctx, out_cap, &h_out))) { fclose(out); return rc; }
+    std::vector<sq_chunk_result> results(ctx->max_batch);
+    std::vector<uint8_t> digests(total_chunks * 16);
+
+    auto fill = [&](Batch *b, uint64_t first, uint64_t *next) {  // host reader pool -> pinned buffer
+        b->spans.clear(); b->used = 0; b->first_gidx = first; b->err = 0;
+        uint64_t g = first;
+        while (g < total_chunks && b->spans.size() < ctx->max_batch) {
+            size_t need = ((size_t)chunks[g].len + 15) & ~(size_t)15;
+            if (b->used + need > b->cap || (b->used >= batch_bytes)) break;
+            b->spans.push_back({b->used, chunks[g].len, 0});
+            b->used += need;
+            g++;
+        }
+        *next = g;
+        std::atomic<int32_t> err{0};
+        parallel_for(b->spans.size(), threads, [&](size_t i) {
+            const ChunkRef &c = chunks[first + i];
+            int fd = open(files[c.file].disk_path.c_str(), O_RDONLY);
+            if (fd < 0) { err = SQ_ERR_IO; return; }
+            size_t got = 0;
+            while (got < c.len) {
+                ssize_t r = pread(fd, b->pinned + b->spans[i].off + got, c.len - got, (off_t)(c.file_off + got));
+                if (r <= 0) { err = SQ_ERR_READER; break; }
+                got += (size_t)r;
+            }
+            close(fd);
+        });
+        b->err = err;
+    };
+
+    uint64_t g = 0, next = 0, unique = 0, payload = 0;
+    int cur = 0;
+    fill(&bufs[cur], 0, &next);
+    while (g < total_chunks && !rc) {
+        Batch *b = &bufs[cur];
+        if (b->err) { rc = sq_set_error(ctx, b->err, "Error reading from squish: input file changed or unreadable"); break; }
+        uint64_t after = next, next2 = next;
+        std::thread prefetch;
+        if (after < total_chunks) prefetch = std::thread([&] { fill(&bufs[cur ^ 1], after, &next2); });
+        const uint32_t n = (uint32_t)b->spans.size();
+        uint64_t used = 0;
+        double td = now_s();
+        rc = sq_pack_host(ctx, b->pinned, b->used, b->spans.data(), n, b->first_gidx, results.data(), h_out, out_cap, &used);
+        t_dev += now_s() - td;
+        if (!rc) {
+            for (uint32_t i = 0; i < n; i++) {
+                memcpy(&digests[(b->first_gidx + i) * 16], results[i].digest, 16);
+                if (!results[i].is_new) continue;
+                uint8_t rec[32];  // chunk record (fsutil/writer.rs:21-36)
+                memcpy(rec, results[i].digest, 16);
+                put64(rec + 16, (uint64_t)SQ_CHUNK_SIZE);  // original_size: chunk_buf.len() (writer.rs:255)
+                put64(rec + 24, results[i].frame_len);
+                werr |= fwrite(rec, 1, 32, out) != 32;
+                werr |= fwrite((uint8_t *)h_out + results[i].frame_off, 1, results[i].frame_len, out) != results[i].frame_len;
+                unique++;
+                payload += results[i].frame_len;
+            }
+        }
+        if (prefetch.joinable()) prefetch.join();
+        g = after; next = next2; cur ^= 1;
+    }
+    if (!rc) {
+        uint64_t dl = 0;
+        rc = sq_dedup_len(ctx, &dl);  // chunk_store.len() (writer.rs:177-184)
+        if (!rc && dl != unique) rc = sq_set_error(ctx, SQ_ERR_OTHER, "Unknown error: dedup index holds %llu digests, %llu records written", (unsigned long long)dl, (unsigned long long)unique);
+    }
+    if (!rc) {
+        uint8_t b8[8], b4[4];
+        put64(b8, unique);
+        fseek(out, count_pos, SEEK_SET);               // patch_u64 (header.rs:224-233)
+        werr |= fwrite(b8, 1, 8, out) != 8;
+        fseek(out, 0, SEEK_END);
+        put32(b4, (uint32_t)files.size());             // write_files_metadata (writer.rs:292-329)
+        werr |= fwrite(b4, 1, 4, out) != 4;
+        for (auto &f : files) {
+            put32(b4, (uint32_t)f.rel_path.size()); werr |= fwrite(b4, 1, 4, out) != 4;
+            werr |= fwrite(f.rel_path.data(), 1, f.rel_path.size(), out) != f.rel_path.size();
+            put64(b8, f.size); werr |= fwrite(b8, 1, 8, out) != 8;
+            put32(b4, f.n_chunks); werr |= fwrite(b4, 1, 4, out) != 4;
+            if (f.n_chunks) werr |= fwrite(&digests[f.first_chunk * 16], 16, f.n_chunks, out) != f.n_chunks;
+        }
+        if (fflush(out)) werr = true;
+        if (werr) rc = sq_set_error(ctx, SQ_ERR_WRITER, "Error writing to squish: %s", output_path);
+    }
+    uint64_t asize = 0;
+    if (!rc) { fseek(out, 0, SEEK_END); asize = (uint64_t)ftell(out); }
+    fclose(out);
+    sq_host_free(ctx, bufs[0].pinned); sq_host_free(ctx, bufs[1].pinned); sq_host_free(ctx, h_out);
+    if (!rc && report) {
+        memset(report, 0, sizeof *report);
+        report->archive_size = asize; report->unique_chunks = unique; report->total_chunks = total_chunks;
+        uint64_t tb = 0; for (auto &f : files) tb += f.size;
+        report->total_input_bytes = tb; report->payload_bytes = payload; report->file_count = (uint32_t)files.size();
+        report->seconds_total = now_s() - t0; report->seconds_device = t_dev;
+    }
+    return rc;
+}
+
+extern "C" int32_t sq_archive_unpack(sq_ctx *ctx, const char *archive_path, const char *output_dir, int32_t threads, sq_summary *summary) {
+    if (!ctx || !archive_path || !output_dir) return SQ_ERR_INVALID_ARG;
+    const double t0 = now_s();
+    double t_dev = 0;
+    if (threads < 1) threads = 1;
+    Archive a;
+    int32_t rc = open_archive(ctx, archive_path, &a, true);
+    if (rc) return rc;
+    std::vector<ManifestEntry> man;
+    uint64_t total = 0;
+    if ((rc = read_manifest(ctx, a, &man, &total))) return rc;
+
+    // read_chunks (reader.rs:259-314): decode every record, keyed by digest; later records overwrite earlier ones
+    struct Decoded { uint64_t off; uint32_t len; };
+    std::vector<Decoded> dec(a.records.size());
+    std::vector<uint64_t> bound(a.records.size());
+    uint64_t total_out = 0;
+    for (size_t i = 0; i < a.records.size(); i++) {
+        const Record &r = a.records[i];
+        if (r.orig > (uint64_t)1 << 40) return sq_set_error(ctx, SQ_ERR_INVALID_CHUNK_SIZE, "Invalid chunk size: %llu bytes", (unsigned long long)r.orig);
+        if (r.orig > 0xFFFFFFFFull || r.comp > 0xFFFFFFFFull) return sq_set_error(ctx, SQ_ERR_READER, "Error reading from squish: chunk record too large");
+        bound[i] = payload_decoded_bound(r.payload, r.comp, r.orig);
+        total_out += (bound[i] + 15) & ~15ull;
+    }
+    uint8_t *store = nullptr;  // all unique data resident in host RAM, like the reference (reader.rs:268)
+    if (total_out) {
+        store = (uint8_t *)malloc(total_out);
+        if (!store) return sq_set_error(ctx, SQ_ERR_OTHER, "Unknown error: cannot allocate %llu bytes", (unsigned long long)total_out);
+    }
+    const uint64_t batch_out = 512ull << 20, batch_in = 256ull << 20;
+    void *h_comp = nullptr, *h_out = nullptr;
+    if ((rc = sq_host_alloc(ctx, batch_in + (4u << 20), &h_comp))) { free(store); return rc; }
+    if ((rc = sq_host_alloc(ctx, batch_out + (4u << 20), &h_out))) { sq_host_free(ctx, h_comp); free(store); return rc; }
+    std::vector<sq_frame> frames;
+    std::vector<sq_frame_result> fres(ctx->max_batch);
+    uint64_t store_off = 0;
+    size_t i = 0;
+    while (i < a.records.size() && !rc) {
+        frames.clear();
+        uint64_t so = 0, dof = 0;
+        size_t first = i;
+        while (i < a.records.size() && frames.size() < ctx->max_batch) {
+            const Record &r = a.records[i];
+            uint64_t sneed = (r.comp + 15) & ~15ull, dneed = (bound[i] + 15) & ~15ull;
+            if (!frames.empty() && (so + sneed > batch_in || dof + dneed > batch_out)) break;
+            if (sneed > batch_in + (4u << 20) || dneed > batch_out + (4u << 20)) { rc = sq_set_error(ctx, SQ_ERR_INVALID_CHUNK_SIZE, "Invalid chunk size: %llu bytes", (unsigned long long)r.orig); break; }
+            frames.push_back({so, dof, (uint32_t)r.comp, (uint32_t)bound[i]});
+            so += sneed; dof += dneed;
+            i++;
+        }
+        if (rc) break;
+        parallel_for(frames.size(), threads, [&](size_t k) { memcpy((uint8_t *)h_comp + frames[k].src_off, a.records[first + k].payload, frames[k].src_len); });
+        double td = now_s();
+        rc = sq_unpack_host(ctx, h_comp, so, frames.data(), (uint32_t)frames.size(), h_out, dof, fres.data());
+        t_dev += now_s() - td;
+        if (rc) break;
+        for (size_t k = 0; k < frames.size(); k++) {
+            if (fres[k].status != SQ_OK) { rc = sq_set_error(ctx, SQ_ERR_READER, "Error reading from squish: chunk %zu failed to decode", first + k); break; }
+            dec[first + k] = {store_off + frames[k].dst_off, fres[k].out_len};
+        }
+        if (rc) break;
+        parallel_for(frames.size(), threads, [&](size_t k) { memcpy(store + store_off + frames[k].dst_off, (uint8_t *)h_out + frames[k].dst_off, fres[k].out_len); });
+        store_off += dof;
+    }
+    sq_host_free(ctx, h_comp); sq_host_free(ctx, h_out);
+    if (rc) { free(store); return rc; }
+
+    struct Key { uint64_t a, b; bool operator==(const Key &o) const { return a == o.a && b == o.b; } };
+    struct KeyHash { size_t operator()(const Key &k) const { return (size_t)(k.a ^ (k.b * 0x9E3779B97F4A7C15ULL)); } };
+    std::unordered_map<Key, size_t, KeyHash> map;
+    map.reserve(a.records.size() * 2);
+    for (size_t k = 0; k < a.records.size(); k++) map[{get64(a.records[k].digest), get64(a.records[k].digest + 8)}] = k;
+
+    // rebuild_files (reader.rs:316-413)
+    std::string outdir(output_dir);
+    mkdir(outdir.c_str(), 0777);
+    std::atomic<int32_t> err{0};
+    std::atomic<size_t> err_idx{0};
+    parallel_for(man.size(), threads, [&](size_t fi) {
+        const ManifestEntry &e = man[fi];
+        std::string full = outdir + "/" + std::string((const char *)e.path, e.path_len);
+        for (size_t p = outdir.size() + 1; p < full.size(); p++)
+            if (full[p] == '/') { full[p] = 0; mkdir(full.c_str(), 0777); full[p] = '/'; }  // create_dir_all(parent)
+        int fd = open(full.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0666);
+        if (fd < 0) { err = SQ_ERR_CREATE_FILE; err_idx = fi; return; }
+        for (uint32_t c = 0; c < e.chunk_count; c++) {
+            auto it = map.find({get64(e.hashes + (size_t)c * 16), get64(e.hashes + (size_t)c * 16 + 8)});
+            if (it == map.end()) { err = SQ_ERR_MISSING_CHUNK; err_idx = fi; break; }  // reader.rs:397-401
+            const Decoded &d = dec[it->second];
+            size_t w = 0;
+            while (w < d.len) {
+                ssize_t r = write(fd, store + d.off + w, d.len - w);
+                if (r <= 0) { err = SQ_ERR_IO; err_idx = fi; break; }
+                w += (size_t)r;
+            }
+        }
+        close(fd);
+    });
+    free(store);
+    if (err) {
+        const ManifestEntry &e = man[err_idx];
+        return sq_set_error(ctx, err, "%s `%.*s`", sq_strerror(err), (int)e.path_len, (const char *)e.path);
+    }
+    if (summary) {
+        memset(summary, 0, sizeof *summary);
+        summary->unique_chunks = a.nchunks; summary->total_original_size = total; summary->archive_size = a.size;
+        summary->timestamp = a.timestamp; summary->file_count = a.file_count;
+        summary->compression_ratio = total ? (double)a.size / (double)total * 100.0 : 0.0;
+        snprintf(summary->version, sizeof summary->version, "%s", a.version);
+        summary->seconds_total = now_s() - t0; summary->seconds_device = t_dev;
+    }
+    return SQ_OK;
+}

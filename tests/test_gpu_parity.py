@@ -1,0 +1,227 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path, called through the C ABI, against
+the CPU oracle on the same inputs.  Bit-exact for digests, dedup verdicts and decoded bytes."""
+import ctypes as C
+import json
+import random
+import struct
+from pathlib import Path
+
+import pytest
+
+from conftest import make_tree, read_tree
+from test_oracle_cpu import kat_cases
+
+pytestmark = pytest.mark.gpu
+GOLD = Path(__file__).resolve().parent / "golden"
+MiB = 1 << 20
+
+
+# ---------------------------------------------------------------- K1 digest
+def test_digest_golden_vectors(ctx):
+    cases = list(kat_cases())
+    got = ctx.digest_batch([d for _, d, _ in cases])
+    for (name, _, want), g in zip(cases, got):
+        assert g == want, name
+
+
+def test_digest_matches_oracle_every_length_class(ctx, oracle):
+    rng = random.Random(11)
+    lens = list(range(1, 300)) + [rng.randrange(300, 5000) for _ in range(200)] + [rng.randrange(5000, 2 * MiB) for _ in range(40)]
+    lens += [1023, 1024, 1025, 2 * MiB - 1, 2 * MiB, 2 * MiB - 63, 2 * MiB - 64, 2 * MiB - 65, MiB + 1]
+    chunks = [rng.randbytes(n) for n in lens]
+    got = ctx.digest_batch(chunks)
+    for c, g in zip(chunks, got):
+        assert g == oracle.hash_chunk(c), len(c)
+
+
+def test_digest_unaligned_spans(ctx, oracle, sq):
+    """spans at arbitrary byte offsets (the slow unaligned path) must give the same digests"""
+    from squishrs_b200 import _lib as L
+    rng = random.Random(5)
+    buf = bytearray(rng.randbytes(3 * MiB))
+    offs = [(1, 241), (3, 1024), (7, 4097), (13, 2 * MiB), (5, 70000), (9, 100), (2, 1025)]
+    spans = (L.SqSpan * len(offs))()
+    for i, (o, n) in enumerate(offs):
+        spans[i].off, spans[i].len = o, n
+    out = (C.c_uint8 * (16 * len(offs)))()
+    ctx.check(ctx.lib.sq_digest_host(ctx.h, (C.c_uint8 * len(buf)).from_buffer(buf), len(buf), spans, len(offs), out))
+    raw = bytes(out)
+    for i, (o, n) in enumerate(offs):
+        assert raw[16 * i:16 * i + 16] == oracle.hash_chunk(bytes(buf[o:o + n])), (o, n)
+
+
+def test_hash_chunk_mirror(sq, ctx, oracle):
+    # reference src/util/tests.rs:88-104
+    h1, h2 = sq.hash_chunk(b"some test data", ctx), sq.hash_chunk(b"some test data", ctx)
+    assert h1 == h2 == bytes.fromhex("8bb490f540ec66cf9f9ea5e575cc3ff2")
+    assert sq.hash_chunk(b"data 1", ctx) != sq.hash_chunk(b"data 2", ctx)
+
+
+# ---------------------------------------------------------------- K2 dedup (ChunkStore)
+def test_insert_first_time_returns_compressed_data(sq, oracle):
+    # reference src/util/tests.rs:106-116
+    store = sq.ChunkStore(sq.Context())
+    data = bytes([1]) * 1024
+    r = store.insert(data)
+    assert r.hash == oracle.hash_chunk(data) and r.compressed_data is not None and store.len() == 1
+
+
+def test_insert_duplicate_returns_none(sq):
+    # reference src/util/tests.rs:118-130
+    store = sq.ChunkStore(sq.Context())
+    data = bytes([2]) * 1024
+    first, second = store.insert(data), store.insert(data)
+    assert first.compressed_data is not None and second.compressed_data is None
+    assert first.hash == second.hash and store.len() == 1 and not store.is_empty()
+
+
+def test_multiple_unique_inserts_increase_len(sq):
+    # reference src/util/tests.rs:132-144
+    store = sq.ChunkStore(sq.Context())
+    assert store.is_empty()
+    for v in (1, 2, 3):
+        store.insert(bytes([v]) * 1024)
+    assert store.len() == 3
+
+
+def test_compressed_data_is_smaller_and_stock_decodable(sq, oracle):
+    # reference src/util/tests.rs:146-166
+    store = sq.ChunkStore(sq.Context())
+    data = bytes([42]) * 2048
+    r = store.insert(data)
+    assert r.compressed_data is not None
+    assert oracle.decompress(r.compressed_data, 2 * MiB) == data
+    assert len(r.compressed_data) < len(data)
+
+
+def test_insert_rejects_bad_sizes(sq):
+    store = sq.ChunkStore(sq.Context())
+    with pytest.raises(sq.SquishError):
+        store.insert(b"")
+    with pytest.raises(sq.SquishError):
+        store.insert(bytes(2 * MiB + 1))
+
+
+def test_dedup_map_matches_oracle_in_one_batch(sq, oracle):
+    """duplicates INSIDE one batch and across batches: verdicts = lowest global chunk index wins"""
+    rng = random.Random(2)
+    uniq = [rng.randbytes(rng.randrange(1, 5000)) for _ in range(300)]
+    seq = [uniq[rng.randrange(len(uniq))] for _ in range(2000)]
+    want_dig, want_new, want_u = oracle.digest_map(seq)  # each blob < 2 MiB => one chunk per blob
+    c = sq.Context()
+    got = []
+    for i in range(0, len(seq), 700):
+        got += c.pack_batch(seq[i:i + 700], gidx_base=i)
+    assert [d for d, _ in got] == want_dig
+    assert [int(f is not None) for _, f in got] == want_new
+    assert c.dedup_len() == want_u
+    c.dedup_reset()
+    assert c.dedup_len() == 0
+
+
+# ---------------------------------------------------------------- K3 encode
+def corpus_samples(sq, sizes=(1, 100, 4096, 70000, 300000, 2 * MiB)):
+    lib = sq.load()
+    out = []
+    for klass in range(7):
+        for n in sizes:
+            b = C.create_string_buffer(n)
+            lib.sq_corpus_fill_host(b, n, 99, klass * 10 + 1, klass)
+            out.append((klass, b.raw))
+    return out
+
+
+def test_frames_decode_with_stock_libzstd(sq, oracle):
+    """every GPU-written frame must decode byte-identically with stock ZSTD_decompress, with
+    capacity == CHUNK_SIZE (what the reference passes, reader.rs:286-303) and exact capacity"""
+    c = sq.Context()
+    samples = corpus_samples(sq)
+    rng = random.Random(4)
+    samples += [(-1, rng.randbytes(n)) for n in (1, 255, 256, 65791, 65792, 131072, 131073, 2 * MiB)]
+    samples += [(-2, bytes(n)) for n in (1, 131072, 2 * MiB)]
+    res = c.pack_batch([s for _, s in samples])
+    for (klass, data), (dig, frame) in zip(samples, res):
+        assert dig == oracle.hash_chunk(data)
+        if frame is None:
+            continue  # duplicate payload (e.g. identical zeros)
+        assert frame[:4] == bytes.fromhex("28b52ffd")
+        assert oracle.decompress(frame, 2 * MiB) == data, (klass, len(data))
+        assert oracle.decompress(frame, len(data)) == data
+        assert len(frame) <= c.lib.sq_encode_bound(len(data))
+
+
+def test_device_corpus_matches_host_corpus(sq, ctx):
+    import torch
+    lib = sq.load()
+    for klass in range(7):
+        n = 300000 + klass
+        t = torch.empty(n + 8, dtype=torch.uint8, device="cuda")
+        ctx.check(lib.sq_corpus_fill_device(ctx.h, t.data_ptr(), n, 1234, 55, klass, None))
+        ctx.check(lib.sq_synchronize(ctx.h, None))
+        h = C.create_string_buffer(n)
+        lib.sq_corpus_fill_host(h, n, 1234, 55, klass)
+        assert bytes(t[:n].cpu().numpy()) == h.raw, klass
+
+
+# ---------------------------------------------------------------- archive level
+def tree_spec():
+    rng = random.Random(8)
+    big = rng.randbytes(2 * MiB)
+    text = (b"the quick brown fox jumps over the lazy dog\n" * 60000)[:2 * MiB + 4321]
+    return {"file.txt": b"hello squish", "a/b/c/nested.txt": b"nested file", "empty.bin": b"", "big.bin": big + big + b"tail",
+            "copy/big2.bin": big + big + b"tail", "text.txt": text, "zeros.bin": bytes(3 * MiB), "exact.bin": big}
+
+
+def test_archive_pack_reference_can_unpack(sq, oracle, tmp_path):
+    """GPU-written archive -> the reference reader (oracle) restores the identical tree;
+    manifest digests and the unique set equal the oracle's own pack of the same tree."""
+    from squishrs_b200.archive import ArchiveReader, ArchiveWriter
+    src = tmp_path / "in"
+    make_tree(src, tree_spec())
+    w = ArchiveWriter(src, tmp_path / "gpu.squish", ctx=sq.Context(), threads=8)
+    size = w.pack()
+    assert size == (tmp_path / "gpu.squish").stat().st_size
+    rc, st = oracle.pack_dir(src, tmp_path / "cpu.squish", threads=8)
+    assert rc == 0
+    assert w.report.unique_chunks == st.unique_chunks and w.report.total_chunks == st.total_chunks
+    rc, _ = oracle.unpack(tmp_path / "gpu.squish", tmp_path / "out")
+    assert rc == 0 and read_tree(tmp_path / "out") == read_tree(src)
+    # manifests as path-keyed maps (walk order is OS dependent)
+    assert parse_manifest(tmp_path / "gpu.squish") == parse_manifest(tmp_path / "cpu.squish")
+    s = ArchiveReader(tmp_path / "gpu.squish").get_summary()
+    assert s.total_original_size == sum(len(v) for v in tree_spec().values()) and len(s.files) == len(tree_spec())
+
+
+def parse_manifest(path):
+    a = Path(path).read_bytes()
+    assert a[:11] == b"squish1.2.0"
+    n = struct.unpack_from("<Q", a, 19)[0]
+    p = 27
+    uniq = set()
+    for _ in range(n):
+        orig, comp = struct.unpack_from("<QQ", a, p + 16)
+        assert orig == 2 * MiB
+        uniq.add(a[p:p + 16])
+        p += 32 + comp
+    nf = struct.unpack_from("<I", a, p)[0]
+    p += 4
+    files = {}
+    for _ in range(nf):
+        pl = struct.unpack_from("<I", a, p)[0]
+        path_s = a[p + 4:p + 4 + pl].decode()
+        p += 4 + pl
+        size, cc = struct.unpack_from("<QI", a, p)
+        p += 12
+        files[path_s] = (size, a[p:p + 16 * cc])
+        p += 16 * cc
+    assert p == len(a)
+    return uniq, files
+
+
+def test_archive_empty_dir(sq, oracle, tmp_path):
+    # tests/cli_tests.rs:55-80
+    from squishrs_b200.archive import ArchiveWriter
+    (tmp_path / "e").mkdir()
+    assert ArchiveWriter(tmp_path / "e", tmp_path / "e.squish", ctx=sq.Context()).pack() == 31
+    rc, s, _ = oracle.list(tmp_path / "e.squish")
+    assert rc == 0 and s.file_count == 0 and s.unique_chunks == 0
