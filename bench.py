@@ -219,8 +219,10 @@ def run_ours(args):
     corpus = torch.empty(n_slots * CHUNK, dtype=torch.uint8, device="cuda")
     d_ids = torch.from_numpy(ids.astype(np.int64)).cuda()
     d_kl = torch.from_numpy(klass.astype(np.int32)).cuda()
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()  # a real (non-NULL) stream: the library launches on it and the events time it
+    torch.cuda.set_stream(stream)
     sp = C.c_void_p(stream.cuda_stream)
+    assert stream.cuda_stream != 0
     t0 = time.perf_counter()
     ctx.check(lib.sq_corpus_fill_slots_device(ctx.h, corpus.data_ptr(), CHUNK, d_ids.data_ptr(), d_kl.data_ptr(), n_slots, SEED, sp))
     torch.cuda.synchronize()

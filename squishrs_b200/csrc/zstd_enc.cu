@@ -11,6 +11,7 @@
 //   place     exclusive scan of frame lengths over the batch -> frame offsets  (enc_scan_kernel)
 //   emit      per block: write header + body (or raw fallback) into d_out      (enc_emit_kernel)
 #include "common.cuh"
+#include "zstd_enc_lz.cuh"
 
 #define SQ_BLOCK_MAX (128u * 1024u)  // zstd Block_Maximum_Size
 #define SQ_MAX_BLOCKS 16u            // 2 MiB / 128 KiB
@@ -21,12 +22,17 @@ struct sq_block_info {   // one per (chunk, block)
 };
 
 struct sq_enc_scratch {
-    sq_block_info *blocks;   // [max_batch * SQ_MAX_BLOCKS]
-    uint32_t *frame_len;     // [max_batch]
-    uint8_t *bodies;         // compressed block bodies, stride SQ_BLOCK_MAX per (chunk, block) of the current wave
-    size_t bodies_cap;
+    sq_block_info *blocks;   // [cap_chunks * SQ_MAX_BLOCKS]
+    uint32_t *frame_len;     // [cap_chunks]
+    uint8_t *bodies;         // compressed block bodies, stride lz::BODY_STRIDE per (chunk, block)
+    zc::Seq *seqs;           // [cap_chunks * lz::MAX_SEQ_PER_CHUNK] parsed sequences
+    lz::BlockMeta *meta;     // [cap_chunks * SQ_MAX_BLOCKS]
+    uint32_t *tab, *head;    // per resident lz CTA: bucketed hash table (never cleared between chunks)
+    uint8_t *lits;           // per entropy warp: gathered literals
+    zc::EncWork *work;       // per entropy warp
+    uint32_t lz_ctas, ent_warps;
     uint32_t cap_chunks;
-    uint32_t *status;        // [0] != 0 => capacity overflow
+    uint32_t *status;        // [0] != 0 => capacity overflow; [1],[2] work counters
 };
 
 namespace {
@@ -158,7 +164,7 @@ __global__ void __launch_bounds__(256) enc_emit_kernel(const uint8_t *__restrict
         f[pos] = (uint8_t)h; f[pos + 1] = (uint8_t)(h >> 8); f[pos + 2] = (uint8_t)(h >> 16);
     }
     const uint8_t *src = bi.type == 0 ? data + spans[c].off + (uint64_t)b * SQ_BLOCK_MAX
-                                      : bodies + ((uint64_t)c * SQ_MAX_BLOCKS + b) * SQ_BLOCK_MAX;
+                                      : bodies + ((uint64_t)c * SQ_MAX_BLOCKS + b) * lz::BODY_STRIDE;
     cta_copy(f + pos + 3, src, bi.body_len);
 }
 
@@ -170,14 +176,28 @@ static int32_t enc_scratch(sq_ctx *ctx, uint32_t n) {
         memset(ctx->enc, 0, sizeof(sq_enc_scratch));
     }
     sq_enc_scratch *e = ctx->enc;
+    if (!e->tab) {  // per-resident-worker state, sized once from the SM count
+        e->lz_ctas = (uint32_t)ctx->sm_count * 4;
+        e->ent_warps = (uint32_t)ctx->sm_count * 16;
+        SQ_CUDA(ctx, cudaMalloc(&e->tab, (size_t)e->lz_ctas * lz::ROWS * lz::ROW_K * sizeof(uint32_t)));
+        SQ_CUDA(ctx, cudaMemset(e->tab, 0, (size_t)e->lz_ctas * lz::ROWS * lz::ROW_K * sizeof(uint32_t)));
+        SQ_CUDA(ctx, cudaMalloc(&e->head, (size_t)e->lz_ctas * lz::ROWS * sizeof(uint32_t)));
+        SQ_CUDA(ctx, cudaMemset(e->head, 0, (size_t)e->lz_ctas * lz::ROWS * sizeof(uint32_t)));
+        SQ_CUDA(ctx, cudaMalloc(&e->lits, (size_t)e->ent_warps * (Z_BLOCK_MAX + 64)));
+        SQ_CUDA(ctx, cudaMalloc(&e->work, (size_t)e->ent_warps * sizeof(zc::EncWork)));
+        SQ_CUDA(ctx, cudaMalloc(&e->status, 8 * sizeof(uint32_t)));
+        SQ_CUDA(ctx, cudaMemset(e->status, 0, 8 * sizeof(uint32_t)));
+    }
     if (e->cap_chunks < n) {
         SQ_CUDA(ctx, cudaDeviceSynchronize());
-        cudaFree(e->blocks); cudaFree(e->frame_len); cudaFree(e->status);
-        uint32_t cap = n > ctx->max_batch ? n : ctx->max_batch;
+        cudaFree(e->blocks); cudaFree(e->frame_len); cudaFree(e->bodies); cudaFree(e->seqs); cudaFree(e->meta);
+        e->blocks = nullptr; e->frame_len = nullptr; e->bodies = nullptr; e->seqs = nullptr; e->meta = nullptr; e->cap_chunks = 0;
+        uint32_t cap = n;
         SQ_CUDA(ctx, cudaMalloc(&e->blocks, (size_t)cap * SQ_MAX_BLOCKS * sizeof(sq_block_info)));
         SQ_CUDA(ctx, cudaMalloc(&e->frame_len, (size_t)cap * sizeof(uint32_t)));
-        SQ_CUDA(ctx, cudaMalloc(&e->status, 4 * sizeof(uint32_t)));
-        SQ_CUDA(ctx, cudaMemset(e->status, 0, 4 * sizeof(uint32_t)));
+        SQ_CUDA(ctx, cudaMalloc(&e->bodies, (size_t)cap * SQ_MAX_BLOCKS * lz::BODY_STRIDE));
+        SQ_CUDA(ctx, cudaMalloc(&e->seqs, (size_t)cap * lz::MAX_SEQ_PER_CHUNK * sizeof(zc::Seq)));
+        SQ_CUDA(ctx, cudaMalloc(&e->meta, (size_t)cap * SQ_MAX_BLOCKS * sizeof(lz::BlockMeta)));
         e->cap_chunks = cap;
     }
     return SQ_OK;
@@ -186,7 +206,8 @@ static int32_t enc_scratch(sq_ctx *ctx, uint32_t n) {
 void sq_enc_destroy(sq_ctx *ctx) {
     sq_enc_scratch *e = ctx->enc;
     if (!e) return;
-    cudaFree(e->blocks); cudaFree(e->frame_len); cudaFree(e->bodies); cudaFree(e->status);
+    cudaFree(e->blocks); cudaFree(e->frame_len); cudaFree(e->bodies); cudaFree(e->status); cudaFree(e->seqs); cudaFree(e->meta);
+    cudaFree(e->tab); cudaFree(e->head); cudaFree(e->lits); cudaFree(e->work);
     delete e;
     ctx->enc = nullptr;
 }
@@ -209,11 +230,20 @@ extern "C" int32_t sq_encode_device(sq_ctx *ctx, const void *d_data, const sq_sp
     cudaStream_t st = sq_stream(ctx, stream);
     const uint32_t nb = n * SQ_MAX_BLOCKS;
     enc_plan_kernel<<<(nb + 255) / 256, 256, 0, st>>>(d_spans, d_select, n, e->blocks);
+    SQ_CUDA(ctx, cudaMemsetAsync(e->status + 1, 0, 2 * sizeof(uint32_t), st));
+    {
+        static_assert(sizeof(lz::BlockOut) == sizeof(sq_block_info), "block info layout");
+        const uint32_t lz_grid = n < e->lz_ctas ? n : e->lz_ctas;
+        lz::lz_kernel<<<lz_grid, lz::THREADS, 0, st>>>((const uint8_t *)d_data, d_spans, d_select, n, e->tab, e->head, e->seqs, e->meta, e->status + 1);
+        const uint32_t ent_ctas = e->ent_warps / 4;
+        lz::entropy_kernel<<<ent_ctas, 128, 0, st>>>((const uint8_t *)d_data, d_spans, d_select, n, e->seqs, e->meta, e->lits, e->bodies,
+                                                     reinterpret_cast<lz::BlockOut *>(e->blocks), e->work, e->status + 2);
+    }
     enc_size_kernel<<<(n + 255) / 256, 256, 0, st>>>(d_spans, d_select, n, e->blocks, e->frame_len);
     enc_scan_kernel<<<1, 1024, 0, st>>>(e->frame_len, n, out_capacity, d_frame_off, d_frame_len, d_total, e->status);
     enc_emit_kernel<<<dim3(SQ_MAX_BLOCKS, n), 256, 0, st>>>((const uint8_t *)d_data, d_spans, n, e->blocks, e->bodies, d_frame_off, d_frame_len,
                                                             (uint8_t *)d_out, e->status);
-    SQ_LAUNCHED(ctx, 4);
+    SQ_LAUNCHED(ctx, 6);
     SQ_CUDA(ctx, cudaGetLastError());
     return SQ_OK;
 }
