@@ -14,7 +14,8 @@ LIB = ROOT / "libsquish_b200.so"
 CLI = ROOT.parent / "bin" / "squishrs"
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-FLAGS = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function", "--expt-relaxed-constexpr"]
+EXTRA = os.environ.get("SQ_NVCC_EXTRA", "").split()
+FLAGS = [*EXTRA, "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function", "--expt-relaxed-constexpr"]
 
 
 def _sources():
@@ -23,6 +24,7 @@ def _sources():
 
 def _fingerprint() -> str:
     h = hashlib.sha256()
+    h.update(os.environ.get("SQ_NVCC_EXTRA", "").encode())
     for p in sorted(list(CSRC.glob("*")) + list((ROOT / "host").glob("*")) + [ROOT.parent / "include" / "squish_b200.h", Path(__file__)]):
         if p.is_file():
             h.update(p.name.encode())

@@ -27,6 +27,7 @@ struct sq_enc_scratch {
     uint8_t *bodies;         // compressed block bodies, stride lz::BODY_STRIDE per (chunk, block)
     zc::Seq *seqs;           // [cap_chunks * lz::MAX_SEQ_PER_CHUNK] parsed sequences
     lz::BlockMeta *meta;     // [cap_chunks * SQ_MAX_BLOCKS]
+    uint32_t *rec;           // [cap_chunks * lz::REC_PER_CHUNK] per-position parse records
     uint32_t *tab, *head;    // per resident lz CTA: bucketed hash table (never cleared between chunks)
     uint8_t *lits;           // per entropy warp: gathered literals
     zc::EncWork *work;       // per entropy warp
@@ -190,14 +191,15 @@ static int32_t enc_scratch(sq_ctx *ctx, uint32_t n) {
     }
     if (e->cap_chunks < n) {
         SQ_CUDA(ctx, cudaDeviceSynchronize());
-        cudaFree(e->blocks); cudaFree(e->frame_len); cudaFree(e->bodies); cudaFree(e->seqs); cudaFree(e->meta);
-        e->blocks = nullptr; e->frame_len = nullptr; e->bodies = nullptr; e->seqs = nullptr; e->meta = nullptr; e->cap_chunks = 0;
+        cudaFree(e->blocks); cudaFree(e->frame_len); cudaFree(e->bodies); cudaFree(e->seqs); cudaFree(e->meta); cudaFree(e->rec);
+        e->rec = nullptr; e->blocks = nullptr; e->frame_len = nullptr; e->bodies = nullptr; e->seqs = nullptr; e->meta = nullptr; e->cap_chunks = 0;
         uint32_t cap = n;
         SQ_CUDA(ctx, cudaMalloc(&e->blocks, (size_t)cap * SQ_MAX_BLOCKS * sizeof(sq_block_info)));
         SQ_CUDA(ctx, cudaMalloc(&e->frame_len, (size_t)cap * sizeof(uint32_t)));
         SQ_CUDA(ctx, cudaMalloc(&e->bodies, (size_t)cap * SQ_MAX_BLOCKS * lz::BODY_STRIDE));
         SQ_CUDA(ctx, cudaMalloc(&e->seqs, (size_t)cap * lz::MAX_SEQ_PER_CHUNK * sizeof(zc::Seq)));
         SQ_CUDA(ctx, cudaMalloc(&e->meta, (size_t)cap * SQ_MAX_BLOCKS * sizeof(lz::BlockMeta)));
+        SQ_CUDA(ctx, cudaMalloc(&e->rec, (size_t)cap * lz::REC_PER_CHUNK * sizeof(uint32_t)));
         e->cap_chunks = cap;
     }
     return SQ_OK;
@@ -206,7 +208,7 @@ static int32_t enc_scratch(sq_ctx *ctx, uint32_t n) {
 void sq_enc_destroy(sq_ctx *ctx) {
     sq_enc_scratch *e = ctx->enc;
     if (!e) return;
-    cudaFree(e->blocks); cudaFree(e->frame_len); cudaFree(e->bodies); cudaFree(e->status); cudaFree(e->seqs); cudaFree(e->meta);
+    cudaFree(e->blocks); cudaFree(e->frame_len); cudaFree(e->bodies); cudaFree(e->status); cudaFree(e->seqs); cudaFree(e->meta); cudaFree(e->rec);
     cudaFree(e->tab); cudaFree(e->head); cudaFree(e->lits); cudaFree(e->work);
     delete e;
     ctx->enc = nullptr;
@@ -234,7 +236,8 @@ extern "C" int32_t sq_encode_device(sq_ctx *ctx, const void *d_data, const sq_sp
     {
         static_assert(sizeof(lz::BlockOut) == sizeof(sq_block_info), "block info layout");
         const uint32_t lz_grid = n < e->lz_ctas ? n : e->lz_ctas;
-        lz::lz_kernel<<<lz_grid, lz::THREADS, 0, st>>>((const uint8_t *)d_data, d_spans, d_select, n, e->tab, e->head, e->seqs, e->meta, e->status + 1);
+        lz::lz_search_kernel<<<lz_grid, lz::THREADS, 0, st>>>((const uint8_t *)d_data, d_spans, d_select, n, e->tab, e->head, e->rec, e->status + 1);
+        lz::lz_chase_kernel<<<(n * SQ_MAX_BLOCKS + 3) / 4, 128, 0, st>>>((const uint8_t *)d_data, d_spans, d_select, n, e->rec, e->seqs, e->meta);
         const uint32_t ent_ctas = e->ent_warps / 4;
         lz::entropy_kernel<<<ent_ctas, 128, 0, st>>>((const uint8_t *)d_data, d_spans, d_select, n, e->seqs, e->meta, e->lits, e->bodies,
                                                      reinterpret_cast<lz::BlockOut *>(e->blocks), e->work, e->status + 2);
@@ -243,7 +246,7 @@ extern "C" int32_t sq_encode_device(sq_ctx *ctx, const void *d_data, const sq_sp
     enc_scan_kernel<<<1, 1024, 0, st>>>(e->frame_len, n, out_capacity, d_frame_off, d_frame_len, d_total, e->status);
     enc_emit_kernel<<<dim3(SQ_MAX_BLOCKS, n), 256, 0, st>>>((const uint8_t *)d_data, d_spans, n, e->blocks, e->bodies, d_frame_off, d_frame_len,
                                                             (uint8_t *)d_out, e->status);
-    SQ_LAUNCHED(ctx, 6);
+    SQ_LAUNCHED(ctx, 7);
     SQ_CUDA(ctx, cudaGetLastError());
     return SQ_OK;
 }
@@ -259,4 +262,18 @@ extern "C" int32_t sq_encode_status(sq_ctx *ctx) {
         return sq_set_error(ctx, SQ_ERR_CAPACITY, "encode output buffer too small");
     }
     return SQ_OK;
+}
+
+// debug: per-phase clock totals of lz_kernel (only when built with -DSQ_LZ_TIMERS); not part of the public ABI
+extern "C" int32_t sq_debug_lz_timers(unsigned long long *out6) {
+#ifdef SQ_LZ_TIMERS
+    cudaDeviceSynchronize();
+    unsigned long long z[8] = {0};
+    if (cudaMemcpyFromSymbol(out6, lz::g_lz_timers, 6 * sizeof(unsigned long long)) != cudaSuccess) return SQ_ERR_CUDA;
+    cudaMemcpyToSymbol(lz::g_lz_timers, z, sizeof z);
+    return SQ_OK;
+#else
+    (void)out6;
+    return SQ_ERR_OTHER;
+#endif
 }

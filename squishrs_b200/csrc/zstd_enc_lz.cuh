@@ -1,23 +1,27 @@
-// K3 stage "compress": LZ match search + parse (lz_kernel) and entropy coding (entropy_kernel).
+// K3 stage "compress": LZ match search (lz_search_kernel), parse (lz_chase_kernel) and entropy coding
+// (entropy_kernel).
 //
-// lz_kernel — one persistent CTA per chunk in flight, 256 threads, the chunk walked in tiles of
+// lz_search_kernel -- one persistent CTA per chunk in flight, 256 threads, the chunk walked in tiles of
 // 1024 positions.  Per tile:
-//   stage   the tile's bytes (+16 lookahead) into shared memory
-//   insert  every position into the chunk's bucketed hash table in HBM: 2^15 rows x 32 entries,
-//           entry = (position+1) | 10-bit tag << 22, ring slot taken with atomicAdd on the row head.
-//           The table is never cleared between chunks: a stale entry is just a candidate position,
-//           and every candidate is verified against the bytes of the CURRENT chunk.
-//   search  every position reads its 128-byte row (4 x 128-bit loads, L1 bypassed), filters by tag,
-//           verifies candidates against the input and keeps the best by 2*len - log2(offset);
-//           also how far the match extends backwards (<= 15 bytes).  Results go to a 2-tile ring in smem.
+//   stage   the tile's bytes (+ lookahead) into shared memory
+//   insert  every position into the chunk's bucketed hash table in HBM: 2^15 rows x 16 entries keyed by a
+//           hash of 6 bytes, entry = (position+1) | 10-bit tag << 22, ring slot taken with atomicAdd on the
+//           row head.  The table is never cleared between chunks: a stale entry is just a candidate
+//           position, and every candidate is verified against the bytes of the CURRENT chunk.
+//   search  every position reads its 64-byte row (L1 bypassed), filters by tag, requests the first 8 bytes
+//           of all sixteen candidates at once, extends the survivors 8 bytes per round in lock-step (up to
+//           64 bytes) and keeps the best by 2*len - log2(offset); plus how far it extends backwards (<= 3).
+//           Results go to a 2-tile ring in shared memory.
 //   decide  every position resolves the lazy (depth 2) choice "if the parser stands here, which match
-//           start does it take" from the ring alone -- no dependence on parser state, so it is parallel.
-//   chase   one lane follows those decisions from the parser cursor, applies backward extension,
-//           substitutes repeat-offset codes, and appends sequences for the block to HBM.
-// Matches never cross a 128 KiB block boundary; repeat-offset knowledge is dropped at every block
-// start so a block that later falls back to raw cannot desynchronise the decoder's history.
+//           start does it take" from the ring alone -- no dependence on parser state, so it is parallel --
+//           and writes a 4-byte record per position to HBM.
+// lz_chase_kernel -- one warp per 128 KiB block follows the records from the block start (windows of 32
+// records per coalesced load, hops by shuffle, literal runs skipped by ballot), extends capped matches
+// warp-wide, applies backward extension, substitutes repeat-offset codes and appends the block's sequences.
+// Matches never cross a block boundary; repeat-offset knowledge is dropped at every block start so a block
+// that later falls back to raw cannot desynchronise the decoder's history.
 //
-// entropy_kernel — one warp per block: gathers literals, then one lane runs the serial block writer
+// entropy_kernel -- one warp per block: gathers literals, then one lane runs the serial block writer
 // (zstd_enc_block.h: Huffman literals, FSE sequence tables, bitstreams) into the block's body slot.
 #pragma once
 #include "common.cuh"
@@ -25,13 +29,19 @@
 
 namespace lz {
 
-constexpr uint32_t ROW_LOG = 15, ROWS = 1u << ROW_LOG, ROW_K = 32, TAG_BITS = 10;
+constexpr uint32_t ROW_LOG = 15, ROWS = 1u << ROW_LOG, ROW_K = 16, TAG_BITS = 10;
 constexpr uint32_t TILE = 1024, RING = 2 * TILE, THREADS = 256, PER_THREAD = TILE / THREADS;
-constexpr uint32_t MIN_MATCH = 5, SEARCH_CAP = 1024, TARGET_LEN = 64, DEFER = 20, MAX_LAZY_ITERS = 8;
+constexpr uint32_t MIN_MATCH = 6, SEARCH_CAP = 64, TARGET_LEN = 64, DEFER = 20, MAX_LAZY_ITERS = 8;
+constexpr uint32_t LOOKAHEAD = SEARCH_CAP + 16;  // bytes staged past the tile so the p-side of every comparison is in smem
 constexpr int32_t ACCEPT_THR = 8;
 constexpr uint32_t BLOCKS_PER_CHUNK = 16;
 constexpr uint32_t BODY_STRIDE = 2 * Z_BLOCK_MAX;  // per-block body slot: literals + <= 8 bytes per sequence always fit
-constexpr uint32_t MAX_SEQ_PER_CHUNK = (2048u * 1024u) / MIN_MATCH + 64;
+constexpr uint32_t SEQ_PER_BLOCK = Z_BLOCK_MAX / MIN_MATCH + 8, MAX_SEQ_PER_CHUNK = BLOCKS_PER_CHUNK * SEQ_PER_BLOCK;
+constexpr uint32_t REC_PER_CHUNK = 2048u * 1024u, MAX_SHIFT = 7;
+
+#ifdef SQ_LZ_TIMERS
+__device__ unsigned long long g_lz_timers[8];
+#endif
 
 struct BlockMeta {  // one per (chunk, block), written by lz_kernel, read by entropy_kernel
     uint32_t seq_start, nseq, last_lits, reserved;
@@ -42,10 +52,8 @@ __device__ __forceinline__ uint64_t ld64_unaligned(const uint8_t *base, uint32_t
     const uintptr_t a = reinterpret_cast<uintptr_t>(base + pos);
     const uint64_t *w = reinterpret_cast<const uint64_t *>(a & ~(uintptr_t)7);
     const uint32_t sh = (uint32_t)(a & 7u) * 8;
-    uint64_t lo = __ldg(w);
-    if (sh == 0) return lo;
-    uint64_t hi = __ldg(w + 1);
-    return (lo >> sh) | (hi << (64 - sh));
+    const uint64_t lo = __ldg(w), hi = __ldg(w + 1);  // branch-free: both loads always issue (memory-level parallelism)
+    return (lo >> sh) | ((hi << 1) << (63 - sh));
 }
 
 // length of the common prefix of in[p..] and in[c..] (c < p), at most maxlen
@@ -68,14 +76,15 @@ __device__ __forceinline__ uint64_t smem_u64(const uint8_t *s, uint32_t li) {
     const uint32_t w0 = s32[0], w1 = s32[1], w2 = s32[2];
     return (uint64_t)__funnelshift_r(w1, w2, sh) << 32 | __funnelshift_r(w0, w1, sh);
 }
-__device__ __forceinline__ uint32_t hash5(uint64_t v) { return (uint32_t)(((v << 24) * 889523592379ULL) >> (64 - (ROW_LOG + TAG_BITS))); }
+// hash of the first MIN_MATCH (6) bytes
+__device__ __forceinline__ uint32_t hash5(uint64_t v) { return (uint32_t)(((v << 16) * 227718039650203ULL) >> (64 - (ROW_LOG + TAG_BITS))); }
 
 __device__ __forceinline__ int32_t sel_score(uint32_t len, uint32_t off) { return (int32_t)(2 * len) - (int32_t)zc::highbit(off + 3); }
 __device__ __forceinline__ int32_t lazy_score(uint32_t len, uint32_t off) { return (int32_t)(4 * len) - (int32_t)zc::highbit(off + 3); }
 
 // Candidate the parser may take at position q (ring lookup + block clamp + acceptance rule)
 struct Cand { uint32_t len, off; int32_t score; };
-__device__ __forceinline__ Cand cand_at(const uint16_t *s_len, const uint32_t *s_off, uint32_t q, uint32_t be) {
+__device__ __forceinline__ Cand cand_at(const uint8_t *s_len, const uint32_t *s_off, uint32_t q, uint32_t be) {
     Cand c = {0, 0, 0};
     if (q >= be) return c;
     uint32_t len = s_len[q & (RING - 1)];
@@ -89,24 +98,36 @@ __device__ __forceinline__ Cand cand_at(const uint16_t *s_len, const uint32_t *s
     return c;
 }
 
-__global__ void __launch_bounds__(THREADS) lz_kernel(const uint8_t *__restrict__ data, const sq_span *__restrict__ spans,
-                                                      const uint8_t *__restrict__ select, uint32_t n_chunks, uint32_t *__restrict__ tab_all,
-                                                      uint32_t *__restrict__ head_all, zc::Seq *__restrict__ seqs_all,
-                                                      BlockMeta *__restrict__ meta_all, uint32_t *__restrict__ counter) {
-    __shared__ __align__(16) uint8_t s_in[TILE + 32];
-    __shared__ uint16_t s_len[RING];
+// Per-position parse record (4 bytes, HBM): what the parser does if its cursor stands on this position.
+//   0                      literal
+//   bits  0-20 offset      bits 21-26 length-1 (length <= SEARCH_CAP; SEARCH_CAP = "at least", extended by the chase)
+//   bits 27-28 backward extension available (<= 3)    bits 29-31 shift from the position to the match start (<= 7)
+__device__ __forceinline__ uint32_t pack_rec(uint32_t off, uint32_t len, uint32_t back, uint32_t shift) {
+    return off | (len - 1) << 21 | back << 27 | shift << 29;
+}
+
+// ---- kernel A: search + decide, fully parallel, one persistent CTA per chunk in flight ----------------
+__global__ void __launch_bounds__(THREADS) lz_search_kernel(const uint8_t *__restrict__ data, const sq_span *__restrict__ spans,
+                                                             const uint8_t *__restrict__ select, uint32_t n_chunks,
+                                                             uint32_t *__restrict__ tab_all, uint32_t *__restrict__ head_all,
+                                                             uint32_t *__restrict__ rec_all, uint32_t *__restrict__ counter) {
+    __shared__ __align__(16) uint8_t s_in[TILE + LOOKAHEAD + 16];
+    __shared__ uint8_t s_len[RING];
     __shared__ uint32_t s_off[RING];
     __shared__ uint8_t s_back[RING];
-    __shared__ uint8_t s_dec[RING];  // 255 = literal, else delta from p to the chosen match start
     __shared__ uint32_t s_chunk;
-    // parser state (owned by thread 0, kept in smem across tiles)
-    __shared__ uint32_t s_cursor, s_anchor, s_nseq, s_blk_seq_start, s_rep[3];
-
+#ifdef SQ_LZ_TIMERS
+    long long tm[6] = {0, 0, 0, 0, 0, 0}, tc = clock64();
+#define LZ_TICK(i) do { long long now_ = clock64(); tm[i] += now_ - tc; tc = now_; } while (0)
+#else
+#define LZ_TICK(i)
+#endif
     uint32_t *tab = tab_all + (size_t)blockIdx.x * ROWS * ROW_K;
     uint32_t *head = head_all + (size_t)blockIdx.x * ROWS;
     const uint32_t tid = threadIdx.x;
 
     for (;;) {
+        __syncthreads();
         if (tid == 0) {
             uint32_t c;
             do { c = atomicAdd(counter, 1u); } while (c < n_chunks && select && !select[c]);
@@ -115,14 +136,12 @@ __global__ void __launch_bounds__(THREADS) lz_kernel(const uint8_t *__restrict__
         __syncthreads();
         const uint32_t chunk = s_chunk;
         if (chunk >= n_chunks) break;
+        LZ_TICK(5);
         const uint8_t *in = data + spans[chunk].off;
         const uint32_t n = spans[chunk].len;
-        const uint32_t n_safe = n;  // unaligned 8-byte loads at pos need pos + 16 <= n
-        zc::Seq *seqs = seqs_all + (size_t)chunk * MAX_SEQ_PER_CHUNK;
-        BlockMeta *meta = meta_all + (size_t)chunk * BLOCKS_PER_CHUNK;
+        uint32_t *rec = rec_all + (size_t)chunk * REC_PER_CHUNK;
         const bool aligned = (reinterpret_cast<uintptr_t>(in) & 7) == 0;
-        if (tid == 0) { s_cursor = 0; s_anchor = 0; s_nseq = 0; s_blk_seq_start = 0; s_rep[0] = 1; s_rep[1] = 4; s_rep[2] = 8; }
-        for (uint32_t i = tid; i < RING; i += THREADS) { s_len[i] = 0; s_dec[i] = 255; }
+        for (uint32_t i = tid; i < RING; i += THREADS) s_len[i] = 0;
         __syncthreads();
 
         const uint32_t n_tiles = (n + TILE - 1) / TILE;
@@ -131,7 +150,7 @@ __global__ void __launch_bounds__(THREADS) lz_kernel(const uint8_t *__restrict__
             const uint32_t be = min(n, (t0 / Z_BLOCK_MAX + 1) * Z_BLOCK_MAX);  // end of the block this tile lies in
             const bool last_tile_of_block = (t1 == be);
             // ---- stage ----
-            for (uint32_t i = tid * 4; i < TILE + 32; i += THREADS * 4) {
+            for (uint32_t i = tid * 4; i < TILE + LOOKAHEAD + 16; i += THREADS * 4) {
                 uint32_t w = 0;
                 const uint32_t g = t0 + i;
                 if (g + 4 <= n && aligned) w = __ldg(reinterpret_cast<const uint32_t *>(in + g));
@@ -139,6 +158,7 @@ __global__ void __launch_bounds__(THREADS) lz_kernel(const uint8_t *__restrict__
                 *reinterpret_cast<uint32_t *>(&s_in[i]) = w;
             }
             __syncthreads();
+            LZ_TICK(0);
             // ---- insert ----
 #pragma unroll
             for (uint32_t k = 0; k < PER_THREAD; k++) {
@@ -151,6 +171,7 @@ __global__ void __launch_bounds__(THREADS) lz_kernel(const uint8_t *__restrict__
                 }
             }
             __syncthreads();
+            LZ_TICK(1);
             // ---- search ----
 #pragma unroll 1
             for (uint32_t k = 0; k < PER_THREAD; k++) {
@@ -160,28 +181,61 @@ __global__ void __launch_bounds__(THREADS) lz_kernel(const uint8_t *__restrict__
                     const uint64_t v = smem_u64(s_in, li);
                     const uint32_t hv = hash5(v);
                     const uint32_t row = hv >> TAG_BITS, tag = hv & ((1u << TAG_BITS) - 1);
-                    const uint32_t maxlen = min(n - p, SEARCH_CAP);
                     int32_t bscore = -1000;
                     const uint4 *r4 = reinterpret_cast<const uint4 *>(tab + row * ROW_K);
-#pragma unroll 1
-                    for (uint32_t j = 0; j < ROW_K / 4 && blen < SEARCH_CAP; j++) {
-                        const uint4 e4 = __ldcg(r4 + j);
-                        const uint32_t e[4] = {e4.x, e4.y, e4.z, e4.w};
+                    static_assert(ROW_K == 16, "the search batches one 16-entry row");
+                    const uint4 ea = __ldcg(r4), eb = __ldcg(r4 + 1), ec = __ldcg(r4 + 2), ed = __ldcg(r4 + 3);
+                    const uint32_t e[16] = {ea.x, ea.y, ea.z, ea.w, eb.x, eb.y, eb.z, eb.w, ec.x, ec.y, ec.z, ec.w, ed.x, ed.y, ed.z, ed.w};
+                    if (p + SEARCH_CAP + 16 <= n) {
+                        // pass 1: the first 8 bytes of all sixteen candidates are requested before any is examined
+                        uint32_t cpos[16];
+                        uint64_t x[16];
+                        uint32_t alive = 0, lens[4] = {0, 0, 0, 0};  // 16 x 8-bit lengths
 #pragma unroll
-                        for (int q = 0; q < 4; q++) {
+                        for (int q = 0; q < 16; q++) {
+                            const uint32_t c = (e[q] & 0x3FFFFFu) - 1u;
+                            const bool ok = (e[q] >> 22) == tag && c < p;
+                            cpos[q] = ok ? c : 0u;
+                            x[q] = ok ? (v ^ ld64_unaligned(in, cpos[q])) : ~0ull;
+                        }
+#pragma unroll
+                        for (int q = 0; q < 16; q++) {
+                            uint32_t l;
+                            if ((uint32_t)x[q]) l = 0;  // tag collision / not a candidate
+                            else if (x[q]) l = (uint32_t)(__ffsll((long long)x[q]) - 1) / 8;
+                            else { l = SEARCH_CAP; alive |= 1u << q; }
+                            lens[q >> 2] |= l << (8 * (q & 3));
+                        }
+                        // extension rounds in lock-step over the survivors: one batch of loads per round
+#pragma unroll 1
+                        for (uint32_t r = 8; r < SEARCH_CAP && alive; r += 8) {
+                            const uint64_t pv = smem_u64(s_in, li + r);
+#pragma unroll
+                            for (int q = 0; q < 16; q++) x[q] = (alive >> q & 1) ? (pv ^ ld64_unaligned(in, cpos[q] + r)) : 0ull;
+#pragma unroll
+                            for (int q = 0; q < 16; q++)
+                                if ((alive >> q & 1) && x[q]) {
+                                    const uint32_t l = r + (uint32_t)(__ffsll((long long)x[q]) - 1) / 8;
+                                    lens[q >> 2] = (lens[q >> 2] & ~(0xFFu << (8 * (q & 3)))) | l << (8 * (q & 3));
+                                    alive &= ~(1u << q);
+                                }
+                        }
+#pragma unroll
+                        for (int q = 0; q < 16; q++) {
+                            const uint32_t l = (lens[q >> 2] >> (8 * (q & 3))) & 0xFF;
+                            if (l < MIN_MATCH) continue;
+                            const uint32_t off = p - cpos[q];
+                            const int32_t sc = sel_score(l, off);
+                            if (sc > bscore) { bscore = sc; blen = l; boff = off; }
+                        }
+                    } else {  // last bytes of the chunk: careful scalar path
+                        const uint32_t maxlen = min(n - p, SEARCH_CAP);
+#pragma unroll 1
+                        for (int q = 0; q < 16; q++) {
                             if ((e[q] >> 22) != tag) continue;
                             const uint32_t c = (e[q] & 0x3FFFFFu) - 1u;
                             if (c >= p) continue;
-                            // first 8 bytes from registers vs the candidate
-                            uint32_t l;
-                            if (c + 16 <= n_safe) {
-                                const uint64_t x = v ^ ld64_unaligned(in, c);
-                                if ((uint32_t)x) continue;  // first 4 bytes differ: tag collision
-                                if (x) l = (uint32_t)(__ffsll((long long)x) - 1) / 8;
-                                else l = 8 + match_length(in, p + 8, c + 8, maxlen - 8, n_safe);
-                            } else {
-                                l = match_length(in, p, c, maxlen, n_safe);
-                            }
+                            const uint32_t l = match_length(in, p, c, maxlen, n);
                             if (l < MIN_MATCH) continue;
                             const uint32_t off = p - c;
                             const int32_t sc = sel_score(l, off);
@@ -190,16 +244,17 @@ __global__ void __launch_bounds__(THREADS) lz_kernel(const uint8_t *__restrict__
                     }
                     if (blen) {
                         const uint32_t c = p - boff;
-                        while (bback < 15 && p > bback && c > bback && in[p - bback - 1] == in[c - bback - 1]) bback++;
+                        while (bback < 3 && p > bback && c > bback && in[p - bback - 1] == in[c - bback - 1]) bback++;
                     }
                 }
                 if (p < t1) {
-                    s_len[p & (RING - 1)] = (uint16_t)blen;
+                    s_len[p & (RING - 1)] = (uint8_t)blen;
                     s_off[p & (RING - 1)] = boff;
                     s_back[p & (RING - 1)] = (uint8_t)bback;
                 }
             }
             __syncthreads();
+            LZ_TICK(2);
             // ---- decide: positions [d0, d1) now have their lookahead window available ----
             const uint32_t d0 = t0 >= DEFER ? t0 - DEFER : 0;
             const uint32_t d1 = last_tile_of_block ? t1 : t1 - DEFER;
@@ -207,71 +262,112 @@ __global__ void __launch_bounds__(THREADS) lz_kernel(const uint8_t *__restrict__
                 // positions before t0 that belong to the previous block were already decided there
                 if (p < t0 && (p / Z_BLOCK_MAX) != (t0 / Z_BLOCK_MAX)) continue;
                 Cand cur = cand_at(s_len, s_off, p, be);
-                uint8_t dec = 255;
+                uint32_t r = 0;
                 if (cur.len) {
                     uint32_t start = p;
-                    for (uint32_t it = 0; it < MAX_LAZY_ITERS && cur.len < TARGET_LEN; it++) {
+                    while (cur.len < TARGET_LEN && start - p + 2 <= MAX_SHIFT) {
                         const Cand c1 = cand_at(s_len, s_off, start + 1, be);
                         if (c1.len && c1.score > cur.score + 4) { cur = c1; start += 1; continue; }
                         const Cand c2 = cand_at(s_len, s_off, start + 2, be);
                         if (c2.len && c2.score > cur.score + 7) { cur = c2; start += 2; continue; }
                         break;
                     }
-                    dec = (uint8_t)(start - p);
+                    r = pack_rec(cur.off, cur.len, s_back[start & (RING - 1)], start - p);
                 }
-                s_dec[p & (RING - 1)] = dec;
+                rec[p] = r;
             }
             __syncthreads();
-            // ---- chase ----
-            if (tid == 0) {
-                uint32_t p = s_cursor, anchor = s_anchor, nseq = s_nseq;
-                uint32_t r0 = s_rep[0], r1 = s_rep[1], r2 = s_rep[2];
-                while (p < d1) {
-                    const uint32_t d = s_dec[p & (RING - 1)];
-                    if (d == 255) { p++; continue; }
-                    uint32_t start = p + d;
-                    uint32_t len = s_len[start & (RING - 1)];
-                    const uint32_t off = s_off[start & (RING - 1)];
-                    if (start + len > be) len = be - start;
-                    if (len >= SEARCH_CAP && start + len < be) {  // capped by the search: extend (rare; long runs)
-                        len += match_length(in, start + len, start + len - off, be - start - len, n_safe);
-                    }
-                    uint32_t k = s_back[start & (RING - 1)];
-                    if (k > start - anchor) k = start - anchor;
-                    start -= k; len += k;
-                    const uint32_t ll = start - anchor;
-                    // repeat-offset code substitution (RFC 8878 3.1.1.5)
-                    uint32_t ob = off + 3;
-                    if (ll) { if (off == r0) ob = 1; else if (off == r1) ob = 2; else if (off == r2) ob = 3; }
-                    else { if (off == r1) ob = 1; else if (off == r2) ob = 2; else if (r0 > 1 && off == r0 - 1) ob = 3; }
-                    if (ob > 3) { r2 = r1; r1 = r0; r0 = off; }
-                    else {
-                        const uint32_t idx = ob - 1 + (ll ? 0 : 1);
-                        if (idx == 1) { const uint32_t tmp = r1; r1 = r0; r0 = tmp; }
-                        else if (idx == 2) { const uint32_t tmp = r2; r2 = r1; r1 = r0; r0 = tmp; }
-                        else if (idx == 3) { const uint32_t tmp = r0 - 1; r2 = r1; r1 = r0; r0 = tmp; }
-                    }
-                    if (nseq < MAX_SEQ_PER_CHUNK) {
-                        zc::Seq sq; sq.ll = ll; sq.ml = len; sq.off_base = ob;
-                        seqs[nseq] = sq;
-                    }
-                    nseq++;
-                    p = start + len;
-                    anchor = p;
-                }
-                if (last_tile_of_block) {  // close the block
-                    const uint32_t b = t0 / Z_BLOCK_MAX;
-                    BlockMeta m;
-                    m.seq_start = s_blk_seq_start; m.nseq = min(nseq, MAX_SEQ_PER_CHUNK) - s_blk_seq_start; m.last_lits = be - anchor; m.reserved = 0;
-                    meta[b] = m;
-                    s_blk_seq_start = min(nseq, MAX_SEQ_PER_CHUNK);
-                    anchor = be; p = be;
-                    r0 = r1 = r2 = 0;  // forget repeat offsets: the next block must not depend on this one being emitted compressed
-                }
-                s_cursor = p; s_anchor = anchor; s_nseq = nseq; s_rep[0] = r0; s_rep[1] = r1; s_rep[2] = r2;
-            }
-            __syncthreads();
+            LZ_TICK(3);
         }
+    }
+#ifdef SQ_LZ_TIMERS
+    if (tid == 0) for (int i = 0; i < 6; i++) atomicAdd(&g_lz_timers[i], (unsigned long long)tm[i]);
+#endif
+}
+
+// ---- kernel B: chase.  One warp per 128 KiB block walks the records from the block start: lanes hold a
+// window of 32 records (one coalesced load), hops inside the window are shuffles, literal runs are skipped
+// with a ballot, capped matches are extended 256 bytes per step by the whole warp. ------------------------
+__device__ __forceinline__ uint32_t warp_extend(const uint8_t *__restrict__ in, uint32_t a, uint32_t b, uint32_t maxlen, uint32_t lane) {
+    // common prefix of in[a..] and in[b..] (b < a), at most maxlen; all lanes return the same value
+    uint32_t done = 0;
+    while (done < maxlen) {
+        const uint32_t i = done + lane * 8;
+        uint32_t m = 8;  // bytes of this lane's 8-byte slot that match (slots past maxlen count as matching)
+        if (i < maxlen) {
+            const uint32_t lim = min(8u, maxlen - i);
+            m = 0;
+            while (m < lim && in[a + i + m] == in[b + i + m]) m++;
+            if (m == lim) m = 8;
+        }
+        const uint32_t bad = __ballot_sync(0xffffffffu, m != 8);
+        if (bad) {
+            const uint32_t first = __ffs((int)bad) - 1;
+            const uint32_t mm = __shfl_sync(0xffffffffu, m, first);
+            return min(maxlen, done + first * 8 + mm);
+        }
+        done += 256;
+    }
+    return maxlen;
+}
+
+__global__ void __launch_bounds__(128) lz_chase_kernel(const uint8_t *__restrict__ data, const sq_span *__restrict__ spans,
+                                                        const uint8_t *__restrict__ select, uint32_t n_chunks,
+                                                        const uint32_t *__restrict__ rec_all, zc::Seq *__restrict__ seqs_all,
+                                                        BlockMeta *__restrict__ meta_all) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t item = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (item >= n_chunks * BLOCKS_PER_CHUNK) return;
+    const uint32_t chunk = item / BLOCKS_PER_CHUNK, b = item % BLOCKS_PER_CHUNK;
+    if (select && !select[chunk]) return;
+    const uint32_t n = spans[chunk].len;
+    const uint32_t bs = b * Z_BLOCK_MAX;
+    if (bs >= n) return;
+    const uint32_t be = min(n, bs + Z_BLOCK_MAX);
+    const uint8_t *in = data + spans[chunk].off;
+    const uint32_t *rec = rec_all + (size_t)chunk * REC_PER_CHUNK;
+    zc::Seq *seqs = seqs_all + (size_t)chunk * MAX_SEQ_PER_CHUNK + (size_t)b * SEQ_PER_BLOCK;
+    uint32_t p = bs, anchor = bs, nseq = 0;
+    uint32_t r0 = 0, r1 = 0, r2 = 0;  // repeat offsets are unknown at a block start (see file header); the frame's first block knows 1,4,8
+    if (b == 0) { r0 = 1; r1 = 4; r2 = 8; }
+    while (p < be) {
+        const uint32_t base = p & ~31u;
+        const uint32_t mine = (base + lane < be) ? __ldg(rec + base + lane) : 0u;
+        uint32_t live = __ballot_sync(0xffffffffu, mine != 0);
+        live &= 0xffffffffu << (p - base);  // records at or after the cursor
+        while (live) {
+            const uint32_t idx = __ffs((int)live) - 1;  // next non-literal record at or after the cursor
+            const uint32_t r = __shfl_sync(0xffffffffu, mine, idx);
+            p = base + idx;
+            uint32_t off = r & 0x1FFFFFu, len = ((r >> 21) & 63u) + 1, back = (r >> 27) & 3u, start = p + (r >> 29);
+            if (len >= SEARCH_CAP && start + len < be) len += warp_extend(in, start + len, start + len - off, be - start - len, lane);
+            if (back > start - anchor) back = start - anchor;
+            start -= back; len += back;
+            const uint32_t ll = start - anchor;
+            // repeat-offset code substitution (RFC 8878 3.1.1.5)
+            uint32_t ob = off + 3;
+            if (ll) { if (off == r0) ob = 1; else if (off == r1) ob = 2; else if (off == r2) ob = 3; }
+            else { if (off == r1) ob = 1; else if (off == r2) ob = 2; else if (r0 > 1 && off == r0 - 1) ob = 3; }
+            if (ob > 3) { r2 = r1; r1 = r0; r0 = off; }
+            else {
+                const uint32_t ix = ob - 1 + (ll ? 0 : 1);
+                if (ix == 1) { const uint32_t tmp = r1; r1 = r0; r0 = tmp; }
+                else if (ix == 2) { const uint32_t tmp = r2; r2 = r1; r1 = r0; r0 = tmp; }
+                else if (ix == 3) { const uint32_t tmp = r0 - 1; r2 = r1; r1 = r0; r0 = tmp; }
+            }
+            if (lane == 0 && nseq < SEQ_PER_BLOCK) { zc::Seq sq; sq.ll = ll; sq.ml = len; sq.off_base = ob; seqs[nseq] = sq; }
+            nseq++;
+            p = start + len;
+            anchor = p;
+            if (p >= base + 32) { live = 0; break; }
+            live &= 0xffffffffu << (p - base);
+        }
+        if (p < base + 32) p = base + 32;  // only literals left in this window
+    }
+    if (lane == 0) {
+        BlockMeta m;
+        m.seq_start = b * SEQ_PER_BLOCK; m.nseq = min(nseq, SEQ_PER_BLOCK); m.last_lits = be - anchor; m.reserved = 0;
+        meta_all[(size_t)chunk * BLOCKS_PER_CHUNK + b] = m;
     }
 }
 

@@ -23,6 +23,9 @@ struct Params {
     int alt_window;    // how many previous positions' offsets are tried as rep candidates (rep_mode 1)
     int sel_mul;       // 0: longest wins; else maximise len*sel_mul - log2(offset)
     int accept_thr;    // a match is used only if len*4 - log2(off_base) >= accept_thr
+    int skip_stride;   // 0 = search every position; S = search p%S==0 first, others inherit if the anchor's match still has >= skip_min left
+    int skip_min;
+    int precheck;      // 1: a candidate must match the 8 bytes ending at the current best length to be examined; 2: + inherit from anchor position (stride 4)
 };
 
 static inline uint64_t rd64(const uint8_t *p) { uint64_t v; memcpy(&v, p, 8); return v; }
@@ -50,6 +53,7 @@ struct Model {
     const uint8_t *s; uint32_t n; Params P;
     std::vector<Match> best, alt;
     std::vector<uint8_t> back;
+    uint64_t nskip = 0, nsearch = 0, nverify = 0, ncheap = 0;
     void search() {
         best.assign(n, {0, 0}); alt.assign(n, {0, 0}); back.assign(n, 0);
         const uint32_t rows = 1u << P.hash_log, K = (uint32_t)P.row_entries;
@@ -62,15 +66,48 @@ struct Model {
                 uint32_t h = hashN(s + p, P.min_match, P.hash_log);
                 tab[(size_t)h * K + (head[h]++ % K)] = p + 1;
             }
+            for (int round = 0; round < 2; round++)
             for (uint32_t p = t0; p < t1 && p + 8 <= n; p++) {
+                if (P.precheck == 2 && !P.skip_stride) { bool anchor_pos = (p & 3) == 0; if ((round == 0) != anchor_pos) continue; }
+                else if (P.skip_stride) {
+                    bool anchor_pos = (p % P.skip_stride) == 0;
+                    if ((round == 0) != anchor_pos) continue;
+                    if (!anchor_pos) {
+                        uint32_t q = p - (p % P.skip_stride);
+                        if (q >= t0 && best[q].len >= (p - q) + (uint32_t)P.skip_min) { best[p] = {best[q].len - (p - q), best[q].off}; nskip++; continue; }
+                    }
+                } else if (round && P.precheck != 2) continue;
+                nsearch++;
                 uint32_t h = hashN(s + p, P.min_match, P.hash_log);
                 Match b = {0, 0};
+                int exttop = getenv("ENC_EXTTOP") ? atoi(getenv("ENC_EXTTOP")) : 0;
+                uint32_t near_off[8]; int nnear = 0;
+                if (exttop) {  // the T nearest candidates whose first 8 bytes match
+                    for (uint32_t k = 0; k < K; k++) {
+                        uint32_t e = tab[(size_t)h * K + k];
+                        if (!e || e - 1 >= p) continue;
+                        uint32_t c = e - 1;
+                        if (rd64(s + c) != rd64(s + p)) continue;
+                        uint32_t off = p - c; int i = nnear < exttop ? nnear++ : exttop;
+                        if (i == exttop) { if (off >= near_off[exttop - 1]) continue; i = exttop - 1; }
+                        near_off[i] = off;
+                        while (i > 0 && near_off[i] < near_off[i - 1]) { std::swap(near_off[i], near_off[i - 1]); i--; }
+                    }
+                }
+                if (P.precheck == 2 && (p & 3) && (p & ~3u) >= t0) {
+                    uint32_t q = p & ~3u;
+                    if (best[q].len >= (p - q) + 8) b = {best[q].len - (p - q), best[q].off};
+                }
                 for (uint32_t k = 0; k < K; k++) {
                     uint32_t e = tab[(size_t)h * K + k];
                     if (!e || e - 1 >= p) continue;
                     uint32_t c = e - 1;
                     if (rd32(s + c) != rd32(s + p)) continue;
+                    if (P.precheck && b.len >= 16 && p + b.len <= n && rd64(s + c + b.len - 8) != rd64(s + p + b.len - 8)) { ncheap++; continue; }
                     uint32_t l = match_len(s, p, c, n);
+                    if (exttop && l > 8) { bool keep = false; for (int i = 0; i < nnear; i++) keep |= near_off[i] == p - c; if (!keep) l = 8; }
+                    if (l > (uint32_t)P.target_len && getenv("ENC_CAPLEN")) l = P.target_len;
+                    nverify++;
                     uint32_t off = p - c;
                     if (P.sel_mul == 0) { if (l > b.len || (l == b.len && off < b.off)) b = {l, off}; }
                     else if (b.len == 0 || (int)l * P.sel_mul - (int)highbit(off + 3) > (int)b.len * P.sel_mul - (int)highbit(b.off + 3)) b = {l, off};
@@ -111,7 +148,7 @@ struct Model {
         for (uint32_t p = 0; p < n; p++) {
             if (best[p].len) {
                 uint32_t o = best[p].off, k = 0;
-                while (k < 15 && p > k && p - k > o && s[p - k - 1] == s[p - k - 1 - o]) k++;
+                while (k < (uint32_t)(getenv("ENC_BACK") ? atoi(getenv("ENC_BACK")) : 15) && p > k && p - k > o && s[p - k - 1] == s[p - k - 1 - o]) k++;
                 back[p] = (uint8_t)k;
             }
             if (P.rep_mode == 3 || P.rep_mode == 5) {  // last two distinct valid offsets seen before p (scan-friendly on the GPU)
@@ -227,6 +264,7 @@ extern "C" long enc_model_frame(const uint8_t *src, uint32_t n, uint8_t *dst, ui
                         if (c2.len && c2.score > cur.score + (d == 1 ? 4 : 7)) { cur = c2; start += d; improved = true; break; }
                     }
                     if (!improved || cur.len >= (uint32_t)P.target_len) break;
+                    if (getenv("ENC_MAXSHIFT") && start - p + 2 > (uint32_t)atoi(getenv("ENC_MAXSHIFT"))) break;
                 }
             }
             // backward extension (only for non-rep matches found by the search; bounded by literal run)
@@ -267,7 +305,7 @@ extern "C" long enc_model_frame(const uint8_t *src, uint32_t n, uint8_t *dst, ui
         }
     }
     delete wk;
-    if (stats) { stats[0] = total_seq; stats[1] = total_lit; stats[2] = rep_seq; stats[3] = of_bits; stats[4] = ml_sum; }
+    if (stats) { stats[0] = total_seq; stats[1] = total_lit; stats[2] = rep_seq; stats[3] = of_bits; stats[4] = ml_sum; stats[5] = (uint32_t)M.nsearch; stats[6] = (uint32_t)M.nskip; stats[7] = (uint32_t)(M.nverify >> 4); }
     return o - dst;
 }
 

@@ -1,0 +1,27 @@
+"""Dev tool: run one pack step built with SQ_NVCC_EXTRA=-DSQ_LZ_TIMERS and print lz_kernel's per-phase clock shares."""
+import ctypes as C, sys, time
+sys.path.insert(0, "/root/repo")
+import numpy as np, torch
+import squishrs_b200 as sq
+from bench import corpus_plan, CHUNK, SEED
+lib = sq.load(); ctx = sq.Context(max_batch_chunks=2048)
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
+ids, kl = corpus_plan(n)
+corpus = torch.empty(n * CHUNK, dtype=torch.uint8, device="cuda")
+d_ids = torch.from_numpy(ids.astype(np.int64)).cuda(); d_kl = torch.from_numpy(kl.astype(np.int32)).cuda()
+ctx.check(lib.sq_corpus_fill_slots_device(ctx.h, corpus.data_ptr(), CHUNK, d_ids.data_ptr(), d_kl.data_ptr(), n, SEED, None))
+ctx.check(lib.sq_synchronize(ctx.h, None))
+sp = np.zeros((n, 2), dtype=np.uint64); sp[:, 0] = np.arange(n) * CHUNK; sp[:, 1] = CHUNK
+d_sp = torch.from_numpy(sp.view(np.int64)).cuda()
+cap = n * int(lib.sq_encode_bound(CHUNK)); out = torch.empty(cap, dtype=torch.uint8, device="cuda")
+res = torch.empty(n * 32, dtype=torch.uint8, device="cuda"); used = C.c_uint64()
+tm = (C.c_ulonglong * 6)()
+for rep in range(2):
+    ctx.dedup_reset(); lib.sq_debug_lz_timers(tm)
+    torch.cuda.synchronize(); t = time.time()
+    ctx.check(lib.sq_pack_device(ctx.h, corpus.data_ptr(), d_sp.data_ptr(), n, 0, res.data_ptr(), out.data_ptr(), cap, C.byref(used), None))
+    dt = time.time() - t
+print(f"pack {n} chunks: {dt*1e3:.1f} ms  {n*CHUNK/dt/1e9:.2f} GB/s  out {used.value/1e6:.1f} MB")
+if lib.sq_debug_lz_timers(tm) == 0:
+    tot = sum(tm); names = ["stage", "insert", "search", "decide", "chase", "fetch"]
+    print("  ".join(f"{nm} {v/tot*100:.1f}%" for nm, v in zip(names, tm)))
