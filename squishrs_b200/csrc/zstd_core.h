@@ -8,7 +8,7 @@
 
 #if defined(__CUDACC__)
 #define ZHD __host__ __device__ __forceinline__
-#define ZHDN __host__ __device__
+#define ZHDN __host__ __device__ inline
 #define ZCONST __constant__ const
 #else
 #define ZHD static inline

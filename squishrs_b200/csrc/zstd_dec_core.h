@@ -1,0 +1,500 @@
+// zstd frame decoder core (K4), written for warp-uniform execution: on the GPU all 32 lanes of a warp
+// run the same control flow over one frame (table parsing and the serial FSE sequence chain are
+// computed redundantly and identically by every lane -- free in SIMT), and the lanes split only where
+// the format allows: the 4 Huffman literal streams and the byte copies of literal runs and matches.
+// On the host the same code compiles with a "warp" of one lane, which is how tests/ check it against
+// frames written by stock libzstd.  Format: RFC 8878.
+#pragma once
+#include "zstd_core.h"
+
+namespace zd {
+
+#if defined(__CUDA_ARCH__)
+#define ZD_LANE() (threadIdx.x & 31u)
+#define ZD_WARP 32u
+#define ZD_SYNC() __syncwarp()
+#else
+#define ZD_LANE() 0u
+#define ZD_WARP 1u
+#define ZD_SYNC() ((void)0)
+#endif
+#if defined(__CUDACC__)
+#define ZD_DEV __host__ __device__ inline
+#else
+#define ZD_DEV static inline
+#endif
+
+struct SeqCell {  // one FSE state of a sequence table, pre-joined with the code's base value / extra bits
+    uint16_t next_base;
+    uint8_t nb_bits;      // state bits to read for the transition
+    uint8_t extra_bits;   // extra bits of the code
+    uint32_t base_value;  // LL/ML: base length; OF: 1 << code
+};
+
+struct Tables {          // per-warp state that persists across the blocks of a frame (treeless / repeat modes)
+    uint16_t huf[1u << Z_HUF_MAXBITS];  // symbol | nb_bits << 8
+    SeqCell ll[1u << Z_LL_MAXLOG], ml[1u << Z_ML_MAXLOG], of[1u << Z_OF_MAXLOG];
+    uint32_t huf_log, ll_log, ml_log, of_log;
+    uint32_t have_huf, have_ll, have_ml, have_of;
+};
+
+enum { ERR_CORRUPT = -1, ERR_CAPACITY = -2 };
+
+// ---- loads ------------------------------------------------------------------------------------------
+ZD_DEV uint64_t load64(const uint8_t *p) {  // unaligned little-endian 8 bytes; caller guarantees p-7 .. p+15 readable
+#if defined(__CUDA_ARCH__)
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const uint64_t *w = reinterpret_cast<const uint64_t *>(a & ~(uintptr_t)7);
+    const uint32_t sh = (uint32_t)(a & 7u) * 8;
+    const uint64_t lo = w[0], hi = w[1];
+    return (lo >> sh) | ((hi << 1) << (63 - sh));
+#else
+    uint64_t v;
+    memcpy(&v, p, 8);
+    return v;
+#endif
+}
+
+// Backward bit reader over [start, start+size): bits are consumed from the top (just below the sentinel).
+struct BitReader {
+    const uint8_t *start;
+    int64_t pos;  // number of unread bits; may go negative on corrupt input (reads then return zeros)
+};
+ZD_DEV int br_init(BitReader *b, const uint8_t *start, uint32_t size) {
+    if (size == 0) return ERR_CORRUPT;
+    const uint8_t last = start[size - 1];
+    if (last == 0) return ERR_CORRUPT;
+    b->start = start;
+    b->pos = (int64_t)(size - 1) * 8 + zc::highbit(last);
+    return 0;
+}
+ZD_DEV uint32_t br_peek(const BitReader *b, uint32_t n) {  // n <= 32; bits [pos-n, pos)
+    if (n == 0) return 0;
+    const int64_t lo = b->pos - (int64_t)n;
+    if (lo >= 0) {
+        const uint64_t v = load64(b->start + (lo >> 3));
+        return (uint32_t)(v >> (lo & 7)) & (uint32_t)((1ull << n) - 1);
+    }
+    if (b->pos <= 0) return 0;
+    // partially past the beginning: the missing low bits read as zero
+    const uint64_t v = load64(b->start);
+    return (uint32_t)((v & ((1ull << b->pos) - 1)) << (uint32_t)(-lo)) & (uint32_t)((1ull << n) - 1);
+}
+ZD_DEV uint32_t br_read(BitReader *b, uint32_t n) {
+    const uint32_t v = br_peek(b, n);
+    b->pos -= n;
+    return v;
+}
+
+// Forward bit reader (FSE table descriptions)
+struct FwdReader { const uint8_t *p; uint32_t size; uint32_t bit; };
+ZD_DEV uint32_t fr_peek(const FwdReader *r, uint32_t n) {
+    const uint32_t byte = r->bit >> 3;
+    uint64_t v = 0;
+    for (uint32_t i = 0; i < 5 && byte + i < r->size; i++) v |= (uint64_t)r->p[byte + i] << (8 * i);
+    return (uint32_t)(v >> (r->bit & 7)) & ((1u << n) - 1);
+}
+
+// FSE table description -> normalised counts.  Returns bytes consumed or < 0.
+ZD_DEV int read_ncount(const uint8_t *src, uint32_t size, int16_t *norm, uint32_t max_sym_cap, uint32_t max_log, uint32_t *max_sym, uint32_t *tl) {
+    if (size < 1) return ERR_CORRUPT;
+    FwdReader r = {src, size, 0};
+    const uint32_t al = fr_peek(&r, 4) + 5;
+    r.bit += 4;
+    if (al > max_log) return ERR_CORRUPT;
+    int32_t remaining = 1 << al;
+    uint32_t s = 0;
+    while (remaining > 0 && s <= max_sym_cap) {
+        if ((r.bit >> 3) >= size) return ERR_CORRUPT;
+        const uint32_t bits = zc::highbit((uint32_t)remaining + 1) + 1;
+        uint32_t v = fr_peek(&r, bits);
+        const uint32_t lower = (1u << (bits - 1)) - 1;
+        const uint32_t thresh = (1u << bits) - 1 - ((uint32_t)remaining + 1);
+        if ((v & lower) < thresh) { r.bit += bits - 1; v &= lower; }
+        else { r.bit += bits; if (v > lower) v -= thresh; }
+        const int32_t prob = (int32_t)v - 1;
+        remaining -= prob < 0 ? 1 : prob;
+        norm[s++] = (int16_t)prob;
+        if (prob == 0) {
+            for (;;) {
+                if ((r.bit >> 3) >= size) return ERR_CORRUPT;
+                const uint32_t rep = fr_peek(&r, 2);
+                r.bit += 2;
+                for (uint32_t i = 0; i < rep && s <= max_sym_cap; i++) norm[s++] = 0;
+                if (rep != 3) break;
+            }
+        }
+    }
+    if (remaining != 0 || s == 0) return ERR_CORRUPT;
+    *max_sym = s - 1;
+    *tl = al;
+    const uint32_t used = (r.bit + 7) >> 3;
+    return used > size ? ERR_CORRUPT : (int)used;
+}
+
+// ---- Huffman literals ---------------------------------------------------------------------------------
+// Reads the tree description at src; fills T->huf.  Returns bytes consumed or < 0.  (Executed uniformly.)
+ZD_DEV int read_huf_tree(const uint8_t *src, uint32_t size, Tables *T, uint8_t *weights /* 256 */, zc::FseDCell *wcells /* 64 */) {
+    if (size < 1) return ERR_CORRUPT;
+    const uint32_t hb = src[0];
+    uint32_t nw = 0, used;
+    if (hb >= 128) {  // direct 4-bit weights
+        nw = hb - 127;
+        used = 1 + (nw + 1) / 2;
+        if (used > size) return ERR_CORRUPT;
+        for (uint32_t i = 0; i < nw; i++) weights[i] = (i & 1) ? (src[1 + i / 2] & 15) : (src[1 + i / 2] >> 4);
+    } else {  // FSE-compressed weights: table description (max log 6) then two interleaved states
+        used = 1 + hb;
+        if (hb == 0 || used > size) return ERR_CORRUPT;
+        int16_t norm[16];
+        uint32_t max_sym = 0, tl = 0;
+        const int hs = read_ncount(src + 1, hb, norm, 12, 6, &max_sym, &tl);
+        if (hs < 0 || (uint32_t)hs >= hb) return ERR_CORRUPT;
+        uint16_t next[16];
+        zc::fse_build_dtable(wcells, norm, max_sym, tl, next);
+        BitReader b;
+        if (br_init(&b, src + 1 + hs, hb - hs) < 0) return ERR_CORRUPT;
+        uint32_t s1 = br_read(&b, tl), s2 = br_read(&b, tl);
+        for (;;) {
+            if (nw >= 254) return ERR_CORRUPT;
+            weights[nw++] = wcells[s1].sym;
+            { const uint32_t nb = wcells[s1].nb_bits; if (b.pos < (int64_t)nb) { weights[nw++] = wcells[s2].sym; break; } s1 = wcells[s1].base + br_read(&b, nb); }
+            if (nw >= 254) return ERR_CORRUPT;
+            weights[nw++] = wcells[s2].sym;
+            { const uint32_t nb = wcells[s2].nb_bits; if (b.pos < (int64_t)nb) { weights[nw++] = wcells[s1].sym; break; } s2 = wcells[s2].base + br_read(&b, nb); }
+        }
+    }
+    if (nw == 0 || nw > 255) return ERR_CORRUPT;
+    // implied last weight completes the sum of 2^(w-1) to a power of two
+    uint32_t sum = 0;
+    for (uint32_t i = 0; i < nw; i++) { if (weights[i] > Z_HUF_MAXBITS) return ERR_CORRUPT; if (weights[i]) sum += 1u << (weights[i] - 1); }
+    if (sum == 0) return ERR_CORRUPT;
+    const uint32_t max_bits = zc::highbit(sum) + 1;
+    if (max_bits > Z_HUF_MAXBITS) return ERR_CORRUPT;
+    const uint32_t rest = (1u << max_bits) - sum;
+    if (rest == 0 || (rest & (rest - 1))) return ERR_CORRUPT;
+    weights[nw] = (uint8_t)(zc::highbit(rest) + 1);
+    const uint32_t nsym = nw + 1;
+    // decode table: weights ascending, symbols ascending, 2^(w-1) consecutive cells each
+    uint32_t idx = 0;
+    for (uint32_t w = 1; w <= max_bits; w++) {
+        const uint32_t span = 1u << (w - 1), nb = max_bits + 1 - w;
+        for (uint32_t s = 0; s < nsym; s++) {
+            if (weights[s] != w) continue;
+            const uint16_t cell = (uint16_t)(s | nb << 8);
+            for (uint32_t k = ZD_LANE(); k < span; k += ZD_WARP) T->huf[idx + k] = cell;  // lanes split the fill
+            idx += span;
+        }
+    }
+    ZD_SYNC();
+    T->huf_log = max_bits;
+    T->have_huf = 1;
+    return (int)used;
+}
+
+// one Huffman stream -> n symbols at out (executed by ONE lane)
+ZD_DEV int huf_decode_stream(const uint8_t *src, uint32_t size, uint8_t *out, uint32_t n, const Tables *T) {
+    BitReader b;
+    if (br_init(&b, src, size) < 0) return ERR_CORRUPT;
+    const uint32_t log = T->huf_log;
+    for (uint32_t i = 0; i < n; i++) {
+        const uint32_t cell = T->huf[br_peek(&b, log)];
+        out[i] = (uint8_t)cell;
+        b.pos -= cell >> 8;
+    }
+    return b.pos == 0 ? 0 : ERR_CORRUPT;
+}
+
+struct Literals { const uint8_t *ptr; uint32_t size; uint32_t rle; uint8_t rle_byte; };
+
+// Literals section.  Returns bytes consumed or < 0.  Decoded Huffman literals land in litbuf (>= 128 KiB + 32).
+ZD_DEV int decode_literals(const uint8_t *src, uint32_t size, Tables *T, uint8_t *litbuf, Literals *L, uint8_t *weights, zc::FseDCell *wcells) {
+    if (size < 1) return ERR_CORRUPT;
+    const uint32_t type = src[0] & 3, sf = (src[0] >> 2) & 3;
+    if (type < 2) {  // Raw / RLE
+        uint32_t hl, n;
+        if (sf == 0 || sf == 2) { hl = 1; n = src[0] >> 3; }
+        else if (sf == 1) { if (size < 2) return ERR_CORRUPT; hl = 2; n = (src[0] | src[1] << 8) >> 4; }
+        else { if (size < 3) return ERR_CORRUPT; hl = 3; n = (src[0] | src[1] << 8 | (uint32_t)src[2] << 16) >> 4; }
+        if (n > Z_BLOCK_MAX) return ERR_CORRUPT;
+        if (type == 0) {
+            if (hl + n > size) return ERR_CORRUPT;
+            L->ptr = src + hl; L->size = n; L->rle = 0;
+            return (int)(hl + n);
+        }
+        if (hl + 1 > size) return ERR_CORRUPT;
+        L->ptr = src + hl; L->size = n; L->rle = 1; L->rle_byte = src[hl];
+        return (int)(hl + 1);
+    }
+    // Compressed (2) / Treeless (3)
+    uint32_t hl, regen, comp, streams;
+    if (sf <= 1) { if (size < 3) return ERR_CORRUPT; hl = 3; const uint32_t v = src[0] | src[1] << 8 | (uint32_t)src[2] << 16; regen = (v >> 4) & 0x3FF; comp = v >> 14; streams = sf == 0 ? 1 : 4; }
+    else if (sf == 2) { if (size < 4) return ERR_CORRUPT; hl = 4; const uint32_t v = src[0] | src[1] << 8 | (uint32_t)src[2] << 16 | (uint32_t)src[3] << 24; regen = (v >> 4) & 0x3FFF; comp = v >> 18; streams = 4; }
+    else { if (size < 5) return ERR_CORRUPT; hl = 5; const uint64_t v = src[0] | src[1] << 8 | (uint32_t)src[2] << 16 | (uint64_t)src[3] << 24 | (uint64_t)src[4] << 32; regen = (uint32_t)(v >> 4) & 0x3FFFF; comp = (uint32_t)(v >> 22); streams = 4; }
+    if (regen > Z_BLOCK_MAX || hl + comp > size || regen == 0) return ERR_CORRUPT;
+    const uint8_t *p = src + hl;
+    uint32_t left = comp;
+    if (type == 2) {
+        const int t = read_huf_tree(p, left, T, weights, wcells);
+        if (t < 0) return t;
+        p += t; left -= (uint32_t)t;
+    } else if (!T->have_huf) return ERR_CORRUPT;
+    int err = 0;
+    if (streams == 1) {
+        if (ZD_LANE() == 0) err = huf_decode_stream(p, left, litbuf, regen, T);
+    } else {
+        if (left < 6) return ERR_CORRUPT;
+        const uint32_t s1 = p[0] | p[1] << 8, s2 = p[2] | p[3] << 8, s3 = p[4] | p[5] << 8;
+        if (6 + s1 + s2 + s3 > left) return ERR_CORRUPT;  // stream 4 may not be empty
+        const uint32_t s4 = left - 6 - s1 - s2 - s3;
+        const uint32_t seg = (regen + 3) / 4;
+        if (3 * seg > regen) return ERR_CORRUPT;
+        const uint32_t off[4] = {6, 6 + s1, 6 + s1 + s2, 6 + s1 + s2 + s3}, sz[4] = {s1, s2, s3, s4};
+#if defined(__CUDA_ARCH__)
+        const uint32_t k = ZD_LANE();
+        if (k < 4) err = huf_decode_stream(p + off[k], sz[k], litbuf + k * seg, k < 3 ? seg : regen - 3 * seg, T);
+#else
+        for (uint32_t k = 0; k < 4 && !err; k++) err = huf_decode_stream(p + off[k], sz[k], litbuf + k * seg, k < 3 ? seg : regen - 3 * seg, T);
+#endif
+    }
+#if defined(__CUDA_ARCH__)
+    err = __any_sync(0xffffffffu, err != 0) ? ERR_CORRUPT : 0;
+#endif
+    ZD_SYNC();
+    if (err) return ERR_CORRUPT;
+    L->ptr = litbuf; L->size = regen; L->rle = 0;
+    return (int)(hl + comp);
+}
+
+// ---- sequence tables -------------------------------------------------------------------------------------
+enum { KIND_LL = 0, KIND_OF = 1, KIND_ML = 2 };
+ZD_DEV void fill_cell(SeqCell *c, uint32_t kind, uint32_t sym, uint32_t nb, uint32_t base) {
+    c->next_base = (uint16_t)base;
+    c->nb_bits = (uint8_t)nb;
+    if (kind == KIND_LL) { c->extra_bits = zc::ZTAB(LL_bits)[sym]; c->base_value = zc::ZTAB(LL_base)[sym]; }
+    else if (kind == KIND_ML) { c->extra_bits = zc::ZTAB(ML_bits)[sym]; c->base_value = zc::ZTAB(ML_base)[sym]; }
+    else { c->extra_bits = (uint8_t)sym; c->base_value = 1u << sym; }
+}
+// builds cells from normalised counts (uniform: every lane executes it; lanes write identical values)
+ZD_DEV int build_seq_table(SeqCell *cells, uint32_t kind, const int16_t *norm, uint32_t max_sym, uint32_t tl, zc::FseDCell *tmp /* 512 */) {
+    const uint32_t sym_cap = kind == KIND_LL ? 35 : kind == KIND_ML ? 52 : 31;
+    if (max_sym > sym_cap) return ERR_CORRUPT;
+    uint16_t next[64];
+    zc::fse_build_dtable(tmp, norm, max_sym, tl, next);
+    const uint32_t size = 1u << tl;
+    for (uint32_t u = 0; u < size; u++) fill_cell(&cells[u], kind, tmp[u].sym, tmp[u].nb_bits, tmp[u].base);
+    return 0;
+}
+// one of LL / OF / ML per its 2-bit mode.  Returns bytes consumed or < 0.
+ZD_DEV int read_seq_table(const uint8_t *src, uint32_t size, uint32_t mode, uint32_t kind, SeqCell *cells, uint32_t *log, uint32_t *have,
+                          zc::FseDCell *tmp) {
+    const uint32_t max_log = kind == KIND_LL ? Z_LL_MAXLOG : kind == KIND_ML ? Z_ML_MAXLOG : Z_OF_MAXLOG;
+    if (mode == 0) {  // Predefined
+        int16_t dn[64];
+        uint32_t ms, tl;
+        if (kind == KIND_LL) { ms = 35; tl = 6; for (uint32_t i = 0; i <= ms; i++) dn[i] = zc::ZTAB(LL_defnorm)[i]; }
+        else if (kind == KIND_ML) { ms = 52; tl = 6; for (uint32_t i = 0; i <= ms; i++) dn[i] = zc::ZTAB(ML_defnorm)[i]; }
+        else { ms = 28; tl = 5; for (uint32_t i = 0; i <= ms; i++) dn[i] = zc::ZTAB(OF_defnorm)[i]; }
+        if (build_seq_table(cells, kind, dn, ms, tl, tmp) < 0) return ERR_CORRUPT;
+        *log = tl; *have = 1;
+        return 0;
+    }
+    if (mode == 1) {  // RLE: a single symbol, zero state bits
+        if (size < 1) return ERR_CORRUPT;
+        const uint32_t sym = src[0];
+        const uint32_t sym_cap = kind == KIND_LL ? 35 : kind == KIND_ML ? 52 : 31;
+        if (sym > sym_cap) return ERR_CORRUPT;
+        fill_cell(&cells[0], kind, sym, 0, 0);
+        *log = 0; *have = 1;
+        return 1;
+    }
+    if (mode == 2) {  // FSE_Compressed
+        int16_t norm[64];
+        uint32_t max_sym = 0, tl = 0;
+        const int used = read_ncount(src, size, norm, kind == KIND_LL ? 35 : kind == KIND_ML ? 52 : 31, max_log, &max_sym, &tl);
+        if (used < 0) return used;
+        if (build_seq_table(cells, kind, norm, max_sym, tl, tmp) < 0) return ERR_CORRUPT;
+        *log = tl; *have = 1;
+        return used;
+    }
+    return *have ? 0 : ERR_CORRUPT;  // Repeat
+}
+
+// ---- byte movers (lanes split the bytes) -------------------------------------------------------------------
+ZD_DEV void copy_bytes(uint8_t *dst, const uint8_t *src, uint32_t n) {
+    for (uint32_t i = ZD_LANE(); i < n; i += ZD_WARP) dst[i] = src[i];
+}
+ZD_DEV void fill_bytes(uint8_t *dst, uint8_t v, uint32_t n) {
+    for (uint32_t i = ZD_LANE(); i < n; i += ZD_WARP) dst[i] = v;
+}
+// match copy with byte-serial semantics: out[pos+i] = out[pos-off+i]; when off < len the source is periodic
+ZD_DEV void copy_match(uint8_t *out, uint32_t pos, uint32_t off, uint32_t len) {
+    const uint8_t *from = out + pos - off;
+    if (off >= len || ZD_WARP == 1) {
+        if (ZD_WARP == 1) { for (uint32_t i = 0; i < len; i++) out[pos + i] = from[i]; }
+        else for (uint32_t i = ZD_LANE(); i < len; i += ZD_WARP) out[pos + i] = from[i];
+    } else {
+        for (uint32_t i = ZD_LANE(); i < len; i += ZD_WARP) out[pos + i] = from[i % off];
+    }
+}
+
+// ---- blocks / frames -----------------------------------------------------------------------------------------
+struct Scratch {  // per warp, not persistent across blocks
+    uint8_t weights[256];
+    zc::FseDCell cells[512];
+};
+
+// One compressed block: literals + sequences executed into out[pos..].  Returns new pos or < 0.
+ZD_DEV int64_t decode_compressed_block(const uint8_t *src, uint32_t size, uint8_t *out, uint32_t pos, uint32_t cap, uint32_t frame_start,
+                                       Tables *T, Scratch *S, uint8_t *litbuf, uint32_t rep[3]) {
+    Literals L;
+    const int lused = decode_literals(src, size, T, litbuf, &L, S->weights, S->cells);
+    if (lused < 0) return lused;
+    const uint8_t *p = src + lused;
+    uint32_t left = size - (uint32_t)lused;
+    if (left < 1) return ERR_CORRUPT;
+    uint32_t nseq = p[0];
+    if (nseq == 0) { p += 1; left -= 1; }
+    else if (nseq < 128) { p += 1; left -= 1; }
+    else if (nseq < 255) { if (left < 2) return ERR_CORRUPT; nseq = ((nseq - 128) << 8) + p[1]; p += 2; left -= 2; }
+    else { if (left < 3) return ERR_CORRUPT; nseq = p[1] + (p[2] << 8) + 0x7F00; p += 3; left -= 3; }
+    uint32_t lit_pos = 0;
+    if (nseq) {
+        if (left < 1) return ERR_CORRUPT;
+        const uint32_t modes = p[0];
+        if (modes & 3) return ERR_CORRUPT;
+        p += 1; left -= 1;
+        int u = read_seq_table(p, left, modes >> 6, KIND_LL, T->ll, &T->ll_log, &T->have_ll, S->cells);
+        if (u < 0) return u;
+        p += u; left -= (uint32_t)u;
+        u = read_seq_table(p, left, (modes >> 4) & 3, KIND_OF, T->of, &T->of_log, &T->have_of, S->cells);
+        if (u < 0) return u;
+        p += u; left -= (uint32_t)u;
+        u = read_seq_table(p, left, (modes >> 2) & 3, KIND_ML, T->ml, &T->ml_log, &T->have_ml, S->cells);
+        if (u < 0) return u;
+        p += u; left -= (uint32_t)u;
+        ZD_SYNC();
+        BitReader b;
+        if (br_init(&b, p, left) < 0) return ERR_CORRUPT;
+        uint32_t s_ll = br_read(&b, T->ll_log), s_of = br_read(&b, T->of_log), s_ml = br_read(&b, T->ml_log);
+        uint32_t r0 = rep[0], r1 = rep[1], r2 = rep[2];
+        for (uint32_t i = 0; i < nseq; i++) {
+            const SeqCell cl = T->ll[s_ll], co = T->of[s_of], cm = T->ml[s_ml];
+            // extra bits: offset, match length, literal length
+            uint32_t ofv = co.base_value + (co.extra_bits ? br_read(&b, co.extra_bits) : 0);
+            const uint32_t ml = cm.base_value + (cm.extra_bits ? br_read(&b, cm.extra_bits) : 0);
+            const uint32_t ll = cl.base_value + (cl.extra_bits ? br_read(&b, cl.extra_bits) : 0);
+            uint32_t off;
+            if (ofv > 3) { off = ofv - 3; r2 = r1; r1 = r0; r0 = off; }
+            else {
+                const uint32_t idx = ofv - 1 + (ll == 0 ? 1 : 0);
+                if (idx == 0) off = r0;
+                else {
+                    off = idx == 1 ? r1 : idx == 2 ? r2 : r0 - 1;
+                    if (off == 0) return ERR_CORRUPT;
+                    if (idx >= 2) r2 = r1;
+                    r1 = r0; r0 = off;
+                }
+            }
+            if (i + 1 < nseq) {  // state updates: LL, ML, OF
+                s_ll = cl.next_base + br_read(&b, cl.nb_bits);
+                s_ml = cm.next_base + br_read(&b, cm.nb_bits);
+                s_of = co.next_base + br_read(&b, co.nb_bits);
+            }
+            if (b.pos < 0) return ERR_CORRUPT;
+            // execute
+            if (lit_pos + ll > L.size) return ERR_CORRUPT;
+            if ((uint64_t)pos + ll + ml > cap) return ERR_CAPACITY;
+            if (off > pos + ll - frame_start) return ERR_CORRUPT;
+            if (L.rle) fill_bytes(out + pos, L.rle_byte, ll); else copy_bytes(out + pos, L.ptr + lit_pos, ll);
+            lit_pos += ll; pos += ll;
+            ZD_SYNC();
+            copy_match(out, pos, off, ml);
+            pos += ml;
+            ZD_SYNC();
+        }
+        if (b.pos != 0) return ERR_CORRUPT;
+        rep[0] = r0; rep[1] = r1; rep[2] = r2;
+    } else if (left != 0) return ERR_CORRUPT;
+    const uint32_t rest = L.size - lit_pos;
+    if ((uint64_t)pos + rest > cap) return ERR_CAPACITY;
+    if (L.rle) fill_bytes(out + pos, L.rle_byte, rest); else copy_bytes(out + pos, L.ptr + lit_pos, rest);
+    ZD_SYNC();
+    return (int64_t)pos + rest;
+}
+
+// A whole chunk-record payload: >= 1 zstd frames and skippable frames, nothing else (what stock
+// ZSTD_decompress accepts).  Returns decoded size or < 0.
+ZD_DEV int64_t decode_payload(const uint8_t *src, uint32_t size, uint8_t *out, uint32_t cap, Tables *T, Scratch *S, uint8_t *litbuf) {
+    uint32_t ip = 0, pos = 0;
+    while (ip < size) {
+        if (size - ip < 4) return ERR_CORRUPT;
+        const uint32_t magic = src[ip] | src[ip + 1] << 8 | (uint32_t)src[ip + 2] << 16 | (uint32_t)src[ip + 3] << 24;
+        if ((magic & 0xFFFFFFF0u) == 0x184D2A50u) {  // skippable frame
+            if (size - ip < 8) return ERR_CORRUPT;
+            const uint32_t n = src[ip + 4] | src[ip + 5] << 8 | (uint32_t)src[ip + 6] << 16 | (uint32_t)src[ip + 7] << 24;
+            if (n > size - ip - 8) return ERR_CORRUPT;
+            ip += 8 + n;
+            continue;
+        }
+        if (magic != Z_MAGIC) return ERR_CORRUPT;
+        if (size - ip < 5) return ERR_CORRUPT;
+        const uint32_t fhd = src[ip + 4];
+        const uint32_t fcs_flag = fhd >> 6, single = (fhd >> 5) & 1, has_checksum = (fhd >> 2) & 1, did = fhd & 3;
+        if (fhd & 0x08) return ERR_CORRUPT;  // reserved bit
+        uint32_t h = 5;
+        if (!single) {
+            if (size - ip < h + 1) return ERR_CORRUPT;
+            const uint32_t wd = src[ip + h], wlog = 10 + (wd >> 3);
+            if (wlog > 31) return ERR_CORRUPT;
+            h += 1;
+        }
+        const uint32_t did_bytes = did == 3 ? 4 : did;
+        if (size - ip < h + did_bytes) return ERR_CORRUPT;
+        for (uint32_t i = 0; i < did_bytes; i++) if (src[ip + h + i]) return ERR_CORRUPT;  // a dictionary is required: not supported, as in the reference
+        h += did_bytes;
+        const uint32_t fcs_bytes = fcs_flag == 0 ? single : fcs_flag == 1 ? 2 : fcs_flag == 2 ? 4 : 8;
+        if (size - ip < h + fcs_bytes) return ERR_CORRUPT;
+        uint64_t fcs = 0;
+        for (uint32_t i = 0; i < fcs_bytes; i++) fcs |= (uint64_t)src[ip + h + i] << (8 * i);
+        if (fcs_flag == 1) fcs += 256;
+        h += fcs_bytes;
+        if (fcs_bytes && fcs > (uint64_t)cap - pos) return ERR_CAPACITY;
+        ip += h;
+        const uint32_t frame_start = pos;
+        uint32_t rep[3] = {1, 4, 8};
+        T->have_huf = T->have_ll = T->have_ml = T->have_of = 0;
+        for (;;) {
+            if (size - ip < 3) return ERR_CORRUPT;
+            const uint32_t bh = src[ip] | src[ip + 1] << 8 | (uint32_t)src[ip + 2] << 16;
+            const uint32_t last = bh & 1, type = (bh >> 1) & 3, bsz = bh >> 3;
+            ip += 3;
+            if (type != 3 && bsz > Z_BLOCK_MAX) return ERR_CORRUPT;
+            if (type == 0) {  // raw
+                if (bsz > size - ip) return ERR_CORRUPT;
+                if (bsz > cap - pos) return ERR_CAPACITY;
+                copy_bytes(out + pos, src + ip, bsz);
+                ZD_SYNC();
+                pos += bsz; ip += bsz;
+            } else if (type == 1) {  // RLE
+                if (size - ip < 1) return ERR_CORRUPT;
+                if (bsz > cap - pos) return ERR_CAPACITY;
+                fill_bytes(out + pos, src[ip], bsz);
+                ZD_SYNC();
+                pos += bsz; ip += 1;
+            } else if (type == 2) {
+                if (bsz > size - ip || bsz > Z_BLOCK_MAX) return ERR_CORRUPT;
+                const int64_t np = decode_compressed_block(src + ip, bsz, out, pos, cap, frame_start, T, S, litbuf, rep);
+                if (np < 0) return np;
+                if ((uint64_t)np - pos > Z_BLOCK_MAX) return ERR_CORRUPT;
+                pos = (uint32_t)np; ip += bsz;
+            } else return ERR_CORRUPT;
+            if (last) break;
+        }
+        if (fcs_bytes && (uint64_t)(pos - frame_start) != fcs) return ERR_CORRUPT;
+        if (has_checksum) { if (size - ip < 4) return ERR_CORRUPT; ip += 4; }  // content checksum is not verified (the reference never writes one)
+    }
+    return pos;
+}
+
+}  // namespace zd

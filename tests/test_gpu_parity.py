@@ -225,3 +225,95 @@ def test_archive_empty_dir(sq, oracle, tmp_path):
     assert ArchiveWriter(tmp_path / "e", tmp_path / "e.squish", ctx=sq.Context()).pack() == 31
     rc, s, _ = oracle.list(tmp_path / "e.squish")
     assert rc == 0 and s.file_count == 0 and s.unique_chunks == 0
+
+
+# ---------------------------------------------------------------- K4 decode
+def test_decode_reference_written_frames(sq, oracle):
+    """frames written by stock libzstd at several levels (what a reference-written archive holds, plus
+    shapes only other levels emit) decode byte-identically; capacity = 2 MiB as the reference passes"""
+    c = sq.Context()
+    samples = [s for _, s in corpus_samples(sq, sizes=(1, 17, 255, 256, 4096, 65536, 131073, 300000, 2 * MiB))]
+    rng = random.Random(9)
+    samples += [rng.randbytes(70000), bytes(3000), bytes(rng.choices(range(3), k=100000))]
+    for lvl in (1, 3, 12, 19):
+        chosen = [s for s in samples if lvl != 19 or len(s) <= 300000]
+        frames = [oracle.compress(s, lvl) for s in chosen]
+        got = c.unpack_batch(frames, [2 * MiB] * len(frames))
+        for s, g in zip(chosen, got):
+            assert g == s, (lvl, len(s))
+
+
+def test_decode_own_frames_roundtrip(sq):
+    c = sq.Context()
+    samples = [s for _, s in corpus_samples(sq)]
+    res = c.pack_batch(samples)
+    frames = [(s, f) for s, (_, f) in zip(samples, res) if f is not None]
+    got = c.unpack_batch([f for _, f in frames], [len(s) for s, _ in frames])  # exact capacity
+    assert got == [s for s, _ in frames]
+
+
+def test_decode_multiframe_skippable_and_errors(sq, oracle):
+    # what stock ZSTD_decompress accepts / rejects (SURVEY Appendix D probes; reader.rs:302-303 semantics)
+    c = sq.Context()
+    two = oracle.compress(b"hello ") + oracle.compress(b"squish")
+    skip = bytes.fromhex("502a4d18") + (3).to_bytes(4, "little") + b"abc"
+    nofcs = bytes.fromhex("28b52ffd") + bytes([0x00, 0x58, 0x21, 0, 0]) + b"test"  # zstd::encode_all shape (src/archive/tests.rs:31)
+    assert c.unpack_batch([two, skip + two, nofcs, oracle.compress(b"")], [64, 64, 4, 0]) == [b"hello squish", b"hello squish", b"test", b""]
+    f = oracle.compress(bytes([42]) * 2048)
+    for bad, cap in ((f, 2047), (f + b"x", 4096), (f[:-3], 4096), (b"garbage!", 64), (f[:4] + b"\xff" + f[5:], 4096)):
+        with pytest.raises(sq.SquishError) as e:
+            c.unpack_batch([bad], [cap])
+        assert e.value.status == -5  # ReaderError
+        assert oracle.decompress(bad, cap) is None  # stock libzstd rejects it too
+
+
+def test_archive_roundtrip_both_directions(sq, oracle, tmp_path):
+    """reference-written archive -> GPU unpack, GPU-written archive -> GPU unpack; trees byte-identical"""
+    from squishrs_b200.archive import ArchiveReader, ArchiveWriter
+    src = tmp_path / "in"
+    make_tree(src, tree_spec())
+    rc, _ = oracle.pack_dir(src, tmp_path / "cpu.squish", threads=8)
+    assert rc == 0
+    c = sq.Context()
+    ArchiveReader(tmp_path / "cpu.squish", ctx=c, threads=8).unpack(tmp_path / "out_from_cpu")
+    assert read_tree(tmp_path / "out_from_cpu") == read_tree(src)
+    ArchiveWriter(src, tmp_path / "gpu.squish", ctx=c, threads=8).pack()
+    ArchiveReader(tmp_path / "gpu.squish", ctx=c, threads=8).unpack(tmp_path / "out_from_gpu")
+    assert read_tree(tmp_path / "out_from_gpu") == read_tree(src)
+
+
+def test_unpack_reference_fixture(sq, tmp_path):
+    # reference src/archive/tests.rs:141-166
+    from squishrs_b200.archive import ArchiveReader
+    a = tmp_path / "dummy.squish"
+    a.write_bytes(bytes.fromhex((GOLD / "dummy_archive.hex").read_text().strip()))
+    ArchiveReader(a, ctx=sq.Context()).unpack(tmp_path / "output")
+    assert (tmp_path / "output" / "file1.txt").read_bytes() == b"test"
+
+
+def test_unpack_missing_chunk(sq, tmp_path):
+    # reader.rs:397-401: a manifest digest with no chunk record -> MissingChunk
+    from squishrs_b200.archive import ArchiveReader
+    a = bytearray(bytes.fromhex((GOLD / "dummy_archive.hex").read_text().strip()))
+    a[-1] ^= 0xFF
+    p = tmp_path / "missing.squish"
+    p.write_bytes(bytes(a))
+    with pytest.raises(sq.SquishError) as e:
+        ArchiveReader(p, ctx=sq.Context()).unpack(tmp_path / "o")
+    assert e.value.status == -16
+
+
+def test_cli_roundtrip(sq, tmp_path):
+    # reference tests/cli_tests.rs:12-53,122-159 through the squishrs binary
+    import subprocess
+    cli = Path(__file__).resolve().parent.parent / "bin" / "squishrs"
+    src = tmp_path / "in"
+    make_tree(src, {"file1.txt": b"Hello, world!\n", "file2.txt": b"Another file\n", "dir1/dir2/nested.txt": b"nested file"})
+    r = subprocess.run([str(cli), "pack", str(src), "-o", str(tmp_path / "a.squish")], capture_output=True, text=True)
+    assert r.returncode == 0 and "Packing complete!" in r.stdout, r.stderr
+    r = subprocess.run([str(cli), "unpack", str(tmp_path / "a.squish"), "-o", str(tmp_path / "out")], capture_output=True, text=True)
+    assert r.returncode == 0 and "Unpacking complete!" in r.stdout, r.stderr
+    assert read_tree(tmp_path / "out") == read_tree(src)
+    (tmp_path / "bad.squish").write_bytes(b"this is not an archive")
+    r = subprocess.run([str(cli), "unpack", str(tmp_path / "bad.squish"), "-o", str(tmp_path / "o2")], capture_output=True, text=True)
+    assert r.returncode != 0 and "Error" in r.stderr
