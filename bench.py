@@ -245,6 +245,11 @@ def run_ours(args):
     stage_ms = {"digest": 0.0, "dedup": 0.0, "encode": 0.0}
     totals = {"in": 0, "out": 0, "new": 0, "chunks": 0}
 
+    sd = None
+    if world > 1:
+        from squishrs_b200.sharded import DeviceOps, ShardedDedup
+        sd = ShardedDedup(DeviceOps(ctx, sp), world, B, "cuda")
+
     def step(i, gidx_base, timed):
         b = i % n_batches
         base = corpus.data_ptr() + b * B * CHUNK
@@ -254,7 +259,10 @@ def run_ours(args):
         ctx.check(lib.sq_digest_device(ctx.h, base, d_spans.data_ptr(), B, d_dig.data_ptr(), sp))
         if timed:
             e[1].record(stream)
-        ctx.check(lib.sq_dedup_insert_device(ctx.h, d_dig.data_ptr(), None, gidx_base, B, d_new.data_ptr(), sp))
+        if sd is None:
+            ctx.check(lib.sq_dedup_insert_device(ctx.h, d_dig.data_ptr(), None, gidx_base, B, d_new.data_ptr(), sp))
+        else:  # digest all-to-all over NCCL to the owner ranks, verdicts back
+            sd.exchange(d_dig, gidx_base, B, d_new)
         if timed:
             e[2].record(stream)
         ctx.check(lib.sq_encode_device(ctx.h, base, d_spans.data_ptr(), d_new.data_ptr(), B, d_out.data_ptr(), out_cap,
@@ -270,7 +278,7 @@ def run_ours(args):
 
     # warm-up on a throwaway index state
     for w in range(args.warmup):
-        step(w, w * B * world, False)
+        step(w, w * B * world + rank * B, False)
     barrier()
     ctx.dedup_reset()
     launches0 = C.c_uint64()

@@ -140,6 +140,22 @@ int32_t sq_dedup_insert_device(sq_ctx *ctx, const void *d_digests, const uint64_
 int32_t sq_dedup_len(sq_ctx *ctx, uint64_t *out);   /* ChunkStore::len (chunk.rs:116-118); synchronizes */
 int32_t sq_dedup_reset(sq_ctx *ctx);                /* ChunkStore::new (chunk.rs:52-56) */
 
+/* ---- K2 across the GPUs of one box: the index is sharded by digest prefix (north_star (2)) ----
+ * One process per GPU.  Per batch: K1 on local chunks -> sq_route_digests_device buckets
+ * {digest, gidx} records by owner = LE64(digest[0..8]) % world into `world` blocks of
+ * cap_per_peer 32-byte records (padding records carry gidx = ~0) -> the caller exchanges the
+ * blocks with an all-to-all over NCCL -> sq_dedup_insert_routed_device inserts what this rank
+ * owns and writes one verdict byte per received record (same layout) -> reverse all-to-all ->
+ * sq_unroute_verdicts_device scatters verdicts back to chunk order.  sq_dedup_len on each rank
+ * counts the digests that rank owns; the store's len() is their sum. */
+int32_t sq_route_digests_device(sq_ctx *ctx, const void *d_digests, uint64_t gidx_base, uint32_t n,
+                                uint32_t world, uint32_t cap_per_peer, void *d_send,
+                                uint32_t *d_send_pos, void *stream);
+int32_t sq_dedup_insert_routed_device(sq_ctx *ctx, const void *d_recv, uint32_t count,
+                                      uint8_t *d_verdict, void *stream);
+int32_t sq_unroute_verdicts_device(sq_ctx *ctx, const uint8_t *d_verdict_back, const uint32_t *d_send_pos,
+                                   uint32_t n, uint8_t *d_is_new, void *stream);
+
 /* ---- K3: encode  == zstd::bulk::compress(chunk, 12) (src/util/chunk.rs:89-90) */
 /* worst-case frame bytes for a chunk of `len` bytes (raw-block fallback) */
 size_t sq_encode_bound(size_t len);

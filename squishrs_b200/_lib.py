@@ -78,6 +78,9 @@ SYMBOLS = {
     "sq_dedup_insert_device": (C.c_int32, [_P, _P, _P, C.c_uint64, C.c_uint32, _P, _P]),
     "sq_dedup_len": (C.c_int32, [_P, C.POINTER(C.c_uint64)]),
     "sq_dedup_reset": (C.c_int32, [_P]),
+    "sq_route_digests_device": (C.c_int32, [_P, _P, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, _P, _P, _P]),
+    "sq_dedup_insert_routed_device": (C.c_int32, [_P, _P, C.c_uint32, _P, _P]),
+    "sq_unroute_verdicts_device": (C.c_int32, [_P, _P, _P, C.c_uint32, _P, _P]),
     "sq_encode_bound": (C.c_size_t, [C.c_size_t]),
     "sq_encode_device": (C.c_int32, [_P, _P, _P, _P, C.c_uint32, _P, C.c_uint64, _P, _P, _P, _P]),
     "sq_encode_status": (C.c_int32, [_P]),

@@ -44,6 +44,7 @@ __global__ void dedup_insert_kernel(const uint4 *__restrict__ digests, const uns
     if (i >= n) return;
     const uint4 d = digests[i];
     const unsigned long long g = gidx ? gidx[i] : gidx_base + i;
+    if (g == ~0ULL) { slot_of[i] = 0xFFFFFFFFu; return; }  // padding record of a routed exchange
     uint64_t s = slot_hash(d) & mask;
     uint32_t my_ref = 0;
     for (uint64_t probes = 0; probes <= mask; probes++, s = (s + 1) & mask) {
@@ -84,6 +85,44 @@ __global__ void dedup_verdict_kernel(const unsigned long long *__restrict__ gidx
     const unsigned long long g = gidx ? gidx[i] : gidx_base + i;
     const uint32_t s = slot_of[i];
     is_new[i] = (s != 0xFFFFFFFFu && min_gidx[s] == g) ? 1 : 0;
+}
+
+
+// ---- multi-GPU: the index is sharded by digest prefix; records travel as 32-byte {digest, gidx, pad} ----
+struct RoutedRec { uint4 digest; unsigned long long gidx, pad; };
+static_assert(sizeof(RoutedRec) == 32, "routed record layout");
+
+__global__ void route_kernel(const uint4 *__restrict__ digests, unsigned long long gidx_base, uint32_t n, uint32_t world, uint32_t cap,
+                             RoutedRec *__restrict__ send, uint32_t *__restrict__ send_pos, uint32_t *__restrict__ peer_count) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint4 d = digests[i];
+    const unsigned long long prefix = (unsigned long long)d.x | (unsigned long long)d.y << 32;  // first 8 digest bytes, LE
+    const uint32_t owner = (uint32_t)(prefix % world);
+    const uint32_t k = atomicAdd(&peer_count[owner], 1u);  // k < cap because cap >= n
+    RoutedRec r;
+    r.digest = d; r.gidx = gidx_base + i; r.pad = 0;
+    send[(size_t)owner * cap + k] = r;
+    send_pos[i] = owner * cap + k;
+}
+__global__ void route_pad_kernel(RoutedRec *__restrict__ send, uint32_t total) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    RoutedRec r;
+    r.digest = make_uint4(0, 0, 0, 0); r.gidx = ~0ULL; r.pad = 0;
+    send[i] = r;
+}
+__global__ void routed_split_kernel(const RoutedRec *__restrict__ recv, uint32_t count, uint4 *__restrict__ digests,
+                                    unsigned long long *__restrict__ gidx) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    digests[i] = recv[i].digest;
+    gidx[i] = recv[i].gidx;
+}
+__global__ void unroute_kernel(const uint8_t *__restrict__ verdict_back, const uint32_t *__restrict__ send_pos, uint32_t n,
+                               uint8_t *__restrict__ is_new) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) is_new[i] = verdict_back[send_pos[i]];
 }
 
 }  // namespace
@@ -147,5 +186,48 @@ extern "C" int32_t sq_dedup_len(sq_ctx *ctx, uint64_t *out) {
     SQ_CUDA(ctx, cudaMemcpy(c, ctx->dedup->counters, sizeof c, cudaMemcpyDeviceToHost));
     if (c[2]) return sq_set_error(ctx, SQ_ERR_CAPACITY, "dedup index overflow: more than %llu inserts", (unsigned long long)ctx->dedup->key_capacity);
     *out = c[1];
+    return SQ_OK;
+}
+
+// ---- sharded index entry points ---------------------------------------------------------
+extern "C" int32_t sq_route_digests_device(sq_ctx *ctx, const void *d_digests, uint64_t gidx_base, uint32_t n, uint32_t world,
+                                           uint32_t cap_per_peer, void *d_send, uint32_t *d_send_pos, void *stream) {
+    if (!ctx || !ctx->dedup) return SQ_ERR_INVALID_ARG;
+    if (!d_digests || !d_send || !d_send_pos || world == 0 || cap_per_peer < n)
+        return sq_set_error(ctx, SQ_ERR_INVALID_ARG, "sq_route_digests_device: bad arguments (cap_per_peer must be >= n)");
+    if (world > 60) return sq_set_error(ctx, SQ_ERR_INVALID_ARG, "at most 60 ranks");
+    cudaStream_t st = sq_stream(ctx, stream);
+    uint32_t *peer_count = ctx->d_work_counter + 4;  // world <= 60 counters
+    SQ_CUDA(ctx, cudaMemsetAsync(peer_count, 0, world * sizeof(uint32_t), st));
+    const uint32_t total = world * cap_per_peer;
+    route_pad_kernel<<<(total + 255) / 256, 256, 0, st>>>((RoutedRec *)d_send, total);
+    if (n) route_kernel<<<(n + 127) / 128, 128, 0, st>>>((const uint4 *)d_digests, gidx_base, n, world, cap_per_peer, (RoutedRec *)d_send, d_send_pos, peer_count);
+    SQ_LAUNCHED(ctx, 2);
+    SQ_CUDA(ctx, cudaGetLastError());
+    return SQ_OK;
+}
+
+extern "C" int32_t sq_dedup_insert_routed_device(sq_ctx *ctx, const void *d_recv, uint32_t count, uint8_t *d_verdict, void *stream) {
+    if (!ctx || !ctx->dedup) return SQ_ERR_INVALID_ARG;
+    if (count == 0) return SQ_OK;
+    if (!d_recv || !d_verdict) return sq_set_error(ctx, SQ_ERR_INVALID_ARG, "sq_dedup_insert_routed_device: null pointer");
+    cudaStream_t st = sq_stream(ctx, stream);
+    int32_t rc = sq_ensure(ctx, &ctx->d_stage_meta, &ctx->stage_meta_cap, (size_t)count * 24 + 256);
+    if (rc) return rc;
+    uint4 *dig = (uint4 *)ctx->d_stage_meta;
+    unsigned long long *gidx = (unsigned long long *)((uint8_t *)ctx->d_stage_meta + (size_t)count * 16);
+    routed_split_kernel<<<(count + 255) / 256, 256, 0, st>>>((const RoutedRec *)d_recv, count, dig, gidx);
+    SQ_LAUNCHED(ctx, 1);
+    return sq_dedup_insert_device(ctx, dig, (const uint64_t *)gidx, 0, count, d_verdict, st);
+}
+
+extern "C" int32_t sq_unroute_verdicts_device(sq_ctx *ctx, const uint8_t *d_verdict_back, const uint32_t *d_send_pos, uint32_t n,
+                                              uint8_t *d_is_new, void *stream) {
+    if (!ctx) return SQ_ERR_INVALID_ARG;
+    if (n == 0) return SQ_OK;
+    if (!d_verdict_back || !d_send_pos || !d_is_new) return sq_set_error(ctx, SQ_ERR_INVALID_ARG, "sq_unroute_verdicts_device: null pointer");
+    unroute_kernel<<<(n + 255) / 256, 256, 0, sq_stream(ctx, stream)>>>(d_verdict_back, d_send_pos, n, d_is_new);
+    SQ_LAUNCHED(ctx, 1);
+    SQ_CUDA(ctx, cudaGetLastError());
     return SQ_OK;
 }
