@@ -56,29 +56,42 @@ ZD_DEV uint64_t load64(const uint8_t *p) {  // unaligned little-endian 8 bytes; 
 }
 
 // Backward bit reader over [start, start+size): bits are consumed from the top (just below the sentinel).
+// A 64-bit window is cached in registers and refilled (one unaligned 8-byte load) only when it runs low.
 struct BitReader {
     const uint8_t *start;
-    int64_t pos;  // number of unread bits; may go negative on corrupt input (reads then return zeros)
+    int64_t pos;    // number of unread bits; may go negative on corrupt input (reads then return zeros)
+    uint64_t win;   // bits [wlo, wlo+64) of the stream
+    int64_t wlo;    // bit index of win's bit 0 (multiple of 8; may be negative near the stream start)
 };
+ZD_DEV void br_refill(BitReader *b) {
+    // place the window so that its top is at or above pos: wlo = byte-aligned, pos - wlo in (56, 64]
+    int64_t lo = ((b->pos + 7) >> 3) * 8 - 64;
+    if (lo >= 0) { b->win = load64(b->start + (lo >> 3)); b->wlo = lo; return; }
+    // within 8 bytes of the stream start: assemble without reading before it; missing low bits read as zero
+    const uint64_t v = load64(b->start);
+    const uint32_t sh = (uint32_t)(-lo);  // multiple of 8, <= 64
+    b->win = sh >= 64 ? 0 : v << sh;
+    b->wlo = lo;
+}
 ZD_DEV int br_init(BitReader *b, const uint8_t *start, uint32_t size) {
     if (size == 0) return ERR_CORRUPT;
     const uint8_t last = start[size - 1];
     if (last == 0) return ERR_CORRUPT;
     b->start = start;
     b->pos = (int64_t)(size - 1) * 8 + zc::highbit(last);
+    br_refill(b);
     return 0;
 }
-ZD_DEV uint32_t br_peek(const BitReader *b, uint32_t n) {  // n <= 32; bits [pos-n, pos)
+ZD_DEV uint32_t br_peek(BitReader *b, uint32_t n) {  // n <= 32; bits [pos-n, pos)
     if (n == 0) return 0;
-    const int64_t lo = b->pos - (int64_t)n;
-    if (lo >= 0) {
-        const uint64_t v = load64(b->start + (lo >> 3));
-        return (uint32_t)(v >> (lo & 7)) & (uint32_t)((1ull << n) - 1);
-    }
     if (b->pos <= 0) return 0;
-    // partially past the beginning: the missing low bits read as zero
-    const uint64_t v = load64(b->start);
-    return (uint32_t)((v & ((1ull << b->pos) - 1)) << (uint32_t)(-lo)) & (uint32_t)((1ull << n) - 1);
+    int64_t lo = b->pos - (int64_t)n;
+    if (lo < b->wlo) br_refill(b);
+    if (lo >= b->wlo) return (uint32_t)(b->win >> (lo - b->wlo)) & (uint32_t)((1ull << n) - 1);
+    // fewer than n bits left in the stream: the missing low bits read as zero (wlo <= 0 here)
+    const uint32_t have = (uint32_t)(b->pos - b->wlo);
+    const uint64_t top = have >= 64 ? b->win : (b->win & ((1ull << have) - 1));
+    return (uint32_t)(top << (uint32_t)(b->wlo - lo)) & (uint32_t)((1ull << n) - 1);
 }
 ZD_DEV uint32_t br_read(BitReader *b, uint32_t n) {
     const uint32_t v = br_peek(b, n);

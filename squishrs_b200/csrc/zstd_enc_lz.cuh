@@ -10,7 +10,7 @@
 //           position, and every candidate is verified against the bytes of the CURRENT chunk.
 //   search  every position reads its 64-byte row (L1 bypassed), filters by tag, requests the first 8 bytes
 //           of all sixteen candidates at once, extends the survivors 8 bytes per round in lock-step (up to
-//           64 bytes) and keeps the best by 2*len - log2(offset); plus how far it extends backwards (<= 3).
+//           24 bytes; longer matches are extended by the chase) and keeps the best by 2*len - log2(offset); plus how far it extends backwards (<= 3).
 //           Results go to a 2-tile ring in shared memory.
 //   decide  every position resolves the lazy (depth 2) choice "if the parser stands here, which match
 //           start does it take" from the ring alone -- no dependence on parser state, so it is parallel --
@@ -31,7 +31,7 @@ namespace lz {
 
 constexpr uint32_t ROW_LOG = 15, ROWS = 1u << ROW_LOG, ROW_K = 16, TAG_BITS = 10;
 constexpr uint32_t TILE = 1024, RING = 2 * TILE, THREADS = 256, PER_THREAD = TILE / THREADS;
-constexpr uint32_t MIN_MATCH = 6, SEARCH_CAP = 64, TARGET_LEN = 64, DEFER = 20, MAX_LAZY_ITERS = 8;
+constexpr uint32_t MIN_MATCH = 6, SEARCH_CAP = 24, TARGET_LEN = 24, DEFER = 20, MAX_LAZY_ITERS = 8;
 constexpr uint32_t LOOKAHEAD = SEARCH_CAP + 16;  // bytes staged past the tile so the p-side of every comparison is in smem
 constexpr int32_t ACCEPT_THR = 8;
 constexpr uint32_t BLOCKS_PER_CHUNK = 16;
@@ -54,6 +54,15 @@ __device__ __forceinline__ uint64_t ld64_unaligned(const uint8_t *base, uint32_t
     const uint32_t sh = (uint32_t)(a & 7u) * 8;
     const uint64_t lo = __ldg(w), hi = __ldg(w + 1);  // branch-free: both loads always issue (memory-level parallelism)
     return (lo >> sh) | ((hi << 1) << (63 - sh));
+}
+
+// unaligned 8 bytes as three aligned 32-bit loads + two funnel shifts (caller guarantees pos + 12 <= chunk length)
+__device__ __forceinline__ uint64_t ld8(const uint8_t *base, uint32_t pos) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(base + pos);
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
+    const uint32_t sh = (uint32_t)(a & 3u) * 8;
+    const uint32_t w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2);
+    return (uint64_t)__funnelshift_r(w1, w2, sh) << 32 | __funnelshift_r(w0, w1, sh);
 }
 
 // length of the common prefix of in[p..] and in[c..] (c < p), at most maxlen
@@ -190,44 +199,37 @@ __global__ void __launch_bounds__(THREADS) lz_search_kernel(const uint8_t *__res
                         // pass 1: the first 8 bytes of all sixteen candidates are requested before any is examined
                         uint32_t cpos[16];
                         uint64_t x[16];
-                        uint32_t alive = 0, lens[4] = {0, 0, 0, 0};  // 16 x 8-bit lengths
+                        uint32_t alive = 0;
+#define LZ_SCORE(l_, q_) do { const uint32_t off_ = p - cpos[q_]; const int32_t sc_ = sel_score((l_), off_); \
+                              if (sc_ > bscore) { bscore = sc_; blen = (l_); boff = off_; } } while (0)
 #pragma unroll
                         for (int q = 0; q < 16; q++) {
                             const uint32_t c = (e[q] & 0x3FFFFFu) - 1u;
                             const bool ok = (e[q] >> 22) == tag && c < p;
                             cpos[q] = ok ? c : 0u;
-                            x[q] = ok ? (v ^ ld64_unaligned(in, cpos[q])) : ~0ull;
+                            x[q] = ok ? (v ^ ld8(in, cpos[q])) : ~0ull;
                         }
 #pragma unroll
                         for (int q = 0; q < 16; q++) {
-                            uint32_t l;
-                            if ((uint32_t)x[q]) l = 0;  // tag collision / not a candidate
-                            else if (x[q]) l = (uint32_t)(__ffsll((long long)x[q]) - 1) / 8;
-                            else { l = SEARCH_CAP; alive |= 1u << q; }
-                            lens[q >> 2] |= l << (8 * (q & 3));
+                            if ((uint32_t)x[q]) continue;  // tag collision / not a candidate
+                            if (x[q]) { const uint32_t l = (uint32_t)(__ffsll((long long)x[q]) - 1) / 8; if (l >= MIN_MATCH) LZ_SCORE(l, q); }
+                            else alive |= 1u << q;
                         }
-                        // extension rounds in lock-step over the survivors: one batch of loads per round
-#pragma unroll 1
-                        for (uint32_t r = 8; r < SEARCH_CAP && alive; r += 8) {
-                            const uint64_t pv = smem_u64(s_in, li + r);
+                        // extension rounds over the survivors: one batch of loads per round, a candidate is scored when it ends
 #pragma unroll
-                            for (int q = 0; q < 16; q++) x[q] = (alive >> q & 1) ? (pv ^ ld64_unaligned(in, cpos[q] + r)) : 0ull;
+                        for (uint32_t r = 8; r < SEARCH_CAP; r += 8) {
+                            if (alive) {
+                                const uint64_t pv = smem_u64(s_in, li + r);
 #pragma unroll
-                            for (int q = 0; q < 16; q++)
-                                if ((alive >> q & 1) && x[q]) {
-                                    const uint32_t l = r + (uint32_t)(__ffsll((long long)x[q]) - 1) / 8;
-                                    lens[q >> 2] = (lens[q >> 2] & ~(0xFFu << (8 * (q & 3)))) | l << (8 * (q & 3));
-                                    alive &= ~(1u << q);
-                                }
+                                for (int q = 0; q < 16; q++) x[q] = (alive >> q & 1) ? (pv ^ ld8(in, cpos[q] + r)) : 0ull;
+#pragma unroll
+                                for (int q = 0; q < 16; q++)
+                                    if (x[q]) { LZ_SCORE(r + (uint32_t)(__ffsll((long long)x[q]) - 1) / 8, q); alive &= ~(1u << q); }
+                            }
                         }
 #pragma unroll
-                        for (int q = 0; q < 16; q++) {
-                            const uint32_t l = (lens[q >> 2] >> (8 * (q & 3))) & 0xFF;
-                            if (l < MIN_MATCH) continue;
-                            const uint32_t off = p - cpos[q];
-                            const int32_t sc = sel_score(l, off);
-                            if (sc > bscore) { bscore = sc; blen = l; boff = off; }
-                        }
+                        for (int q = 0; q < 16; q++) if (alive >> q & 1) LZ_SCORE(SEARCH_CAP, q);
+#undef LZ_SCORE
                     } else {  // last bytes of the chunk: careful scalar path
                         const uint32_t maxlen = min(n - p, SEARCH_CAP);
 #pragma unroll 1
