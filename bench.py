@@ -37,17 +37,34 @@ def log(*a):
 
 
 # --------------------------------------------------------------------------- corpus definition
-def corpus_plan(n_slots: int, first_slot: int = 0, dup_frac: float = 0.2, seed: int = SEED):
-    """Slot table of the config-2 stream: (payload id, class) per 2 MiB slot; with p = dup_frac a slot
-    copies a uniformly chosen EARLIER slot of the global stream (so duplicates cross rank shards)."""
+WORKLOADS = {
+    "config2": "configs[1]: mixed logs/JSON/binary corpus, 20% duplicate 2 MiB slots, device-resident pack",
+    "config3": "configs[2]: VM-image-like corpus (35% zero / 45% fs-like mixed / 20% random slots, ~70% duplicate slots), device-resident pack",
+    "config4": "configs[3]: incompressible random corpus, 0% duplicates (raw-block fallback, hash/dedup ceiling)",
+}
+
+
+def corpus_plan(n_slots: int, first_slot: int = 0, dup_frac: float = 0.2, seed: int = SEED, workload: str = "config2"):
+    """Slot table of a corpus stream: (payload id, class) per 2 MiB slot.  A duplicate slot copies an EARLIER slot
+    of the global stream (so duplicates cross rank shards): uniformly chosen for config2, Zipf-popular for config3."""
     import numpy as np
     total = first_slot + n_slots
-    rng = np.random.default_rng(seed)
+    rng = np.random.default_rng(seed + {"config2": 0, "config3": 1, "config4": 2}[workload])
     u = rng.random(total)
-    klass = np.where(u < 0.4, 1, np.where(u < 0.7, 2, 3)).astype(np.uint32)  # 1 log, 2 json, 3 binary
-    is_dup = rng.random(total) < dup_frac
-    src = (rng.random(total) * np.arange(total)).astype(np.int64)
+    if workload == "config2":
+        klass = np.where(u < 0.4, 1, np.where(u < 0.7, 2, 3)).astype(np.uint32)  # 1 log, 2 json, 3 binary
+        is_dup = rng.random(total) < dup_frac
+        src = (rng.random(total) * np.arange(total)).astype(np.int64)
+    elif workload == "config3":
+        klass = np.where(u < 0.35, 5, np.where(u < 0.80, 6, 4)).astype(np.uint32)  # 5 zeros, 6 fs-like mix, 4 random
+        is_dup = rng.random(total) < 0.54  # + all-zero slots being duplicates of each other gives ~70% duplicate slots
+        src = (np.arange(total) * rng.random(total) ** 3).astype(np.int64)  # popular (early) slots are copied more often
+    else:
+        klass = np.full(total, 4, dtype=np.uint32)
+        is_dup = np.zeros(total, dtype=bool)
+        src = np.zeros(total, dtype=np.int64)
     ids = np.arange(total, dtype=np.uint64)
+    ids[klass == 5] = 0  # every all-zero slot is the same payload
     is_dup[0] = False
     for i in range(total):  # resolve copy chains so ids[i] names the original payload
         if is_dup[i]:
@@ -167,7 +184,7 @@ def run_reference(args):
     oracle = load_oracle()
     cores = os.cpu_count() or 1
     n = args.ref_chunks or max(64, min(2048, cores * 16))
-    ids, klass = corpus_plan(n)
+    ids, klass = corpus_plan(n, workload=args.workload)
     buf = host_corpus(lib, ids, klass)
     for _ in range(args.warmup):
         cpu_pack(oracle, buf, min(n, max(8, cores)), cores)
@@ -180,7 +197,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "pack_gb_per_s", "value": gbs, "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": t / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "configs[1] mixed logs/JSON/binary 20% dup, CPU sample", "sample_chunks": n, "chunk_bytes": CHUNK,
+            "config": {"workload": WORKLOADS[args.workload] + " (CPU sample)", "sample_chunks": n, "chunk_bytes": CHUNK,
                        "zstd_level": 12, "libzstd": oracle.L.sqo_zstd_version()},
             "cpu_baseline": {"value": gbs, "unit": "GB/s", "cores": cores, "kind": "port",
                              "sample": f"{n} x 2 MiB slots of the configs[1] stream per step, in memory, archive to /dev/shm"},
@@ -215,7 +232,7 @@ def run_ours(args):
     n_slots = n_batches * B
     ctx = sq.Context(device=local, dedup_capacity=max(1 << 20, 4 * n_slots * max(world, 1) * (args.steps + args.warmup + 4) // max(n_batches, 1) + n_slots * 4),
                      max_batch_chunks=B * max(world, 1))
-    ids, klass = corpus_plan(n_slots, first_slot=rank * n_slots)
+    ids, klass = corpus_plan(n_slots, first_slot=rank * n_slots, workload=args.workload)
     corpus = torch.empty(n_slots * CHUNK, dtype=torch.uint8, device="cuda")
     d_ids = torch.from_numpy(ids.astype(np.int64)).cuda()
     d_kl = torch.from_numpy(klass.astype(np.int32)).cuda()
@@ -383,7 +400,10 @@ def run_ours(args):
     alg = {"digest": local_in, "dedup": totals["chunks"] * 48, "encode": u_bytes + local_out}[dom]
     ach = alg / (stage_ms[dom] * 1e-3) / 1e9 if stage_ms[dom] > 0 else 0.0
     roof = {"bound": "hbm", "kernel": {"digest": "xxh3_128_kernel (K1)", "dedup": "dedup_insert_kernel (K2)", "encode": "zstd encode stages (K3)"}[dom],
-            "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+            "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+            # dram bytes/launch of the dominant kernel: 197 B per unique input byte measured by ncu --set full on lz_search_kernel
+            # (profiles/r1_lz_search_v2_raw.csv: 122.4 GB read+write for 296 chunks); K1 reads its input once (ncu: 1.00x)
+            "traffic": int(197 * u_bytes / args.steps) if dom == "encode" else (alg // args.steps if dom == "digest" else None),
             "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
             "algorithmic_bytes_per_step": alg // args.steps,
             "stage_ms_per_step": {k: v / args.steps for k, v in stage_ms.items()},
@@ -392,12 +412,14 @@ def run_ours(args):
 
     # ---- CPU baseline: the oracle timed on this box's host cores on a bounded sample ----
     cpu = None
+    cpu_n = 0
     if not args.no_cpu:
         try:
             oracle = load_oracle()
             cores = os.cpu_count() or 1
             n = args.ref_chunks or max(64, min(2048, cores * 16))
-            n = min(n, n_slots)
+            n = min(n, n_slots, B)
+            cpu_n = n
             sample = corpus[: n * CHUNK].cpu().numpy()
             buf = (C.c_uint8 * (n * CHUNK)).from_buffer(sample)
             dt, st = cpu_pack(oracle, buf, n, cores)
@@ -408,14 +430,49 @@ def run_ours(args):
         except Exception as e:  # the baseline is a report, never a reason to lose the bench line
             log("cpu_baseline failed:", repr(e))
 
+    # ---- unpack (K4) on the frames of one packed batch, device-resident, + same-sample ratio vs the oracle ----
+    unpack = None
+    try:
+        uctx = sq.Context(device=local, dedup_capacity=1 << 20, max_batch_chunks=B)
+        res = torch.empty(B * 32, dtype=torch.uint8, device="cuda")
+        used = C.c_uint64()
+        uctx.check(lib.sq_pack_device(uctx.h, corpus.data_ptr(), d_spans.data_ptr(), B, 0, res.data_ptr(), d_out.data_ptr(), out_cap - 64, C.byref(used), sp))
+        r = np.frombuffer(res.cpu().numpy().tobytes(), dtype=np.dtype([("d", "u1", 16), ("off", "<u8"), ("len", "<u4"), ("new", "u1"), ("pad", "u1", 3)]))
+        sel = np.nonzero(r["new"])[0]
+        fr = np.zeros(len(sel), dtype=np.dtype([("src", "<u8"), ("dst", "<u8"), ("len", "<u4"), ("cap", "<u4")]))
+        fr["src"], fr["dst"], fr["len"], fr["cap"] = r["off"][sel], np.arange(len(sel)) * CHUNK, r["len"][sel], CHUNK
+        d_fr = torch.frombuffer(bytearray(fr.tobytes()), dtype=torch.uint8).cuda()
+        dec = torch.empty(len(sel) * CHUNK, dtype=torch.uint8, device="cuda")
+        d_res = torch.empty(len(sel) * 8, dtype=torch.uint8, device="cuda")
+        t_dec = []
+        for _ in range(4):
+            e0, e1 = ev(), ev()
+            e0.record(stream)
+            uctx.check(lib.sq_decode_device(uctx.h, d_out.data_ptr(), d_fr.data_ptr(), len(sel), dec.data_ptr(), d_res.data_ptr(), sp))
+            e1.record(stream)
+            torch.cuda.synchronize()
+            t_dec.append(e0.elapsed_time(e1))
+        ok = all(bool(torch.equal(dec[k * CHUNK:(k + 1) * CHUNK], corpus[int(i) * CHUNK:(int(i) + 1) * CHUNK])) for k, i in enumerate(sel[:64]))
+        st = np.frombuffer(d_res.cpu().numpy().tobytes(), dtype="<i4").reshape(-1, 2)
+        unpack = {"value": len(sel) * CHUNK / (min(t_dec[1:]) * 1e-3) / 1e9, "unit": "GB/s", "frames": int(len(sel)), "what": "K4 decode of one packed batch, device-resident, restored bytes/s",
+                  "byte_identical": ok and int((st[:, 1] != 0).sum()) == 0, "algorithmic_gbs": (int(r["len"][sel].sum()) + len(sel) * CHUNK) / (min(t_dec[1:]) * 1e-3) / 1e9}
+        if cpu and cpu.get("ratio"):
+            m = sel[sel < cpu_n]
+            gpu_ratio = float(r["len"][m].sum()) / (len(m) * CHUNK) if len(m) else None
+            cpu["gpu_ratio_same_sample"] = gpu_ratio
+            cpu["ratio_delta_pct"] = (gpu_ratio / cpu["ratio"] - 1) * 100 if gpu_ratio else None
+        uctx.close()
+    except Exception as e:
+        log("unpack section failed:", repr(e))
+
     line = {"metric": "pack_gb_per_s", "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
             "data": "synthetic",
-            "config": {"workload": "configs[1]: mixed logs/JSON/binary corpus, 20% duplicate 2 MiB slots, device-resident pack",
+            "config": {"workload": WORKLOADS[args.workload],
                        "corpus_gib_per_gpu": n_slots * CHUNK / GiB, "batch_chunks": B, "chunk_bytes": CHUNK,
                        "l2_policy": f"inputs larger than L2: each step reads a fresh {B * CHUNK / GiB:.0f} GiB batch",
                        "parallelism": f"dp{world} (chunks sharded by rank" + (", digest all-to-all over NCCL)" if world > 1 else ")")},
-            "gpu_launches": int(launches1.value - launches0.value), "clocks": clk, "e2e": e2e, "roofline": roof, "cpu_baseline": cpu,
+            "gpu_launches": int(launches1.value - launches0.value), "clocks": clk, "e2e": e2e, "roofline": roof, "cpu_baseline": cpu, "unpack": unpack,
             "ratio": {"compressed_over_unique": out_bytes / (n_new * CHUNK) if n_new else None, "unique_fraction": n_new * CHUNK / in_bytes}}
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -428,6 +485,7 @@ def main():
     ap.add_argument("--steps", type=int, default=16)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS))
     ap.add_argument("--batch-chunks", type=int, default=2048)
     ap.add_argument("--corpus-gib", type=int, default=64)
     ap.add_argument("--e2e-chunks", type=int, default=512)
