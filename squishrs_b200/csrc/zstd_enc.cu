@@ -30,7 +30,7 @@ struct sq_enc_scratch {
     uint32_t *rec;           // [cap_chunks * lz::REC_PER_CHUNK] per-position parse records
     uint32_t *tab, *head;    // per resident lz CTA: bucketed hash table (never cleared between chunks)
     uint8_t *lits;           // per entropy warp: gathered literals
-    zc::EncWork *work;       // per entropy warp
+    uint32_t *sbits;         // per entropy warp: FSE state-transition records, 3 x SEQ_PER_BLOCK
     uint32_t lz_ctas, ent_warps;
     uint32_t cap_chunks;
     uint32_t *status;        // [0] != 0 => capacity overflow; [1],[2] work counters
@@ -185,7 +185,7 @@ static int32_t enc_scratch(sq_ctx *ctx, uint32_t n) {
         SQ_CUDA(ctx, cudaMalloc(&e->head, (size_t)e->lz_ctas * lz::ROWS * sizeof(uint32_t)));
         SQ_CUDA(ctx, cudaMemset(e->head, 0, (size_t)e->lz_ctas * lz::ROWS * sizeof(uint32_t)));
         SQ_CUDA(ctx, cudaMalloc(&e->lits, (size_t)e->ent_warps * (Z_BLOCK_MAX + 64)));
-        SQ_CUDA(ctx, cudaMalloc(&e->work, (size_t)e->ent_warps * sizeof(zc::EncWork)));
+        SQ_CUDA(ctx, cudaMalloc(&e->sbits, (size_t)e->ent_warps * 3 * lz::SEQ_PER_BLOCK * sizeof(uint32_t)));
         SQ_CUDA(ctx, cudaMalloc(&e->status, 8 * sizeof(uint32_t)));
         SQ_CUDA(ctx, cudaMemset(e->status, 0, 8 * sizeof(uint32_t)));
     }
@@ -209,7 +209,7 @@ void sq_enc_destroy(sq_ctx *ctx) {
     sq_enc_scratch *e = ctx->enc;
     if (!e) return;
     cudaFree(e->blocks); cudaFree(e->frame_len); cudaFree(e->bodies); cudaFree(e->status); cudaFree(e->seqs); cudaFree(e->meta); cudaFree(e->rec);
-    cudaFree(e->tab); cudaFree(e->head); cudaFree(e->lits); cudaFree(e->work);
+    cudaFree(e->tab); cudaFree(e->head); cudaFree(e->lits); cudaFree(e->sbits);
     delete e;
     ctx->enc = nullptr;
 }
@@ -240,7 +240,7 @@ extern "C" int32_t sq_encode_device(sq_ctx *ctx, const void *d_data, const sq_sp
         lz::lz_chase_kernel<<<(n * SQ_MAX_BLOCKS + 3) / 4, 128, 0, st>>>((const uint8_t *)d_data, d_spans, d_select, n, e->rec, e->seqs, e->meta);
         const uint32_t ent_ctas = e->ent_warps / 4;
         lz::entropy_kernel<<<ent_ctas, 128, 0, st>>>((const uint8_t *)d_data, d_spans, d_select, n, e->seqs, e->meta, e->lits, e->bodies,
-                                                     reinterpret_cast<lz::BlockOut *>(e->blocks), e->work, e->status + 2);
+                                                     reinterpret_cast<lz::BlockOut *>(e->blocks), e->sbits, e->status + 2);
     }
     enc_size_kernel<<<(n + 255) / 256, 256, 0, st>>>(d_spans, d_select, n, e->blocks, e->frame_len);
     enc_scan_kernel<<<1, 1024, 0, st>>>(e->frame_len, n, out_capacity, d_frame_off, d_frame_len, d_total, e->status);

@@ -21,11 +21,12 @@
 // Matches never cross a block boundary; repeat-offset knowledge is dropped at every block start so a block
 // that later falls back to raw cannot desynchronise the decoder's history.
 //
-// entropy_kernel -- one warp per block: gathers literals, then one lane runs the serial block writer
-// (zstd_enc_block.h: Huffman literals, FSE sequence tables, bitstreams) into the block's body slot.
+// entropy_kernel -- one warp per block: gathers literals, then writes the block body warp-parallel
+// (zstd_enc_entropy.cuh: histograms, segment-parallel Huffman / FSE bit packing; tables by one lane).
 #pragma once
 #include "common.cuh"
 #include "zstd_enc_block.h"
+#include "zstd_enc_entropy.cuh"
 
 namespace lz {
 
@@ -380,11 +381,13 @@ __global__ void __launch_bounds__(128) entropy_kernel(const uint8_t *__restrict_
                                                        const uint8_t *__restrict__ select, uint32_t n_chunks,
                                                        const zc::Seq *__restrict__ seqs_all, const BlockMeta *__restrict__ meta_all,
                                                        uint8_t *__restrict__ lit_all, uint8_t *__restrict__ bodies, BlockOut *__restrict__ blocks,
-                                                       zc::EncWork *__restrict__ work_all, uint32_t *__restrict__ counter) {
+                                                       uint32_t *__restrict__ sbits_all, uint32_t *__restrict__ counter) {
+    __shared__ ent::WarpWork s_work[4];
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    zc::EncWork *wk = work_all + warp_global;
+    ent::WarpWork *W = &s_work[threadIdx.x >> 5];
     uint8_t *lits = lit_all + (size_t)warp_global * (Z_BLOCK_MAX + 64);
+    uint32_t *sbits = sbits_all + (size_t)warp_global * 3 * SEQ_PER_BLOCK;
     for (;;) {
         uint32_t item = 0;
         if (lane == 0) item = atomicAdd(counter, 1u);
@@ -400,8 +403,7 @@ __global__ void __launch_bounds__(128) entropy_kernel(const uint8_t *__restrict_
         if (blen == 0) { if (lane == 0) { BlockOut o0; o0.type = 0; o0.body_len = 0; blocks[(size_t)chunk * BLOCKS_PER_CHUNK + b] = o0; } continue; }
         const BlockMeta m = meta_all[(size_t)chunk * BLOCKS_PER_CHUNK + b];
         const zc::Seq *seqs = seqs_all + (size_t)chunk * MAX_SEQ_PER_CHUNK + m.seq_start;
-        // gather literals: lanes stride over sequences; source positions from a running prefix kept by lane order
-        // (serial prefix over sequences by chunks of 32 with warp scan)
+        // gather literals: 32 sequences at a time, a warp scan gives every lane its source and destination offsets
         uint32_t src_pos = bs, lit_pos = 0;
         for (uint32_t base = 0; base < m.nseq; base += 32) {
             const uint32_t i = base + lane;
@@ -421,16 +423,15 @@ __global__ void __launch_bounds__(128) entropy_kernel(const uint8_t *__restrict_
         for (uint32_t k = lane; k < m.last_lits; k += 32) lits[lit_pos + k] = in[src_pos + k];
         const uint32_t nlits = lit_pos + m.last_lits;
         __syncwarp();
+        __threadfence_block();
         BlockOut out;
         out.type = 0; out.body_len = blen;  // raw unless the compressed body is smaller
-        if (lane == 0 && src_pos + m.last_lits == be && blen > 0) {
+        // the body slot holds literals + <= 8 bytes per sequence; a parse that cannot fit cannot beat raw either
+        if (src_pos + m.last_lits == be && zc::block_body_bound(nlits, m.nseq) <= BODY_STRIDE) {
             uint8_t *dst = bodies + ((size_t)chunk * BLOCKS_PER_CHUNK + b) * (size_t)BODY_STRIDE;
-            // worst case body is literals + sequences; both fit the slot only if the parse actually saves bytes,
-            // so bound the attempt: sequences cost <= 8 bytes each
-            if (zc::block_body_bound(nlits, m.nseq) <= BODY_STRIDE) {
-                const uint32_t sz = zc::write_block_body(dst, lits, nlits, seqs, m.nseq, wk);
-                if (sz < blen) { out.type = 2; out.body_len = sz; }
-            }
+            uint32_t sz = ent::warp_write_literals(dst, lits, nlits, W, lane);
+            sz += ent::warp_write_sequences(dst + sz, seqs, m.nseq, W, sbits, lane);
+            if (sz < blen) { out.type = 2; out.body_len = sz; }
         }
         if (lane == 0) blocks[(size_t)chunk * BLOCKS_PER_CHUNK + b] = out;
         __syncwarp();
