@@ -125,6 +125,8 @@ __global__ void __launch_bounds__(THREADS) lz_search_kernel(const uint8_t *__res
     __shared__ uint8_t s_len[RING];
     __shared__ uint32_t s_off[RING];
     __shared__ uint8_t s_back[RING];
+    __shared__ uint32_t s_queue[(THREADS / 32) * 32 * ROW_K];  // per warp: compacted (position | candidate << 10) pairs
+    __shared__ uint32_t s_best[TILE];                           // per position: (score+9) << 26 | (len-6) << 21 | off  (0 = none)
     __shared__ uint32_t s_chunk;
 #ifdef SQ_LZ_TIMERS
     long long tm[6] = {0, 0, 0, 0, 0, 0}, tc = clock64();
@@ -183,70 +185,103 @@ __global__ void __launch_bounds__(THREADS) lz_search_kernel(const uint8_t *__res
             __syncthreads();
             LZ_TICK(1);
             // ---- search ----
+            // Each warp takes 32 consecutive positions at a time.  Lanes first filter their own row by tag (no data access),
+            // the warp compacts the surviving (position, candidate) pairs into a dense queue, and the lanes then verify
+            // pairs -- not row slots -- so no issue slot is spent on empty slots.  The best candidate per position is kept
+            // with a 32-bit atomicMax on (score, length, offset) in shared memory.
 #pragma unroll 1
             for (uint32_t k = 0; k < PER_THREAD; k++) {
                 const uint32_t li = tid + k * THREADS, p = t0 + li;
-                uint32_t blen = 0, boff = 0, bback = 0;
-                if (p + 8 <= n) {
-                    const uint64_t v = smem_u64(s_in, li);
-                    const uint32_t hv = hash5(v);
-                    const uint32_t row = hv >> TAG_BITS, tag = hv & ((1u << TAG_BITS) - 1);
-                    int32_t bscore = -1000;
+                const uint32_t wq = tid >> 5, lane = tid & 31;
+                uint32_t *queue = s_queue + wq * (32 * ROW_K);
+                uint32_t mask = 0, cand[ROW_K];
+                const bool searchable = p + 8 <= n;
+                const bool fast = p + SEARCH_CAP + 16 <= n;  // every comparison stays inside the chunk and the staged window
+                uint32_t tag = 0;
+                if (searchable) {
+                    const uint32_t hv = hash5(smem_u64(s_in, li));
+                    const uint32_t row = hv >> TAG_BITS;
+                    tag = hv & ((1u << TAG_BITS) - 1);
                     const uint4 *r4 = reinterpret_cast<const uint4 *>(tab + row * ROW_K);
-                    static_assert(ROW_K == 16, "the search batches one 16-entry row");
+                    static_assert(ROW_K == 16, "the search reads one 16-entry row");
                     const uint4 ea = __ldcg(r4), eb = __ldcg(r4 + 1), ec = __ldcg(r4 + 2), ed = __ldcg(r4 + 3);
                     const uint32_t e[16] = {ea.x, ea.y, ea.z, ea.w, eb.x, eb.y, eb.z, eb.w, ec.x, ec.y, ec.z, ec.w, ed.x, ed.y, ed.z, ed.w};
-                    if (p + SEARCH_CAP + 16 <= n) {
-                        // pass 1: the first 8 bytes of all sixteen candidates are requested before any is examined
-                        uint32_t cpos[16];
-                        uint64_t x[16];
-                        uint32_t alive = 0;
-#define LZ_SCORE(l_, q_) do { const uint32_t off_ = p - cpos[q_]; const int32_t sc_ = sel_score((l_), off_); \
-                              if (sc_ > bscore) { bscore = sc_; blen = (l_); boff = off_; } } while (0)
 #pragma unroll
-                        for (int q = 0; q < 16; q++) {
-                            const uint32_t c = (e[q] & 0x3FFFFFu) - 1u;
-                            const bool ok = (e[q] >> 22) == tag && c < p;
-                            cpos[q] = ok ? c : 0u;
-                            x[q] = ok ? (v ^ ld8(in, cpos[q])) : ~0ull;
-                        }
+                    for (int q = 0; q < 16; q++) {
+                        cand[q] = (e[q] & 0x3FFFFFu) - 1u;
+                        if ((e[q] >> 22) == tag && cand[q] < p) mask |= 1u << q;
+                    }
+                }
+                s_best[li] = 0u;
+                uint32_t total;
+                const uint32_t cnt = fast ? __popc(mask) : 0u;
+                uint32_t wpos = ent::warp_excl_scan(cnt, lane, &total);
+                if (fast) {
 #pragma unroll
-                        for (int q = 0; q < 16; q++) {
-                            if ((uint32_t)x[q]) continue;  // tag collision / not a candidate
-                            if (x[q]) { const uint32_t l = (uint32_t)(__ffsll((long long)x[q]) - 1) / 8; if (l >= MIN_MATCH) LZ_SCORE(l, q); }
-                            else alive |= 1u << q;
-                        }
-                        // extension rounds over the survivors: one batch of loads per round, a candidate is scored when it ends
-#pragma unroll
-                        for (uint32_t r = 8; r < SEARCH_CAP; r += 8) {
-                            if (alive) {
-                                const uint64_t pv = smem_u64(s_in, li + r);
-#pragma unroll
-                                for (int q = 0; q < 16; q++) x[q] = (alive >> q & 1) ? (pv ^ ld8(in, cpos[q] + r)) : 0ull;
-#pragma unroll
-                                for (int q = 0; q < 16; q++)
-                                    if (x[q]) { LZ_SCORE(r + (uint32_t)(__ffsll((long long)x[q]) - 1) / 8, q); alive &= ~(1u << q); }
-                            }
-                        }
-#pragma unroll
-                        for (int q = 0; q < 16; q++) if (alive >> q & 1) LZ_SCORE(SEARCH_CAP, q);
-#undef LZ_SCORE
-                    } else {  // last bytes of the chunk: careful scalar path
-                        const uint32_t maxlen = min(n - p, SEARCH_CAP);
+                    for (int q = 0; q < 16; q++)
+                        if (mask >> q & 1) queue[wpos++] = li | cand[q] << 10;
+                }
+                __syncwarp();
 #pragma unroll 1
-                        for (int q = 0; q < 16; q++) {
-                            if ((e[q] >> 22) != tag) continue;
-                            const uint32_t c = (e[q] & 0x3FFFFFu) - 1u;
-                            if (c >= p) continue;
-                            const uint32_t l = match_length(in, p, c, maxlen, n);
-                            if (l < MIN_MATCH) continue;
-                            const uint32_t off = p - c;
-                            const int32_t sc = sel_score(l, off);
-                            if (sc > bscore) { bscore = sc; blen = l; boff = off; }
+                for (uint32_t i = lane; i < total; i += 64) {
+                    // two pairs per lane per trip: both candidates' first 8 bytes are requested before either is examined
+                    const uint32_t pr0 = queue[i], pr1 = i + 32 < total ? queue[i + 32] : 0xFFFFFFFFu;
+                    const uint32_t l0 = pr0 & 1023u, c0 = pr0 >> 10, l1 = pr1 & 1023u, c1 = pr1 == 0xFFFFFFFFu ? 0u : pr1 >> 10;
+                    uint64_t x0 = smem_u64(s_in, l0) ^ ld8(in, c0);
+                    uint64_t x1 = pr1 == 0xFFFFFFFFu ? ~0ull : smem_u64(s_in, l1) ^ ld8(in, c1);
+                    uint32_t m0 = 0, m1 = 0;  // match lengths
+                    bool a0 = false, a1 = false;
+                    if ((uint32_t)x0 == 0) { if (x0) m0 = (uint32_t)(__ffsll((long long)x0) - 1) / 8; else a0 = true; }
+                    if ((uint32_t)x1 == 0) { if (x1) m1 = (uint32_t)(__ffsll((long long)x1) - 1) / 8; else a1 = true; }
+#pragma unroll
+                    for (uint32_t r = 8; r < SEARCH_CAP; r += 8) {
+                        if (a0 | a1) {
+                            x0 = a0 ? smem_u64(s_in, l0 + r) ^ ld8(in, c0 + r) : 0ull;
+                            x1 = a1 ? smem_u64(s_in, l1 + r) ^ ld8(in, c1 + r) : 0ull;
+                            if (a0 && x0) { m0 = r + (uint32_t)(__ffsll((long long)x0) - 1) / 8; a0 = false; }
+                            if (a1 && x1) { m1 = r + (uint32_t)(__ffsll((long long)x1) - 1) / 8; a1 = false; }
                         }
                     }
-                    if (blen) {
-                        const uint32_t c = p - boff;
+                    if (a0) m0 = SEARCH_CAP;
+                    if (a1) m1 = SEARCH_CAP;
+                    if (m0 >= MIN_MATCH) {
+                        const uint32_t off = t0 + l0 - c0;
+                        atomicMax(&s_best[l0], (uint32_t)(sel_score(m0, off) + 9) << 26 | (m0 - MIN_MATCH) << 21 | off);
+                    }
+                    if (m1 >= MIN_MATCH) {
+                        const uint32_t off = t0 + l1 - c1;
+                        atomicMax(&s_best[l1], (uint32_t)(sel_score(m1, off) + 9) << 26 | (m1 - MIN_MATCH) << 21 | off);
+                    }
+                }
+                __syncwarp();
+                uint32_t blen = 0, boff = 0, bback = 0;
+                if (searchable && !fast) {  // last bytes of the chunk: careful scalar path
+                    const uint32_t maxlen = min(n - p, SEARCH_CAP);
+                    int32_t bscore = -1000;
+#pragma unroll 1
+                    for (int q = 0; q < 16; q++) {
+                        if (!(mask >> q & 1)) continue;
+                        uint32_t c = 0;
+#pragma unroll
+                        for (int z = 0; z < 16; z++) if (z == q) c = cand[z];
+                        const uint32_t l = match_length(in, p, c, maxlen, n);
+                        if (l < MIN_MATCH) continue;
+                        const uint32_t off = p - c;
+                        const int32_t sc = sel_score(l, off);
+                        if (sc > bscore) { bscore = sc; blen = l; boff = off; }
+                    }
+                } else if (searchable) {
+                    const uint32_t best = s_best[li];
+                    if (best) { blen = ((best >> 21) & 31u) + MIN_MATCH; boff = best & 0x1FFFFFu; }
+                }
+                if (blen) {
+                    const uint32_t c = p - boff;
+                    if (c >= 4 && p + 8 <= n) {  // one unaligned load each side: bytes [x-4, x)
+                        const uint32_t dp = (uint32_t)ld8(in, p - 4), dc = (uint32_t)ld8(in, c - 4);
+                        const uint32_t diff = dp ^ dc;  // byte 3 is the byte just before the position
+                        bback = diff == 0 ? 3u : (uint32_t)__clz((int)diff) >> 3;
+                        if (bback > 3) bback = 3;
+                    } else {
                         while (bback < 3 && p > bback && c > bback && in[p - bback - 1] == in[c - bback - 1]) bback++;
                     }
                 }
