@@ -10,6 +10,7 @@
 //   size      per chunk: frame length from the block bodies                    (enc_size_kernel)
 //   place     exclusive scan of frame lengths over the batch -> frame offsets  (enc_scan_kernel)
 //   emit      per block: write header + body (or raw fallback) into d_out      (enc_emit_kernel)
+#include <stdlib.h>
 #include "common.cuh"
 #include "zstd_enc_lz.cuh"
 
@@ -178,7 +179,11 @@ static int32_t enc_scratch(sq_ctx *ctx, uint32_t n) {
     }
     sq_enc_scratch *e = ctx->enc;
     if (!e->tab) {  // per-resident-worker state, sized once from the SM count
-        e->lz_ctas = (uint32_t)ctx->sm_count * 4;
+        {
+            const char *ov = getenv("SQ_LZ_CTAS_PER_SM");  // tuning knob; default = what the register budget allows
+            const uint32_t per_sm = ov && atoi(ov) > 0 ? (uint32_t)atoi(ov) : 3u;
+            e->lz_ctas = (uint32_t)ctx->sm_count * per_sm;
+        }
         e->ent_warps = (uint32_t)ctx->sm_count * 16;
         SQ_CUDA(ctx, cudaMalloc(&e->tab, (size_t)e->lz_ctas * lz::ROWS * lz::ROW_K * sizeof(uint32_t)));
         SQ_CUDA(ctx, cudaMemset(e->tab, 0, (size_t)e->lz_ctas * lz::ROWS * lz::ROW_K * sizeof(uint32_t)));

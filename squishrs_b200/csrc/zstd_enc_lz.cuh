@@ -189,6 +189,13 @@ __global__ void __launch_bounds__(THREADS) lz_search_kernel(const uint8_t *__res
             // the warp compacts the surviving (position, candidate) pairs into a dense queue, and the lanes then verify
             // pairs -- not row slots -- so no issue slot is spent on empty slots.  The best candidate per position is kept
             // with a 32-bit atomicMax on (score, length, offset) in shared memory.
+            // rows are software-pipelined: the row of the NEXT group of 32 positions is requested before this group's pairs are verified
+            uint4 nea, neb, nec, ned;
+            {
+                const uint32_t hv0 = hash5(smem_u64(s_in, tid));
+                const uint4 *r0 = reinterpret_cast<const uint4 *>(tab + (hv0 >> TAG_BITS) * ROW_K);
+                nea = __ldcg(r0); neb = __ldcg(r0 + 1); nec = __ldcg(r0 + 2); ned = __ldcg(r0 + 3);
+            }
 #pragma unroll 1
             for (uint32_t k = 0; k < PER_THREAD; k++) {
                 const uint32_t li = tid + k * THREADS, p = t0 + li;
@@ -198,18 +205,22 @@ __global__ void __launch_bounds__(THREADS) lz_search_kernel(const uint8_t *__res
                 const bool searchable = p + 8 <= n;
                 const bool fast = p + SEARCH_CAP + 16 <= n;  // every comparison stays inside the chunk and the staged window
                 uint32_t tag = 0;
-                if (searchable) {
+                {
                     const uint32_t hv = hash5(smem_u64(s_in, li));
-                    const uint32_t row = hv >> TAG_BITS;
                     tag = hv & ((1u << TAG_BITS) - 1);
-                    const uint4 *r4 = reinterpret_cast<const uint4 *>(tab + row * ROW_K);
                     static_assert(ROW_K == 16, "the search reads one 16-entry row");
-                    const uint4 ea = __ldcg(r4), eb = __ldcg(r4 + 1), ec = __ldcg(r4 + 2), ed = __ldcg(r4 + 3);
-                    const uint32_t e[16] = {ea.x, ea.y, ea.z, ea.w, eb.x, eb.y, eb.z, eb.w, ec.x, ec.y, ec.z, ec.w, ed.x, ed.y, ed.z, ed.w};
+                    const uint32_t e[16] = {nea.x, nea.y, nea.z, nea.w, neb.x, neb.y, neb.z, neb.w, nec.x, nec.y, nec.z, nec.w, ned.x, ned.y, ned.z, ned.w};
+                    if (k + 1 < PER_THREAD) {  // prefetch the next group's row (table rows exist for any hash value)
+                        const uint32_t hvn = hash5(smem_u64(s_in, li + THREADS));
+                        const uint4 *rn = reinterpret_cast<const uint4 *>(tab + (hvn >> TAG_BITS) * ROW_K);
+                        nea = __ldcg(rn); neb = __ldcg(rn + 1); nec = __ldcg(rn + 2); ned = __ldcg(rn + 3);
+                    }
+                    if (searchable) {
 #pragma unroll
-                    for (int q = 0; q < 16; q++) {
-                        cand[q] = (e[q] & 0x3FFFFFu) - 1u;
-                        if ((e[q] >> 22) == tag && cand[q] < p) mask |= 1u << q;
+                        for (int q = 0; q < 16; q++) {
+                            cand[q] = (e[q] & 0x3FFFFFu) - 1u;
+                            if ((e[q] >> 22) == tag && cand[q] < p) mask |= 1u << q;
+                        }
                     }
                 }
                 s_best[li] = 0u;
