@@ -13,8 +13,8 @@
 // 2*(l%4), 2*(l%4)+1, with its four secret words fixed in registers for the whole chunk.
 // Three xor-butterfly shuffle steps (4,8,16) sum the 8 lanes that share an acc pair, then
 // every lane scrambles its copy of the pair.  Warps are persistent and pull chunk indices
-// from an atomic counter so ragged tails balance.  Two blocks (4 x LDG.128 per lane,
-// 2 KiB per warp) are kept in flight.
+// from an atomic counter so ragged tails balance.  Four blocks (8 x LDG.128 per lane,
+// 4 KiB per warp) are kept in flight by a register double buffer.
 #include "common.cuh"
 
 namespace {
@@ -158,13 +158,23 @@ __device__ void xxh3_long_warp(const uint8_t *in, uint32_t len, int lane, uint64
     const uint32_t nb_blocks = (len - 1) >> 10;
     const uint8_t *p = in + 16 * lane;
     uint32_t b = 0;
-    // main loop: two blocks per iteration (4 loads in flight per lane)
-    for (; b + 2 <= nb_blocks; b += 2, p += 2048) {
-        uint64_t v0, v1, w0, w1, x0, x1, y0, y1;
+    // main loop: two blocks per iteration, software-pipelined in registers: the loads of the NEXT two blocks are
+    // issued before the current two are reduced, so 8 x 16 B per lane (4 KiB per warp) are in flight
+    uint64_t v0 = 0, v1 = 0, w0 = 0, w1 = 0, x0 = 0, x1 = 0, y0 = 0, y1 = 0;
+    if (nb_blocks >= 2) {
         load16<ALIGNED>(p, v0, v1);
         load16<ALIGNED>(p + 512, w0, w1);
         load16<ALIGNED>(p + 1024, x0, x1);
         load16<ALIGNED>(p + 1536, y0, y1);
+    }
+    for (; b + 2 <= nb_blocks; b += 2, p += 2048) {
+        uint64_t nv0 = 0, nv1 = 0, nw0 = 0, nw1 = 0, nx0 = 0, nx1 = 0, ny0 = 0, ny1 = 0;
+        if (b + 4 <= nb_blocks) {
+            load16<ALIGNED>(p + 2048, nv0, nv1);
+            load16<ALIGNED>(p + 2560, nw0, nw1);
+            load16<ALIGNED>(p + 3072, nx0, nx1);
+            load16<ALIGNED>(p + 3584, ny0, ny1);
+        }
         uint64_t a0 = 0, a1 = 0;
         stripe_acc(a0, a1, v0, v1, k00, k01);
         stripe_acc(a0, a1, w0, w1, k10, k11);
@@ -181,6 +191,7 @@ __device__ void xxh3_long_warp(const uint8_t *in, uint32_t len, int lane, uint64
         acc0 += a0; acc1 += a1;
         acc0 = ((acc0 ^ (acc0 >> 47)) ^ ks0) * P32_1;
         acc1 = ((acc1 ^ (acc1 >> 47)) ^ ks1) * P32_1;
+        v0 = nv0; v1 = nv1; w0 = nw0; w1 = nw1; x0 = nx0; x1 = nx1; y0 = ny0; y1 = ny1;
     }
     for (; b < nb_blocks; b++, p += 1024) {
         uint64_t v0, v1, w0, w1;
@@ -234,7 +245,7 @@ __device__ void xxh3_long_warp(const uint8_t *in, uint32_t len, int lane, uint64
     }
 }
 
-__global__ void __launch_bounds__(256, 4) xxh3_128_kernel(const uint8_t *__restrict__ data, const sq_span *__restrict__ spans,
+__global__ void __launch_bounds__(256, 3) xxh3_128_kernel(const uint8_t *__restrict__ data, const sq_span *__restrict__ spans,
                                                          uint32_t n, uint8_t *__restrict__ out, uint32_t *__restrict__ counter) {
     const int lane = threadIdx.x & 31;
     for (;;) {
@@ -282,7 +293,7 @@ extern "C" int32_t sq_digest_device(sq_ctx *ctx, const void *d_data, const sq_sp
     cudaStream_t st = sq_stream(ctx, stream);
     SQ_CUDA(ctx, cudaMemsetAsync(ctx->d_work_counter, 0, sizeof(uint32_t), st));
     // persistent warps: 8 warps per CTA, up to 8 CTAs per SM, never more warps than chunks
-    uint32_t ctas = (n + 7) / 8, max_ctas = (uint32_t)ctx->sm_count * 8;
+    uint32_t ctas = (n + 7) / 8, max_ctas = (uint32_t)ctx->sm_count * 3;
     if (ctas > max_ctas) ctas = max_ctas;
     xxh3_128_kernel<<<ctas, 256, 0, st>>>((const uint8_t *)d_data, d_spans, n, (uint8_t *)d_digests, ctx->d_work_counter);
     SQ_LAUNCHED(ctx, 1);
