@@ -125,6 +125,7 @@ __global__ void __launch_bounds__(THREADS) lz_search_kernel(const uint8_t *__res
     __shared__ uint8_t s_len[RING];
     __shared__ uint32_t s_off[RING];
     __shared__ uint8_t s_back[RING];
+    __shared__ int16_t s_sc[RING];  // lazy score of the position's usable match, -1 = none
     __shared__ uint32_t s_queue[(THREADS / 32) * 32 * ROW_K];  // per warp: compacted (position | candidate << 10) pairs
     __shared__ uint32_t s_best[TILE];                           // per position: (score+9) << 26 | (len-6) << 21 | off  (0 = none)
     __shared__ uint32_t s_chunk;
@@ -153,7 +154,7 @@ __global__ void __launch_bounds__(THREADS) lz_search_kernel(const uint8_t *__res
         const uint32_t n = spans[chunk].len;
         uint32_t *rec = rec_all + (size_t)chunk * REC_PER_CHUNK;
         const bool aligned = (reinterpret_cast<uintptr_t>(in) & 7) == 0;
-        for (uint32_t i = tid; i < RING; i += THREADS) s_len[i] = 0;
+        for (uint32_t i = tid; i < RING; i += THREADS) { s_len[i] = 0; s_sc[i] = -1; }
         __syncthreads();
 
         const uint32_t n_tiles = (n + TILE - 1) / TILE;
@@ -297,7 +298,12 @@ __global__ void __launch_bounds__(THREADS) lz_search_kernel(const uint8_t *__res
                     }
                 }
                 if (p < t1) {
-                    s_len[p & (RING - 1)] = (uint8_t)blen;
+                    // what the parser may take here: clamp to the block end, apply the acceptance rule, keep the lazy score
+                    if (p + blen > be) blen = be - p;
+                    int32_t lsc = -1;
+                    if (blen >= MIN_MATCH) { lsc = lazy_score(blen, boff); if (lsc < ACCEPT_THR) lsc = -1; }
+                    s_sc[p & (RING - 1)] = (int16_t)lsc;
+                    s_len[p & (RING - 1)] = (uint8_t)(lsc >= 0 ? blen : 0u);
                     s_off[p & (RING - 1)] = boff;
                     s_back[p & (RING - 1)] = (uint8_t)bback;
                 }
@@ -310,18 +316,18 @@ __global__ void __launch_bounds__(THREADS) lz_search_kernel(const uint8_t *__res
             for (uint32_t p = d0 + tid; p < d1; p += THREADS) {
                 // positions before t0 that belong to the previous block were already decided there
                 if (p < t0 && (p / Z_BLOCK_MAX) != (t0 / Z_BLOCK_MAX)) continue;
-                Cand cur = cand_at(s_len, s_off, p, be);
+                int32_t sc = s_sc[p & (RING - 1)];
                 uint32_t r = 0;
-                if (cur.len) {
+                if (sc >= 0) {
                     uint32_t start = p;
-                    while (cur.len < TARGET_LEN && start - p + 2 <= MAX_SHIFT) {
-                        const Cand c1 = cand_at(s_len, s_off, start + 1, be);
-                        if (c1.len && c1.score > cur.score + 4) { cur = c1; start += 1; continue; }
-                        const Cand c2 = cand_at(s_len, s_off, start + 2, be);
-                        if (c2.len && c2.score > cur.score + 7) { cur = c2; start += 2; continue; }
+                    while (s_len[start & (RING - 1)] < TARGET_LEN && start - p + 2 <= MAX_SHIFT) {
+                        const int32_t s1 = start + 1 < be ? (int32_t)s_sc[(start + 1) & (RING - 1)] : -1;
+                        if (s1 > sc + 4) { sc = s1; start += 1; continue; }
+                        const int32_t s2 = start + 2 < be ? (int32_t)s_sc[(start + 2) & (RING - 1)] : -1;
+                        if (s2 > sc + 7) { sc = s2; start += 2; continue; }
                         break;
                     }
-                    r = pack_rec(cur.off, cur.len, s_back[start & (RING - 1)], start - p);
+                    r = pack_rec(s_off[start & (RING - 1)], s_len[start & (RING - 1)], s_back[start & (RING - 1)], start - p);
                 }
                 rec[p] = r;
             }
