@@ -183,6 +183,8 @@ static int32_t enc_scratch(sq_ctx *ctx, uint32_t n) {
             const char *ov = getenv("SQ_LZ_CTAS_PER_SM");  // tuning knob; default = what the register budget allows
             const uint32_t per_sm = ov && atoi(ov) > 0 ? (uint32_t)atoi(ov) : 3u;
             e->lz_ctas = (uint32_t)ctx->sm_count * per_sm;
+            const char *tot = getenv("SQ_LZ_CTAS_TOTAL");  // experiment knob: cap the number of chunks in flight
+            if (tot && atoi(tot) > 0) e->lz_ctas = (uint32_t)atoi(tot);
         }
         e->ent_warps = (uint32_t)ctx->sm_count * 16;
         SQ_CUDA(ctx, cudaMalloc(&e->tab, (size_t)e->lz_ctas * lz::ROWS * lz::ROW_K * sizeof(uint32_t)));
