@@ -354,7 +354,8 @@ def run_ours(args):
         used = C.c_uint64()
         e2e_in = e2e_out = 0
         times = []
-        ectx = sq.Context(device=local, dedup_capacity=1 << 20, max_batch_chunks=eb)
+        ectx = ctx  # reuse the main context (and its scratch) with a fresh dedup index
+        ectx.dedup_reset()
         n_e2e = max(3, min(args.steps, 8))
         for k in range(-2, n_e2e):
             b = (k + 2) % n_batches
@@ -378,7 +379,6 @@ def run_ours(args):
             dist.all_reduce(et, op=dist.ReduceOp.MAX)
         e2e = {"value": world * e2e_in / float(et.item()) / 1e9, "unit": "GB/s", "h2d_bytes_per_step": eb * CHUNK + eb * 16,
                "d2h_bytes_per_step": e2e_out // len(times), "chunks_per_step": eb}
-        ectx.close()
         lib.sq_host_free(ctx.h, hp)
         lib.sq_host_free(ctx.h, ho)
 
@@ -433,7 +433,8 @@ def run_ours(args):
     # ---- unpack (K4) on the frames of one packed batch, device-resident, + same-sample ratio vs the oracle ----
     unpack = None
     try:
-        uctx = sq.Context(device=local, dedup_capacity=1 << 20, max_batch_chunks=B)
+        uctx = ctx  # reuse the main context (and its scratch) with a fresh dedup index
+        uctx.dedup_reset()
         res = torch.empty(B * 32, dtype=torch.uint8, device="cuda")
         used = C.c_uint64()
         uctx.check(lib.sq_pack_device(uctx.h, corpus.data_ptr(), d_spans.data_ptr(), B, 0, res.data_ptr(), d_out.data_ptr(), out_cap - 64, C.byref(used), sp))
@@ -461,7 +462,6 @@ def run_ours(args):
             gpu_ratio = float(r["len"][m].sum()) / (len(m) * CHUNK) if len(m) else None
             cpu["gpu_ratio_same_sample"] = gpu_ratio
             cpu["ratio_delta_pct"] = (gpu_ratio / cpu["ratio"] - 1) * 100 if gpu_ratio else None
-        uctx.close()
     except Exception as e:
         log("unpack section failed:", repr(e))
 
