@@ -439,3 +439,23 @@ def test_full_size_batch_properties(sq, oracle):
     ratio_gpu = sum(len(f) for _, _, f in frames)
     ratio_cpu = sum(len(oracle.compress(s)) for s, _, _ in frames)
     assert ratio_gpu <= 1.03 * ratio_cpu, (ratio_gpu, ratio_cpu)
+
+
+def test_ragged_sizes_every_class_roundtrip(sq, oracle):
+    """ragged chunk lengths around every internal boundary (8-byte hash window, 24-byte search cap, 1 KiB tiles,
+    128 KiB blocks) for every corpus class: GPU frames decode with stock libzstd and with K4, and K4 decodes the
+    reference's frames of the same inputs"""
+    c = sq.Context()
+    rng = random.Random(3)
+    chunks = []
+    for k in range(7):
+        for n in (1, 7, 8, 9, 23, 24, 25, 40, 63, 300, 1023, 1025, 4096, 70001, 131072, 131073, 262149):
+            chunks.append(gen(sq, k, n, k * 100 + n % 97))
+    chunks += [rng.randbytes(n) for n in (1, 100, 5000)]
+    res = c.pack_batch(chunks)
+    frames = [(s, f) for s, (_, f) in zip(chunks, res) if f is not None]
+    for s, f in frames:
+        assert oracle.decompress(f, len(s)) == s, len(s)
+    assert c.unpack_batch([f for _, f in frames], [len(s) for s, _ in frames]) == [s for s, _ in frames]
+    ref = [oracle.compress(s, 12) for s, _ in frames]
+    assert c.unpack_batch(ref, [2 * MiB] * len(ref)) == [s for s, _ in frames]
