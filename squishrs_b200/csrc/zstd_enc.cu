@@ -179,6 +179,16 @@ static int32_t enc_scratch(sq_ctx *ctx, uint32_t n) {
     }
     sq_enc_scratch *e = ctx->enc;
     if (!e->tab) {  // per-resident-worker state, sized once from the SM count
+        {   // The search kernel leans on L1 for candidate bytes: give shared memory only what the resident CTAs need.
+            cudaFuncAttributes fa;
+            SQ_CUDA(ctx, cudaFuncGetAttributes(&fa, lz::lz_search_kernel));
+            const char *ov = getenv("SQ_LZ_CTAS_PER_SM");
+            const int per_sm = ov && atoi(ov) > 0 ? atoi(ov) : 3;
+            int carve = (int)((per_sm * (fa.sharedSizeBytes + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024));
+            if (const char *cv = getenv("SQ_LZ_CARVEOUT")) carve = atoi(cv);
+            if (carve > 100) carve = 100;
+            SQ_CUDA(ctx, cudaFuncSetAttribute(lz::lz_search_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+        }
         {
             const char *ov = getenv("SQ_LZ_CTAS_PER_SM");  // tuning knob; default = what the register budget allows
             const uint32_t per_sm = ov && atoi(ov) > 0 ? (uint32_t)atoi(ov) : 3u;

@@ -11,7 +11,7 @@
 //   search  every position reads its 64-byte row (L1 bypassed), filters by tag, requests the first 8 bytes
 //           of all sixteen candidates at once, extends the survivors 8 bytes per round in lock-step (up to
 //           24 bytes; longer matches are extended by the chase) and keeps the best by 2*len - log2(offset); plus how far it extends backwards (<= 3).
-//           Results go to a 2-tile ring in shared memory.
+//           Results go to a one-tile window (+ 32-position halo of the previous tile) in shared memory.
 //   decide  every position resolves the lazy (depth 2) choice "if the parser stands here, which match
 //           start does it take" from the ring alone -- no dependence on parser state, so it is parallel --
 //           and writes a 4-byte record per position to HBM.
@@ -31,7 +31,7 @@
 namespace lz {
 
 constexpr uint32_t ROW_LOG = 15, ROWS = 1u << ROW_LOG, ROW_K = 16, TAG_BITS = 10;
-constexpr uint32_t TILE = 1024, RING = 2 * TILE, THREADS = 256, PER_THREAD = TILE / THREADS;
+constexpr uint32_t TILE = 1024, HALO = 32, RING = TILE + HALO, THREADS = 256, PER_THREAD = TILE / THREADS;
 constexpr uint32_t MIN_MATCH = 6, SEARCH_CAP = 24, TARGET_LEN = 24, DEFER = 20, MAX_LAZY_ITERS = 8;
 constexpr uint32_t LOOKAHEAD = SEARCH_CAP + 16;  // bytes staged past the tile so the p-side of every comparison is in smem
 constexpr int32_t ACCEPT_THR = 8;
@@ -91,22 +91,6 @@ __device__ __forceinline__ uint32_t hash5(uint64_t v) { return (uint32_t)(((v <<
 
 __device__ __forceinline__ int32_t sel_score(uint32_t len, uint32_t off) { return (int32_t)(2 * len) - (int32_t)zc::highbit(off + 3); }
 __device__ __forceinline__ int32_t lazy_score(uint32_t len, uint32_t off) { return (int32_t)(4 * len) - (int32_t)zc::highbit(off + 3); }
-
-// Candidate the parser may take at position q (ring lookup + block clamp + acceptance rule)
-struct Cand { uint32_t len, off; int32_t score; };
-__device__ __forceinline__ Cand cand_at(const uint8_t *s_len, const uint32_t *s_off, uint32_t q, uint32_t be) {
-    Cand c = {0, 0, 0};
-    if (q >= be) return c;
-    uint32_t len = s_len[q & (RING - 1)];
-    if (!len) return c;
-    if (q + len > be) len = be - q;
-    if (len < MIN_MATCH) return c;
-    const uint32_t off = s_off[q & (RING - 1)];
-    const int32_t sc = lazy_score(len, off);
-    if (sc < ACCEPT_THR) return c;
-    c.len = len; c.off = off; c.score = sc;
-    return c;
-}
 
 // Per-position parse record (4 bytes, HBM): what the parser does if its cursor stands on this position.
 //   0                      literal
@@ -169,6 +153,9 @@ __global__ void __launch_bounds__(THREADS) lz_search_kernel(const uint8_t *__res
                 if (g + 4 <= n && aligned) w = __ldg(reinterpret_cast<const uint32_t *>(in + g));
                 else for (uint32_t k = 0; k < 4; k++) if (g + k < n) w |= (uint32_t)in[g + k] << (8 * k);
                 *reinterpret_cast<uint32_t *>(&s_in[i]) = w;
+            }
+            if (tid < HALO) {  // slide the result window: the previous tile's last HALO positions stay addressable for the deferred decisions
+                s_len[tid] = s_len[TILE + tid]; s_off[tid] = s_off[TILE + tid]; s_back[tid] = s_back[TILE + tid]; s_sc[tid] = s_sc[TILE + tid];
             }
             __syncthreads();
             LZ_TICK(0);
@@ -302,10 +289,10 @@ __global__ void __launch_bounds__(THREADS) lz_search_kernel(const uint8_t *__res
                     if (p + blen > be) blen = be - p;
                     int32_t lsc = -1;
                     if (blen >= MIN_MATCH) { lsc = lazy_score(blen, boff); if (lsc < ACCEPT_THR) lsc = -1; }
-                    s_sc[p & (RING - 1)] = (int16_t)lsc;
-                    s_len[p & (RING - 1)] = (uint8_t)(lsc >= 0 ? blen : 0u);
-                    s_off[p & (RING - 1)] = boff;
-                    s_back[p & (RING - 1)] = (uint8_t)bback;
+                    s_sc[p - t0 + HALO] = (int16_t)lsc;
+                    s_len[p - t0 + HALO] = (uint8_t)(lsc >= 0 ? blen : 0u);
+                    s_off[p - t0 + HALO] = boff;
+                    s_back[p - t0 + HALO] = (uint8_t)bback;
                 }
             }
             __syncthreads();
@@ -316,18 +303,18 @@ __global__ void __launch_bounds__(THREADS) lz_search_kernel(const uint8_t *__res
             for (uint32_t p = d0 + tid; p < d1; p += THREADS) {
                 // positions before t0 that belong to the previous block were already decided there
                 if (p < t0 && (p / Z_BLOCK_MAX) != (t0 / Z_BLOCK_MAX)) continue;
-                int32_t sc = s_sc[p & (RING - 1)];
+                int32_t sc = s_sc[p - t0 + HALO];
                 uint32_t r = 0;
                 if (sc >= 0) {
                     uint32_t start = p;
-                    while (s_len[start & (RING - 1)] < TARGET_LEN && start - p + 2 <= MAX_SHIFT) {
-                        const int32_t s1 = start + 1 < be ? (int32_t)s_sc[(start + 1) & (RING - 1)] : -1;
+                    while (s_len[start - t0 + HALO] < TARGET_LEN && start - p + 2 <= MAX_SHIFT) {
+                        const int32_t s1 = start + 1 < be ? (int32_t)s_sc[start + 1 - t0 + HALO] : -1;
                         if (s1 > sc + 4) { sc = s1; start += 1; continue; }
-                        const int32_t s2 = start + 2 < be ? (int32_t)s_sc[(start + 2) & (RING - 1)] : -1;
+                        const int32_t s2 = start + 2 < be ? (int32_t)s_sc[start + 2 - t0 + HALO] : -1;
                         if (s2 > sc + 7) { sc = s2; start += 2; continue; }
                         break;
                     }
-                    r = pack_rec(s_off[start & (RING - 1)], s_len[start & (RING - 1)], s_back[start & (RING - 1)], start - p);
+                    r = pack_rec(s_off[start - t0 + HALO], s_len[start - t0 + HALO], s_back[start - t0 + HALO], start - p);
                 }
                 rec[p] = r;
             }
