@@ -359,7 +359,7 @@ struct Scratch {  // per warp, not persistent across blocks
 
 // One compressed block: literals + sequences executed into out[pos..].  Returns new pos or < 0.
 ZD_DEV int64_t decode_compressed_block(const uint8_t *src, uint32_t size, uint8_t *out, uint32_t pos, uint32_t cap, uint32_t frame_start,
-                                       Tables *T, Scratch *S, uint8_t *litbuf, uint32_t rep[3]) {
+                                       Tables *T, Scratch *S, uint8_t *litbuf, uint32_t rep[3], uint32_t *synced) {
     Literals L;
     const int lused = decode_literals(src, size, T, litbuf, &L, S->weights, S->cells);
     if (lused < 0) return lused;
@@ -421,10 +421,12 @@ ZD_DEV int64_t decode_compressed_block(const uint8_t *src, uint32_t size, uint8_
             if (off > pos + ll - frame_start) return ERR_CORRUPT;
             if (L.rle) fill_bytes(out + pos, L.rle_byte, ll); else copy_bytes(out + pos, L.ptr + lit_pos, ll);
             lit_pos += ll; pos += ll;
-            ZD_SYNC();
+            // Lazy ordering: lanes only need each other's earlier stores when this match reads output that was written
+            // since the last warp sync.  Far matches (the common case) read older data and cost no sync at all.
+            const uint32_t src_end = pos - off + (off < ml ? off : ml);
+            if (src_end > *synced) { ZD_SYNC(); *synced = pos; }
             copy_match(out, pos, off, ml);
             pos += ml;
-            ZD_SYNC();
         }
         if (b.pos != 0) return ERR_CORRUPT;
         rep[0] = r0; rep[1] = r1; rep[2] = r2;
@@ -440,6 +442,7 @@ ZD_DEV int64_t decode_compressed_block(const uint8_t *src, uint32_t size, uint8_
 // ZSTD_decompress accepts).  Returns decoded size or < 0.
 ZD_DEV int64_t decode_payload(const uint8_t *src, uint32_t size, uint8_t *out, uint32_t cap, Tables *T, Scratch *S, uint8_t *litbuf) {
     uint32_t ip = 0, pos = 0;
+    uint32_t synced = 0;  // output below this position is visible to every lane
     while (ip < size) {
         if (size - ip < 4) return ERR_CORRUPT;
         const uint32_t magic = src[ip] | src[ip + 1] << 8 | (uint32_t)src[ip + 2] << 16 | (uint32_t)src[ip + 3] << 24;
@@ -488,16 +491,17 @@ ZD_DEV int64_t decode_payload(const uint8_t *src, uint32_t size, uint8_t *out, u
                 if (bsz > cap - pos) return ERR_CAPACITY;
                 copy_bytes(out + pos, src + ip, bsz);
                 ZD_SYNC();
-                pos += bsz; ip += bsz;
+                pos += bsz; ip += bsz; synced = pos;
             } else if (type == 1) {  // RLE
                 if (size - ip < 1) return ERR_CORRUPT;
                 if (bsz > cap - pos) return ERR_CAPACITY;
                 fill_bytes(out + pos, src[ip], bsz);
                 ZD_SYNC();
-                pos += bsz; ip += 1;
+                pos += bsz; ip += 1; synced = pos;
             } else if (type == 2) {
                 if (bsz > size - ip || bsz > Z_BLOCK_MAX) return ERR_CORRUPT;
-                const int64_t np = decode_compressed_block(src + ip, bsz, out, pos, cap, frame_start, T, S, litbuf, rep);
+                const int64_t np = decode_compressed_block(src + ip, bsz, out, pos, cap, frame_start, T, S, litbuf, rep, &synced);
+                if (np >= 0) synced = (uint32_t)np;  // the block ends with a warp sync
                 if (np < 0) return np;
                 if ((uint64_t)np - pos > Z_BLOCK_MAX) return ERR_CORRUPT;
                 pos = (uint32_t)np; ip += bsz;
