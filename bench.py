@@ -457,6 +457,41 @@ def run_ours(args):
         st = np.frombuffer(d_res.cpu().numpy().tobytes(), dtype="<i4").reshape(-1, 2)
         unpack = {"value": len(sel) * CHUNK / (min(t_dec[1:]) * 1e-3) / 1e9, "unit": "GB/s", "frames": int(len(sel)), "what": "K4 decode of one packed batch, device-resident, restored bytes/s",
                   "byte_identical": ok and int((st[:, 1] != 0).sum()) == 0, "algorithmic_gbs": (int(r["len"][sel].sum()) + len(sel) * CHUNK) / (min(t_dec[1:]) * 1e-3) / 1e9}
+        # e2e unpack through the host-buffer C-ABI call (H2D payloads + K4 + D2H restored bytes), <= 1024 frames per call
+        try:
+            ne = int(min(len(sel), 1024))
+            host_out = d_out[: int(used.value)].cpu().numpy()
+            payloads = [host_out[int(r["off"][i]): int(r["off"][i]) + int(r["len"][i])] for i in sel[:ne]]
+            hf = (L.SqFrame * ne)()
+            so = 0
+            for k, pl in enumerate(payloads):
+                hf[k].src_off, hf[k].dst_off, hf[k].src_len, hf[k].capacity = so, k * CHUNK, len(pl), CHUNK
+                so += (len(pl) + 15) & ~15
+            hc = C.c_void_p(); hd = C.c_void_p()
+            ctx.check(lib.sq_host_alloc(ctx.h, so + 64, C.byref(hc)))
+            ctx.check(lib.sq_host_alloc(ctx.h, ne * CHUNK, C.byref(hd)))
+            stage = np.frombuffer((C.c_uint8 * (so + 64)).from_address(hc.value), dtype=np.uint8)
+            for k, pl in enumerate(payloads):
+                stage[hf[k].src_off: hf[k].src_off + len(pl)] = pl
+            hres = (L.SqFrameResult * ne)()
+            te = []
+            for _ in range(4):
+                t0 = time.perf_counter()
+                ctx.check(lib.sq_unpack_host(ctx.h, hc, so + 64, hf, ne, hd, ne * CHUNK, hres))
+                te.append(time.perf_counter() - t0)
+            unpack["e2e"] = {"value": ne * CHUNK / min(te[1:]) / 1e9, "unit": "GB/s", "frames": ne, "h2d_bytes_per_step": so, "d2h_bytes_per_step": ne * CHUNK}
+            # CPU baseline for unpack: the reference decodes serially on ONE thread (reader.rs:276-311)
+            if not args.no_cpu:
+                oracle_u = load_oracle()
+                nd = min(ne, 64)
+                t0 = time.perf_counter()
+                for pl in payloads[:nd]:
+                    assert oracle_u.decompress(pl.tobytes(), CHUNK) is not None
+                unpack["cpu_baseline"] = {"value": nd * CHUNK / (time.perf_counter() - t0) / 1e9, "unit": "GB/s", "cores": 1, "kind": "port",
+                                          "sample": f"{nd} GPU-written frames decoded by stock libzstd on one thread, as the reference's read_chunks does"}
+            lib.sq_host_free(ctx.h, hc); lib.sq_host_free(ctx.h, hd)
+        except Exception as e:
+            log("unpack e2e section failed:", repr(e))
         if cpu and cpu.get("ratio"):
             m = sel[sel < cpu_n]
             gpu_ratio = float(r["len"][m].sum()) / (len(m) * CHUNK) if len(m) else None

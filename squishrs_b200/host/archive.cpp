@@ -435,7 +435,7 @@ extern "C" int32_t sq_archive_unpack(sq_ctx *ctx, const char *archive_path, cons
         store = (uint8_t *)malloc(total_out);
         if (!store) return sq_set_error(ctx, SQ_ERR_OTHER, "Unknown error: cannot allocate %llu bytes", (unsigned long long)total_out);
     }
-    const uint64_t batch_out = 512ull << 20, batch_in = 256ull << 20;
+    const uint64_t batch_out = 2048ull << 20, batch_in = 1024ull << 20;  // a frame decodes on one warp: many frames per call keep the GPU full
     void *h_comp = nullptr, *h_out = nullptr;
     if ((rc = sq_host_alloc(ctx, batch_in + (4u << 20), &h_comp))) { free(store); return rc; }
     if ((rc = sq_host_alloc(ctx, batch_out + (4u << 20), &h_out))) { sq_host_free(ctx, h_comp); free(store); return rc; }
