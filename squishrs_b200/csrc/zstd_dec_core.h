@@ -57,45 +57,41 @@ ZD_DEV uint64_t load64(const uint8_t *p) {  // unaligned little-endian 8 bytes; 
 
 // Backward bit reader over [start, start+size): bits are consumed from the top (just below the sentinel).
 // A 64-bit window is cached in registers and refilled (one unaligned 8-byte load) only when it runs low.
+// Positions are 32-bit: a stream is at most a block (< 2^20 bits).
 struct BitReader {
     const uint8_t *start;
-    int64_t pos;    // number of unread bits; may go negative on corrupt input (reads then return zeros)
-    uint64_t win;   // bits [wlo, wlo+64) of the stream
-    int64_t wlo;    // bit index of win's bit 0 (multiple of 8; may be negative near the stream start)
+    int32_t pos;    // number of unread bits; goes negative on corrupt input (reads then return zeros)
+    int32_t wlo;    // bit index of win's bit 0 (multiple of 8; negative near the stream start)
+    uint64_t win;   // bits [wlo, wlo+64) of the stream, zero where that lies before the stream
 };
 ZD_DEV void br_refill(BitReader *b) {
-    // place the window so that its top is at or above pos: wlo = byte-aligned, pos - wlo in (56, 64]
-    int64_t lo = ((b->pos + 7) >> 3) * 8 - 64;
-    if (lo >= 0) { b->win = load64(b->start + (lo >> 3)); b->wlo = lo; return; }
-    // within 8 bytes of the stream start: assemble without reading before it; missing low bits read as zero
-    const uint64_t v = load64(b->start);
-    const uint32_t sh = (uint32_t)(-lo);  // multiple of 8, <= 64
-    b->win = sh >= 64 ? 0 : v << sh;
+    if (b->pos <= 0) { b->win = 0; b->wlo = b->pos - 64; return; }  // exhausted / overrun: zeros
+    // place the window so that pos - wlo is in (56, 64]
+    const int32_t lo = ((b->pos + 7) >> 3) * 8 - 64;
     b->wlo = lo;
+    if (lo >= 0) { b->win = load64(b->start + (lo >> 3)); return; }
+    // within 8 bytes of the stream start: never read before it; the missing low bits are zero
+    const uint32_t sh = (uint32_t)(-lo);  // multiple of 8, 8..56
+    b->win = load64(b->start) << sh;
 }
 ZD_DEV int br_init(BitReader *b, const uint8_t *start, uint32_t size) {
     if (size == 0) return ERR_CORRUPT;
     const uint8_t last = start[size - 1];
     if (last == 0) return ERR_CORRUPT;
     b->start = start;
-    b->pos = (int64_t)(size - 1) * 8 + zc::highbit(last);
+    b->pos = (int32_t)((size - 1) * 8 + zc::highbit(last));
     br_refill(b);
     return 0;
 }
-ZD_DEV uint32_t br_peek(BitReader *b, uint32_t n) {  // n <= 32; bits [pos-n, pos)
-    if (n == 0) return 0;
-    if (b->pos <= 0) return 0;
-    int64_t lo = b->pos - (int64_t)n;
+ZD_DEV uint32_t br_peek(BitReader *b, uint32_t n) {  // n <= 31; bits [pos-n, pos), zero-filled below the stream start
+    const int32_t lo = b->pos - (int32_t)n;
     if (lo < b->wlo) br_refill(b);
-    if (lo >= b->wlo) return (uint32_t)(b->win >> (lo - b->wlo)) & (uint32_t)((1ull << n) - 1);
-    // fewer than n bits left in the stream: the missing low bits read as zero (wlo <= 0 here)
-    const uint32_t have = (uint32_t)(b->pos - b->wlo);
-    const uint64_t top = have >= 64 ? b->win : (b->win & ((1ull << have) - 1));
-    return (uint32_t)(top << (uint32_t)(b->wlo - lo)) & (uint32_t)((1ull << n) - 1);
+    const uint32_t sh = (uint32_t)(lo - b->wlo) & 63u;
+    return (uint32_t)(b->win >> sh) & ((1u << n) - 1u);
 }
 ZD_DEV uint32_t br_read(BitReader *b, uint32_t n) {
     const uint32_t v = br_peek(b, n);
-    b->pos -= n;
+    b->pos -= (int32_t)n;
     return v;
 }
 
@@ -171,10 +167,10 @@ ZD_DEV int read_huf_tree(const uint8_t *src, uint32_t size, Tables *T, uint8_t *
         for (;;) {
             if (nw >= 254) return ERR_CORRUPT;
             weights[nw++] = wcells[s1].sym;
-            { const uint32_t nb = wcells[s1].nb_bits; if (b.pos < (int64_t)nb) { weights[nw++] = wcells[s2].sym; break; } s1 = wcells[s1].base + br_read(&b, nb); }
+            { const uint32_t nb = wcells[s1].nb_bits; if (b.pos < (int32_t)nb) { weights[nw++] = wcells[s2].sym; break; } s1 = wcells[s1].base + br_read(&b, nb); }
             if (nw >= 254) return ERR_CORRUPT;
             weights[nw++] = wcells[s2].sym;
-            { const uint32_t nb = wcells[s2].nb_bits; if (b.pos < (int64_t)nb) { weights[nw++] = wcells[s1].sym; break; } s2 = wcells[s2].base + br_read(&b, nb); }
+            { const uint32_t nb = wcells[s2].nb_bits; if (b.pos < (int32_t)nb) { weights[nw++] = wcells[s1].sym; break; } s2 = wcells[s2].base + br_read(&b, nb); }
         }
     }
     if (nw == 0 || nw > 255) return ERR_CORRUPT;
@@ -333,7 +329,22 @@ ZD_DEV int read_seq_table(const uint8_t *src, uint32_t size, uint32_t mode, uint
     return *have ? 0 : ERR_CORRUPT;  // Repeat
 }
 
-// ---- byte movers (lanes split the bytes) -------------------------------------------------------------------
+// ---- byte movers -------------------------------------------------------------------------------------------
+// one lane moves n bytes (non-overlapping): 8 loads are issued before the 8 stores so their latencies overlap
+ZD_DEV void lane_copy(uint8_t *dst, const uint8_t *src, uint32_t n) {
+    uint32_t t = 0;
+    for (; t + 8 <= n; t += 8) {
+        const uint8_t b0 = src[t], b1 = src[t + 1], b2 = src[t + 2], b3 = src[t + 3], b4 = src[t + 4], b5 = src[t + 5], b6 = src[t + 6], b7 = src[t + 7];
+        dst[t] = b0; dst[t + 1] = b1; dst[t + 2] = b2; dst[t + 3] = b3; dst[t + 4] = b4; dst[t + 5] = b5; dst[t + 6] = b6; dst[t + 7] = b7;
+    }
+    if (t + 4 <= n) {
+        const uint8_t b0 = src[t], b1 = src[t + 1], b2 = src[t + 2], b3 = src[t + 3];
+        dst[t] = b0; dst[t + 1] = b1; dst[t + 2] = b2; dst[t + 3] = b3;
+        t += 4;
+    }
+    for (; t < n; t++) dst[t] = src[t];
+}
+// (the warp-cooperative movers below split the bytes over the lanes)
 ZD_DEV void copy_bytes(uint8_t *dst, const uint8_t *src, uint32_t n) {
     for (uint32_t i = ZD_LANE(); i < n; i += ZD_WARP) dst[i] = src[i];
 }
@@ -391,42 +402,97 @@ ZD_DEV int64_t decode_compressed_block(const uint8_t *src, uint32_t size, uint8_
         if (br_init(&b, p, left) < 0) return ERR_CORRUPT;
         uint32_t s_ll = br_read(&b, T->ll_log), s_of = br_read(&b, T->of_log), s_ml = br_read(&b, T->ml_log);
         uint32_t r0 = rep[0], r1 = rep[1], r2 = rep[2];
-        for (uint32_t i = 0; i < nseq; i++) {
-            const SeqCell cl = T->ll[s_ll], co = T->of[s_of], cm = T->ml[s_ml];
-            // extra bits: offset, match length, literal length
-            uint32_t ofv = co.base_value + (co.extra_bits ? br_read(&b, co.extra_bits) : 0);
-            const uint32_t ml = cm.base_value + (cm.extra_bits ? br_read(&b, cm.extra_bits) : 0);
-            const uint32_t ll = cl.base_value + (cl.extra_bits ? br_read(&b, cl.extra_bits) : 0);
-            uint32_t off;
-            if (ofv > 3) { off = ofv - 3; r2 = r1; r1 = r0; r0 = off; }
-            else {
-                const uint32_t idx = ofv - 1 + (ll == 0 ? 1 : 0);
-                if (idx == 0) off = r0;
+        // Sequences are handled in batches of one per lane.  Phase A walks the serial FSE chain (identical on every lane)
+        // and lane j keeps sequence j; phase B turns lengths into positions with a warp scan; phase C copies all literal runs
+        // at once; phase D copies matches -- those that only read output older than the batch go lane-parallel, the rest
+        // in order with the whole warp on each.
+        for (uint32_t i0 = 0; i0 < nseq; i0 += ZD_WARP) {
+            const uint32_t nbatch = nseq - i0 < ZD_WARP ? nseq - i0 : ZD_WARP;
+            uint32_t my_ll = 0, my_ml = 0, my_off = 1;
+            int err = 0;
+            for (uint32_t k = 0; k < nbatch; k++) {
+                const SeqCell cl = T->ll[s_ll], co = T->of[s_of], cm = T->ml[s_ml];
+                // extra bits: offset, match length, literal length
+                const uint32_t ofv = co.base_value + br_read(&b, co.extra_bits);
+                const uint32_t ml = cm.base_value + br_read(&b, cm.extra_bits);
+                const uint32_t ll = cl.base_value + br_read(&b, cl.extra_bits);
+                uint32_t off;
+                if (ofv > 3) { off = ofv - 3; r2 = r1; r1 = r0; r0 = off; }
                 else {
-                    off = idx == 1 ? r1 : idx == 2 ? r2 : r0 - 1;
-                    if (off == 0) return ERR_CORRUPT;
-                    if (idx >= 2) r2 = r1;
-                    r1 = r0; r0 = off;
+                    const uint32_t idx = ofv - 1 + (ll == 0 ? 1 : 0);
+                    if (idx == 0) off = r0;
+                    else {
+                        off = idx == 1 ? r1 : idx == 2 ? r2 : r0 - 1;
+                        if (off == 0) { err = 1; off = 1; }
+                        if (idx >= 2) r2 = r1;
+                        r1 = r0; r0 = off;
+                    }
                 }
+                if (i0 + k + 1 < nseq) {  // state updates: LL, ML, OF
+                    s_ll = cl.next_base + br_read(&b, cl.nb_bits);
+                    s_ml = cm.next_base + br_read(&b, cm.nb_bits);
+                    s_of = co.next_base + br_read(&b, co.nb_bits);
+                }
+                if (k == ZD_LANE()) { my_ll = ll; my_ml = ml; my_off = off; }
             }
-            if (i + 1 < nseq) {  // state updates: LL, ML, OF
-                s_ll = cl.next_base + br_read(&b, cl.nb_bits);
-                s_ml = cm.next_base + br_read(&b, cm.nb_bits);
-                s_of = co.next_base + br_read(&b, co.nb_bits);
+            if (err || b.pos < 0) return ERR_CORRUPT;
+            // phase B: positions
+            uint32_t lit_excl, out_excl, lit_tot, out_tot;
+#if defined(__CUDA_ARCH__)
+            {
+                uint32_t xl = my_ll, xo = my_ll + my_ml;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t yl = __shfl_up_sync(0xffffffffu, xl, d), yo = __shfl_up_sync(0xffffffffu, xo, d);
+                    if ((int)ZD_LANE() >= d) { xl += yl; xo += yo; }
+                }
+                lit_excl = xl - my_ll; out_excl = xo - (my_ll + my_ml);
+                lit_tot = __shfl_sync(0xffffffffu, xl, 31); out_tot = __shfl_sync(0xffffffffu, xo, 31);
             }
-            if (b.pos < 0) return ERR_CORRUPT;
-            // execute
-            if (lit_pos + ll > L.size) return ERR_CORRUPT;
-            if ((uint64_t)pos + ll + ml > cap) return ERR_CAPACITY;
-            if (off > pos + ll - frame_start) return ERR_CORRUPT;
-            if (L.rle) fill_bytes(out + pos, L.rle_byte, ll); else copy_bytes(out + pos, L.ptr + lit_pos, ll);
-            lit_pos += ll; pos += ll;
-            // Lazy ordering: lanes only need each other's earlier stores when this match reads output that was written
-            // since the last warp sync.  Far matches (the common case) read older data and cost no sync at all.
-            const uint32_t src_end = pos - off + (off < ml ? off : ml);
-            if (src_end > *synced) { ZD_SYNC(); *synced = pos; }
-            copy_match(out, pos, off, ml);
-            pos += ml;
+#else
+            lit_excl = 0; out_excl = 0; lit_tot = my_ll; out_tot = my_ll + my_ml;
+#endif
+            if (lit_pos + lit_tot > L.size) return ERR_CORRUPT;
+            if ((uint64_t)pos + out_tot > cap) return ERR_CAPACITY;
+            const uint32_t my_lit_out = pos + out_excl, my_match = my_lit_out + my_ll;
+            const bool mine = ZD_LANE() < nbatch;
+            int bad = mine && my_off > my_match - frame_start;
+#if defined(__CUDA_ARCH__)
+            bad = __any_sync(0xffffffffu, bad);
+#endif
+            if (bad) return ERR_CORRUPT;
+            // phase C: literal runs (sources are the literal buffer / the input, never the output): each lane its own run
+            if (mine) {
+                const uint8_t *ls = L.ptr + lit_pos + lit_excl;
+                if (L.rle) for (uint32_t t = 0; t < my_ll; t++) out[my_lit_out + t] = L.rle_byte;
+                else lane_copy(out + my_lit_out, ls, my_ll);
+            }
+            // phase D: matches.  A match is independent if everything it reads was synced before this batch started.
+            const uint32_t batch_synced = *synced;
+            const uint32_t src_end = my_match - my_off + (my_off < my_ml ? my_off : my_ml);
+            const bool indep = mine && src_end <= batch_synced;
+            if (indep) {
+                const uint8_t *from = out + my_match - my_off;  // non-overlapping with anything written in this batch
+                if (my_off >= my_ml) lane_copy(out + my_match, from, my_ml);
+                else for (uint32_t t = 0; t < my_ml; t++) out[my_match + t] = from[t % my_off];
+            }
+#if defined(__CUDA_ARCH__)
+            uint32_t dep_mask = __ballot_sync(0xffffffffu, mine && !indep);
+            __syncwarp();  // literals and independent matches of the batch are visible
+            while (dep_mask) {
+                const int k = __ffs((int)dep_mask) - 1;
+                dep_mask &= dep_mask - 1;
+                const uint32_t mpos = __shfl_sync(0xffffffffu, my_match, k), moff = __shfl_sync(0xffffffffu, my_off, k),
+                               mlen = __shfl_sync(0xffffffffu, my_ml, k);
+                copy_match(out, mpos, moff, mlen);
+                __syncwarp();
+            }
+#else
+            if (mine && !indep) copy_match(out, my_match, my_off, my_ml);
+#endif
+            lit_pos += lit_tot;
+            pos += out_tot;
+            *synced = pos;
         }
         if (b.pos != 0) return ERR_CORRUPT;
         rep[0] = r0; rep[1] = r1; rep[2] = r2;
