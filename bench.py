@@ -341,46 +341,69 @@ def run_ours(args):
     # ---- e2e through the host-buffer C-ABI call (rank-local; pinned input, H2D + kernels + D2H) ----
     e2e = None
     if not args.no_e2e:
+        # Through the reference-facing host-buffer calls: sq_pack_submit / sq_pack_wait, two batches in flight, inputs in
+        # pinned host memory.  Every step uploads its batch (H2D) and downloads results + frames (D2H) inside the timed region.
         eb = min(B, args.e2e_chunks)
-        hp = C.c_void_p()
-        ctx.check(lib.sq_host_alloc(ctx.h, eb * CHUNK, C.byref(hp)))
-        ho = C.c_void_p()
         ocap = eb * int(lib.sq_encode_bound(CHUNK))
-        ctx.check(lib.sq_host_alloc(ctx.h, ocap, C.byref(ho)))
-        res = (L.SqChunkResult * eb)()
+        hp, ho, hres = [], [], []
+        for _ in range(2):
+            a_, b_, r_ = C.c_void_p(), C.c_void_p(), C.c_void_p()
+            ctx.check(lib.sq_host_alloc(ctx.h, eb * CHUNK, C.byref(a_)))
+            ctx.check(lib.sq_host_alloc(ctx.h, ocap, C.byref(b_)))
+            ctx.check(lib.sq_host_alloc(ctx.h, eb * C.sizeof(L.SqChunkResult), C.byref(r_)))
+            hp.append(a_); ho.append(b_); hres.append(r_)
         hspans = (L.SqSpan * eb)()
         for i in range(eb):
             hspans[i].off, hspans[i].len = i * CHUNK, CHUNK
-        used = C.c_uint64()
-        e2e_in = e2e_out = 0
-        times = []
-        ectx = ctx  # reuse the main context (and its scratch) with a fresh dedup index
-        ectx.dedup_reset()
-        n_e2e = max(3, min(args.steps, 8))
-        for k in range(-2, n_e2e):
-            b = (k + 2) % n_batches
-            # stage this step's input in pinned host memory (outside the timed region)
-            torch.cuda.synchronize()
+        ctx.dedup_reset()
+        n_e2e = max(4, min(args.steps, 8))
+        n_warm = 2
+
+        def stage_input(k):  # device corpus -> pinned host buffer (outside the timed region)
+            b = k % n_batches
             src = corpus[b * B * CHUNK: b * B * CHUNK + eb * CHUNK]
-            host_view = torch.frombuffer((C.c_uint8 * (eb * CHUNK)).from_address(hp.value), dtype=torch.uint8)
+            host_view = torch.frombuffer((C.c_uint8 * (eb * CHUNK)).from_address(hp[k % 2].value), dtype=torch.uint8)
             host_view.copy_(src)
             torch.cuda.synchronize()
+
+        tickets = [None, None]
+        used = C.c_uint64()
+        e2e_out = 0
+        # inputs of the first two steps are staged up front; later inputs are staged while nothing of ours is timed? No:
+        # staging costs PCIe time too, so every input is staged BEFORE the clock starts.
+        total_steps = n_warm + n_e2e
+        # the pinned ring only holds two batches, so time in rounds of two steps
+        times = []
+        k = 0
+        while k < total_steps:
+            cnt = min(2, total_steps - k)
+            for j in range(cnt):
+                stage_input(k + j)
             if world > 1:
                 dist.barrier()
             t0 = time.perf_counter()
-            ectx.check(lib.sq_pack_host(ectx.h, hp, eb * CHUNK, hspans, eb, (k + 2) * eb, res, ho, ocap, C.byref(used)))
+            for j in range(cnt):
+                t = C.c_void_p()
+                ctx.check(lib.sq_pack_submit(ctx.h, hp[(k + j) % 2], eb * CHUNK, hspans, eb, (k + j) * eb, hres[(k + j) % 2], ho[(k + j) % 2], ocap, C.byref(t)))
+                tickets[(k + j) % 2] = t
+            for j in range(cnt):
+                ctx.check(lib.sq_pack_wait(ctx.h, tickets[(k + j) % 2], C.byref(used)))
+                if k + j >= n_warm:
+                    e2e_out += used.value + eb * C.sizeof(L.SqChunkResult)
             dt = time.perf_counter() - t0
-            if k >= 0:
-                times.append(dt)
-                e2e_in += eb * CHUNK
-                e2e_out += used.value + eb * C.sizeof(L.SqChunkResult)
-        et = torch.tensor([sum(times)], dtype=torch.float64, device="cuda")
+            if k >= n_warm:
+                times.append((dt, cnt))
+            k += cnt
+        tsum = sum(t for t, _ in times)
+        nsteps = sum(c for _, c in times)
+        et = torch.tensor([tsum], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(et, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * e2e_in / float(et.item()) / 1e9, "unit": "GB/s", "h2d_bytes_per_step": eb * CHUNK + eb * 16,
-               "d2h_bytes_per_step": e2e_out // len(times), "chunks_per_step": eb}
-        lib.sq_host_free(ctx.h, hp)
-        lib.sq_host_free(ctx.h, ho)
+        e2e = {"value": world * nsteps * eb * CHUNK / float(et.item()) / 1e9, "unit": "GB/s", "h2d_bytes_per_step": eb * CHUNK + eb * 16,
+               "d2h_bytes_per_step": e2e_out // max(nsteps, 1), "chunks_per_step": eb, "steps": nsteps,
+               "api": "sq_pack_submit/sq_pack_wait, two batches in flight, pinned host buffers"}
+        for i in range(2):
+            lib.sq_host_free(ctx.h, hp[i]); lib.sq_host_free(ctx.h, ho[i]); lib.sq_host_free(ctx.h, hres[i])
 
     if rank != 0:
         if world > 1:
@@ -523,7 +546,7 @@ def main():
     ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS))
     ap.add_argument("--batch-chunks", type=int, default=2048)
     ap.add_argument("--corpus-gib", type=int, default=64)
-    ap.add_argument("--e2e-chunks", type=int, default=512)
+    ap.add_argument("--e2e-chunks", type=int, default=1024)
     ap.add_argument("--ref-chunks", type=int, default=0)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

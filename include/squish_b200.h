@@ -190,6 +190,16 @@ int32_t sq_pack_device(sq_ctx *ctx, const void *d_data, const sq_span *d_spans, 
 int32_t sq_pack_host(sq_ctx *ctx, const void *h_data, size_t data_len, const sq_span *h_spans,
                      uint32_t n, uint64_t gidx_base, sq_chunk_result *h_results, void *h_out,
                      uint64_t out_capacity, uint64_t *out_used);
+/* Asynchronous twin of sq_pack_host for a double-buffered host pipeline (north_star: "pinned,
+ * double-buffered cudaMemcpyAsync uploads"): submit returns as soon as the upload, kernels and
+ * result download are queued; at most two tickets may be in flight.  sq_pack_wait blocks for
+ * one ticket and downloads exactly the frame bytes it produced.  h_data / h_results / h_out
+ * must stay valid (and should be pinned) until the ticket is waited on. */
+typedef struct sq_ticket sq_ticket;
+int32_t sq_pack_submit(sq_ctx *ctx, const void *h_data, size_t data_len, const sq_span *h_spans,
+                       uint32_t n, uint64_t gidx_base, sq_chunk_result *h_results, void *h_out,
+                       uint64_t out_capacity, sq_ticket **ticket);
+int32_t sq_pack_wait(sq_ctx *ctx, sq_ticket *ticket, uint64_t *out_used);
 /* read_chunks for a batch through HOST buffers: H2D payloads, decode, D2H output. */
 int32_t sq_unpack_host(sq_ctx *ctx, const void *h_comp, size_t comp_len, const sq_frame *h_frames,
                        uint32_t n, void *h_out, size_t out_len, sq_frame_result *h_results);

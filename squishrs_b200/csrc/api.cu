@@ -91,6 +91,12 @@ extern "C" int32_t sq_create(const sq_config *cfg, sq_ctx **out) {
     auto init = [&]() -> int32_t {
         SQ_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
         SQ_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        SQ_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; i++) {
+            SQ_CUDA(ctx, cudaEventCreateWithFlags(&ctx->slots[i].h2d_done, cudaEventDisableTiming));
+            SQ_CUDA(ctx, cudaEventCreateWithFlags(&ctx->slots[i].compute_done, cudaEventDisableTiming));
+            SQ_CUDA(ctx, cudaHostAlloc((void **)&ctx->slots[i].h_total, 64, cudaHostAllocDefault));
+        }
         SQ_CUDA(ctx, cudaMalloc(&ctx->d_work_counter, 64 * sizeof(uint32_t)));
         SQ_CUDA(ctx, cudaMemset(ctx->d_work_counter, 0, 64 * sizeof(uint32_t)));
         int32_t r = sq_xxh3_init(ctx);
@@ -114,6 +120,15 @@ extern "C" void sq_destroy(sq_ctx *ctx) {
     if (ctx->d_stage_in) cudaFree(ctx->d_stage_in);
     if (ctx->d_stage_out) cudaFree(ctx->d_stage_out);
     if (ctx->d_stage_meta) cudaFree(ctx->d_stage_meta);
+    for (int i = 0; i < 2; i++) {
+        if (ctx->slots[i].d_in) cudaFree(ctx->slots[i].d_in);
+        if (ctx->slots[i].d_out) cudaFree(ctx->slots[i].d_out);
+        if (ctx->slots[i].d_meta) cudaFree(ctx->slots[i].d_meta);
+        if (ctx->slots[i].h2d_done) cudaEventDestroy(ctx->slots[i].h2d_done);
+        if (ctx->slots[i].compute_done) cudaEventDestroy(ctx->slots[i].compute_done);
+        if (ctx->slots[i].h_total) cudaFreeHost(ctx->slots[i].h_total);
+    }
+    if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     free(ctx);

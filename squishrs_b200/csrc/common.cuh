@@ -37,6 +37,15 @@ struct sq_ctx {
     void *d_stage_in; size_t stage_in_cap;
     void *d_stage_out; size_t stage_out_cap;
     void *d_stage_meta; size_t stage_meta_cap;
+    // double-buffered host pipeline (sq_pack_submit / sq_pack_wait): two slots, each with its own device staging
+    struct pack_slot {
+        void *d_in, *d_out, *d_meta; size_t in_cap, out_cap, meta_cap;
+        cudaEvent_t h2d_done, compute_done;
+        uint64_t *h_total;            // pinned
+        uint32_t n; uint64_t out_capacity; void *h_out; int busy;
+    } slots[2];
+    cudaStream_t d2h_stream;
+    int next_slot;
 };
 
 int32_t sq_set_error(sq_ctx *ctx, int32_t code, const char *fmt, ...);

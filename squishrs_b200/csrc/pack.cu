@@ -26,18 +26,33 @@ struct pack_meta {
     uint8_t *digests; uint8_t *is_new; uint64_t *frame_off; uint32_t *frame_len; uint64_t *total;
     sq_span *spans; sq_chunk_result *results; sq_frame *frames; sq_frame_result *fres;
 };
-static int32_t meta_layout(sq_ctx *ctx, uint32_t n, pack_meta *m) {
+static int32_t meta_layout_in(sq_ctx *ctx, void **buf, size_t *cap, uint32_t n, pack_meta *m) {
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
     size_t o_dig = take((size_t)n * 16), o_new = take(n), o_fo = take((size_t)n * 8), o_fl = take((size_t)n * 4), o_tot = take(8),
            o_sp = take((size_t)n * sizeof(sq_span)), o_res = take((size_t)n * sizeof(sq_chunk_result)),
            o_fr = take((size_t)n * sizeof(sq_frame)), o_frs = take((size_t)n * sizeof(sq_frame_result));
-    int32_t rc = sq_ensure(ctx, &ctx->d_stage_meta, &ctx->stage_meta_cap, off);
+    int32_t rc = sq_ensure(ctx, buf, cap, off);
     if (rc) return rc;
-    uint8_t *b = (uint8_t *)ctx->d_stage_meta;
+    uint8_t *b = (uint8_t *)*buf;
     m->digests = b + o_dig; m->is_new = b + o_new; m->frame_off = (uint64_t *)(b + o_fo); m->frame_len = (uint32_t *)(b + o_fl);
     m->total = (uint64_t *)(b + o_tot); m->spans = (sq_span *)(b + o_sp); m->results = (sq_chunk_result *)(b + o_res);
     m->frames = (sq_frame *)(b + o_fr); m->fres = (sq_frame_result *)(b + o_frs);
+    return SQ_OK;
+}
+
+static int32_t meta_layout(sq_ctx *ctx, uint32_t n, pack_meta *m) { return meta_layout_in(ctx, &ctx->d_stage_meta, &ctx->stage_meta_cap, n, m); }
+
+// digest -> dedup -> encode -> results, all asynchronous on `st`, with caller-provided metadata scratch
+static int32_t pack_device_impl(sq_ctx *ctx, const void *d_data, const sq_span *d_spans, uint32_t n, uint64_t gidx_base, const pack_meta &m,
+                                sq_chunk_result *d_results, void *d_out, uint64_t out_capacity, cudaStream_t st) {
+    int32_t rc;
+    if ((rc = sq_digest_device(ctx, d_data, d_spans, n, m.digests, st))) return rc;
+    if ((rc = sq_dedup_insert_device(ctx, m.digests, nullptr, gidx_base, n, m.is_new, st))) return rc;
+    if ((rc = sq_encode_device(ctx, d_data, d_spans, m.is_new, n, d_out, out_capacity, m.frame_off, m.frame_len, m.total, st))) return rc;
+    pack_results_kernel<<<(n + 127) / 128, 128, 0, st>>>((const uint4 *)m.digests, m.is_new, m.frame_off, m.frame_len, n, d_results);
+    SQ_LAUNCHED(ctx, 1);
+    SQ_CUDA(ctx, cudaGetLastError());
     return SQ_OK;
 }
 
@@ -50,12 +65,7 @@ extern "C" int32_t sq_pack_device(sq_ctx *ctx, const void *d_data, const sq_span
     int32_t rc = meta_layout(ctx, n, &m);
     if (rc) return rc;
     cudaStream_t st = sq_stream(ctx, stream);
-    if ((rc = sq_digest_device(ctx, d_data, d_spans, n, m.digests, st))) return rc;
-    if ((rc = sq_dedup_insert_device(ctx, m.digests, nullptr, gidx_base, n, m.is_new, st))) return rc;
-    if ((rc = sq_encode_device(ctx, d_data, d_spans, m.is_new, n, d_out, out_capacity, m.frame_off, m.frame_len, m.total, st))) return rc;
-    pack_results_kernel<<<(n + 127) / 128, 128, 0, st>>>((const uint4 *)m.digests, m.is_new, m.frame_off, m.frame_len, n, d_results);
-    SQ_LAUNCHED(ctx, 1);
-    SQ_CUDA(ctx, cudaGetLastError());
+    if ((rc = pack_device_impl(ctx, d_data, d_spans, n, gidx_base, m, d_results, d_out, out_capacity, st))) return rc;
     if (out_used) {
         SQ_CUDA(ctx, cudaMemcpyAsync(out_used, m.total, 8, cudaMemcpyDeviceToHost, st));
         SQ_CUDA(ctx, cudaStreamSynchronize(st));
@@ -64,33 +74,71 @@ extern "C" int32_t sq_pack_device(sq_ctx *ctx, const void *d_data, const sq_span
     return SQ_OK;
 }
 
-extern "C" int32_t sq_pack_host(sq_ctx *ctx, const void *h_data, size_t data_len, const sq_span *h_spans, uint32_t n,
-                                uint64_t gidx_base, sq_chunk_result *h_results, void *h_out, uint64_t out_capacity, uint64_t *out_used) {
-    if (!ctx) return SQ_ERR_INVALID_ARG;
-    if (n == 0) { if (out_used) *out_used = 0; return SQ_OK; }
-    if (!h_spans || !h_results || !h_out || (!h_data && data_len)) return sq_set_error(ctx, SQ_ERR_INVALID_ARG, "sq_pack_host: null pointer");
+// ---- double-buffered host pipeline ------------------------------------------------------------------------------
+// submit: H2D of the batch on the copy stream -> kernels on the compute stream -> results + total D2H; returns at once.
+// wait:   blocks until the batch's kernels are done, then copies exactly the used frame bytes D2H on a third stream.
+// With two tickets in flight the upload of batch k+1 and the frame download of batch k-1 overlap the kernels of batch k
+// (north_star: "pinned, double-buffered cudaMemcpyAsync uploads").
+struct sq_ticket { int slot; };
+static sq_ticket g_tickets[2] = {{0}, {1}};
+
+extern "C" int32_t sq_pack_submit(sq_ctx *ctx, const void *h_data, size_t data_len, const sq_span *h_spans, uint32_t n,
+                                  uint64_t gidx_base, sq_chunk_result *h_results, void *h_out, uint64_t out_capacity, sq_ticket **ticket) {
+    if (!ctx || !ticket) return SQ_ERR_INVALID_ARG;
+    if (n == 0 || !h_spans || !h_results || !h_out || (!h_data && data_len)) return sq_set_error(ctx, SQ_ERR_INVALID_ARG, "sq_pack_submit: bad arguments");
     uint64_t bound = 0;
     for (uint32_t i = 0; i < n; i++) {
         if (h_spans[i].off + h_spans[i].len > data_len || h_spans[i].len > ctx->chunk_size || h_spans[i].len == 0)
             return sq_set_error(ctx, SQ_ERR_INVALID_CHUNK_SIZE, "span %u [%llu,+%u) invalid", i, (unsigned long long)h_spans[i].off, h_spans[i].len);
         bound += sq_encode_bound(h_spans[i].len);
     }
+    const int si = ctx->next_slot;
+    sq_ctx::pack_slot &sl = ctx->slots[si];
+    if (sl.busy) return sq_set_error(ctx, SQ_ERR_OTHER, "sq_pack_submit: both pipeline slots are in flight; call sq_pack_wait first");
     int32_t rc;
-    if ((rc = sq_ensure(ctx, &ctx->d_stage_in, &ctx->stage_in_cap, data_len + 64))) return rc;
-    if ((rc = sq_ensure(ctx, &ctx->d_stage_out, &ctx->stage_out_cap, bound))) return rc;
+    if ((rc = sq_ensure(ctx, &sl.d_in, &sl.in_cap, data_len + 64))) return rc;
+    if ((rc = sq_ensure(ctx, &sl.d_out, &sl.out_cap, bound + 64))) return rc;
     pack_meta m;
-    if ((rc = meta_layout(ctx, n, &m))) return rc;
-    cudaStream_t st = ctx->stream;
-    SQ_CUDA(ctx, cudaMemcpyAsync(ctx->d_stage_in, h_data, data_len, cudaMemcpyHostToDevice, st));
-    SQ_CUDA(ctx, cudaMemcpyAsync(m.spans, h_spans, (size_t)n * sizeof(sq_span), cudaMemcpyHostToDevice, st));
-    uint64_t used = 0;
-    if ((rc = sq_pack_device(ctx, ctx->d_stage_in, m.spans, n, gidx_base, m.results, ctx->d_stage_out, bound, &used, st))) return rc;
-    if (used > out_capacity) return sq_set_error(ctx, SQ_ERR_CAPACITY, "pack output needs %llu bytes, caller gave %llu", (unsigned long long)used, (unsigned long long)out_capacity);
-    SQ_CUDA(ctx, cudaMemcpyAsync(h_results, m.results, (size_t)n * sizeof(sq_chunk_result), cudaMemcpyDeviceToHost, st));
-    if (used) SQ_CUDA(ctx, cudaMemcpyAsync(h_out, ctx->d_stage_out, used, cudaMemcpyDeviceToHost, st));
-    SQ_CUDA(ctx, cudaStreamSynchronize(st));
+    if ((rc = meta_layout_in(ctx, &sl.d_meta, &sl.meta_cap, n, &m))) return rc;
+    SQ_CUDA(ctx, cudaMemcpyAsync(sl.d_in, h_data, data_len, cudaMemcpyHostToDevice, ctx->copy_stream));
+    SQ_CUDA(ctx, cudaMemcpyAsync(m.spans, h_spans, (size_t)n * sizeof(sq_span), cudaMemcpyHostToDevice, ctx->copy_stream));
+    SQ_CUDA(ctx, cudaEventRecord(sl.h2d_done, ctx->copy_stream));
+    SQ_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, sl.h2d_done, 0));
+    if ((rc = pack_device_impl(ctx, sl.d_in, m.spans, n, gidx_base, m, m.results, sl.d_out, bound, ctx->stream))) return rc;
+    SQ_CUDA(ctx, cudaMemcpyAsync(h_results, m.results, (size_t)n * sizeof(sq_chunk_result), cudaMemcpyDeviceToHost, ctx->stream));
+    SQ_CUDA(ctx, cudaMemcpyAsync(sl.h_total, m.total, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    SQ_CUDA(ctx, cudaEventRecord(sl.compute_done, ctx->stream));
+    sl.busy = 1; sl.n = n; sl.out_capacity = out_capacity; sl.h_out = h_out;
+    ctx->next_slot = si ^ 1;
+    *ticket = &g_tickets[si];
+    return SQ_OK;
+}
+
+extern "C" int32_t sq_pack_wait(sq_ctx *ctx, sq_ticket *ticket, uint64_t *out_used) {
+    if (!ctx || !ticket) return SQ_ERR_INVALID_ARG;
+    sq_ctx::pack_slot &sl = ctx->slots[ticket->slot];
+    if (!sl.busy) return sq_set_error(ctx, SQ_ERR_INVALID_ARG, "sq_pack_wait: ticket is not in flight");
+    sl.busy = 0;
+    SQ_CUDA(ctx, cudaEventSynchronize(sl.compute_done));
+    const uint64_t used = *sl.h_total;
+    if (used > sl.out_capacity)
+        return sq_set_error(ctx, SQ_ERR_CAPACITY, "pack output needs %llu bytes, caller gave %llu", (unsigned long long)used, (unsigned long long)sl.out_capacity);
+    if (used) {
+        SQ_CUDA(ctx, cudaMemcpyAsync(sl.h_out, sl.d_out, used, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+        SQ_CUDA(ctx, cudaStreamSynchronize(ctx->d2h_stream));
+    }
     if (out_used) *out_used = used;
     return SQ_OK;
+}
+
+extern "C" int32_t sq_pack_host(sq_ctx *ctx, const void *h_data, size_t data_len, const sq_span *h_spans, uint32_t n,
+                                uint64_t gidx_base, sq_chunk_result *h_results, void *h_out, uint64_t out_capacity, uint64_t *out_used) {
+    if (!ctx) return SQ_ERR_INVALID_ARG;
+    if (n == 0) { if (out_used) *out_used = 0; return SQ_OK; }
+    sq_ticket *t = nullptr;
+    int32_t rc = sq_pack_submit(ctx, h_data, data_len, h_spans, n, gidx_base, h_results, h_out, out_capacity, &t);
+    if (rc) return rc;
+    return sq_pack_wait(ctx, t, out_used);
 }
 
 extern "C" int32_t sq_unpack_host(sq_ctx *ctx, const void *h_comp, size_t comp_len, const sq_frame *h_frames, uint32_t n, void *h_out,

@@ -306,9 +306,12 @@ extern "C" int32_t sq_archive_pack(sq_ctx *ctx, const char *input_dir, const cha
         b.pinned = (uint8_t *)p; b.cap = slot_cap;
     }
     uint64_t out_cap = sq_encode_bound(cs) * (uint64_t)(batch_bytes / cs + 1) + batch_bytes / 16;
-    void *h_out = nullptr;
-    if ((rc = sq_host_alloc(ctx, out_cap, &h_out))) { fclose(out); return rc; }
-    std::vector<sq_chunk_result> results(ctx->max_batch);
+    struct Stage { std::vector<sq_chunk_result> res; void *h_out = nullptr; sq_ticket *ticket = nullptr; };
+    Stage stages[2];
+    for (auto &s : stages) {
+        s.res.resize(ctx->max_batch);
+        if ((rc = sq_host_alloc(ctx, out_cap, &s.h_out))) { fclose(out); return rc; }
+    }
     std::vector<uint8_t> digests(total_chunks * 16);
 
     auto fill = [&](Batch *b, uint64_t first, uint64_t *next) {  // host reader pool -> pinned buffer
@@ -338,36 +341,47 @@ extern "C" int32_t sq_archive_pack(sq_ctx *ctx, const char *input_dir, const cha
         b->err = err;
     };
 
-    uint64_t g = 0, next = 0, unique = 0, payload = 0;
-    int cur = 0;
-    fill(&bufs[cur], 0, &next);
-    while (g < total_chunks && !rc) {
-        Batch *b = &bufs[cur];
-        if (b->err) { rc = sq_set_error(ctx, b->err, "Error reading from squish: input file changed or unreadable"); break; }
-        uint64_t after = next, next2 = next;
-        std::thread prefetch;
-        if (after < total_chunks) prefetch = std::thread([&] { fill(&bufs[cur ^ 1], after, &next2); });
-        const uint32_t n = (uint32_t)b->spans.size();
+    // Software pipeline over two slots: while batch k is on the GPU (sq_pack_submit), the host threads read batch k+1
+    // into the other pinned buffer; sq_pack_wait(k) then overlaps its frame download with the kernels of batch k+1.
+    uint64_t next = 0, unique = 0, payload = 0;
+    int head = 0, tail = 0, inflight = 0;
+    while ((next < total_chunks || inflight) && !rc) {
+        if (next < total_chunks && inflight < 2) {
+            Batch *b = &bufs[head];
+            fill(b, next, &next);
+            if (b->err) { rc = sq_set_error(ctx, b->err, "Error reading from squish: input file changed or unreadable"); break; }
+            double td = now_s();
+            rc = sq_pack_submit(ctx, b->pinned, b->used, b->spans.data(), (uint32_t)b->spans.size(), b->first_gidx, stages[head].res.data(),
+                                stages[head].h_out, out_cap, &stages[head].ticket);
+            t_dev += now_s() - td;
+            head ^= 1; inflight++;
+            continue;
+        }
+        Batch *b = &bufs[tail];
+        Stage &sg = stages[tail];
         uint64_t used = 0;
         double td = now_s();
-        rc = sq_pack_host(ctx, b->pinned, b->used, b->spans.data(), n, b->first_gidx, results.data(), h_out, out_cap, &used);
+        rc = sq_pack_wait(ctx, sg.ticket, &used);
         t_dev += now_s() - td;
         if (!rc) {
+            const uint32_t n = (uint32_t)b->spans.size();
             for (uint32_t i = 0; i < n; i++) {
-                memcpy(&digests[(b->first_gidx + i) * 16], results[i].digest, 16);
-                if (!results[i].is_new) continue;
+                memcpy(&digests[(b->first_gidx + i) * 16], sg.res[i].digest, 16);
+                if (!sg.res[i].is_new) continue;
                 uint8_t rec[32];  // chunk record (fsutil/writer.rs:21-36)
-                memcpy(rec, results[i].digest, 16);
+                memcpy(rec, sg.res[i].digest, 16);
                 put64(rec + 16, (uint64_t)SQ_CHUNK_SIZE);  // original_size: chunk_buf.len() (writer.rs:255)
-                put64(rec + 24, results[i].frame_len);
+                put64(rec + 24, sg.res[i].frame_len);
                 werr |= fwrite(rec, 1, 32, out) != 32;
-                werr |= fwrite((uint8_t *)h_out + results[i].frame_off, 1, results[i].frame_len, out) != results[i].frame_len;
+                werr |= fwrite((uint8_t *)sg.h_out + sg.res[i].frame_off, 1, sg.res[i].frame_len, out) != sg.res[i].frame_len;
                 unique++;
-                payload += results[i].frame_len;
+                payload += sg.res[i].frame_len;
             }
         }
-        if (prefetch.joinable()) prefetch.join();
-        g = after; next = next2; cur ^= 1;
+        tail ^= 1; inflight--;
+    }
+    if (rc) {  // drain whatever is still in flight before the buffers go away
+        for (int i = 0; i < 2; i++) if (ctx->slots[i].busy) { uint64_t u; sq_pack_wait(ctx, stages[i].ticket, &u); }
     }
     if (!rc) {
         uint64_t dl = 0;
@@ -395,7 +409,7 @@ extern "C" int32_t sq_archive_pack(sq_ctx *ctx, const char *input_dir, const cha
     uint64_t asize = 0;
     if (!rc) { fseek(out, 0, SEEK_END); asize = (uint64_t)ftell(out); }
     fclose(out);
-    sq_host_free(ctx, bufs[0].pinned); sq_host_free(ctx, bufs[1].pinned); sq_host_free(ctx, h_out);
+    sq_host_free(ctx, bufs[0].pinned); sq_host_free(ctx, bufs[1].pinned); sq_host_free(ctx, stages[0].h_out); sq_host_free(ctx, stages[1].h_out);
     if (!rc && report) {
         memset(report, 0, sizeof *report);
         report->archive_size = asize; report->unique_chunks = unique; report->total_chunks = total_chunks;
