@@ -36,6 +36,25 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+# Libraries (NCCL prints its version banner on stdout) must not pollute the one-JSON-line contract: fd 1 is pointed at
+# stderr for the whole run and the result line is written to the saved original stdout.
+_REAL_STDOUT = None
+
+
+def protect_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
+
+
 # --------------------------------------------------------------------------- corpus definition
 WORKLOADS = {
     "config2": "configs[1]: mixed logs/JSON/binary corpus, 20% duplicate 2 MiB slots, device-resident pack",
@@ -203,7 +222,7 @@ def run_reference(args):
                              "sample": f"{n} x 2 MiB slots of the configs[1] stream per step, in memory, archive to /dev/shm"},
             "e2e": {"value": gbs, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "ratio": stats.payload_bytes / (stats.unique_chunks * CHUNK) if stats and stats.unique_chunks else None}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # --------------------------------------------------------------------------- our arm (GPU)
@@ -532,7 +551,7 @@ def run_ours(args):
                        "parallelism": f"dp{world} (chunks sharded by rank" + (", digest all-to-all over NCCL)" if world > 1 else ")")},
             "gpu_launches": int(launches1.value - launches0.value), "clocks": clk, "e2e": e2e, "roofline": roof, "cpu_baseline": cpu, "unpack": unpack,
             "ratio": {"compressed_over_unique": out_bytes / (n_new * CHUNK) if n_new else None, "unique_fraction": n_new * CHUNK / in_bytes}}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -551,6 +570,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
+    protect_stdout()
     if args.warmup < 3 and args.impl == "ours":
         log("note: fewer than 3 warm-up steps requested; the timing rules ask for >= 3")
     if args.impl == "reference":
