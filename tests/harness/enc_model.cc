@@ -267,7 +267,7 @@ extern "C" long enc_model_frame(const uint8_t *src, uint32_t n, uint8_t *dst, ui
                     if (getenv("ENC_MAXSHIFT") && start - p + 2 > (uint32_t)atoi(getenv("ENC_MAXSHIFT"))) break;
                 }
             }
-            if (getenv("ENC_CAPLEN") && cur.len >= (uint32_t)P.target_len) { uint32_t full = match_len(src, start, start - cur.off, n); if (start + full > be) full = be - start; if (full > cur.len) cur.len = full; }
+            if (getenv("ENC_CAPLEN") && cur.len + 3 >= (uint32_t)P.target_len) { uint32_t full = match_len(src, start, start - cur.off, n); if (start + full > be) full = be - start; if (full > cur.len) cur.len = full; }
             // backward extension (only for non-rep matches found by the search; bounded by literal run)
             if (cur.off_base > 3 && M.best[start].off == cur.off && M.best[start].len) {
                 uint32_t k = std::min<uint32_t>(M.back[start], start - anchor);
