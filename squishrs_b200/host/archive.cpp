@@ -34,6 +34,9 @@ namespace {
 const char kPrefix[] = "squish";           // header.rs:10
 const char kVersion[] = SQ_FORMAT_VERSION;  // lib.rs:17
 
+static bool sq_timing() { static int v = -1; if (v < 0) v = getenv("SQ_TIMING") ? 1 : 0; return v == 1; }
+#define SQ_T(msg) do { if (sq_timing()) fprintf(stderr, "[sq %8.3f] %s\n", now_s() - t0, msg); } while (0)
+double now_s();
 double now_s() {
     timespec ts;
     clock_gettime(CLOCK_MONOTONIC, &ts);
@@ -72,6 +75,20 @@ int32_t walk_dir(sq_ctx *ctx, const std::string &root, std::vector<std::string> 
     }
     return SQ_OK;
 }
+
+// Host staging for a job: pinned memory moves at full link speed but costs ~0.4 s per GiB to pin, so jobs under a few GiB
+// use ordinary page-aligned memory (the driver stages it) and only large jobs pay for pinning once.
+struct Staging {
+    void *p = nullptr; bool pinned = false;
+    int32_t alloc(sq_ctx *ctx, size_t bytes, bool pin) {
+        pinned = pin;
+        if (pin) return sq_host_alloc(ctx, bytes, &p);
+        p = aligned_alloc(4096, (bytes + 4095) & ~(size_t)4095);
+        return p ? SQ_OK : sq_set_error(ctx, SQ_ERR_OTHER, "Unknown error: cannot allocate %zu bytes of staging", bytes);
+    }
+    void release(sq_ctx *ctx) { if (!p) return; if (pinned) sq_host_free(ctx, p); else free(p); p = nullptr; }
+};
+constexpr uint64_t kPinThreshold = 4ull << 30;
 
 template <class F>
 void parallel_for(size_t n, int threads, F fn) {
@@ -262,6 +279,7 @@ extern "C" int32_t sq_archive_pack(sq_ctx *ctx, const char *input_dir, const cha
     int32_t rc = walk_dir(ctx, root, &paths);
     if (rc) return rc;
 
+    SQ_T("walk done");
     std::vector<FileItem> files(paths.size());
     std::atomic<int32_t> ferr{0};
     parallel_for(paths.size(), threads, [&](size_t i) {
@@ -283,6 +301,7 @@ extern "C" int32_t sq_archive_pack(sq_ctx *ctx, const char *input_dir, const cha
     if (total_chunks > ctx->dedup_capacity)
         return sq_set_error(ctx, SQ_ERR_CAPACITY, "%llu chunks exceed the context's dedup_capacity %llu", (unsigned long long)total_chunks,
                             (unsigned long long)ctx->dedup_capacity);
+    SQ_T("stat + chunk plan done");
     if ((rc = sq_dedup_reset(ctx))) return rc;  // ChunkStore::new (writer.rs:88)
 
     FILE *out = fopen(output_path, "wb+");
@@ -297,20 +316,26 @@ extern "C" int32_t sq_archive_pack(sq_ctx *ctx, const char *input_dir, const cha
     bool werr = fwrite(pre, 1, hl + 16, out) != hl + 16;
 
     // batches: up to batch_bytes of chunk payload or max_batch chunks
-    const size_t batch_bytes = 256u << 20;
+    // Batches of up to 512 MiB of chunk payload: one chunk occupies one search CTA for its whole encode, so a batch should
+    // offer a few hundred chunks; pinned staging is sized to the job, because pinning memory costs ~0.4 s per GiB.
+    uint64_t total_bytes_all = 0;
+    for (auto &f : files) total_bytes_all += f.size + 16;
+    const size_t batch_bytes = (size_t)std::min<uint64_t>(512ull << 20, std::max<uint64_t>(total_bytes_all, 1u << 20));
     const size_t slot_cap = batch_bytes + (size_t)cs;
+    const bool pin = total_bytes_all >= kPinThreshold;
     Batch bufs[2];
-    for (auto &b : bufs) {
-        void *p = nullptr;
-        if ((rc = sq_host_alloc(ctx, slot_cap, &p))) { fclose(out); return rc; }
-        b.pinned = (uint8_t *)p; b.cap = slot_cap;
+    Staging in_stage[2], out_stage[2];
+    for (int i = 0; i < 2; i++) {
+        if ((rc = in_stage[i].alloc(ctx, slot_cap, pin))) { fclose(out); return rc; }
+        bufs[i].pinned = (uint8_t *)in_stage[i].p; bufs[i].cap = slot_cap;
     }
     uint64_t out_cap = sq_encode_bound(cs) * (uint64_t)(batch_bytes / cs + 1) + batch_bytes / 16;
     struct Stage { std::vector<sq_chunk_result> res; void *h_out = nullptr; sq_ticket *ticket = nullptr; };
     Stage stages[2];
-    for (auto &s : stages) {
-        s.res.resize(ctx->max_batch);
-        if ((rc = sq_host_alloc(ctx, out_cap, &s.h_out))) { fclose(out); return rc; }
+    for (int i = 0; i < 2; i++) {
+        stages[i].res.resize(ctx->max_batch);
+        if ((rc = out_stage[i].alloc(ctx, out_cap, pin))) { fclose(out); return rc; }
+        stages[i].h_out = out_stage[i].p;
     }
     std::vector<uint8_t> digests(total_chunks * 16);
 
@@ -341,6 +366,7 @@ extern "C" int32_t sq_archive_pack(sq_ctx *ctx, const char *input_dir, const cha
         b->err = err;
     };
 
+    SQ_T("pinned buffers allocated");
     // Software pipeline over two slots: while batch k is on the GPU (sq_pack_submit), the host threads read batch k+1
     // into the other pinned buffer; sq_pack_wait(k) then overlaps its frame download with the kernels of batch k+1.
     uint64_t next = 0, unique = 0, payload = 0;
@@ -383,6 +409,7 @@ extern "C" int32_t sq_archive_pack(sq_ctx *ctx, const char *input_dir, const cha
     if (rc) {  // drain whatever is still in flight before the buffers go away
         for (int i = 0; i < 2; i++) if (ctx->slots[i].busy) { uint64_t u; sq_pack_wait(ctx, stages[i].ticket, &u); }
     }
+    SQ_T("all batches packed + records written");
     if (!rc) {
         uint64_t dl = 0;
         rc = sq_dedup_len(ctx, &dl);  // chunk_store.len() (writer.rs:177-184)
@@ -406,10 +433,11 @@ extern "C" int32_t sq_archive_pack(sq_ctx *ctx, const char *input_dir, const cha
         if (fflush(out)) werr = true;
         if (werr) rc = sq_set_error(ctx, SQ_ERR_WRITER, "Error writing to squish: %s", output_path);
     }
+    SQ_T("manifest written");
     uint64_t asize = 0;
     if (!rc) { fseek(out, 0, SEEK_END); asize = (uint64_t)ftell(out); }
     fclose(out);
-    sq_host_free(ctx, bufs[0].pinned); sq_host_free(ctx, bufs[1].pinned); sq_host_free(ctx, stages[0].h_out); sq_host_free(ctx, stages[1].h_out);
+    for (int i = 0; i < 2; i++) { in_stage[i].release(ctx); out_stage[i].release(ctx); }
     if (!rc && report) {
         memset(report, 0, sizeof *report);
         report->archive_size = asize; report->unique_chunks = unique; report->total_chunks = total_chunks;
@@ -432,6 +460,7 @@ extern "C" int32_t sq_archive_unpack(sq_ctx *ctx, const char *archive_path, cons
     uint64_t total = 0;
     if ((rc = read_manifest(ctx, a, &man, &total))) return rc;
 
+    SQ_T("index scan + manifest parsed");
     // read_chunks (reader.rs:259-314): decode every record, keyed by digest; later records overwrite earlier ones
     struct Decoded { uint64_t off; uint32_t len; };
     std::vector<Decoded> dec(a.records.size());
@@ -449,10 +478,17 @@ extern "C" int32_t sq_archive_unpack(sq_ctx *ctx, const char *archive_path, cons
         store = (uint8_t *)malloc(total_out);
         if (!store) return sq_set_error(ctx, SQ_ERR_OTHER, "Unknown error: cannot allocate %llu bytes", (unsigned long long)total_out);
     }
-    const uint64_t batch_out = 2048ull << 20, batch_in = 1024ull << 20;  // a frame decodes on one warp: many frames per call keep the GPU full
-    void *h_comp = nullptr, *h_out = nullptr;
-    if ((rc = sq_host_alloc(ctx, batch_in + (4u << 20), &h_comp))) { free(store); return rc; }
-    if ((rc = sq_host_alloc(ctx, batch_out + (4u << 20), &h_out))) { sq_host_free(ctx, h_comp); free(store); return rc; }
+    // a frame decodes on one warp: many frames per call keep the GPU full; pinned staging is sized to the job
+    uint64_t total_comp = 0;
+    for (auto &r : a.records) total_comp += (r.comp + 15) & ~15ull;
+    const uint64_t batch_out = std::min<uint64_t>(2048ull << 20, std::max<uint64_t>(total_out, 1u << 20)),
+                   batch_in = std::min<uint64_t>(1024ull << 20, std::max<uint64_t>(total_comp, 1u << 20));
+    Staging comp_stage, out_stage;
+    const bool pin = total_out >= kPinThreshold;
+    if ((rc = comp_stage.alloc(ctx, batch_in + (4u << 20), pin))) { free(store); return rc; }
+    if ((rc = out_stage.alloc(ctx, batch_out + (4u << 20), pin))) { comp_stage.release(ctx); free(store); return rc; }
+    void *h_comp = comp_stage.p, *h_out = out_stage.p;
+    SQ_T("unpack buffers allocated");
     std::vector<sq_frame> frames;
     std::vector<sq_frame_result> fres(ctx->max_batch);
     uint64_t store_off = 0;
@@ -484,7 +520,8 @@ extern "C" int32_t sq_archive_unpack(sq_ctx *ctx, const char *archive_path, cons
         parallel_for(frames.size(), threads, [&](size_t k) { memcpy(store + store_off + frames[k].dst_off, (uint8_t *)h_out + frames[k].dst_off, fres[k].out_len); });
         store_off += dof;
     }
-    sq_host_free(ctx, h_comp); sq_host_free(ctx, h_out);
+    SQ_T("all chunks decoded");
+    comp_stage.release(ctx); out_stage.release(ctx);
     if (rc) { free(store); return rc; }
 
     struct Key { uint64_t a, b; bool operator==(const Key &o) const { return a == o.a && b == o.b; } };
@@ -518,6 +555,7 @@ extern "C" int32_t sq_archive_unpack(sq_ctx *ctx, const char *archive_path, cons
         }
         close(fd);
     });
+    SQ_T("files rebuilt");
     free(store);
     if (err) {
         const ManifestEntry &e = man[err_idx];

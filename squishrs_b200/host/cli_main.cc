@@ -12,6 +12,9 @@
 
 #include "squish_b200.h"
 
+static double now_s() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + ts.tv_nsec * 1e-9; }
+static void tmark(const char *what, double t0) { if (getenv("SQ_TIMING")) fprintf(stderr, "[cli %8.3f] %s\n", now_s() - t0, what); }
+
 static std::string format_bytes(uint64_t b) {  // byte-unit Decimal, "{:.2} {unit}" (cmd/mod.rs:161-165)
     const char *u[] = {"B", "KB", "MB", "GB", "TB", "PB", "EB"};
     double v = (double)b;
@@ -114,9 +117,11 @@ int main(int argc, char **argv) {
         return 0;
     }
 
+    const double t_start = now_s();
     sq_config cfg = {device, 0, 1ull << 22, 4096, 0};
     sq_ctx *ctx = nullptr;
     int32_t rc = sq_create(&cfg, &ctx);
+    tmark("sq_create done", t_start);
     if (rc) return fail(sq_last_error(nullptr));
     if (cmd == "pack") {  // lib.rs:26-56
         if (!have_out) output = arg + ".squish";  // default uses the UNtrimmed input (lib.rs:31)
@@ -136,6 +141,8 @@ int main(int argc, char **argv) {
         if (rc) { std::string m = sq_last_error(ctx); sq_destroy(ctx); return fail(m.c_str()); }
         printf("\033[32mUnpacking complete!\033[0m\n%s was unsquished into /%s\n", arg.c_str(), output.c_str());
     }
+    tmark("command done", t_start);
     sq_destroy(ctx);
+    tmark("sq_destroy done", t_start);
     return 0;
 }
