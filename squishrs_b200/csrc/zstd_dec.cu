@@ -11,7 +11,7 @@
 // construction and the serial FSE sequence chain are evaluated redundantly by every lane from shared-memory
 // tables, which costs nothing in SIMT and needs no broadcast; lanes split the 4 Huffman literal streams,
 // the decode-table fills, and the bytes of every literal run and match copy (coalesced within a copy).
-// Per-warp tables (Huffman 4 KB, LL/ML/OF cells 10 KB) live in shared memory; decoded Huffman literals go
+// Per-warp tables (Huffman 4 KB, LL/ML/OF cells 5 KB) live in shared memory; decoded Huffman literals go
 // to a 128 KiB per-warp slot in HBM (L2 resident).  Algorithmic traffic = payload bytes read + decoded
 // bytes written.
 #include "common.cuh"

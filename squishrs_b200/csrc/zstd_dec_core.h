@@ -24,11 +24,10 @@ namespace zd {
 #define ZD_DEV static inline
 #endif
 
-struct SeqCell {  // one FSE state of a sequence table, pre-joined with the code's base value / extra bits
-    uint16_t next_base;
+struct SeqCell {  // one FSE state of a sequence table (4 bytes: the per-warp tables must stay small, they bound residency);
+    uint16_t next_base;   // base value / extra-bit count of the code come from the constant code tables
     uint8_t nb_bits;      // state bits to read for the transition
-    uint8_t extra_bits;   // extra bits of the code
-    uint32_t base_value;  // LL/ML: base length; OF: 1 << code
+    uint8_t sym;          // the LL / ML / OF code
 };
 
 struct Tables {          // per-warp state that persists across the blocks of a frame (treeless / repeat modes)
@@ -278,11 +277,10 @@ ZD_DEV int decode_literals(const uint8_t *src, uint32_t size, Tables *T, uint8_t
 // ---- sequence tables -------------------------------------------------------------------------------------
 enum { KIND_LL = 0, KIND_OF = 1, KIND_ML = 2 };
 ZD_DEV void fill_cell(SeqCell *c, uint32_t kind, uint32_t sym, uint32_t nb, uint32_t base) {
+    (void)kind;
     c->next_base = (uint16_t)base;
     c->nb_bits = (uint8_t)nb;
-    if (kind == KIND_LL) { c->extra_bits = zc::ZTAB(LL_bits)[sym]; c->base_value = zc::ZTAB(LL_base)[sym]; }
-    else if (kind == KIND_ML) { c->extra_bits = zc::ZTAB(ML_bits)[sym]; c->base_value = zc::ZTAB(ML_base)[sym]; }
-    else { c->extra_bits = (uint8_t)sym; c->base_value = 1u << sym; }
+    c->sym = (uint8_t)sym;
 }
 // builds cells from normalised counts (uniform: every lane executes it; lanes write identical values)
 ZD_DEV int build_seq_table(SeqCell *cells, uint32_t kind, const int16_t *norm, uint32_t max_sym, uint32_t tl, zc::FseDCell *tmp /* 512 */) {
@@ -413,9 +411,9 @@ ZD_DEV int64_t decode_compressed_block(const uint8_t *src, uint32_t size, uint8_
             for (uint32_t k = 0; k < nbatch; k++) {
                 const SeqCell cl = T->ll[s_ll], co = T->of[s_of], cm = T->ml[s_ml];
                 // extra bits: offset, match length, literal length
-                const uint32_t ofv = co.base_value + br_read(&b, co.extra_bits);
-                const uint32_t ml = cm.base_value + br_read(&b, cm.extra_bits);
-                const uint32_t ll = cl.base_value + br_read(&b, cl.extra_bits);
+                const uint32_t ofv = (1u << co.sym) + br_read(&b, co.sym);
+                const uint32_t ml = zc::ZTAB(ML_base)[cm.sym] + br_read(&b, zc::ZTAB(ML_bits)[cm.sym]);
+                const uint32_t ll = zc::ZTAB(LL_base)[cl.sym] + br_read(&b, zc::ZTAB(LL_bits)[cl.sym]);
                 uint32_t off;
                 if (ofv > 3) { off = ofv - 3; r2 = r1; r1 = r0; r0 = off; }
                 else {

@@ -442,6 +442,20 @@ __global__ void __launch_bounds__(128) entropy_kernel(const uint8_t *__restrict_
         if (blen == 0) { if (lane == 0) { BlockOut o0; o0.type = 0; o0.body_len = 0; blocks[(size_t)chunk * BLOCKS_PER_CHUNK + b] = o0; } continue; }
         const BlockMeta m = meta_all[(size_t)chunk * BLOCKS_PER_CHUNK + b];
         const zc::Seq *seqs = seqs_all + (size_t)chunk * MAX_SEQ_PER_CHUNK + m.seq_start;
+        if (m.nseq <= 2) {  // a block this regular may be one repeated byte: then it is an RLE block (1-byte body)
+            const uint8_t v0 = in[bs];
+            bool same = true;
+            for (uint32_t i = bs + lane; i < be && same; i += 32) same = in[i] == v0;
+            if (__all_sync(0xffffffffu, same)) {
+                if (lane == 0) {
+                    uint8_t *dst = bodies + ((size_t)chunk * BLOCKS_PER_CHUNK + b) * (size_t)BODY_STRIDE;
+                    dst[0] = v0;
+                    BlockOut o1; o1.type = 1; o1.body_len = 1;
+                    blocks[(size_t)chunk * BLOCKS_PER_CHUNK + b] = o1;
+                }
+                continue;
+            }
+        }
         // gather literals: 32 sequences at a time, a warp scan gives every lane its source and destination offsets
         uint32_t src_pos = bs, lit_pos = 0;
         for (uint32_t base = 0; base < m.nseq; base += 32) {
