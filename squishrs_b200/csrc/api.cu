@@ -93,6 +93,8 @@ extern "C" int32_t sq_create(const sq_config *cfg, sq_ctx **out) {
         SQ_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
         SQ_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking));
         for (int i = 0; i < 2; i++) {
+            SQ_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->slot_stream[i], cudaStreamNonBlocking));
+            SQ_CUDA(ctx, cudaEventCreateWithFlags(&ctx->dedup_done[i], cudaEventDisableTiming));
             SQ_CUDA(ctx, cudaEventCreateWithFlags(&ctx->slots[i].h2d_done, cudaEventDisableTiming));
             SQ_CUDA(ctx, cudaEventCreateWithFlags(&ctx->slots[i].compute_done, cudaEventDisableTiming));
             SQ_CUDA(ctx, cudaHostAlloc((void **)&ctx->slots[i].h_total, 64, cudaHostAllocDefault));
@@ -127,6 +129,8 @@ extern "C" void sq_destroy(sq_ctx *ctx) {
         if (ctx->slots[i].h2d_done) cudaEventDestroy(ctx->slots[i].h2d_done);
         if (ctx->slots[i].compute_done) cudaEventDestroy(ctx->slots[i].compute_done);
         if (ctx->slots[i].h_total) cudaFreeHost(ctx->slots[i].h_total);
+        if (ctx->slot_stream[i]) cudaStreamDestroy(ctx->slot_stream[i]);
+        if (ctx->dedup_done[i]) cudaEventDestroy(ctx->dedup_done[i]);
     }
     if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);

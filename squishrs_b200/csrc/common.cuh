@@ -31,7 +31,7 @@ struct sq_ctx {
     // K2
     sq_dedup_table *dedup;
     // K3 / K4 scratch (lazily sized)
-    sq_enc_scratch *enc;
+    sq_enc_scratch *enc_sets[2];  // two independent encoder scratch sets: the pipeline slots may encode concurrently
     sq_dec_scratch *dec;
     // staging for the *_host entry points (lazily grown)
     void *d_stage_in; size_t stage_in_cap;
@@ -45,6 +45,9 @@ struct sq_ctx {
         uint32_t n; uint64_t out_capacity; void *h_out; int busy;
     } slots[2];
     cudaStream_t d2h_stream;
+    cudaStream_t slot_stream[2];   // one compute stream per pipeline slot: the tail of one batch overlaps the head of the next
+    cudaEvent_t dedup_done[2];     // K1/K2 of consecutive batches stay ordered across the two slot streams
+    int dedup_done_valid[2];
     int next_slot;
 };
 
@@ -66,4 +69,6 @@ static inline cudaStream_t sq_stream(sq_ctx *ctx, void *s) { return s ? (cudaStr
 int32_t sq_dedup_create(sq_ctx *ctx);
 void sq_dedup_destroy(sq_ctx *ctx);
 void sq_enc_destroy(sq_ctx *ctx);
+int32_t sq_encode_device_set(sq_ctx *ctx, int set, const void *d_data, const sq_span *d_spans, const uint8_t *d_select, uint32_t n, void *d_out,
+                             uint64_t out_capacity, uint64_t *d_frame_off, uint32_t *d_frame_len, uint64_t *d_total, cudaStream_t st);
 void sq_dec_destroy(sq_ctx *ctx);

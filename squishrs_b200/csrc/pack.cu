@@ -45,11 +45,13 @@ static int32_t meta_layout(sq_ctx *ctx, uint32_t n, pack_meta *m) { return meta_
 
 // digest -> dedup -> encode -> results, all asynchronous on `st`, with caller-provided metadata scratch
 static int32_t pack_device_impl(sq_ctx *ctx, const void *d_data, const sq_span *d_spans, uint32_t n, uint64_t gidx_base, const pack_meta &m,
-                                sq_chunk_result *d_results, void *d_out, uint64_t out_capacity, cudaStream_t st) {
+                                sq_chunk_result *d_results, void *d_out, uint64_t out_capacity, cudaStream_t st, int set = 0,
+                                cudaEvent_t after_dedup = nullptr) {
     int32_t rc;
     if ((rc = sq_digest_device(ctx, d_data, d_spans, n, m.digests, st))) return rc;
     if ((rc = sq_dedup_insert_device(ctx, m.digests, nullptr, gidx_base, n, m.is_new, st))) return rc;
-    if ((rc = sq_encode_device(ctx, d_data, d_spans, m.is_new, n, d_out, out_capacity, m.frame_off, m.frame_len, m.total, st))) return rc;
+    if (after_dedup) SQ_CUDA(ctx, cudaEventRecord(after_dedup, st));
+    if ((rc = sq_encode_device_set(ctx, set, d_data, d_spans, m.is_new, n, d_out, out_capacity, m.frame_off, m.frame_len, m.total, st))) return rc;
     pack_results_kernel<<<(n + 127) / 128, 128, 0, st>>>((const uint4 *)m.digests, m.is_new, m.frame_off, m.frame_len, n, d_results);
     SQ_LAUNCHED(ctx, 1);
     SQ_CUDA(ctx, cudaGetLastError());
@@ -103,11 +105,17 @@ extern "C" int32_t sq_pack_submit(sq_ctx *ctx, const void *h_data, size_t data_l
     SQ_CUDA(ctx, cudaMemcpyAsync(sl.d_in, h_data, data_len, cudaMemcpyHostToDevice, ctx->copy_stream));
     SQ_CUDA(ctx, cudaMemcpyAsync(m.spans, h_spans, (size_t)n * sizeof(sq_span), cudaMemcpyHostToDevice, ctx->copy_stream));
     SQ_CUDA(ctx, cudaEventRecord(sl.h2d_done, ctx->copy_stream));
-    SQ_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, sl.h2d_done, 0));
-    if ((rc = pack_device_impl(ctx, sl.d_in, m.spans, n, gidx_base, m, m.results, sl.d_out, bound, ctx->stream))) return rc;
-    SQ_CUDA(ctx, cudaMemcpyAsync(h_results, m.results, (size_t)n * sizeof(sq_chunk_result), cudaMemcpyDeviceToHost, ctx->stream));
-    SQ_CUDA(ctx, cudaMemcpyAsync(sl.h_total, m.total, 8, cudaMemcpyDeviceToHost, ctx->stream));
-    SQ_CUDA(ctx, cudaEventRecord(sl.compute_done, ctx->stream));
+    // Each slot has its own compute stream and encoder scratch set: the long encode of this batch may overlap the tail of the
+    // previous one (a chunk occupies one search CTA for ~0.1 s, so tails would otherwise idle most SMs).  Digest and dedup of
+    // consecutive batches stay ordered through dedup_done (they share the digest work counter and the index's batch scratch).
+    cudaStream_t cs = ctx->slot_stream[si];
+    SQ_CUDA(ctx, cudaStreamWaitEvent(cs, sl.h2d_done, 0));
+    if (ctx->dedup_done_valid[si ^ 1]) SQ_CUDA(ctx, cudaStreamWaitEvent(cs, ctx->dedup_done[si ^ 1], 0));
+    if ((rc = pack_device_impl(ctx, sl.d_in, m.spans, n, gidx_base, m, m.results, sl.d_out, bound, cs, si, ctx->dedup_done[si]))) return rc;
+    ctx->dedup_done_valid[si] = 1;
+    SQ_CUDA(ctx, cudaMemcpyAsync(h_results, m.results, (size_t)n * sizeof(sq_chunk_result), cudaMemcpyDeviceToHost, cs));
+    SQ_CUDA(ctx, cudaMemcpyAsync(sl.h_total, m.total, 8, cudaMemcpyDeviceToHost, cs));
+    SQ_CUDA(ctx, cudaEventRecord(sl.compute_done, cs));
     sl.busy = 1; sl.n = n; sl.out_capacity = out_capacity; sl.h_out = h_out;
     ctx->next_slot = si ^ 1;
     *ticket = &g_tickets[si];

@@ -172,12 +172,12 @@ __global__ void __launch_bounds__(256) enc_emit_kernel(const uint8_t *__restrict
 
 }  // namespace
 
-static int32_t enc_scratch(sq_ctx *ctx, uint32_t n) {
-    if (!ctx->enc) {
-        ctx->enc = new sq_enc_scratch();
-        memset(ctx->enc, 0, sizeof(sq_enc_scratch));
+static int32_t enc_scratch(sq_ctx *ctx, uint32_t n, int set) {
+    if (!ctx->enc_sets[set]) {
+        ctx->enc_sets[set] = new sq_enc_scratch();
+        memset(ctx->enc_sets[set], 0, sizeof(sq_enc_scratch));
     }
-    sq_enc_scratch *e = ctx->enc;
+    sq_enc_scratch *e = ctx->enc_sets[set];
     if (!e->tab) {  // per-resident-worker state, sized once from the SM count
         {   // The search kernel leans on L1 for candidate bytes: give shared memory only what the resident CTAs need.
             cudaFuncAttributes fa;
@@ -223,12 +223,14 @@ static int32_t enc_scratch(sq_ctx *ctx, uint32_t n) {
 }
 
 void sq_enc_destroy(sq_ctx *ctx) {
-    sq_enc_scratch *e = ctx->enc;
-    if (!e) return;
-    cudaFree(e->blocks); cudaFree(e->frame_len); cudaFree(e->bodies); cudaFree(e->status); cudaFree(e->seqs); cudaFree(e->meta); cudaFree(e->rec);
-    cudaFree(e->tab); cudaFree(e->head); cudaFree(e->lits); cudaFree(e->sbits);
-    delete e;
-    ctx->enc = nullptr;
+    for (int set = 0; set < 2; set++) {
+        sq_enc_scratch *e = ctx->enc_sets[set];
+        if (!e) continue;
+        cudaFree(e->blocks); cudaFree(e->frame_len); cudaFree(e->bodies); cudaFree(e->status); cudaFree(e->seqs); cudaFree(e->meta); cudaFree(e->rec);
+        cudaFree(e->tab); cudaFree(e->head); cudaFree(e->lits); cudaFree(e->sbits);
+        delete e;
+        ctx->enc_sets[set] = nullptr;
+    }
 }
 
 extern "C" size_t sq_encode_bound(size_t len) {
@@ -240,13 +242,18 @@ extern "C" int32_t sq_encode_device(sq_ctx *ctx, const void *d_data, const sq_sp
                                     void *d_out, uint64_t out_capacity, uint64_t *d_frame_off, uint32_t *d_frame_len, uint64_t *d_total,
                                     void *stream) {
     if (!ctx) return SQ_ERR_INVALID_ARG;
+    return sq_encode_device_set(ctx, 0, d_data, d_spans, d_select, n, d_out, out_capacity, d_frame_off, d_frame_len, d_total, sq_stream(ctx, stream));
+}
+
+// `set` selects one of two independent scratch sets, so two batches on two streams can be in the encoder at the same time
+int32_t sq_encode_device_set(sq_ctx *ctx, int set, const void *d_data, const sq_span *d_spans, const uint8_t *d_select, uint32_t n, void *d_out,
+                             uint64_t out_capacity, uint64_t *d_frame_off, uint32_t *d_frame_len, uint64_t *d_total, cudaStream_t st) {
     if (n == 0) return SQ_OK;
     if (!d_data || !d_spans || !d_out || !d_frame_off || !d_frame_len || !d_total)
         return sq_set_error(ctx, SQ_ERR_INVALID_ARG, "sq_encode_device: null pointer");
-    int32_t rc = enc_scratch(ctx, n);
+    int32_t rc = enc_scratch(ctx, n, set);
     if (rc) return rc;
-    sq_enc_scratch *e = ctx->enc;
-    cudaStream_t st = sq_stream(ctx, stream);
+    sq_enc_scratch *e = ctx->enc_sets[set];
     const uint32_t nb = n * SQ_MAX_BLOCKS;
     enc_plan_kernel<<<(nb + 255) / 256, 256, 0, st>>>(d_spans, d_select, n, e->blocks);
     SQ_CUDA(ctx, cudaMemsetAsync(e->status + 1, 0, 2 * sizeof(uint32_t), st));
@@ -270,13 +277,16 @@ extern "C" int32_t sq_encode_device(sq_ctx *ctx, const void *d_data, const sq_sp
 
 // status of the most recent encode on this context (synchronizes): SQ_ERR_CAPACITY if d_out was too small
 extern "C" int32_t sq_encode_status(sq_ctx *ctx) {
-    if (!ctx || !ctx->enc) return SQ_OK;
-    uint32_t s = 0;
+    if (!ctx) return SQ_OK;
     SQ_CUDA(ctx, cudaDeviceSynchronize());
-    SQ_CUDA(ctx, cudaMemcpy(&s, ctx->enc->status, sizeof s, cudaMemcpyDeviceToHost));
-    if (s) {
-        cudaMemset(ctx->enc->status, 0, sizeof s);
-        return sq_set_error(ctx, SQ_ERR_CAPACITY, "encode output buffer too small");
+    for (int set = 0; set < 2; set++) {
+        if (!ctx->enc_sets[set]) continue;
+        uint32_t s = 0;
+        SQ_CUDA(ctx, cudaMemcpy(&s, ctx->enc_sets[set]->status, sizeof s, cudaMemcpyDeviceToHost));
+        if (s) {
+            cudaMemset(ctx->enc_sets[set]->status, 0, sizeof s);
+            return sq_set_error(ctx, SQ_ERR_CAPACITY, "encode output buffer too small");
+        }
     }
     return SQ_OK;
 }
