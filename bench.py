@@ -270,12 +270,6 @@ def run_ours(args):
     spans_np[:, 1] = CHUNK  # len in the low 32 bits, reserved = 0
     d_spans = torch.from_numpy(spans_np.view(np.int64)).cuda()
     out_cap = B * int(lib.sq_encode_bound(CHUNK))
-    d_out = torch.empty(out_cap, dtype=torch.uint8, device="cuda")
-    d_dig = torch.empty(B * 16, dtype=torch.uint8, device="cuda")
-    d_new = torch.empty(B, dtype=torch.uint8, device="cuda")
-    d_foff = torch.empty(B, dtype=torch.int64, device="cuda")
-    d_flen = torch.empty(B, dtype=torch.int32, device="cuda")
-    d_total = torch.zeros(1, dtype=torch.int64, device="cuda")
 
     ev = lambda: torch.cuda.Event(enable_timing=True)
     stage_ms = {"digest": 0.0, "dedup": 0.0, "encode": 0.0}
@@ -286,28 +280,52 @@ def run_ours(args):
         from squishrs_b200.sharded import DeviceOps, ShardedDedup
         sd = ShardedDedup(DeviceOps(ctx, sp), world, B, "cuda")
 
+    # Two streams alternate between steps: the long encode of step k+1 starts while the last chunks of step k are still in
+    # flight (one chunk occupies one search CTA for ~0.1 s, so a step's tail would otherwise leave most SMs idle).  The
+    # library gives each stream its own encoder scratch; digest + dedup of consecutive steps are ordered with events.
+    stream_b = torch.cuda.Stream()
+    streams = [stream, stream_b] if not args.single_stream else [stream, stream]
+    sps = [C.c_void_p(x.cuda_stream) for x in streams]
+    bufs = []
+    for _ in range(2):
+        bufs.append(dict(out=torch.empty(out_cap, dtype=torch.uint8, device="cuda"), dig=torch.empty(B * 16, dtype=torch.uint8, device="cuda"),
+                         new=torch.empty(B, dtype=torch.uint8, device="cuda"), foff=torch.empty(B, dtype=torch.int64, device="cuda"),
+                         flen=torch.empty(B, dtype=torch.int32, device="cuda"), total=torch.zeros(1, dtype=torch.int64, device="cuda")))
+    d_out, d_dig, d_new, d_foff, d_flen, d_total = (bufs[0][k] for k in ("out", "dig", "new", "foff", "flen", "total"))
+    last_dedup = [None]
+
     def step(i, gidx_base, timed):
         b = i % n_batches
+        st, spx, bf = streams[i % 2], sps[i % 2], bufs[i % 2]
         base = corpus.data_ptr() + b * B * CHUNK
         e = [ev() for _ in range(4)] if timed else None
-        if timed:
-            e[0].record(stream)
-        ctx.check(lib.sq_digest_device(ctx.h, base, d_spans.data_ptr(), B, d_dig.data_ptr(), sp))
-        if timed:
-            e[1].record(stream)
-        if sd is None:
-            ctx.check(lib.sq_dedup_insert_device(ctx.h, d_dig.data_ptr(), None, gidx_base, B, d_new.data_ptr(), sp))
-        else:  # digest all-to-all over NCCL to the owner ranks, verdicts back
-            sd.exchange(d_dig, gidx_base, B, d_new)
-        if timed:
-            e[2].record(stream)
-        ctx.check(lib.sq_encode_device(ctx.h, base, d_spans.data_ptr(), d_new.data_ptr(), B, d_out.data_ptr(), out_cap,
-                                       d_foff.data_ptr(), d_flen.data_ptr(), d_total.data_ptr(), sp))
-        if timed:
-            e[3].record(stream)
-        return e
+        with torch.cuda.stream(st):
+            if last_dedup[0] is not None:
+                st.wait_event(last_dedup[0])
+            if timed:
+                e[0].record(st)
+            ctx.check(lib.sq_digest_device(ctx.h, base, d_spans.data_ptr(), B, bf["dig"].data_ptr(), spx))
+            if timed:
+                e[1].record(st)
+            if sd is None:
+                ctx.check(lib.sq_dedup_insert_device(ctx.h, bf["dig"].data_ptr(), None, gidx_base, B, bf["new"].data_ptr(), spx))
+            else:  # digest all-to-all over NCCL to the owner ranks, verdicts back
+                sd.ops.sp = spx
+                sd.exchange(bf["dig"], gidx_base, B, bf["new"])
+            dd = torch.cuda.Event()
+            dd.record(st)
+            last_dedup[0] = dd
+            if timed:
+                e[2].record(st)
+            ctx.check(lib.sq_encode_device(ctx.h, base, d_spans.data_ptr(), bf["new"].data_ptr(), B, bf["out"].data_ptr(), out_cap,
+                                           bf["foff"].data_ptr(), bf["flen"].data_ptr(), bf["total"].data_ptr(), spx))
+            if timed:
+                e[3].record(st)
+            tot = (bf["total"].clone(), bf["new"].sum(dtype=torch.int64)) if timed else None
+        return e, tot
 
     def barrier():
+        torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -328,8 +346,10 @@ def run_ours(args):
     evs = []
     outs = []
     for k in range(args.steps):
-        evs.append(step(k, k * B * world + rank * B, True))
-        outs.append((d_total.clone(), d_new.sum(dtype=torch.int64)))  # tiny device-side reads, no sync
+        e_k, tot_k = step(k, k * B * world + rank * B, True)
+        evs.append(e_k)
+        outs.append(tot_k)  # tiny device-side reads on the step's stream, no sync
+    stream.wait_stream(stream_b)  # the timed region ends when BOTH streams have drained
     stop.record(stream)
     barrier()
     elapsed_ms = start.elapsed_time(stop)
@@ -339,10 +359,28 @@ def run_ours(args):
     rc = lib.sq_encode_status(ctx.h)
     if rc != 0:
         raise SystemExit(f"encode overflow: {rc}")
-    for e in evs:
+    # Per-stage durations for the roofline: with two streams the launches of consecutive steps overlap on the device, so their
+    # event durations double-count.  A short single-stream pass on fresh dedup state (same batches, same kernels, CUDA events on
+    # the launching stream) gives clean per-launch times; the headline value above is untouched by it.
+    overlapped = not args.single_stream
+    if overlapped:
+        ctx.dedup_reset()
+        last_dedup[0] = None
+        save_streams, save_sps = list(streams), list(sps)
+        streams[1], sps[1] = streams[0], sps[0]
+        prof = [step(k, k * B * world + rank * B, True) for k in range(min(args.steps, 3))]
+        barrier()
+        streams[:], sps[:] = save_streams, save_sps
+        stage_evs, stage_outs, stage_steps = [p[0] for p in prof], [p[1] for p in prof], len(prof)
+    else:
+        stage_evs, stage_outs, stage_steps = evs, outs, args.steps
+    for e in stage_evs:
         stage_ms["digest"] += e[0].elapsed_time(e[1])
         stage_ms["dedup"] += e[1].elapsed_time(e[2])
         stage_ms["encode"] += e[2].elapsed_time(e[3])
+    stage_in = stage_steps * B * CHUNK
+    stage_out = sum(int(t.item()) for t, _ in stage_outs)
+    stage_new = sum(int(nw.item()) for _, nw in stage_outs)
     for tot, new in outs:
         totals["out"] += int(tot.item())
         totals["new"] += int(new.item())
@@ -438,19 +476,21 @@ def run_ours(args):
     peak = float(peaks.get("hbm_gbs", 6650.0))
     dom = max(stage_ms, key=stage_ms.get)
     local_in, local_out, local_new = totals["in"], totals["out"], totals["new"]
-    u_bytes = local_new * CHUNK
-    alg = {"digest": local_in, "dedup": totals["chunks"] * 48, "encode": u_bytes + local_out}[dom]
+    u_stage = stage_new * CHUNK
+    alg = {"digest": stage_in, "dedup": stage_steps * B * 48, "encode": u_stage + stage_out}[dom]
     ach = alg / (stage_ms[dom] * 1e-3) / 1e9 if stage_ms[dom] > 0 else 0.0
-    roof = {"bound": "hbm", "kernel": {"digest": "xxh3_128_kernel (K1)", "dedup": "dedup_insert_kernel (K2)", "encode": "zstd encode stages (K3)"}[dom],
+    roof = {"bound": "hbm", "kernel": {"digest": "xxh3_128_kernel (K1)", "dedup": "dedup_insert_kernel (K2)", "encode": "zstd encode stages (K3), lz_search_kernel ~88% of it"}[dom],
             "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
             # dram bytes/launch of the dominant kernel: 197 B per unique input byte measured by ncu --set full on lz_search_kernel
             # (profiles/r1_lz_search_v2_raw.csv: 122.4 GB read+write for 296 chunks); K1 reads its input once (ncu: 1.00x)
-            "traffic": int(197 * u_bytes / args.steps) if dom == "encode" else (alg // args.steps if dom == "digest" else None),
+            "traffic": int(197 * u_stage / stage_steps) if dom == "encode" else (alg // stage_steps if dom == "digest" else None),
             "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
-            "algorithmic_bytes_per_step": alg // args.steps,
-            "stage_ms_per_step": {k: v / args.steps for k, v in stage_ms.items()},
-            "stage_achieved_gbs": {"digest": local_in / (stage_ms["digest"] * 1e-3) / 1e9 if stage_ms["digest"] else None,
-                                   "encode": (u_bytes + local_out) / (stage_ms["encode"] * 1e-3) / 1e9 if stage_ms["encode"] else None}}
+            "algorithmic_bytes_per_step": alg // stage_steps,
+            "timing": ("per-launch CUDA-event durations from a %d-step single-stream pass after the timed region (the timed region itself "
+                       "overlaps consecutive steps on two streams)" % stage_steps) if overlapped else "CUDA events over the timed region",
+            "stage_ms_per_step": {k: v / stage_steps for k, v in stage_ms.items()},
+            "stage_achieved_gbs": {"digest": stage_in / (stage_ms["digest"] * 1e-3) / 1e9 if stage_ms["digest"] else None,
+                                   "encode": (u_stage + stage_out) / (stage_ms["encode"] * 1e-3) / 1e9 if stage_ms["encode"] else None}}
 
     # ---- CPU baseline: the oracle timed on this box's host cores on a bounded sample ----
     cpu = None
@@ -548,6 +588,7 @@ def run_ours(args):
             "config": {"workload": WORKLOADS[args.workload],
                        "corpus_gib_per_gpu": n_slots * CHUNK / GiB, "batch_chunks": B, "chunk_bytes": CHUNK,
                        "l2_policy": f"inputs larger than L2: each step reads a fresh {B * CHUNK / GiB:.0f} GiB batch",
+                       "streams": 1 if args.single_stream else 2,
                        "parallelism": f"dp{world} (chunks sharded by rank" + (", digest all-to-all over NCCL)" if world > 1 else ")")},
             "gpu_launches": int(launches1.value - launches0.value), "clocks": clk, "e2e": e2e, "roofline": roof, "cpu_baseline": cpu, "unpack": unpack,
             "ratio": {"compressed_over_unique": out_bytes / (n_new * CHUNK) if n_new else None, "unique_fraction": n_new * CHUNK / in_bytes}}
@@ -567,6 +608,7 @@ def main():
     ap.add_argument("--corpus-gib", type=int, default=64)
     ap.add_argument("--e2e-chunks", type=int, default=1024)
     ap.add_argument("--ref-chunks", type=int, default=0)
+    ap.add_argument("--single-stream", action="store_true", help="run every step on one stream (no overlap between consecutive steps)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

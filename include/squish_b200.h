@@ -164,7 +164,9 @@ size_t sq_encode_bound(size_t len);
  * packed back to back into d_out in ascending i; d_frame_off[i]/d_frame_len[i]
  * receive their placement (len 0 for unselected).  *d_total (device u64) = bytes used.
  * Fails with SQ_ERR_CAPACITY (reported at the next sync point via sq_encode_status)
- * if out_capacity is too small. */
+ * if out_capacity is too small.  Calls on two different streams use two independent
+ * scratch sets and may overlap on the device; a further stream takes over the least
+ * recently used set and is ordered behind that set's previous call. */
 int32_t sq_encode_device(sq_ctx *ctx, const void *d_data, const sq_span *d_spans,
                          const uint8_t *d_select, uint32_t n, void *d_out, uint64_t out_capacity,
                          uint64_t *d_frame_off, uint32_t *d_frame_len, uint64_t *d_total, void *stream);

@@ -49,6 +49,10 @@ struct sq_ctx {
     cudaEvent_t dedup_done[2];     // K1/K2 of consecutive batches stay ordered across the two slot streams
     int dedup_done_valid[2];
     int next_slot;
+    cudaStream_t enc_set_stream[2];  // which caller stream each encoder scratch set is bound to (sq_encode_device)
+    int enc_set_bound[2];
+    cudaEvent_t enc_set_done[2];     // recorded after each encode on the set; a new stream taking the set over waits on it
+    int enc_set_lru;
 };
 
 int32_t sq_set_error(sq_ctx *ctx, int32_t code, const char *fmt, ...);

@@ -230,6 +230,8 @@ void sq_enc_destroy(sq_ctx *ctx) {
         cudaFree(e->tab); cudaFree(e->head); cudaFree(e->lits); cudaFree(e->sbits);
         delete e;
         ctx->enc_sets[set] = nullptr;
+        if (ctx->enc_set_done[set]) cudaEventDestroy(ctx->enc_set_done[set]);
+        ctx->enc_set_done[set] = nullptr;
     }
 }
 
@@ -242,7 +244,16 @@ extern "C" int32_t sq_encode_device(sq_ctx *ctx, const void *d_data, const sq_sp
                                     void *d_out, uint64_t out_capacity, uint64_t *d_frame_off, uint32_t *d_frame_len, uint64_t *d_total,
                                     void *stream) {
     if (!ctx) return SQ_ERR_INVALID_ARG;
-    return sq_encode_device_set(ctx, 0, d_data, d_spans, d_select, n, d_out, out_capacity, d_frame_off, d_frame_len, d_total, sq_stream(ctx, stream));
+    // Calls issued on two different streams get two independent scratch sets and may run concurrently (the tail of one batch
+    // then overlaps the head of the next).  A further stream takes over the least recently used set; sq_encode_device_set orders
+    // it behind that set's previous work with an event.  The caller orders the K1/K2 calls of consecutive batches itself.
+    cudaStream_t st = sq_stream(ctx, stream);
+    int set = -1;
+    for (int i = 0; i < 2 && set < 0; i++) if (ctx->enc_set_bound[i] && ctx->enc_set_stream[i] == st) set = i;
+    for (int i = 0; i < 2 && set < 0; i++) if (!ctx->enc_set_bound[i]) set = i;
+    if (set < 0) set = ctx->enc_set_lru;
+    ctx->enc_set_lru = set ^ 1;
+    return sq_encode_device_set(ctx, set, d_data, d_spans, d_select, n, d_out, out_capacity, d_frame_off, d_frame_len, d_total, st);
 }
 
 // `set` selects one of two independent scratch sets, so two batches on two streams can be in the encoder at the same time
@@ -254,6 +265,11 @@ int32_t sq_encode_device_set(sq_ctx *ctx, int set, const void *d_data, const sq_
     int32_t rc = enc_scratch(ctx, n, set);
     if (rc) return rc;
     sq_enc_scratch *e = ctx->enc_sets[set];
+    if (!ctx->enc_set_done[set]) SQ_CUDA(ctx, cudaEventCreateWithFlags(&ctx->enc_set_done[set], cudaEventDisableTiming));
+    if (ctx->enc_set_bound[set] && ctx->enc_set_stream[set] != st)  // the set changes hands: wait for its previous user
+        SQ_CUDA(ctx, cudaStreamWaitEvent(st, ctx->enc_set_done[set], 0));
+    ctx->enc_set_bound[set] = 1;
+    ctx->enc_set_stream[set] = st;
     const uint32_t nb = n * SQ_MAX_BLOCKS;
     enc_plan_kernel<<<(nb + 255) / 256, 256, 0, st>>>(d_spans, d_select, n, e->blocks);
     SQ_CUDA(ctx, cudaMemsetAsync(e->status + 1, 0, 2 * sizeof(uint32_t), st));
@@ -272,6 +288,7 @@ int32_t sq_encode_device_set(sq_ctx *ctx, int set, const void *d_data, const sq_
                                                             (uint8_t *)d_out, e->status);
     SQ_LAUNCHED(ctx, 7);
     SQ_CUDA(ctx, cudaGetLastError());
+    SQ_CUDA(ctx, cudaEventRecord(ctx->enc_set_done[set], st));
     return SQ_OK;
 }
 

@@ -459,3 +459,37 @@ def test_ragged_sizes_every_class_roundtrip(sq, oracle):
     assert c.unpack_batch([f for _, f in frames], [len(s) for s, _ in frames]) == [s for s, _ in frames]
     ref = [oracle.compress(s, 12) for s, _ in frames]
     assert c.unpack_batch(ref, [2 * MiB] * len(ref)) == [s for s, _ in frames]
+
+
+def test_encode_device_on_several_streams(sq, oracle):
+    """sq_encode_device called on three streams of one context (two scratch sets; the third stream takes a set over and is
+    ordered behind its previous user): every batch's frames still decode to their own input with stock libzstd"""
+    import numpy as np
+    import torch
+    c = sq.Context()
+    lib = c.lib
+    n, size = 12, 300000
+    streams = [torch.cuda.Stream() for _ in range(3)]
+    jobs = []
+    for r in range(6):  # two rounds over the three streams, all in flight together
+        blobs = [gen(sq, (r + k) % 5, size, 7000 + r * 100 + k) for k in range(n)]
+        st = streams[r % 3]
+        with torch.cuda.stream(st):
+            data = torch.frombuffer(bytearray(b"".join(blobs)), dtype=torch.uint8).cuda()
+            spans = torch.tensor([[k * size, size] for k in range(n)], dtype=torch.int64).cuda()
+            cap = n * lib.sq_encode_bound(size)
+            out = torch.empty(cap, dtype=torch.uint8, device="cuda")
+            foff = torch.empty(n, dtype=torch.int64, device="cuda")
+            flen = torch.empty(n, dtype=torch.int32, device="cuda")
+            total = torch.zeros(1, dtype=torch.int64, device="cuda")
+            c.check(lib.sq_encode_device(c.h, data.data_ptr(), spans.data_ptr(), None, n, out.data_ptr(), cap, foff.data_ptr(),
+                                         flen.data_ptr(), total.data_ptr(), C.c_void_p(st.cuda_stream)))
+        jobs.append((blobs, data, spans, out, foff, flen, total))
+    torch.cuda.synchronize()
+    assert lib.sq_encode_status(c.h) == 0
+    for blobs, _, _, out, foff, flen, total in jobs:
+        o = out.cpu().numpy()
+        fo, fl = foff.cpu().tolist(), flen.cpu().tolist()
+        assert int(total.item()) == sum(fl)
+        for k, b in enumerate(blobs):
+            assert oracle.decompress(o[fo[k]:fo[k] + fl[k]].tobytes(), size) == b, k
