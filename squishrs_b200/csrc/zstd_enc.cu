@@ -312,8 +312,8 @@ extern "C" int32_t sq_encode_status(sq_ctx *ctx) {
 extern "C" int32_t sq_debug_lz_timers(unsigned long long *out6) {
 #ifdef SQ_LZ_TIMERS
     cudaDeviceSynchronize();
-    unsigned long long z[8] = {0};
-    if (cudaMemcpyFromSymbol(out6, lz::g_lz_timers, 6 * sizeof(unsigned long long)) != cudaSuccess) return SQ_ERR_CUDA;
+    unsigned long long z[12] = {0};
+    if (cudaMemcpyFromSymbol(out6, lz::g_lz_timers, 10 * sizeof(unsigned long long)) != cudaSuccess) return SQ_ERR_CUDA;
     cudaMemcpyToSymbol(lz::g_lz_timers, z, sizeof z);
     return SQ_OK;
 #else

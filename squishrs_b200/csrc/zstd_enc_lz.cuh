@@ -41,7 +41,7 @@ constexpr uint32_t SEQ_PER_BLOCK = Z_BLOCK_MAX / MIN_MATCH + 8, MAX_SEQ_PER_CHUN
 constexpr uint32_t REC_PER_CHUNK = 2048u * 1024u, MAX_SHIFT = 7;
 
 #ifdef SQ_LZ_TIMERS
-__device__ unsigned long long g_lz_timers[8];
+__device__ unsigned long long g_lz_timers[12];
 #endif
 
 struct BlockMeta {  // one per (chunk, block), written by lz_kernel, read by entropy_kernel
@@ -94,10 +94,10 @@ __device__ __forceinline__ int32_t lazy_score(uint32_t len, uint32_t off) { retu
 
 // Per-position parse record (4 bytes, HBM): what the parser does if its cursor stands on this position.
 //   0                      literal
-//   bits  0-20 offset      bits 21-26 length-1 (length <= SEARCH_CAP; SEARCH_CAP = "at least", extended by the chase)
+//   bits  0-20 offset      bits 21-25 verified length-1 (<= SEARCH_CAP)      bit 26 "may be longer": the chase extends it
 //   bits 27-28 backward extension available (<= 3)    bits 29-31 shift from the position to the match start (<= 7)
-__device__ __forceinline__ uint32_t pack_rec(uint32_t off, uint32_t len, uint32_t back, uint32_t shift) {
-    return off | (len - 1) << 21 | back << 27 | shift << 29;
+__device__ __forceinline__ uint32_t pack_rec(uint32_t off, uint32_t len, uint32_t extend, uint32_t back, uint32_t shift) {
+    return off | (len - 1) << 21 | extend << 26 | back << 27 | shift << 29;
 }
 
 // ---- kernel A: search + decide, fully parallel, one persistent CTA per chunk in flight ----------------
@@ -110,11 +110,11 @@ __global__ void __launch_bounds__(THREADS) lz_search_kernel(const uint8_t *__res
     __shared__ uint32_t s_off[RING];
     __shared__ uint8_t s_back[RING];
     __shared__ int16_t s_sc[RING];  // lazy score of the position's usable match, -1 = none
-    __shared__ uint32_t s_queue[(THREADS / 32) * 32 * ROW_K];  // per warp: compacted (position | candidate << 10) pairs
+    __shared__ __align__(16) uint32_t s_queue[(THREADS / 32) * 32 * ROW_K];  // per warp: compacted (position | candidate << 10) pairs
     __shared__ uint32_t s_best[TILE];                           // per position: (score+9) << 26 | (len-6) << 21 | off  (0 = none)
     __shared__ uint32_t s_chunk;
 #ifdef SQ_LZ_TIMERS
-    long long tm[6] = {0, 0, 0, 0, 0, 0}, tc = clock64();
+    long long tm[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, tc = clock64();
 #define LZ_TICK(i) do { long long now_ = clock64(); tm[i] += now_ - tc; tc = now_; } while (0)
 #else
 #define LZ_TICK(i)
@@ -212,6 +212,33 @@ __global__ void __launch_bounds__(THREADS) lz_search_kernel(const uint8_t *__res
                     }
                 }
                 s_best[li] = 0u;
+                LZ_TICK(6);
+                // ---- continuation filter ----
+                // A pair (p, c) whose left neighbour pair (p-1, c-1) is also a candidate pair continues a match that is verified at
+                // its first position; it is dropped here and its result arrives by inheritance below.  Membership is tested through a
+                // direct-mapped table of (lane, offset) keys that borrows the queue's memory; a key collision only loses a drop.
+                // Lanes 0 and 16 keep every pair, so a long match is re-verified every 16 positions and inheritance never runs dry.
+                {
+                    uint16_t *T = reinterpret_cast<uint16_t *>(queue);
+                    uint4 *Tz = reinterpret_cast<uint4 *>(queue);
+#pragma unroll
+                    for (int z = 0; z < 4; z++) Tz[lane + 32 * z] = make_uint4(0u, 0u, 0u, 0u);
+                    __syncwarp();
+#pragma unroll
+                    for (int q = 0; q < 16; q++)
+                        if (mask >> q & 1) { const uint32_t o = p - cand[q]; T[(o & 31u) * 32u + lane] = (uint16_t)((o >> 5) + 1u); }
+                    __syncwarp();
+                    if (lane & 15u) {
+#pragma unroll
+                        for (int q = 0; q < 16; q++)
+                            if (mask >> q & 1) {
+                                const uint32_t o = p - cand[q];
+                                if (T[(o & 31u) * 32u + lane - 1u] == (uint16_t)((o >> 5) + 1u)) mask &= ~(1u << q);
+                            }
+                    }
+                    __syncwarp();
+                }
+                LZ_TICK(7);
                 uint32_t total;
                 const uint32_t cnt = fast ? __popc(mask) : 0u;
                 uint32_t wpos = ent::warp_excl_scan(cnt, lane, &total);
@@ -221,6 +248,7 @@ __global__ void __launch_bounds__(THREADS) lz_search_kernel(const uint8_t *__res
                         if (mask >> q & 1) queue[wpos++] = li | cand[q] << 10;
                 }
                 __syncwarp();
+                LZ_TICK(8);
 #pragma unroll 1
                 for (uint32_t i = lane; i < total; i += 64) {
                     // two pairs per lane per trip: both candidates' first 8 bytes are requested before either is examined
@@ -253,6 +281,7 @@ __global__ void __launch_bounds__(THREADS) lz_search_kernel(const uint8_t *__res
                     }
                 }
                 __syncwarp();
+                LZ_TICK(9);
                 uint32_t blen = 0, boff = 0, bback = 0;
                 if (searchable && !fast) {  // last bytes of the chunk: careful scalar path
                     const uint32_t maxlen = min(n - p, SEARCH_CAP);
@@ -273,6 +302,27 @@ __global__ void __launch_bounds__(THREADS) lz_search_kernel(const uint8_t *__res
                     const uint32_t best = s_best[li];
                     if (best) { blen = ((best >> 21) & 31u) + MIN_MATCH; boff = best & 0x1FFFFFu; }
                 }
+                // ---- inheritance: a match (off, len) at lane j is a match (off, len - d) at lane j + d.  Candidates are ranked by
+                // 2 * end - log2(off), which does not depend on the position, so one max-scan over the warp serves every lane.
+                uint32_t known = blen;  // verified bytes; a capped match may be longer (the chase extends it from `known`)
+                {
+                    const uint32_t own = blen ? (lane + blen) << 22 | (blen >= SEARCH_CAP ? 1u : 0u) << 21 | boff : 0u;
+                    uint32_t v = own;
+                    int32_t e = blen ? (int32_t)(2 * (lane + blen)) - (int32_t)zc::highbit(boff + 3) : -1000;
+#pragma unroll
+                    for (uint32_t d = 1; d < 32; d <<= 1) {
+                        const uint32_t u = __shfl_up_sync(0xffffffffu, v, d);
+                        const int32_t eu = __shfl_up_sync(0xffffffffu, e, d);
+                        if (lane >= d && eu > e) { v = u; e = eu; }
+                    }
+                    if (v != own) {
+                        const uint32_t end = v >> 22;
+                        if (end >= lane + MIN_MATCH && searchable) {
+                            known = end - lane; boff = v & 0x1FFFFFu;
+                            blen = (v >> 21 & 1u) ? SEARCH_CAP : known;
+                        }
+                    }
+                }
                 if (blen) {
                     const uint32_t c = p - boff;
                     if (c >= 4 && p + 8 <= n) {  // one unaligned load each side: bytes [x-4, x)
@@ -287,12 +337,13 @@ __global__ void __launch_bounds__(THREADS) lz_search_kernel(const uint8_t *__res
                 if (p < t1) {
                     // what the parser may take here: clamp to the block end, apply the acceptance rule, keep the lazy score
                     if (p + blen > be) blen = be - p;
+                    if (p + known > be) known = be - p;
                     int32_t lsc = -1;
-                    if (blen >= MIN_MATCH) { lsc = lazy_score(blen, boff); if (lsc < ACCEPT_THR) lsc = -1; }
+                    if (known >= MIN_MATCH) { lsc = lazy_score(blen, boff); if (lsc < ACCEPT_THR) lsc = -1; }
                     s_sc[p - t0 + HALO] = (int16_t)lsc;
                     s_len[p - t0 + HALO] = (uint8_t)(lsc >= 0 ? blen : 0u);
                     s_off[p - t0 + HALO] = boff;
-                    s_back[p - t0 + HALO] = (uint8_t)bback;
+                    s_back[p - t0 + HALO] = (uint8_t)(bback | known << 2);
                 }
             }
             __syncthreads();
@@ -314,7 +365,8 @@ __global__ void __launch_bounds__(THREADS) lz_search_kernel(const uint8_t *__res
                         if (s2 > sc + 7) { sc = s2; start += 2; continue; }
                         break;
                     }
-                    r = pack_rec(s_off[start - t0 + HALO], s_len[start - t0 + HALO], s_back[start - t0 + HALO], start - p);
+                    const uint32_t kb = s_back[start - t0 + HALO];
+                    r = pack_rec(s_off[start - t0 + HALO], kb >> 2, s_len[start - t0 + HALO] >= TARGET_LEN, kb & 3u, start - p);
                 }
                 rec[p] = r;
             }
@@ -323,7 +375,7 @@ __global__ void __launch_bounds__(THREADS) lz_search_kernel(const uint8_t *__res
         }
     }
 #ifdef SQ_LZ_TIMERS
-    if (tid == 0) for (int i = 0; i < 6; i++) atomicAdd(&g_lz_timers[i], (unsigned long long)tm[i]);
+    if (tid == 0) for (int i = 0; i < 10; i++) atomicAdd(&g_lz_timers[i], (unsigned long long)tm[i]);
 #endif
 }
 
@@ -381,8 +433,8 @@ __global__ void __launch_bounds__(128) lz_chase_kernel(const uint8_t *__restrict
             const uint32_t idx = __ffs((int)live) - 1;  // next non-literal record at or after the cursor
             const uint32_t r = __shfl_sync(0xffffffffu, mine, idx);
             p = base + idx;
-            uint32_t off = r & 0x1FFFFFu, len = ((r >> 21) & 63u) + 1, back = (r >> 27) & 3u, start = p + (r >> 29);
-            if (len >= SEARCH_CAP && start + len < be) len += warp_extend(in, start + len, start + len - off, be - start - len, lane);
+            uint32_t off = r & 0x1FFFFFu, len = ((r >> 21) & 31u) + 1, back = (r >> 27) & 3u, start = p + (r >> 29);
+            if ((r >> 26 & 1u) && start + len < be) len += warp_extend(in, start + len, start + len - off, be - start - len, lane);
             if (back > start - anchor) back = start - anchor;
             start -= back; len += back;
             const uint32_t ll = start - anchor;

@@ -52,10 +52,15 @@ struct Match { uint32_t len, off; };
 struct Model {
     const uint8_t *s; uint32_t n; Params P;
     std::vector<Match> best, alt;
-    std::vector<uint8_t> back;
+    std::vector<uint8_t> back, capflag;
+    std::vector<uint32_t> srcpos, known;
     uint64_t nskip = 0, nsearch = 0, nverify = 0, ncheap = 0;
     void search() {
-        best.assign(n, {0, 0}); alt.assign(n, {0, 0}); back.assign(n, 0);
+        best.assign(n, {0, 0}); alt.assign(n, {0, 0}); back.assign(n, 0); capflag.assign(n, 0); srcpos.assign(n, 0); known.assign(n, 0);
+        static const bool cont = getenv("ENC_CONT") != nullptr;
+        static const uint32_t cont_fresh = getenv("ENC_CONT_FRESH") ? (uint32_t)atoi(getenv("ENC_CONT_FRESH")) : 16;
+        std::vector<uint32_t> prevc, curc;
+        int run_e = -1000; uint32_t run_end = 0, run_off = 0, run_src = 0; bool run_cap = false;
         const uint32_t rows = 1u << P.hash_log, K = (uint32_t)P.row_entries;
         std::vector<uint32_t> tab((size_t)rows * K, 0), head(rows, 0);
         const uint32_t T = (uint32_t)P.tile;
@@ -74,6 +79,13 @@ struct Model {
                     if ((round == 0) != anchor_pos) continue;
                     if (!anchor_pos) {
                         uint32_t q = p - (p % P.skip_stride);
+                        static const bool skipcap = getenv("ENC_SKIPCAP") != nullptr;
+                        if (skipcap) {  // anchor's match is capped: verify only the inherited candidate (one pair) instead of the row
+                            if (q >= t0 && best[q].len >= (uint32_t)P.target_len) {
+                                uint32_t l = match_len(s, p, p - best[q].off, n); if (l > (uint32_t)P.target_len) l = P.target_len;
+                                best[p] = {l, best[q].off}; nskip++; nverify++; continue;
+                            }
+                        } else
                         if (q >= t0 && best[q].len >= (p - q) + (uint32_t)P.skip_min) { best[p] = {best[q].len - (p - q), best[q].off}; nskip++; continue; }
                     }
                 } else if (round && P.precheck != 2) continue;
@@ -98,21 +110,43 @@ struct Model {
                     uint32_t q = p & ~3u;
                     if (best[q].len >= (p - q) + 8) b = {best[q].len - (p - q), best[q].off};
                 }
+                if (cont) { prevc.swap(curc); curc.clear(); if (p == t0) prevc.clear(); }
                 for (uint32_t k = 0; k < K; k++) {
                     uint32_t e = tab[(size_t)h * K + k];
                     if (!e || e - 1 >= p) continue;
                     uint32_t c = e - 1;
-                    if (rd32(s + c) != rd32(s + p)) continue;
+                    if (rd32(s + c) != rd32(s + p) || (cont && (rd64(s + c) ^ rd64(s + p)) << 16)) continue;
+                    if (cont) {
+                        curc.push_back(c);
+                        static const int cont_mode = getenv("ENC_CONT_MODE") ? atoi(getenv("ENC_CONT_MODE")) : 0;
+                        bool is_cont = c > 0 && std::find(prevc.begin(), prevc.end(), c - 1) != prevc.end();
+                        if (cont_mode == 1) is_cont = is_cont && p > 0 && best[p - 1].len && best[p - 1].off == p - c;  // only the represented chain is dropped
+                        if (((p - t0) % cont_fresh) != 0 && is_cont) { ncheap++; continue; }
+                    }
                     if (P.precheck && b.len >= 16 && p + b.len <= n && rd64(s + c + b.len - 8) != rd64(s + p + b.len - 8)) { ncheap++; continue; }
                     uint32_t l = match_len(s, p, c, n);
                     if (exttop && l > 8) { bool keep = false; for (int i = 0; i < nnear; i++) keep |= near_off[i] == p - c; if (!keep) l = 8; }
                     if (l > (uint32_t)P.target_len && getenv("ENC_CAPLEN")) l = P.target_len;
                     nverify++;
+                    if (p > 0 && c > 0 && s[p - 1] == s[c - 1]) ncheap++;  // continuation of a match that started earlier
                     uint32_t off = p - c;
                     if (P.sel_mul == 0) { if (l > b.len || (l == b.len && off < b.off)) b = {l, off}; }
                     else if (b.len == 0 || (int)l * P.sel_mul - (int)highbit(off + 3) > (int)b.len * P.sel_mul - (int)highbit(b.off + 3)) b = {l, off};
                 }
                 if (b.len < (uint32_t)P.min_match) b = {0, 0};
+                if (cont) {  // mirrors lz_search_kernel: max-scan of (2*end - log2(off)) over the 32-position group, expired winner -> own
+                    srcpos[p] = p;
+                    if (((p - t0) % 32) == 0) run_e = -1000;
+                    const bool own_cap = b.len >= (uint32_t)P.target_len;
+                    const int eo = b.len ? 2 * (int)(p + b.len) - (int)highbit(b.off + 3) : -1000;
+                    const Match own = b;
+                    known[p] = b.len; capflag[p] = own_cap;
+                    if (run_e > eo && run_end >= p + (uint32_t)P.min_match) {
+                        known[p] = run_end - p; capflag[p] = run_cap; srcpos[p] = run_src;
+                        b = {run_cap ? (uint32_t)P.target_len : run_end - p, run_off};
+                    }
+                    if (own.len && eo >= run_e) { run_e = eo; run_end = p + own.len; run_off = own.off; run_cap = own_cap; run_src = p; }
+                }
                 best[p] = b;
             }
         }
@@ -146,7 +180,8 @@ struct Model {
         }
         // backward extension of each best match (bounded), and neighbour-offset alternates
         for (uint32_t p = 0; p < n; p++) {
-            if (best[p].len) {
+            if (best[p].len && cont && !getenv("ENC_CONT_TRUEBACK")) back[p] = (uint8_t)std::min<uint32_t>(3, p - srcpos[p]);
+            else if (best[p].len) {
                 uint32_t o = best[p].off, k = 0;
                 while (k < (uint32_t)(getenv("ENC_BACK") ? atoi(getenv("ENC_BACK")) : 15) && p > k && p - k > o && s[p - k - 1] == s[p - k - 1 - o]) k++;
                 back[p] = (uint8_t)k;
@@ -220,6 +255,8 @@ extern "C" long enc_model_frame(const uint8_t *src, uint32_t n, uint8_t *dst, ui
     EncWork *wk = new EncWork;
     uint32_t total_seq = 0, total_lit = 0, rep_seq = 0, of_bits = 0, ml_sum = 0;
     uint32_t nblocks = n ? (n + Z_BLOCK_MAX - 1) / Z_BLOCK_MAX : 1;
+    const uint32_t win_w = getenv("ENC_WINDOW") ? (uint32_t)atoi(getenv("ENC_WINDOW")) : 0;  // sequential-parser study: steps of W positions
+    uint32_t win_lo = ~0u - 64, win_steps = 0;
     for (uint32_t b = 0; b < nblocks; b++) {
         const uint32_t bs = b * Z_BLOCK_MAX, be = std::min(n, bs + Z_BLOCK_MAX);
         seqs.clear(); lits.clear();
@@ -229,6 +266,7 @@ extern "C" long enc_model_frame(const uint8_t *src, uint32_t n, uint8_t *dst, ui
         auto pick = [&](uint32_t q, uint32_t anchor_) -> Cand {
             Cand c = {0, 0, 0, -1000000};
             if (q >= be) return c;
+            if (win_w && !(q >= win_lo && q < win_lo + win_w)) { win_lo = q; win_steps++; }
             const bool ll0 = (q == anchor_);
             auto consider = [&](uint32_t len, uint32_t off) {
                 if (!len || off > q) return;
@@ -267,7 +305,8 @@ extern "C" long enc_model_frame(const uint8_t *src, uint32_t n, uint8_t *dst, ui
                     if (getenv("ENC_MAXSHIFT") && start - p + 2 > (uint32_t)atoi(getenv("ENC_MAXSHIFT"))) break;
                 }
             }
-            if (getenv("ENC_CAPLEN") && cur.len + 3 >= (uint32_t)P.target_len) { uint32_t full = match_len(src, start, start - cur.off, n); if (start + full > be) full = be - start; if (full > cur.len) cur.len = full; }
+            if (getenv("ENC_CONT") && cur.off_base > 3 && M.best[start].off == cur.off && M.capflag[start]) { uint32_t full = match_len(src, start, start - cur.off, n); if (start + full > be) full = be - start; cur.len = full; }
+            else if (getenv("ENC_CAPLEN") && cur.len + 3 >= (uint32_t)P.target_len) { uint32_t full = match_len(src, start, start - cur.off, n); if (start + full > be) full = be - start; if (full > cur.len) cur.len = full; }
             // backward extension (only for non-rep matches found by the search; bounded by literal run)
             if (cur.off_base > 3 && M.best[start].off == cur.off && M.best[start].len) {
                 uint32_t k = std::min<uint32_t>(M.back[start], start - anchor);
@@ -306,7 +345,7 @@ extern "C" long enc_model_frame(const uint8_t *src, uint32_t n, uint8_t *dst, ui
         }
     }
     delete wk;
-    if (stats) { stats[0] = total_seq; stats[1] = total_lit; stats[2] = rep_seq; stats[3] = of_bits; stats[4] = ml_sum; stats[5] = (uint32_t)M.nsearch; stats[6] = (uint32_t)M.nskip; stats[7] = (uint32_t)(M.nverify >> 4); }
+    if (stats) { stats[0] = total_seq; stats[1] = total_lit; stats[2] = rep_seq; stats[3] = of_bits; stats[4] = ml_sum; stats[5] = win_w ? win_steps : (uint32_t)M.nsearch; stats[6] = getenv("ENC_COUNTCONT") ? (uint32_t)(M.ncheap >> 4) : (uint32_t)M.nskip; stats[7] = (uint32_t)(M.nverify >> 4); }
     return o - dst;
 }
 

@@ -9,7 +9,7 @@ import squishrs_b200 as sq
 class Params(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("hash_log", "row_entries", "min_match", "lazy_depth", "rep_mode", "tile", "target_len", "alt_window", "sel_mul", "accept_thr", "skip_stride", "skip_min", "precheck")]
 
-M = C.CDLL(str(ROOT / "tests/harness/libencmodel.so"))
+M = C.CDLL(str(ROOT / "tests/harness/libenc_model.so"))
 M.enc_model_frame.restype = C.c_long
 M.enc_model_frame.argtypes = [C.c_char_p, C.c_uint32, C.c_char_p, C.c_uint32, C.POINTER(Params), C.POINTER(C.c_uint32)]
 O = Oracle(); lib = sq.load()
@@ -33,7 +33,7 @@ def run(P, data):
     assert n > 0
     back = O.decompress(dst.raw[:n], len(data))
     assert back == data, "stock libzstd could not decode the model's frame"
-    return n, st[0], st[1], st[2], dt, st[3], st[7] * 16 / max(len(data), 1)
+    return n, st[0], st[1], st[2], dt, (st[5], st[6] * 16 / max(len(data), 1)), st[7] * 16 / max(len(data), 1)
 
 if __name__ == "__main__":
     S = samples()
@@ -49,8 +49,9 @@ if __name__ == "__main__":
     print(f"{'config':34s}" + "".join(f"{k:>11s}" for k in S) + "    total")
     print(f"{'libzstd L12 ratio':34s}" + "".join(f"{ref[k] / len(S[k]):11.4f}" for k in S))
     for name, P in configs.items():
-        row = []; tot = 0; tref = 0; ver = []
+        row = []; tot = 0; tref = 0; ver = []; info = []
         for k, v in S.items():
-            n, ns, nl, nr, dt, _, vpb = run(P, v)
-            row.append(n / ref[k]); tot += n; tref += ref[k]; ver.append(vpb)
+            n, ns, nl, nr, dt, steps, vpb = run(P, v)
+            row.append(n / ref[k]); tot += n; tref += ref[k]; ver.append(vpb); info.append(f"{k}: seq {ns} lit {nl} steps {steps}")
         print(f"{name:34s}" + "".join(f"{(x - 1) * 100:+10.1f}%" for x in row) + f"  {(tot / tref - 1) * 100:+6.1f}%" + "  verif/byte " + " ".join(f"{x:.1f}" for x in ver))
+        if os.environ.get("ENC_WINDOW"): print("    " + " | ".join(info))

@@ -15,7 +15,7 @@ sp = np.zeros((n, 2), dtype=np.uint64); sp[:, 0] = np.arange(n) * CHUNK; sp[:, 1
 d_sp = torch.from_numpy(sp.view(np.int64)).cuda()
 cap = n * int(lib.sq_encode_bound(CHUNK)); out = torch.empty(cap, dtype=torch.uint8, device="cuda")
 res = torch.empty(n * 32, dtype=torch.uint8, device="cuda"); used = C.c_uint64()
-tm = (C.c_ulonglong * 6)()
+tm = (C.c_ulonglong * 10)()
 for rep in range(2):
     ctx.dedup_reset(); lib.sq_debug_lz_timers(tm)
     torch.cuda.synchronize(); t = time.time()
@@ -23,5 +23,5 @@ for rep in range(2):
     dt = time.time() - t
 print(f"pack {n} chunks: {dt*1e3:.1f} ms  {n*CHUNK/dt/1e9:.2f} GB/s  out {used.value/1e6:.1f} MB")
 if lib.sq_debug_lz_timers(tm) == 0:
-    tot = sum(tm); names = ["stage", "insert", "search", "decide", "chase", "fetch"]
+    tot = sum(tm); names = ["stage", "insert", "search-tail", "decide", "-", "fetch", "s-rowfilter", "s-contfilter", "s-compact", "s-verify"]
     print("  ".join(f"{nm} {v/tot*100:.1f}%" for nm, v in zip(names, tm)))
