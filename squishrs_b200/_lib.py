@@ -4,10 +4,12 @@ no Python or CPU fallback for any entry point."""
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 _HERE = Path(__file__).resolve().parent
-LIB_PATH = _HERE / "libsquish_b200.so"
+# SQ_B200_LIB points the loader at another build of the same library (A/B runs of kernel variants)
+LIB_PATH = Path(os.environ["SQ_B200_LIB"]) if os.environ.get("SQ_B200_LIB") else _HERE / "libsquish_b200.so"
 
 CHUNK_SIZE = 2048 * 1024
 DIGEST_BYTES = 16

@@ -101,18 +101,39 @@ __device__ __forceinline__ uint32_t pack_rec(uint32_t off, uint32_t len, uint32_
 }
 
 // ---- kernel A: search + decide, fully parallel, one persistent CTA per chunk in flight ----------------
-__global__ void __launch_bounds__(THREADS) lz_search_kernel(const uint8_t *__restrict__ data, const sq_span *__restrict__ spans,
+// Tile pipeline (two barriers per tile):
+//   reserve   ring slots for the NEXT tile's positions are taken now (atomicAdd on the row heads), so the round trip
+//             of the atomics hides behind this tile's search; the entries themselves are stored after the search,
+//             so the search sees exactly the table "everything up to and including this tile"
+//   prefetch  the bytes of the tile after next travel through registers into the free half of the double-buffered stage
+//   search    warps take groups of 32 positions from a shared counter (balances the warps of a CTA)
+//   publish   store the next tile's entries                                                   | barrier
+//   decide    lazy choice per position; warp 0 also slides the result window's halo             | barrier
+constexpr uint32_t SIN = TILE + LOOKAHEAD + 24, SIN_WORDS = SIN / 4;  // staged bytes per tile (multiple of 16)
+static_assert(SIN % 16 == 0 && SIN_WORDS <= 2 * THREADS && SIN >= TILE + SEARCH_CAP + 8, "stage buffer shape");
+
+__device__ __forceinline__ uint32_t stage_word(const uint8_t *__restrict__ in, uint32_t g, uint32_t n, bool aligned) {
+    if (g + 4 <= n && aligned) return __ldg(reinterpret_cast<const uint32_t *>(in + g));
+    uint32_t w = 0;
+    for (uint32_t k = 0; k < 4; k++) if (g + k < n) w |= (uint32_t)in[g + k] << (8 * k);
+    return w;
+}
+
+#ifndef SQ_LZ_MINB
+#define SQ_LZ_MINB 3  // resident CTAs per SM the register budget is held to
+#endif
+__global__ void __launch_bounds__(THREADS, SQ_LZ_MINB) lz_search_kernel(const uint8_t *__restrict__ data, const sq_span *__restrict__ spans,
                                                              const uint8_t *__restrict__ select, uint32_t n_chunks,
                                                              uint32_t *__restrict__ tab_all, uint32_t *__restrict__ head_all,
                                                              uint32_t *__restrict__ rec_all, uint32_t *__restrict__ counter) {
-    __shared__ __align__(16) uint8_t s_in[TILE + LOOKAHEAD + 16];
+    __shared__ __align__(16) uint8_t s_in2[2][SIN];
     __shared__ uint8_t s_len[RING];
     __shared__ uint32_t s_off[RING];
     __shared__ uint8_t s_back[RING];
     __shared__ int16_t s_sc[RING];  // lazy score of the position's usable match, -1 = none
     __shared__ __align__(16) uint32_t s_queue[(THREADS / 32) * 32 * ROW_K];  // per warp: compacted (position | candidate << 10) pairs
     __shared__ uint32_t s_best[TILE];                           // per position: (score+9) << 26 | (len-6) << 21 | off  (0 = none)
-    __shared__ uint32_t s_chunk;
+    __shared__ uint32_t s_chunk, s_gctr;
 #ifdef SQ_LZ_TIMERS
     long long tm[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, tc = clock64();
 #define LZ_TICK(i) do { long long now_ = clock64(); tm[i] += now_ - tc; tc = now_; } while (0)
@@ -121,7 +142,9 @@ __global__ void __launch_bounds__(THREADS) lz_search_kernel(const uint8_t *__res
 #endif
     uint32_t *tab = tab_all + (size_t)blockIdx.x * ROWS * ROW_K;
     uint32_t *head = head_all + (size_t)blockIdx.x * ROWS;
-    const uint32_t tid = threadIdx.x;
+    const uint32_t tid = threadIdx.x, wq = tid >> 5, lane = tid & 31;
+    uint32_t *queue = s_queue + wq * (32 * ROW_K);
+    constexpr uint32_t GROUPS = TILE / 32, TAG_MASK = (1u << TAG_BITS) - 1;
 
     for (;;) {
         __syncthreads();
@@ -129,6 +152,7 @@ __global__ void __launch_bounds__(THREADS) lz_search_kernel(const uint8_t *__res
             uint32_t c;
             do { c = atomicAdd(counter, 1u); } while (c < n_chunks && select && !select[c]);
             s_chunk = c;
+            s_gctr = THREADS / 32;
         }
         __syncthreads();
         const uint32_t chunk = s_chunk;
@@ -139,6 +163,21 @@ __global__ void __launch_bounds__(THREADS) lz_search_kernel(const uint8_t *__res
         uint32_t *rec = rec_all + (size_t)chunk * REC_PER_CHUNK;
         const bool aligned = (reinterpret_cast<uintptr_t>(in) & 7) == 0;
         for (uint32_t i = tid; i < RING; i += THREADS) { s_len[i] = 0; s_sc[i] = -1; }
+        // prologue: stage tiles 0 and 1, insert tile 0
+        for (uint32_t i = tid; i < 2 * SIN_WORDS; i += THREADS) {
+            const uint32_t b = i >= SIN_WORDS ? 1u : 0u, w = i - b * SIN_WORDS;
+            reinterpret_cast<uint32_t *>(s_in2[b])[w] = stage_word(in, b * TILE + w * 4, n, aligned);
+        }
+        __syncthreads();
+#pragma unroll
+        for (uint32_t k = 0; k < PER_THREAD; k++) {
+            const uint32_t li = tid + k * THREADS;
+            if (li + 8 <= n) {
+                const uint32_t hv = hash5(smem_u64(s_in2[0], li)), row = hv >> TAG_BITS;
+                const uint32_t slot = atomicAdd(&head[row], 1u) & (ROW_K - 1);
+                __stcg(&tab[row * ROW_K + slot], (li + 1) | (hv & TAG_MASK) << 22);
+            }
+        }
         __syncthreads();
 
         const uint32_t n_tiles = (n + TILE - 1) / TILE;
@@ -146,69 +185,66 @@ __global__ void __launch_bounds__(THREADS) lz_search_kernel(const uint8_t *__res
             const uint32_t t0 = t * TILE, t1 = min(n, t0 + TILE);
             const uint32_t be = min(n, (t0 / Z_BLOCK_MAX + 1) * Z_BLOCK_MAX);  // end of the block this tile lies in
             const bool last_tile_of_block = (t1 == be);
-            // ---- stage ----
-            for (uint32_t i = tid * 4; i < TILE + LOOKAHEAD + 16; i += THREADS * 4) {
-                uint32_t w = 0;
-                const uint32_t g = t0 + i;
-                if (g + 4 <= n && aligned) w = __ldg(reinterpret_cast<const uint32_t *>(in + g));
-                else for (uint32_t k = 0; k < 4; k++) if (g + k < n) w |= (uint32_t)in[g + k] << (8 * k);
-                *reinterpret_cast<uint32_t *>(&s_in[i]) = w;
-            }
-            if (tid < HALO) {  // slide the result window: the previous tile's last HALO positions stay addressable for the deferred decisions
-                s_len[tid] = s_len[TILE + tid]; s_off[tid] = s_off[TILE + tid]; s_back[tid] = s_back[TILE + tid]; s_sc[tid] = s_sc[TILE + tid];
-            }
-            __syncthreads();
-            LZ_TICK(0);
-            // ---- insert ----
+            const uint8_t *s_in = s_in2[t & 1];
+            const uint8_t *s_nx = s_in2[(t + 1) & 1];
+            // ---- reserve: ring slots for the next tile's positions (results are consumed after the search) ----
+            uint32_t slot_raw[PER_THREAD];
 #pragma unroll
             for (uint32_t k = 0; k < PER_THREAD; k++) {
-                const uint32_t li = tid + k * THREADS, p = t0 + li;
-                const uint32_t hv = hash5(smem_u64(s_in, li));
-                if (p + 8 <= n) {
-                    const uint32_t row = hv >> TAG_BITS;
-                    const uint32_t slot = atomicAdd(&head[row], 1u) & (ROW_K - 1);
-                    __stcg(&tab[row * ROW_K + slot], (p + 1) | (hv & ((1u << TAG_BITS) - 1)) << 22);
+                const uint32_t li = tid + k * THREADS, p = t0 + TILE + li;
+                slot_raw[k] = 0;
+                if (p + 8 <= n) slot_raw[k] = atomicAdd(&head[hash5(smem_u64(s_nx, li)) >> TAG_BITS], 1u);
+            }
+            // ---- prefetch: bytes of tile t+2 (stored into this tile's stage buffer once the search is done) ----
+            uint32_t sw0 = 0, sw1 = 0;
+            {
+                const uint32_t g2 = t0 + 2 * TILE;
+                if (g2 < n) {
+                    sw0 = stage_word(in, g2 + tid * 4, n, aligned);
+                    if (tid < SIN_WORDS - THREADS) sw1 = stage_word(in, g2 + (THREADS + tid) * 4, n, aligned);
                 }
             }
-            __syncthreads();
-            LZ_TICK(1);
+            LZ_TICK(0);
             // ---- search ----
             // Each warp takes 32 consecutive positions at a time.  Lanes first filter their own row by tag (no data access),
             // the warp compacts the surviving (position, candidate) pairs into a dense queue, and the lanes then verify
             // pairs -- not row slots -- so no issue slot is spent on empty slots.  The best candidate per position is kept
             // with a 32-bit atomicMax on (score, length, offset) in shared memory.
-            // rows are software-pipelined: the row of the NEXT group of 32 positions is requested before this group's pairs are verified
+            // rows are software-pipelined: the row of the warp's NEXT group is requested before this group's pairs are verified
+            uint32_t g = wq, gn = 0;
+            if (lane == 0) gn = atomicAdd(&s_gctr, 1u);
+            gn = __shfl_sync(0xffffffffu, gn, 0);
             uint4 nea, neb, nec, ned;
             {
-                const uint32_t hv0 = hash5(smem_u64(s_in, tid));
+                const uint32_t hv0 = hash5(smem_u64(s_in, g * 32 + lane));
                 const uint4 *r0 = reinterpret_cast<const uint4 *>(tab + (hv0 >> TAG_BITS) * ROW_K);
                 nea = __ldcg(r0); neb = __ldcg(r0 + 1); nec = __ldcg(r0 + 2); ned = __ldcg(r0 + 3);
             }
 #pragma unroll 1
-            for (uint32_t k = 0; k < PER_THREAD; k++) {
-                const uint32_t li = tid + k * THREADS, p = t0 + li;
-                const uint32_t wq = tid >> 5, lane = tid & 31;
-                uint32_t *queue = s_queue + wq * (32 * ROW_K);
-                uint32_t mask = 0, cand[ROW_K];
+            while (g < GROUPS) {
+                const uint32_t li = g * 32 + lane, p = t0 + li;
+                uint32_t mask = 0, off[ROW_K];  // off[q] = p - candidate, 0 = not a candidate
                 const bool searchable = p + 8 <= n;
                 const bool fast = p + SEARCH_CAP + 16 <= n;  // every comparison stays inside the chunk and the staged window
-                uint32_t tag = 0;
                 {
                     const uint32_t hv = hash5(smem_u64(s_in, li));
-                    tag = hv & ((1u << TAG_BITS) - 1);
+                    const uint32_t tagsh = (hv & TAG_MASK) << 22;
                     static_assert(ROW_K == 16, "the search reads one 16-entry row");
                     const uint32_t e[16] = {nea.x, nea.y, nea.z, nea.w, neb.x, neb.y, neb.z, neb.w, nec.x, nec.y, nec.z, nec.w, ned.x, ned.y, ned.z, ned.w};
-                    if (k + 1 < PER_THREAD) {  // prefetch the next group's row (table rows exist for any hash value)
-                        const uint32_t hvn = hash5(smem_u64(s_in, li + THREADS));
+                    if (gn < GROUPS) {  // prefetch the next group's row (table rows exist for any hash value)
+                        const uint32_t hvn = hash5(smem_u64(s_in, gn * 32 + lane));
                         const uint4 *rn = reinterpret_cast<const uint4 *>(tab + (hvn >> TAG_BITS) * ROW_K);
                         nea = __ldcg(rn); neb = __ldcg(rn + 1); nec = __ldcg(rn + 2); ned = __ldcg(rn + 3);
                     }
-                    if (searchable) {
+                    // entry = (candidate + 1) | tag << 22: after xor with the tag the value is candidate + 1 iff the tags agree
+                    // (anything else is 0 or >= 2^22), so one unsigned compare checks tag, emptiness and candidate < p at once
+                    const uint32_t plim = searchable ? p : 0u;
 #pragma unroll
-                        for (int q = 0; q < 16; q++) {
-                            cand[q] = (e[q] & 0x3FFFFFu) - 1u;
-                            if ((e[q] >> 22) == tag && cand[q] < p) mask |= 1u << q;
-                        }
+                    for (int q = 0; q < 16; q++) {
+                        const uint32_t om1 = p - (e[q] ^ tagsh);
+                        const bool v = om1 < plim;
+                        off[q] = v ? om1 + 1u : 0u;
+                        mask |= (v ? 1u : 0u) << q;
                     }
                 }
                 s_best[li] = 0u;
@@ -218,6 +254,7 @@ __global__ void __launch_bounds__(THREADS) lz_search_kernel(const uint8_t *__res
                 // its first position; it is dropped here and its result arrives by inheritance below.  Membership is tested through a
                 // direct-mapped table of (lane, offset) keys that borrows the queue's memory; a key collision only loses a drop.
                 // Lanes 0 and 16 keep every pair, so a long match is re-verified every 16 positions and inheritance never runs dry.
+                // Both passes are branch-free (predicated stores, then sixteen independent loads) so the loads overlap.
                 {
                     uint16_t *T = reinterpret_cast<uint16_t *>(queue);
                     uint4 *Tz = reinterpret_cast<uint4 *>(queue);
@@ -226,16 +263,16 @@ __global__ void __launch_bounds__(THREADS) lz_search_kernel(const uint8_t *__res
                     __syncwarp();
 #pragma unroll
                     for (int q = 0; q < 16; q++)
-                        if (mask >> q & 1) { const uint32_t o = p - cand[q]; T[(o & 31u) * 32u + lane] = (uint16_t)((o >> 5) + 1u); }
+                        if (off[q]) T[(off[q] & 31u) * 32u + lane] = (uint16_t)((off[q] >> 5) + 1u);
                     __syncwarp();
-                    if (lane & 15u) {
+                    const uint16_t *Tl = T + ((lane & 15u) ? lane - 1u : lane);
+                    uint32_t hit = 0;
 #pragma unroll
-                        for (int q = 0; q < 16; q++)
-                            if (mask >> q & 1) {
-                                const uint32_t o = p - cand[q];
-                                if (T[(o & 31u) * 32u + lane - 1u] == (uint16_t)((o >> 5) + 1u)) mask &= ~(1u << q);
-                            }
+                    for (int q = 0; q < 16; q++) {
+                        const uint32_t o = off[q];
+                        hit |= (Tl[(o & 31u) * 32u] == (uint16_t)((o >> 5) + 1u) ? 1u : 0u) << q;
                     }
+                    if (lane & 15u) mask &= ~hit;
                     __syncwarp();
                 }
                 LZ_TICK(7);
@@ -243,41 +280,63 @@ __global__ void __launch_bounds__(THREADS) lz_search_kernel(const uint8_t *__res
                 const uint32_t cnt = fast ? __popc(mask) : 0u;
                 uint32_t wpos = ent::warp_excl_scan(cnt, lane, &total);
                 if (fast) {
+                    const uint32_t pbase = li | p << 10;
 #pragma unroll
                     for (int q = 0; q < 16; q++)
-                        if (mask >> q & 1) queue[wpos++] = li | cand[q] << 10;
+                        if (mask >> q & 1) queue[wpos++] = pbase - (off[q] << 10);
                 }
                 __syncwarp();
                 LZ_TICK(8);
 #pragma unroll 1
                 for (uint32_t i = lane; i < total; i += 64) {
-                    // two pairs per lane per trip: both candidates' first 8 bytes are requested before either is examined
-                    const uint32_t pr0 = queue[i], pr1 = i + 32 < total ? queue[i + 32] : 0xFFFFFFFFu;
-                    const uint32_t l0 = pr0 & 1023u, c0 = pr0 >> 10, l1 = pr1 & 1023u, c1 = pr1 == 0xFFFFFFFFu ? 0u : pr1 >> 10;
-                    uint64_t x0 = smem_u64(s_in, l0) ^ ld8(in, c0);
-                    uint64_t x1 = pr1 == 0xFFFFFFFFu ? ~0ull : smem_u64(s_in, l1) ^ ld8(in, c1);
-                    uint32_t m0 = 0, m1 = 0;  // match lengths
-                    bool a0 = false, a1 = false;
-                    if ((uint32_t)x0 == 0) { if (x0) m0 = (uint32_t)(__ffsll((long long)x0) - 1) / 8; else a0 = true; }
-                    if ((uint32_t)x1 == 0) { if (x1) m1 = (uint32_t)(__ffsll((long long)x1) - 1) / 8; else a1 = true; }
-#pragma unroll
-                    for (uint32_t r = 8; r < SEARCH_CAP; r += 8) {
-                        if (a0 | a1) {
-                            x0 = a0 ? smem_u64(s_in, l0 + r) ^ ld8(in, c0 + r) : 0ull;
-                            x1 = a1 ? smem_u64(s_in, l1 + r) ^ ld8(in, c1 + r) : 0ull;
-                            if (a0 && x0) { m0 = r + (uint32_t)(__ffsll((long long)x0) - 1) / 8; a0 = false; }
-                            if (a1 && x1) { m1 = r + (uint32_t)(__ffsll((long long)x1) - 1) / 8; a1 = false; }
+                    // two pairs per lane per trip: both candidates' first 8 bytes are requested before either is examined; pairs
+                    // that match all 8 fetch bytes 8..23 in ONE further round (four more words each side)
+                    const bool h1 = i + 32 < total;
+                    const uint32_t pr0 = queue[i], pr1 = queue[h1 ? i + 32 : i];
+                    const uint32_t l0 = pr0 & 1023u, c0 = pr0 >> 10, l1 = pr1 & 1023u, c1 = pr1 >> 10;
+                    const uint32_t *wp0 = reinterpret_cast<const uint32_t *>(s_in) + (l0 >> 2), *wp1 = reinterpret_cast<const uint32_t *>(s_in) + (l1 >> 2);
+                    const uintptr_t ga0 = reinterpret_cast<uintptr_t>(in + c0), ga1 = reinterpret_cast<uintptr_t>(in + c1);
+                    const uint32_t *wc0 = reinterpret_cast<const uint32_t *>(ga0 & ~(uintptr_t)3), *wc1 = reinterpret_cast<const uint32_t *>(ga1 & ~(uintptr_t)3);
+                    const uint32_t sp0 = (l0 & 3u) * 8, sp1 = (l1 & 3u) * 8, sc0 = (uint32_t)(ga0 & 3u) * 8, sc1 = (uint32_t)(ga1 & 3u) * 8;
+                    const uint32_t a0w = __ldg(wc0), a1w = __ldg(wc0 + 1), a2w = __ldg(wc0 + 2);
+                    const uint32_t b0w = __ldg(wc1), b1w = __ldg(wc1 + 1), b2w = __ldg(wc1 + 2);
+                    const uint32_t p0w = wp0[0], p1w = wp0[1], p2w = wp0[2], q0w = wp1[0], q1w = wp1[1], q2w = wp1[2];
+                    const uint32_t x0lo = __funnelshift_r(p0w, p1w, sp0) ^ __funnelshift_r(a0w, a1w, sc0);
+                    const uint32_t x0hi = __funnelshift_r(p1w, p2w, sp0) ^ __funnelshift_r(a1w, a2w, sc0);
+                    const uint32_t x1lo = __funnelshift_r(q0w, q1w, sp1) ^ __funnelshift_r(b0w, b1w, sc1);
+                    const uint32_t x1hi = __funnelshift_r(q1w, q2w, sp1) ^ __funnelshift_r(b1w, b2w, sc1);
+                    // bytes 0..3 must agree (minimum match is 6); the first difference inside bytes 4..7 ends the match there
+                    uint32_t m0 = x0lo ? 0u : x0hi ? 4u + (uint32_t)(__ffs((int)x0hi) - 1) / 8 : 8u;
+                    uint32_t m1 = x1lo ? 0u : x1hi ? 4u + (uint32_t)(__ffs((int)x1hi) - 1) / 8 : 8u;
+                    const bool g0 = m0 == 8u, g1 = m1 == 8u;
+                    if (g0 | g1) {
+                        uint32_t a3w = 0, a4w = 0, a5w = 0, a6w = 0, b3w = 0, b4w = 0, b5w = 0, b6w = 0;
+                        if (g0) { a3w = __ldg(wc0 + 3); a4w = __ldg(wc0 + 4); a5w = __ldg(wc0 + 5); a6w = __ldg(wc0 + 6); }
+                        if (g1) { b3w = __ldg(wc1 + 3); b4w = __ldg(wc1 + 4); b5w = __ldg(wc1 + 5); b6w = __ldg(wc1 + 6); }
+                        if (g0) {
+                            const uint32_t p3w = wp0[3], p4w = wp0[4], p5w = wp0[5], p6w = wp0[6];
+                            const uint64_t z0 = (uint64_t)(__funnelshift_r(p3w, p4w, sp0) ^ __funnelshift_r(a3w, a4w, sc0)) << 32 |
+                                                (__funnelshift_r(p2w, p3w, sp0) ^ __funnelshift_r(a2w, a3w, sc0));
+                            const uint64_t z1 = (uint64_t)(__funnelshift_r(p5w, p6w, sp0) ^ __funnelshift_r(a5w, a6w, sc0)) << 32 |
+                                                (__funnelshift_r(p4w, p5w, sp0) ^ __funnelshift_r(a4w, a5w, sc0));
+                            m0 = z0 ? 8u + (uint32_t)(__ffsll((long long)z0) - 1) / 8 : z1 ? 16u + (uint32_t)(__ffsll((long long)z1) - 1) / 8 : SEARCH_CAP;
+                        }
+                        if (g1) {
+                            const uint32_t q3w = wp1[3], q4w = wp1[4], q5w = wp1[5], q6w = wp1[6];
+                            const uint64_t z0 = (uint64_t)(__funnelshift_r(q3w, q4w, sp1) ^ __funnelshift_r(b3w, b4w, sc1)) << 32 |
+                                                (__funnelshift_r(q2w, q3w, sp1) ^ __funnelshift_r(b2w, b3w, sc1));
+                            const uint64_t z1 = (uint64_t)(__funnelshift_r(q5w, q6w, sp1) ^ __funnelshift_r(b5w, b6w, sc1)) << 32 |
+                                                (__funnelshift_r(q4w, q5w, sp1) ^ __funnelshift_r(b4w, b5w, sc1));
+                            m1 = z0 ? 8u + (uint32_t)(__ffsll((long long)z0) - 1) / 8 : z1 ? 16u + (uint32_t)(__ffsll((long long)z1) - 1) / 8 : SEARCH_CAP;
                         }
                     }
-                    if (a0) m0 = SEARCH_CAP;
-                    if (a1) m1 = SEARCH_CAP;
                     if (m0 >= MIN_MATCH) {
-                        const uint32_t off = t0 + l0 - c0;
-                        atomicMax(&s_best[l0], (uint32_t)(sel_score(m0, off) + 9) << 26 | (m0 - MIN_MATCH) << 21 | off);
+                        const uint32_t off0 = t0 + l0 - c0;
+                        atomicMax(&s_best[l0], (uint32_t)(sel_score(m0, off0) + 9) << 26 | (m0 - MIN_MATCH) << 21 | off0);
                     }
-                    if (m1 >= MIN_MATCH) {
-                        const uint32_t off = t0 + l1 - c1;
-                        atomicMax(&s_best[l1], (uint32_t)(sel_score(m1, off) + 9) << 26 | (m1 - MIN_MATCH) << 21 | off);
+                    if (h1 && m1 >= MIN_MATCH) {
+                        const uint32_t off1 = t0 + l1 - c1;
+                        atomicMax(&s_best[l1], (uint32_t)(sel_score(m1, off1) + 9) << 26 | (m1 - MIN_MATCH) << 21 | off1);
                     }
                 }
                 __syncwarp();
@@ -289,14 +348,13 @@ __global__ void __launch_bounds__(THREADS) lz_search_kernel(const uint8_t *__res
 #pragma unroll 1
                     for (int q = 0; q < 16; q++) {
                         if (!(mask >> q & 1)) continue;
-                        uint32_t c = 0;
+                        uint32_t o = 0;
 #pragma unroll
-                        for (int z = 0; z < 16; z++) if (z == q) c = cand[z];
-                        const uint32_t l = match_length(in, p, c, maxlen, n);
+                        for (int z = 0; z < 16; z++) if (z == q) o = off[z];
+                        const uint32_t l = match_length(in, p, p - o, maxlen, n);
                         if (l < MIN_MATCH) continue;
-                        const uint32_t off = p - c;
-                        const int32_t sc = sel_score(l, off);
-                        if (sc > bscore) { bscore = sc; blen = l; boff = off; }
+                        const int32_t sc = sel_score(l, o);
+                        if (sc > bscore) { bscore = sc; blen = l; boff = o; }
                     }
                 } else if (searchable) {
                     const uint32_t best = s_best[li];
@@ -340,36 +398,67 @@ __global__ void __launch_bounds__(THREADS) lz_search_kernel(const uint8_t *__res
                     if (p + known > be) known = be - p;
                     int32_t lsc = -1;
                     if (known >= MIN_MATCH) { lsc = lazy_score(blen, boff); if (lsc < ACCEPT_THR) lsc = -1; }
-                    s_sc[p - t0 + HALO] = (int16_t)lsc;
-                    s_len[p - t0 + HALO] = (uint8_t)(lsc >= 0 ? blen : 0u);
-                    s_off[p - t0 + HALO] = boff;
-                    s_back[p - t0 + HALO] = (uint8_t)(bback | known << 2);
+                    s_sc[li + HALO] = (int16_t)lsc;
+                    s_len[li + HALO] = (uint8_t)(lsc >= 0 ? blen : 0u);
+                    s_off[li + HALO] = boff;
+                    s_back[li + HALO] = (uint8_t)(bback | known << 2);
+                }
+                g = gn;
+                if (lane == 0) gn = atomicAdd(&s_gctr, 1u);
+                gn = __shfl_sync(0xffffffffu, gn, 0);
+            }
+            LZ_TICK(2);
+            // ---- publish the next tile's entries into the slots reserved above ----
+#pragma unroll
+            for (uint32_t k = 0; k < PER_THREAD; k++) {
+                const uint32_t li = tid + k * THREADS, p = t0 + TILE + li;
+                if (p + 8 <= n) {
+                    const uint32_t hv = hash5(smem_u64(s_nx, li));
+                    __stcg(&tab[(hv >> TAG_BITS) * ROW_K + (slot_raw[k] & (ROW_K - 1))], (p + 1) | (hv & TAG_MASK) << 22);
                 }
             }
             __syncthreads();
-            LZ_TICK(2);
+            LZ_TICK(1);
             // ---- decide: positions [d0, d1) now have their lookahead window available ----
             const uint32_t d0 = t0 >= DEFER ? t0 - DEFER : 0;
             const uint32_t d1 = last_tile_of_block ? t1 : t1 - DEFER;
-            for (uint32_t p = d0 + tid; p < d1; p += THREADS) {
+            bool first = true;
+            for (uint32_t p = d0 + tid; p < d1 || first; p += THREADS) {
                 // positions before t0 that belong to the previous block were already decided there
-                if (p < t0 && (p / Z_BLOCK_MAX) != (t0 / Z_BLOCK_MAX)) continue;
-                int32_t sc = s_sc[p - t0 + HALO];
-                uint32_t r = 0;
-                if (sc >= 0) {
-                    uint32_t start = p;
-                    while (s_len[start - t0 + HALO] < TARGET_LEN && start - p + 2 <= MAX_SHIFT) {
-                        const int32_t s1 = start + 1 < be ? (int32_t)s_sc[start + 1 - t0 + HALO] : -1;
-                        if (s1 > sc + 4) { sc = s1; start += 1; continue; }
-                        const int32_t s2 = start + 2 < be ? (int32_t)s_sc[start + 2 - t0 + HALO] : -1;
-                        if (s2 > sc + 7) { sc = s2; start += 2; continue; }
-                        break;
+                if (p < d1 && !(p < t0 && (p / Z_BLOCK_MAX) != (t0 / Z_BLOCK_MAX))) {
+                    int32_t sc = s_sc[p - t0 + HALO];
+                    uint32_t r = 0;
+                    if (sc >= 0) {
+                        uint32_t start = p;
+                        while (s_len[start - t0 + HALO] < TARGET_LEN && start - p + 2 <= MAX_SHIFT) {
+                            const int32_t s1 = start + 1 < be ? (int32_t)s_sc[start + 1 - t0 + HALO] : -1;
+                            if (s1 > sc + 4) { sc = s1; start += 1; continue; }
+                            const int32_t s2 = start + 2 < be ? (int32_t)s_sc[start + 2 - t0 + HALO] : -1;
+                            if (s2 > sc + 7) { sc = s2; start += 2; continue; }
+                            break;
+                        }
+                        const uint32_t kb = s_back[start - t0 + HALO];
+                        r = pack_rec(s_off[start - t0 + HALO], kb >> 2, s_len[start - t0 + HALO] >= TARGET_LEN, kb & 3u, start - p);
                     }
-                    const uint32_t kb = s_back[start - t0 + HALO];
-                    r = pack_rec(s_off[start - t0 + HALO], kb >> 2, s_len[start - t0 + HALO] >= TARGET_LEN, kb & 3u, start - p);
+                    rec[p] = r;
                 }
-                rec[p] = r;
+                if (first) {
+                    first = false;
+                    // Only warp 0's first trip reads window slots below HALO (positions before t0), so once that trip is over
+                    // warp 0 slides the window: the tile's last HALO results become the next tile's halo.
+                    if (tid < HALO) {
+                        __syncwarp();
+                        s_len[tid] = s_len[TILE + tid]; s_off[tid] = s_off[TILE + tid]; s_back[tid] = s_back[TILE + tid]; s_sc[tid] = s_sc[TILE + tid];
+                    }
+                }
             }
+            // the stage buffer of this tile is free now: it receives tile t+2
+            {
+                uint32_t *dst = reinterpret_cast<uint32_t *>(s_in2[t & 1]);
+                dst[tid] = sw0;
+                if (tid < SIN_WORDS - THREADS) dst[THREADS + tid] = sw1;
+            }
+            if (tid == 0) s_gctr = THREADS / 32;
             __syncthreads();
             LZ_TICK(3);
         }
