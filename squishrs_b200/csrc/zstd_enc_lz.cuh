@@ -211,40 +211,56 @@ __global__ void __launch_bounds__(THREADS, SQ_LZ_MINB) lz_search_kernel(const ui
             // pairs -- not row slots -- so no issue slot is spent on empty slots.  The best candidate per position is kept
             // with a 32-bit atomicMax on (score, length, offset) in shared memory.
             // rows are software-pipelined: the row of the warp's NEXT group is requested before this group's pairs are verified
+            // Rows are read cooperatively: four lanes share one 64-byte row (one 16-byte load each), so a load instruction
+            // touches 8 rows instead of 32 and the L1 sees a quarter of the tag requests.  Lane l therefore filters, for
+            // k = 0..3, entries [4 (l & 3), +4) of the row of group position 8 k + (l >> 2); everything downstream works on
+            // (position, offset) pairs and does not care which lane found them.
             uint32_t g = wq, gn = 0;
             if (lane == 0) gn = atomicAdd(&s_gctr, 1u);
             gn = __shfl_sync(0xffffffffu, gn, 0);
-            uint4 nea, neb, nec, ned;
-            {
-                const uint32_t hv0 = hash5(smem_u64(s_in, g * 32 + lane));
-                const uint4 *r0 = reinterpret_cast<const uint4 *>(tab + (hv0 >> TAG_BITS) * ROW_K);
-                nea = __ldcg(r0); neb = __ldcg(r0 + 1); nec = __ldcg(r0 + 2); ned = __ldcg(r0 + 3);
+            const uint32_t sub = lane >> 2, part = lane & 3u;
+            const uint32_t droppable = ((sub & 15u) ? 0x0F0Fu : 0u) | 0xF0F0u;  // positions 0 and 16 of a group keep every pair
+            uint32_t hv_cur = hash5(smem_u64(s_in, g * 32 + lane));
+            uint4 ne[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const uint32_t hk = __shfl_sync(0xffffffffu, hv_cur, 8 * k + sub);
+                ne[k] = __ldcg(reinterpret_cast<const uint4 *>(tab + (hk >> TAG_BITS) * ROW_K) + part);
             }
 #pragma unroll 1
             while (g < GROUPS) {
-                const uint32_t li = g * 32 + lane, p = t0 + li;
-                uint32_t mask = 0, off[ROW_K];  // off[q] = p - candidate, 0 = not a candidate
+                const uint32_t gl = g * 32, li = gl + lane, p = t0 + li;
+                uint32_t mask = 0, off[ROW_K];  // off[4 k + m] = position - candidate, 0 = not a candidate
                 const bool searchable = p + 8 <= n;
-                const bool fast = p + SEARCH_CAP + 16 <= n;  // every comparison stays inside the chunk and the staged window
+                const bool gfast = t0 + gl + 32 + SEARCH_CAP + 16 <= n;  // every comparison of the group stays inside the chunk and the staged window
                 {
-                    const uint32_t hv = hash5(smem_u64(s_in, li));
-                    const uint32_t tagsh = (hv & TAG_MASK) << 22;
                     static_assert(ROW_K == 16, "the search reads one 16-entry row");
-                    const uint32_t e[16] = {nea.x, nea.y, nea.z, nea.w, neb.x, neb.y, neb.z, neb.w, nec.x, nec.y, nec.z, nec.w, ned.x, ned.y, ned.z, ned.w};
-                    if (gn < GROUPS) {  // prefetch the next group's row (table rows exist for any hash value)
-                        const uint32_t hvn = hash5(smem_u64(s_in, gn * 32 + lane));
-                        const uint4 *rn = reinterpret_cast<const uint4 *>(tab + (hvn >> TAG_BITS) * ROW_K);
-                        nea = __ldcg(rn); neb = __ldcg(rn + 1); nec = __ldcg(rn + 2); ned = __ldcg(rn + 3);
+                    const uint32_t e[16] = {ne[0].x, ne[0].y, ne[0].z, ne[0].w, ne[1].x, ne[1].y, ne[1].z, ne[1].w,
+                                            ne[2].x, ne[2].y, ne[2].z, ne[2].w, ne[3].x, ne[3].y, ne[3].z, ne[3].w};
+                    uint32_t tg[4];
+#pragma unroll
+                    for (int k = 0; k < 4; k++) tg[k] = (__shfl_sync(0xffffffffu, hv_cur, 8 * k + sub) & TAG_MASK) << 22;
+                    if (gn < GROUPS) {  // prefetch the next group's rows (table rows exist for any hash value)
+                        hv_cur = hash5(smem_u64(s_in, gn * 32 + lane));
+#pragma unroll
+                        for (int k = 0; k < 4; k++) {
+                            const uint32_t hk = __shfl_sync(0xffffffffu, hv_cur, 8 * k + sub);
+                            ne[k] = __ldcg(reinterpret_cast<const uint4 *>(tab + (hk >> TAG_BITS) * ROW_K) + part);
+                        }
                     }
                     // entry = (candidate + 1) | tag << 22: after xor with the tag the value is candidate + 1 iff the tags agree
                     // (anything else is 0 or >= 2^22), so one unsigned compare checks tag, emptiness and candidate < p at once
-                    const uint32_t plim = searchable ? p : 0u;
 #pragma unroll
-                    for (int q = 0; q < 16; q++) {
-                        const uint32_t om1 = p - (e[q] ^ tagsh);
-                        const bool v = om1 < plim;
-                        off[q] = v ? om1 + 1u : 0u;
-                        mask |= (v ? 1u : 0u) << q;
+                    for (int k = 0; k < 4; k++) {
+                        const uint32_t pk = t0 + gl + 8 * k + sub;
+                        const uint32_t plim = pk + 8 <= n ? pk : 0u;
+#pragma unroll
+                        for (int m = 0; m < 4; m++) {
+                            const uint32_t om1 = pk - (e[4 * k + m] ^ tg[k]);
+                            const bool v = om1 < plim;
+                            off[4 * k + m] = v ? om1 + 1u : 0u;
+                            mask |= (v ? 1u : 0u) << (4 * k + m);
+                        }
                     }
                 }
                 s_best[li] = 0u;
@@ -252,8 +268,8 @@ __global__ void __launch_bounds__(THREADS, SQ_LZ_MINB) lz_search_kernel(const ui
                 // ---- continuation filter ----
                 // A pair (p, c) whose left neighbour pair (p-1, c-1) is also a candidate pair continues a match that is verified at
                 // its first position; it is dropped here and its result arrives by inheritance below.  Membership is tested through a
-                // direct-mapped table of (lane, offset) keys that borrows the queue's memory; a key collision only loses a drop.
-                // Lanes 0 and 16 keep every pair, so a long match is re-verified every 16 positions and inheritance never runs dry.
+                // direct-mapped table of (position, offset) keys that borrows the queue's memory; a key collision only loses a drop.
+                // Positions 0 and 16 keep every pair, so a long match is re-verified every 16 positions and inheritance never runs dry.
                 // Both passes are branch-free (predicated stores, then sixteen independent loads) so the loads overlap.
                 {
                     uint16_t *T = reinterpret_cast<uint16_t *>(queue);
@@ -263,100 +279,98 @@ __global__ void __launch_bounds__(THREADS, SQ_LZ_MINB) lz_search_kernel(const ui
                     __syncwarp();
 #pragma unroll
                     for (int q = 0; q < 16; q++)
-                        if (off[q]) T[(off[q] & 31u) * 32u + lane] = (uint16_t)((off[q] >> 5) + 1u);
+                        if (off[q]) T[(off[q] & 31u) * 32u + 8 * (q >> 2) + sub] = (uint16_t)((off[q] >> 5) + 1u);
                     __syncwarp();
-                    const uint16_t *Tl = T + ((lane & 15u) ? lane - 1u : lane);
                     uint32_t hit = 0;
 #pragma unroll
                     for (int q = 0; q < 16; q++) {
-                        const uint32_t o = off[q];
-                        hit |= (Tl[(o & 31u) * 32u] == (uint16_t)((o >> 5) + 1u) ? 1u : 0u) << q;
+                        const uint32_t o = off[q], col = 8 * (q >> 2) + sub;
+                        hit |= (T[(o & 31u) * 32u + (col ? col - 1u : 0u)] == (uint16_t)((o >> 5) + 1u) ? 1u : 0u) << q;
                     }
-                    if (lane & 15u) mask &= ~hit;
+                    mask &= ~(hit & droppable);
                     __syncwarp();
                 }
                 LZ_TICK(7);
                 uint32_t total;
-                const uint32_t cnt = fast ? __popc(mask) : 0u;
-                uint32_t wpos = ent::warp_excl_scan(cnt, lane, &total);
-                if (fast) {
-                    const uint32_t pbase = li | p << 10;
+                uint32_t wpos = ent::warp_excl_scan(__popc(mask), lane, &total);
 #pragma unroll
-                    for (int q = 0; q < 16; q++)
-                        if (mask >> q & 1) queue[wpos++] = pbase - (off[q] << 10);
+                for (int k = 0; k < 4; k++) {
+                    const uint32_t lk = gl + 8 * k + sub, pbase = lk | (t0 + lk) << 10;
+#pragma unroll
+                    for (int m = 0; m < 4; m++)
+                        if (mask >> (4 * k + m) & 1) queue[wpos++] = pbase - (off[4 * k + m] << 10);
                 }
                 __syncwarp();
                 LZ_TICK(8);
+                if (gfast) {
 #pragma unroll 1
-                for (uint32_t i = lane; i < total; i += 64) {
-                    // two pairs per lane per trip: both candidates' first 8 bytes are requested before either is examined; pairs
-                    // that match all 8 fetch bytes 8..23 in ONE further round (four more words each side)
-                    const bool h1 = i + 32 < total;
-                    const uint32_t pr0 = queue[i], pr1 = queue[h1 ? i + 32 : i];
-                    const uint32_t l0 = pr0 & 1023u, c0 = pr0 >> 10, l1 = pr1 & 1023u, c1 = pr1 >> 10;
-                    const uint32_t *wp0 = reinterpret_cast<const uint32_t *>(s_in) + (l0 >> 2), *wp1 = reinterpret_cast<const uint32_t *>(s_in) + (l1 >> 2);
-                    const uintptr_t ga0 = reinterpret_cast<uintptr_t>(in + c0), ga1 = reinterpret_cast<uintptr_t>(in + c1);
-                    const uint32_t *wc0 = reinterpret_cast<const uint32_t *>(ga0 & ~(uintptr_t)3), *wc1 = reinterpret_cast<const uint32_t *>(ga1 & ~(uintptr_t)3);
-                    const uint32_t sp0 = (l0 & 3u) * 8, sp1 = (l1 & 3u) * 8, sc0 = (uint32_t)(ga0 & 3u) * 8, sc1 = (uint32_t)(ga1 & 3u) * 8;
-                    const uint32_t a0w = __ldg(wc0), a1w = __ldg(wc0 + 1), a2w = __ldg(wc0 + 2);
-                    const uint32_t b0w = __ldg(wc1), b1w = __ldg(wc1 + 1), b2w = __ldg(wc1 + 2);
-                    const uint32_t p0w = wp0[0], p1w = wp0[1], p2w = wp0[2], q0w = wp1[0], q1w = wp1[1], q2w = wp1[2];
-                    const uint32_t x0lo = __funnelshift_r(p0w, p1w, sp0) ^ __funnelshift_r(a0w, a1w, sc0);
-                    const uint32_t x0hi = __funnelshift_r(p1w, p2w, sp0) ^ __funnelshift_r(a1w, a2w, sc0);
-                    const uint32_t x1lo = __funnelshift_r(q0w, q1w, sp1) ^ __funnelshift_r(b0w, b1w, sc1);
-                    const uint32_t x1hi = __funnelshift_r(q1w, q2w, sp1) ^ __funnelshift_r(b1w, b2w, sc1);
-                    // bytes 0..3 must agree (minimum match is 6); the first difference inside bytes 4..7 ends the match there
-                    uint32_t m0 = x0lo ? 0u : x0hi ? 4u + (uint32_t)(__ffs((int)x0hi) - 1) / 8 : 8u;
-                    uint32_t m1 = x1lo ? 0u : x1hi ? 4u + (uint32_t)(__ffs((int)x1hi) - 1) / 8 : 8u;
-                    const bool g0 = m0 == 8u, g1 = m1 == 8u;
-                    if (g0 | g1) {
-                        uint32_t a3w = 0, a4w = 0, a5w = 0, a6w = 0, b3w = 0, b4w = 0, b5w = 0, b6w = 0;
-                        if (g0) { a3w = __ldg(wc0 + 3); a4w = __ldg(wc0 + 4); a5w = __ldg(wc0 + 5); a6w = __ldg(wc0 + 6); }
-                        if (g1) { b3w = __ldg(wc1 + 3); b4w = __ldg(wc1 + 4); b5w = __ldg(wc1 + 5); b6w = __ldg(wc1 + 6); }
-                        if (g0) {
-                            const uint32_t p3w = wp0[3], p4w = wp0[4], p5w = wp0[5], p6w = wp0[6];
-                            const uint64_t z0 = (uint64_t)(__funnelshift_r(p3w, p4w, sp0) ^ __funnelshift_r(a3w, a4w, sc0)) << 32 |
-                                                (__funnelshift_r(p2w, p3w, sp0) ^ __funnelshift_r(a2w, a3w, sc0));
-                            const uint64_t z1 = (uint64_t)(__funnelshift_r(p5w, p6w, sp0) ^ __funnelshift_r(a5w, a6w, sc0)) << 32 |
-                                                (__funnelshift_r(p4w, p5w, sp0) ^ __funnelshift_r(a4w, a5w, sc0));
-                            m0 = z0 ? 8u + (uint32_t)(__ffsll((long long)z0) - 1) / 8 : z1 ? 16u + (uint32_t)(__ffsll((long long)z1) - 1) / 8 : SEARCH_CAP;
+                    for (uint32_t i = lane; i < total; i += 64) {
+                        // two pairs per lane per trip: both candidates' first 8 bytes (two aligned 8-byte loads each) are requested
+                        // before either is examined; pairs that match all 8 fetch bytes 8..23 in ONE further round
+                        const bool h1 = i + 32 < total;
+                        const uint32_t pr0 = queue[i], pr1 = queue[h1 ? i + 32 : i];
+                        const uint32_t l0 = pr0 & 1023u, c0 = pr0 >> 10, l1 = pr1 & 1023u, c1 = pr1 >> 10;
+                        const uint32_t *wp0 = reinterpret_cast<const uint32_t *>(s_in) + (l0 >> 2), *wp1 = reinterpret_cast<const uint32_t *>(s_in) + (l1 >> 2);
+                        const uintptr_t ga0 = reinterpret_cast<uintptr_t>(in + c0), ga1 = reinterpret_cast<uintptr_t>(in + c1);
+                        const uint2 *wc0 = reinterpret_cast<const uint2 *>(ga0 & ~(uintptr_t)7), *wc1 = reinterpret_cast<const uint2 *>(ga1 & ~(uintptr_t)7);
+                        const uint32_t sp0 = (l0 & 3u) * 8, sp1 = (l1 & 3u) * 8, sc0 = (uint32_t)(ga0 & 3u) * 8, sc1 = (uint32_t)(ga1 & 3u) * 8;
+                        const bool u0 = (ga0 & 4u) != 0, u1 = (ga1 & 4u) != 0;  // the candidate starts in the upper word of its first 8 bytes
+                        const uint2 A0 = __ldg(wc0), A1 = __ldg(wc0 + 1), B0 = __ldg(wc1), B1 = __ldg(wc1 + 1);
+                        const uint32_t p0w = wp0[0], p1w = wp0[1], p2w = wp0[2], q0w = wp1[0], q1w = wp1[1], q2w = wp1[2];
+                        const uint32_t a0w = u0 ? A0.y : A0.x, a1w = u0 ? A1.x : A0.y, a2w = u0 ? A1.y : A1.x;
+                        const uint32_t b0w = u1 ? B0.y : B0.x, b1w = u1 ? B1.x : B0.y, b2w = u1 ? B1.y : B1.x;
+                        const uint32_t x0lo = __funnelshift_r(p0w, p1w, sp0) ^ __funnelshift_r(a0w, a1w, sc0);
+                        const uint32_t x0hi = __funnelshift_r(p1w, p2w, sp0) ^ __funnelshift_r(a1w, a2w, sc0);
+                        const uint32_t x1lo = __funnelshift_r(q0w, q1w, sp1) ^ __funnelshift_r(b0w, b1w, sc1);
+                        const uint32_t x1hi = __funnelshift_r(q1w, q2w, sp1) ^ __funnelshift_r(b1w, b2w, sc1);
+                        // bytes 0..3 must agree (minimum match is 6); the first difference inside bytes 4..7 ends the match there
+                        uint32_t m0 = x0lo ? 0u : x0hi ? 4u + (uint32_t)(__ffs((int)x0hi) - 1) / 8 : 8u;
+                        uint32_t m1 = x1lo ? 0u : x1hi ? 4u + (uint32_t)(__ffs((int)x1hi) - 1) / 8 : 8u;
+                        const bool g0 = m0 == 8u, g1 = m1 == 8u;
+                        if (g0 | g1) {
+                            uint2 A2 = make_uint2(0u, 0u), A3 = A2, B2 = A2, B3 = A2;
+                            if (g0) { A2 = __ldg(wc0 + 2); A3 = __ldg(wc0 + 3); }
+                            if (g1) { B2 = __ldg(wc1 + 2); B3 = __ldg(wc1 + 3); }
+                            if (g0) {
+                                const uint32_t a3w = u0 ? A2.x : A1.y, a4w = u0 ? A2.y : A2.x, a5w = u0 ? A3.x : A2.y, a6w = u0 ? A3.y : A3.x;
+                                const uint32_t p3w = wp0[3], p4w = wp0[4], p5w = wp0[5], p6w = wp0[6];
+                                const uint64_t z0 = (uint64_t)(__funnelshift_r(p3w, p4w, sp0) ^ __funnelshift_r(a3w, a4w, sc0)) << 32 |
+                                                    (__funnelshift_r(p2w, p3w, sp0) ^ __funnelshift_r(a2w, a3w, sc0));
+                                const uint64_t z1 = (uint64_t)(__funnelshift_r(p5w, p6w, sp0) ^ __funnelshift_r(a5w, a6w, sc0)) << 32 |
+                                                    (__funnelshift_r(p4w, p5w, sp0) ^ __funnelshift_r(a4w, a5w, sc0));
+                                m0 = z0 ? 8u + (uint32_t)(__ffsll((long long)z0) - 1) / 8 : z1 ? 16u + (uint32_t)(__ffsll((long long)z1) - 1) / 8 : SEARCH_CAP;
+                            }
+                            if (g1) {
+                                const uint32_t b3w = u1 ? B2.x : B1.y, b4w = u1 ? B2.y : B2.x, b5w = u1 ? B3.x : B2.y, b6w = u1 ? B3.y : B3.x;
+                                const uint32_t q3w = wp1[3], q4w = wp1[4], q5w = wp1[5], q6w = wp1[6];
+                                const uint64_t z0 = (uint64_t)(__funnelshift_r(q3w, q4w, sp1) ^ __funnelshift_r(b3w, b4w, sc1)) << 32 |
+                                                    (__funnelshift_r(q2w, q3w, sp1) ^ __funnelshift_r(b2w, b3w, sc1));
+                                const uint64_t z1 = (uint64_t)(__funnelshift_r(q5w, q6w, sp1) ^ __funnelshift_r(b5w, b6w, sc1)) << 32 |
+                                                    (__funnelshift_r(q4w, q5w, sp1) ^ __funnelshift_r(b4w, b5w, sc1));
+                                m1 = z0 ? 8u + (uint32_t)(__ffsll((long long)z0) - 1) / 8 : z1 ? 16u + (uint32_t)(__ffsll((long long)z1) - 1) / 8 : SEARCH_CAP;
+                            }
                         }
-                        if (g1) {
-                            const uint32_t q3w = wp1[3], q4w = wp1[4], q5w = wp1[5], q6w = wp1[6];
-                            const uint64_t z0 = (uint64_t)(__funnelshift_r(q3w, q4w, sp1) ^ __funnelshift_r(b3w, b4w, sc1)) << 32 |
-                                                (__funnelshift_r(q2w, q3w, sp1) ^ __funnelshift_r(b2w, b3w, sc1));
-                            const uint64_t z1 = (uint64_t)(__funnelshift_r(q5w, q6w, sp1) ^ __funnelshift_r(b5w, b6w, sc1)) << 32 |
-                                                (__funnelshift_r(q4w, q5w, sp1) ^ __funnelshift_r(b4w, b5w, sc1));
-                            m1 = z0 ? 8u + (uint32_t)(__ffsll((long long)z0) - 1) / 8 : z1 ? 16u + (uint32_t)(__ffsll((long long)z1) - 1) / 8 : SEARCH_CAP;
+                        if (m0 >= MIN_MATCH) {
+                            const uint32_t off0 = t0 + l0 - c0;
+                            atomicMax(&s_best[l0], (uint32_t)(sel_score(m0, off0) + 9) << 26 | (m0 - MIN_MATCH) << 21 | off0);
+                        }
+                        if (h1 && m1 >= MIN_MATCH) {
+                            const uint32_t off1 = t0 + l1 - c1;
+                            atomicMax(&s_best[l1], (uint32_t)(sel_score(m1, off1) + 9) << 26 | (m1 - MIN_MATCH) << 21 | off1);
                         }
                     }
-                    if (m0 >= MIN_MATCH) {
-                        const uint32_t off0 = t0 + l0 - c0;
-                        atomicMax(&s_best[l0], (uint32_t)(sel_score(m0, off0) + 9) << 26 | (m0 - MIN_MATCH) << 21 | off0);
-                    }
-                    if (h1 && m1 >= MIN_MATCH) {
-                        const uint32_t off1 = t0 + l1 - c1;
-                        atomicMax(&s_best[l1], (uint32_t)(sel_score(m1, off1) + 9) << 26 | (m1 - MIN_MATCH) << 21 | off1);
+                } else {  // the last bytes of the chunk: careful scalar comparison, one pair per lane per trip
+#pragma unroll 1
+                    for (uint32_t i = lane; i < total; i += 32) {
+                        const uint32_t pr = queue[i], l0 = pr & 1023u, c0 = pr >> 10, pp = t0 + l0;
+                        const uint32_t m0 = match_length(in, pp, c0, min(n - pp, SEARCH_CAP), n);
+                        if (m0 >= MIN_MATCH) atomicMax(&s_best[l0], (uint32_t)(sel_score(m0, pp - c0) + 9) << 26 | (m0 - MIN_MATCH) << 21 | (pp - c0));
                     }
                 }
                 __syncwarp();
                 LZ_TICK(9);
                 uint32_t blen = 0, boff = 0, bback = 0;
-                if (searchable && !fast) {  // last bytes of the chunk: careful scalar path
-                    const uint32_t maxlen = min(n - p, SEARCH_CAP);
-                    int32_t bscore = -1000;
-#pragma unroll 1
-                    for (int q = 0; q < 16; q++) {
-                        if (!(mask >> q & 1)) continue;
-                        uint32_t o = 0;
-#pragma unroll
-                        for (int z = 0; z < 16; z++) if (z == q) o = off[z];
-                        const uint32_t l = match_length(in, p, p - o, maxlen, n);
-                        if (l < MIN_MATCH) continue;
-                        const int32_t sc = sel_score(l, o);
-                        if (sc > bscore) { bscore = sc; blen = l; boff = o; }
-                    }
-                } else if (searchable) {
+                if (searchable) {
                     const uint32_t best = s_best[li];
                     if (best) { blen = ((best >> 21) & 31u) + MIN_MATCH; boff = best & 0x1FFFFFu; }
                 }
