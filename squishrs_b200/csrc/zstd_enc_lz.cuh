@@ -240,14 +240,6 @@ __global__ void __launch_bounds__(THREADS, SQ_LZ_MINB) lz_search_kernel(const ui
                     uint32_t tg[4];
 #pragma unroll
                     for (int k = 0; k < 4; k++) tg[k] = (__shfl_sync(0xffffffffu, hv_cur, 8 * k + sub) & TAG_MASK) << 22;
-                    if (gn < GROUPS) {  // prefetch the next group's rows (table rows exist for any hash value)
-                        hv_cur = hash5(smem_u64(s_in, gn * 32 + lane));
-#pragma unroll
-                        for (int k = 0; k < 4; k++) {
-                            const uint32_t hk = __shfl_sync(0xffffffffu, hv_cur, 8 * k + sub);
-                            ne[k] = __ldcg(reinterpret_cast<const uint4 *>(tab + (hk >> TAG_BITS) * ROW_K) + part);
-                        }
-                    }
                     // entry = (candidate + 1) | tag << 22: after xor with the tag the value is candidate + 1 iff the tags agree
                     // (anything else is 0 or >= 2^22), so one unsigned compare checks tag, emptiness and candidate < p at once
 #pragma unroll
@@ -263,6 +255,16 @@ __global__ void __launch_bounds__(THREADS, SQ_LZ_MINB) lz_search_kernel(const ui
                         }
                     }
                 }
+                // prefetch the next group's rows only now that this group's entries are consumed: the loads land straight in
+                // the registers they are read from one group later (table rows exist for any hash value)
+                if (gn < GROUPS) {
+                    hv_cur = hash5(smem_u64(s_in, gn * 32 + lane));
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const uint32_t hk = __shfl_sync(0xffffffffu, hv_cur, 8 * k + sub);
+                        ne[k] = __ldcg(reinterpret_cast<const uint4 *>(tab + (hk >> TAG_BITS) * ROW_K) + part);
+                    }
+                }
                 s_best[li] = 0u;
                 LZ_TICK(6);
                 // ---- continuation filter ----
@@ -270,7 +272,8 @@ __global__ void __launch_bounds__(THREADS, SQ_LZ_MINB) lz_search_kernel(const ui
                 // its first position; it is dropped here and its result arrives by inheritance below.  Membership is tested through a
                 // direct-mapped table of (position, offset) keys that borrows the queue's memory; a key collision only loses a drop.
                 // Positions 0 and 16 keep every pair, so a long match is re-verified every 16 positions and inheritance never runs dry.
-                // Both passes are branch-free (predicated stores, then sixteen independent loads) so the loads overlap.
+                // Both passes are branch-free (predicated stores, then sixteen independent loads) so the loads overlap; the column
+                // is rotated by bits 1..4 of the offset so that the four lanes filtering one row spread over the banks.
                 {
                     uint16_t *T = reinterpret_cast<uint16_t *>(queue);
                     uint4 *Tz = reinterpret_cast<uint4 *>(queue);
@@ -279,13 +282,13 @@ __global__ void __launch_bounds__(THREADS, SQ_LZ_MINB) lz_search_kernel(const ui
                     __syncwarp();
 #pragma unroll
                     for (int q = 0; q < 16; q++)
-                        if (off[q]) T[(off[q] & 31u) * 32u + 8 * (q >> 2) + sub] = (uint16_t)((off[q] >> 5) + 1u);
+                        if (off[q]) T[(off[q] & 31u) * 32u + ((8 * (q >> 2) + sub + (off[q] & 30u)) & 31u)] = (uint16_t)((off[q] >> 5) + 1u);
                     __syncwarp();
                     uint32_t hit = 0;
 #pragma unroll
                     for (int q = 0; q < 16; q++) {
                         const uint32_t o = off[q], col = 8 * (q >> 2) + sub;
-                        hit |= (T[(o & 31u) * 32u + (col ? col - 1u : 0u)] == (uint16_t)((o >> 5) + 1u) ? 1u : 0u) << q;
+                        hit |= (T[(o & 31u) * 32u + (((col ? col - 1u : 0u) + (o & 30u)) & 31u)] == (uint16_t)((o >> 5) + 1u) ? 1u : 0u) << q;
                     }
                     mask &= ~(hit & droppable);
                     __syncwarp();
@@ -423,6 +426,9 @@ __global__ void __launch_bounds__(THREADS, SQ_LZ_MINB) lz_search_kernel(const ui
             }
             LZ_TICK(2);
             // ---- publish the next tile's entries into the slots reserved above ----
+            // (the empty asm keeps the compiler from consuming the atomics' results -- and waiting for them -- before the search)
+            static_assert(PER_THREAD == 4, "slot barrier lists four registers");
+            asm volatile("" : "+r"(slot_raw[0]), "+r"(slot_raw[1]), "+r"(slot_raw[2]), "+r"(slot_raw[3]), "+r"(sw0), "+r"(sw1) :: "memory");
 #pragma unroll
             for (uint32_t k = 0; k < PER_THREAD; k++) {
                 const uint32_t li = tid + k * THREADS, p = t0 + TILE + li;
