@@ -67,9 +67,13 @@ struct Model {
         for (uint32_t t0 = 0; t0 < n; t0 += T) {
             uint32_t t1 = std::min(n, t0 + T);
             // insert the whole tile first (ring per row), as the GPU does
+            static const uint32_t ins_stride = getenv("ENC_INS_STRIDE") ? (uint32_t)atoi(getenv("ENC_INS_STRIDE")) : 1;
+            static const uint32_t search_stride = getenv("ENC_SEARCH_STRIDE") ? (uint32_t)atoi(getenv("ENC_SEARCH_STRIDE")) : 1;
+            static const bool slot_by_pos = getenv("ENC_SLOT_BY_POS") != nullptr;
             for (uint32_t p = t0; p < t1 && p + 8 <= n; p++) {
+                if (p % ins_stride) continue;
                 uint32_t h = hashN(s + p, P.min_match, P.hash_log);
-                tab[(size_t)h * K + (head[h]++ % K)] = p + 1;
+                tab[(size_t)h * K + (slot_by_pos ? (p / ins_stride) % K : head[h]++ % K)] = p + 1;
             }
             for (int round = 0; round < 2; round++)
             for (uint32_t p = t0; p < t1 && p + 8 <= n; p++) {
@@ -112,6 +116,7 @@ struct Model {
                 }
                 if (cont) { prevc.swap(curc); curc.clear(); if (p == t0) prevc.clear(); }
                 for (uint32_t k = 0; k < K; k++) {
+                    if (p % search_stride) break;
                     uint32_t e = tab[(size_t)h * K + k];
                     if (!e || e - 1 >= p) continue;
                     uint32_t c = e - 1;
