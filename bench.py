@@ -402,55 +402,57 @@ def run_ours(args):
         # pinned host memory.  Every step uploads its batch (H2D) and downloads results + frames (D2H) inside the timed region.
         eb = min(B, args.e2e_chunks)
         ocap = eb * int(lib.sq_encode_bound(CHUNK))
-        hp, ho, hres = [], [], []
-        for _ in range(2):
-            a_, b_, r_ = C.c_void_p(), C.c_void_p(), C.c_void_p()
-            ctx.check(lib.sq_host_alloc(ctx.h, eb * CHUNK, C.byref(a_)))
-            ctx.check(lib.sq_host_alloc(ctx.h, ocap, C.byref(b_)))
-            ctx.check(lib.sq_host_alloc(ctx.h, eb * C.sizeof(L.SqChunkResult), C.byref(r_)))
-            hp.append(a_); ho.append(b_); hres.append(r_)
-        hspans = (L.SqSpan * eb)()
-        for i in range(eb):
-            hspans[i].off, hspans[i].len = i * CHUNK, CHUNK
         ctx.dedup_reset()
         n_e2e = max(4, min(args.steps, 8))
         n_warm = 2
-
-        def stage_input(k):  # device corpus -> pinned host buffer (outside the timed region)
+        total_steps = n_warm + n_e2e
+        # Every step's input sits in its own pinned host buffer BEFORE the clock starts (staging it costs PCIe time that is not
+        # part of the workload); outputs and results use a ring of two, like the two pipeline slots.
+        hp, ho, hres = [], [], []
+        for k in range(total_steps):
+            a_ = C.c_void_p()
+            ctx.check(lib.sq_host_alloc(ctx.h, eb * CHUNK, C.byref(a_)))
+            hp.append(a_)
             b = k % n_batches
             src = corpus[b * B * CHUNK: b * B * CHUNK + eb * CHUNK]
-            host_view = torch.frombuffer((C.c_uint8 * (eb * CHUNK)).from_address(hp[k % 2].value), dtype=torch.uint8)
+            host_view = torch.frombuffer((C.c_uint8 * (eb * CHUNK)).from_address(a_.value), dtype=torch.uint8)
             host_view.copy_(src)
-            torch.cuda.synchronize()
+        torch.cuda.synchronize()
+        for _ in range(2):
+            b_, r_ = C.c_void_p(), C.c_void_p()
+            ctx.check(lib.sq_host_alloc(ctx.h, ocap, C.byref(b_)))
+            ctx.check(lib.sq_host_alloc(ctx.h, eb * C.sizeof(L.SqChunkResult), C.byref(r_)))
+            ho.append(b_); hres.append(r_)
+        hspans = (L.SqSpan * eb)()
+        for i in range(eb):
+            hspans[i].off, hspans[i].len = i * CHUNK, CHUNK
 
         tickets = [None, None]
         used = C.c_uint64()
         e2e_out = 0
-        # inputs of the first two steps are staged up front; later inputs are staged while nothing of ours is timed? No:
-        # staging costs PCIe time too, so every input is staged BEFORE the clock starts.
-        total_steps = n_warm + n_e2e
-        # the pinned ring only holds two batches, so time in rounds of two steps
-        times = []
-        k = 0
-        while k < total_steps:
-            cnt = min(2, total_steps - k)
-            for j in range(cnt):
-                stage_input(k + j)
-            if world > 1:
-                dist.barrier()
-            t0 = time.perf_counter()
-            for j in range(cnt):
-                t = C.c_void_p()
-                ctx.check(lib.sq_pack_submit(ctx.h, hp[(k + j) % 2], eb * CHUNK, hspans, eb, (k + j) * eb, hres[(k + j) % 2], ho[(k + j) % 2], ocap, C.byref(t)))
-                tickets[(k + j) % 2] = t
-            for j in range(cnt):
-                ctx.check(lib.sq_pack_wait(ctx.h, tickets[(k + j) % 2], C.byref(used)))
-                if k + j >= n_warm:
-                    e2e_out += used.value + eb * C.sizeof(L.SqChunkResult)
-            dt = time.perf_counter() - t0
+
+        def submit(k):
+            t = C.c_void_p()
+            ctx.check(lib.sq_pack_submit(ctx.h, hp[k], eb * CHUNK, hspans, eb, k * eb, hres[k % 2], ho[k % 2], ocap, C.byref(t)))
+            tickets[k % 2] = t
+
+        # Rolling two-slot pipeline, the way the archive packer drives it: wait(k) then submit(k+2), so the upload of the next
+        # batch and the frame download of the previous one overlap the kernels of the current one.  The clock starts when the
+        # last warm-up step has been delivered and stops when the last step's frames are in host memory.
+        if world > 1:
+            dist.barrier()
+        submit(0)
+        submit(1)
+        t0 = None
+        for k in range(total_steps):
+            ctx.check(lib.sq_pack_wait(ctx.h, tickets[k % 2], C.byref(used)))
+            if k == n_warm - 1:
+                t0 = time.perf_counter()
             if k >= n_warm:
-                times.append((dt, cnt))
-            k += cnt
+                e2e_out += used.value + eb * C.sizeof(L.SqChunkResult)
+            if k + 2 < total_steps:
+                submit(k + 2)
+        times = [(time.perf_counter() - t0, n_e2e)]
         tsum = sum(t for t, _ in times)
         nsteps = sum(c for _, c in times)
         et = torch.tensor([tsum], dtype=torch.float64, device="cuda")
@@ -458,9 +460,9 @@ def run_ours(args):
             dist.all_reduce(et, op=dist.ReduceOp.MAX)
         e2e = {"value": world * nsteps * eb * CHUNK / float(et.item()) / 1e9, "unit": "GB/s", "h2d_bytes_per_step": eb * CHUNK + eb * 16,
                "d2h_bytes_per_step": e2e_out // max(nsteps, 1), "chunks_per_step": eb, "steps": nsteps,
-               "api": "sq_pack_submit/sq_pack_wait, two batches in flight, pinned host buffers"}
-        for i in range(2):
-            lib.sq_host_free(ctx.h, hp[i]); lib.sq_host_free(ctx.h, ho[i]); lib.sq_host_free(ctx.h, hres[i])
+               "api": "sq_pack_submit/sq_pack_wait, rolling two-slot pipeline (wait k, submit k+2), pinned host buffers"}
+        for h_ in hp + ho + hres:
+            lib.sq_host_free(ctx.h, h_)
 
     if rank != 0:
         if world > 1:
