@@ -31,7 +31,7 @@ struct sq_enc_scratch {
     uint32_t *rec;           // [cap_chunks * lz::REC_PER_CHUNK] per-position parse records
     uint32_t *tab, *head;    // per resident lz CTA: bucketed hash table (never cleared between chunks)
     uint8_t *lits;           // per entropy warp: gathered literals
-    uint32_t *sbits;         // per entropy warp: FSE state-transition records, 3 x SEQ_PER_BLOCK
+    uint32_t *sbits;         // per entropy warp: FSE state-transition records + packed symbol codes, 4 x SEQ_PER_BLOCK
     uint32_t lz_ctas, ent_warps;
     uint32_t cap_chunks;
     uint32_t *status;        // [0] != 0 => capacity overflow; [1],[2] work counters
@@ -196,13 +196,17 @@ static int32_t enc_scratch(sq_ctx *ctx, uint32_t n, int set) {
             const char *tot = getenv("SQ_LZ_CTAS_TOTAL");  // experiment knob: cap the number of chunks in flight
             if (tot && atoi(tot) > 0) e->lz_ctas = (uint32_t)atoi(tot);
         }
-        e->ent_warps = (uint32_t)ctx->sm_count * 16;
+        {   // entropy stage: one warp per block, 4 warps per CTA; shared memory (42.8 KB per CTA) allows 5 CTAs per SM
+            const char *ov = getenv("SQ_ENT_WARPS_PER_SM");
+            e->ent_warps = (uint32_t)ctx->sm_count * (ov && atoi(ov) > 0 ? (uint32_t)atoi(ov) : 20u);
+            SQ_CUDA(ctx, cudaFuncSetAttribute(lz::entropy_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        }
         SQ_CUDA(ctx, cudaMalloc(&e->tab, (size_t)e->lz_ctas * lz::ROWS * lz::ROW_K * sizeof(uint32_t)));
         SQ_CUDA(ctx, cudaMemset(e->tab, 0, (size_t)e->lz_ctas * lz::ROWS * lz::ROW_K * sizeof(uint32_t)));
         SQ_CUDA(ctx, cudaMalloc(&e->head, (size_t)e->lz_ctas * lz::ROWS * sizeof(uint32_t)));
         SQ_CUDA(ctx, cudaMemset(e->head, 0, (size_t)e->lz_ctas * lz::ROWS * sizeof(uint32_t)));
         SQ_CUDA(ctx, cudaMalloc(&e->lits, (size_t)e->ent_warps * (Z_BLOCK_MAX + 64)));
-        SQ_CUDA(ctx, cudaMalloc(&e->sbits, (size_t)e->ent_warps * 3 * lz::SEQ_PER_BLOCK * sizeof(uint32_t)));
+        SQ_CUDA(ctx, cudaMalloc(&e->sbits, (size_t)e->ent_warps * 4 * lz::SEQ_PER_BLOCK * sizeof(uint32_t)));
         SQ_CUDA(ctx, cudaMalloc(&e->status, 8 * sizeof(uint32_t)));
         SQ_CUDA(ctx, cudaMemset(e->status, 0, 8 * sizeof(uint32_t)));
     }

@@ -190,20 +190,25 @@ __device__ uint32_t warp_write_literals(uint8_t *dst, const uint8_t *lits, uint3
 }
 
 // ---- sequences section ------------------------------------------------------------------------------------------------
-// sbits: per-warp scratch of 3 * nseq u32 (state-transition bits | count << 16 for LL, OF, ML)
+// sbits: per-warp scratch of 4 * nseq u32: state-transition bits | count << 16 for LL, OF, ML, then the packed symbol codes
+// (LL code | OF code << 8 | ML code << 16), computed once by all lanes so that the serial passes never recompute them
 __device__ uint32_t warp_write_sequences(uint8_t *dst, const zc::Seq *seqs, uint32_t nseq, WarpWork *W, uint32_t *sbits, uint32_t lane) {
     zc::EncWork *wk = &W->wk;
     if (nseq == 0) { if (lane == 0) dst[0] = 0; __syncwarp(); return 1; }
     // code histograms
     for (uint32_t s = lane; s < 192; s += 32) wk->hist[s / 64][s % 64] = 0;
     __syncwarp();
+    uint32_t *codes = sbits + 3 * (size_t)nseq;
     for (uint32_t i = lane; i < nseq; i += 32) {
         const zc::Seq q = seqs[i];
-        atomicAdd(&wk->hist[0][zc::ll_code(q.ll)], 1u);
-        atomicAdd(&wk->hist[1][zc::highbit(q.off_base)], 1u);
-        atomicAdd(&wk->hist[2][zc::ml_code(q.ml)], 1u);
+        const uint32_t lc = zc::ll_code(q.ll), oc = zc::highbit(q.off_base), mc = zc::ml_code(q.ml);
+        atomicAdd(&wk->hist[0][lc], 1u);
+        atomicAdd(&wk->hist[1][oc], 1u);
+        atomicAdd(&wk->hist[2][mc], 1u);
+        codes[i] = lc | oc << 8 | mc << 16;
     }
     __syncwarp();
+    __threadfence_block();
     if (lane == 0) {
         uint8_t *p = dst;
         if (nseq < 128) *p++ = (uint8_t)nseq;
@@ -227,17 +232,35 @@ __device__ uint32_t warp_write_sequences(uint8_t *dst, const zc::Seq *seqs, uint
         const zc::FseCTable *ct = &wk->ct[lane];
         const bool rle = mode_of_lane[lane] == 1;
         uint32_t *out = sbits + (size_t)lane * nseq;
-        auto code_of = [&](const zc::Seq &q) -> uint32_t { return lane == 0 ? zc::ll_code(q.ll) : lane == 1 ? zc::highbit(q.off_base) : zc::ml_code(q.ml); };
-        uint32_t state = rle ? 0 : zc::fse_init_state(ct, code_of(seqs[nseq - 1]));
-        for (uint32_t i = nseq - 1; i-- > 0;) {
-            uint32_t rec = 0;
-            if (!rle) {
-                const uint32_t c = code_of(seqs[i]);
+        const uint32_t csh = 8 * lane;  // this lane's byte of the packed codes
+        uint32_t state = 0;
+        if (rle) {
+            for (uint32_t i = 0; i + 1 < nseq; i++) out[i] = 0;
+        } else {
+            state = zc::fse_init_state(ct, codes[nseq - 1] >> csh & 0xFFu);
+            // the chain itself is serial (one shared-memory lookup per symbol depends on the previous state); the symbol codes
+            // and their per-symbol table entries do not, so they are fetched four symbols ahead of the chain
+            uint32_t i = nseq - 1;
+            while (i >= 4) {
+                uint32_t c[4], dn[4]; int32_t df[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) c[k] = codes[i - 1 - k] >> csh & 0xFFu;
+#pragma unroll
+                for (int k = 0; k < 4; k++) { dn[k] = ct->delta_nb_bits[c[k]]; df[k] = ct->delta_find_state[c[k]]; }
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const uint32_t nb = (state + dn[k]) >> 16;
+                    out[i - 1 - k] = (state & ((1u << nb) - 1)) | nb << 16;
+                    state = ct->next_state[(int32_t)(state >> nb) + df[k]];
+                }
+                i -= 4;
+            }
+            while (i-- > 0) {
+                const uint32_t c = codes[i] >> csh & 0xFFu;
                 const uint32_t nb = (state + ct->delta_nb_bits[c]) >> 16;
-                rec = (state & ((1u << nb) - 1)) | nb << 16;
+                out[i] = (state & ((1u << nb) - 1)) | nb << 16;
                 state = ct->next_state[(int32_t)(state >> nb) + ct->delta_find_state[c]];
             }
-            out[i] = rec;
         }
         W->scalars[4 + lane] = rle ? 0 : (state & ((1u << ct->tl) - 1)) | ct->tl << 16;  // final state flush
     }
@@ -250,8 +273,8 @@ __device__ uint32_t warp_write_sequences(uint8_t *dst, const zc::Seq *seqs, uint
     // pass B1: bits per segment
     uint32_t bits = 0;
     for (uint32_t i = lo; i < hi; i++) {
-        const zc::Seq s = seqs[i];
-        bits += zc::ZTAB(LL_bits)[zc::ll_code(s.ll)] + zc::ZTAB(ML_bits)[zc::ml_code(s.ml)] + zc::highbit(s.off_base);
+        const uint32_t cd = codes[i];
+        bits += zc::ZTAB(LL_bits)[cd & 0xFFu] + zc::ZTAB(ML_bits)[cd >> 16] + (cd >> 8 & 0xFFu);
         if (i + 1 < nseq) bits += (sb_ll[i] >> 16) + (sb_of[i] >> 16) + (sb_ml[i] >> 16);
     }
     if (owns_end) bits += (W->scalars[4] >> 16) + (W->scalars[5] >> 16) + (W->scalars[6] >> 16) + 1;
@@ -268,7 +291,7 @@ __device__ uint32_t warp_write_sequences(uint8_t *dst, const zc::Seq *seqs, uint
         for (uint32_t i = hi; i > lo; i--) {
             const uint32_t k = i - 1;
             const zc::Seq s = seqs[k];
-            const uint32_t lc = zc::ll_code(s.ll), mc = zc::ml_code(s.ml), oc = zc::highbit(s.off_base);
+            const uint32_t cd = codes[k], lc = cd & 0xFFu, oc = cd >> 8 & 0xFFu, mc = cd >> 16;
             if (k + 1 < nseq) {
                 const uint32_t a = sb_of[k], b = sb_ml[k], c = sb_ll[k];
                 seg_put(&w, a & 0xFFFF, a >> 16);

@@ -609,7 +609,7 @@ __global__ void __launch_bounds__(128) entropy_kernel(const uint8_t *__restrict_
     const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     ent::WarpWork *W = &s_work[threadIdx.x >> 5];
     uint8_t *lits = lit_all + (size_t)warp_global * (Z_BLOCK_MAX + 64);
-    uint32_t *sbits = sbits_all + (size_t)warp_global * 3 * SEQ_PER_BLOCK;
+    uint32_t *sbits = sbits_all + (size_t)warp_global * 4 * SEQ_PER_BLOCK;
     for (;;) {
         uint32_t item = 0;
         if (lane == 0) item = atomicAdd(counter, 1u);
