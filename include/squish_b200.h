@@ -202,6 +202,14 @@ int32_t sq_pack_submit(sq_ctx *ctx, const void *h_data, size_t data_len, const s
                        uint32_t n, uint64_t gidx_base, sq_chunk_result *h_results, void *h_out,
                        uint64_t out_capacity, sq_ticket **ticket);
 int32_t sq_pack_wait(sq_ctx *ctx, sq_ticket *ticket, uint64_t *out_used);
+/* Asynchronous twin of sq_unpack_host (same arguments): at most two tickets in flight; the upload of
+ * batch k+1 and the download of batch k-1 overlap the decode of batch k.  h_comp / h_frames may be
+ * reused once submit returns only if they are pageable; pinned buffers must stay untouched until the
+ * ticket is waited on, like h_out / h_results. */
+int32_t sq_unpack_submit(sq_ctx *ctx, const void *h_comp, size_t comp_len, const sq_frame *h_frames,
+                         uint32_t n, void *h_out, size_t out_len, sq_frame_result *h_results,
+                         sq_ticket **ticket);
+int32_t sq_unpack_wait(sq_ctx *ctx, sq_ticket *ticket);
 /* read_chunks for a batch through HOST buffers: H2D payloads, decode, D2H output. */
 int32_t sq_unpack_host(sq_ctx *ctx, const void *h_comp, size_t comp_len, const sq_frame *h_frames,
                        uint32_t n, void *h_out, size_t out_len, sq_frame_result *h_results);

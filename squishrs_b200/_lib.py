@@ -92,6 +92,8 @@ SYMBOLS = {
     "sq_pack_submit": (C.c_int32, [_P, _P, C.c_size_t, _P, C.c_uint32, C.c_uint64, _P, _P, C.c_uint64, C.POINTER(_P)]),
     "sq_pack_wait": (C.c_int32, [_P, _P, C.POINTER(C.c_uint64)]),
     "sq_unpack_host": (C.c_int32, [_P, _P, C.c_size_t, _P, C.c_uint32, _P, C.c_size_t, _P]),
+    "sq_unpack_submit": (C.c_int32, [_P, _P, C.c_size_t, _P, C.c_uint32, _P, C.c_size_t, _P, C.POINTER(_P)]),
+    "sq_unpack_wait": (C.c_int32, [_P, _P]),
     "sq_archive_pack": (C.c_int32, [_P, C.c_char_p, C.c_char_p, C.c_int32, C.POINTER(SqPackReport)]),
     "sq_archive_unpack": (C.c_int32, [_P, C.c_char_p, C.c_char_p, C.c_int32, C.POINTER(SqSummary)]),
     "sq_archive_list": (C.c_int32, [C.c_char_p, C.POINTER(SqSummary), C.POINTER(C.c_char_p)]),

@@ -97,6 +97,9 @@ extern "C" int32_t sq_create(const sq_config *cfg, sq_ctx **out) {
             SQ_CUDA(ctx, cudaEventCreateWithFlags(&ctx->dedup_done[i], cudaEventDisableTiming));
             SQ_CUDA(ctx, cudaEventCreateWithFlags(&ctx->slots[i].h2d_done, cudaEventDisableTiming));
             SQ_CUDA(ctx, cudaEventCreateWithFlags(&ctx->slots[i].compute_done, cudaEventDisableTiming));
+            SQ_CUDA(ctx, cudaEventCreateWithFlags(&ctx->uslots[i].h2d_done, cudaEventDisableTiming));
+            SQ_CUDA(ctx, cudaEventCreateWithFlags(&ctx->uslots[i].compute_done, cudaEventDisableTiming));
+            SQ_CUDA(ctx, cudaEventCreateWithFlags(&ctx->uslots[i].d2h_done, cudaEventDisableTiming));
             SQ_CUDA(ctx, cudaHostAlloc((void **)&ctx->slots[i].h_total, 64, cudaHostAllocDefault));
         }
         SQ_CUDA(ctx, cudaMalloc(&ctx->d_work_counter, 64 * sizeof(uint32_t)));
@@ -126,6 +129,12 @@ extern "C" void sq_destroy(sq_ctx *ctx) {
         if (ctx->slots[i].d_in) cudaFree(ctx->slots[i].d_in);
         if (ctx->slots[i].d_out) cudaFree(ctx->slots[i].d_out);
         if (ctx->slots[i].d_meta) cudaFree(ctx->slots[i].d_meta);
+        if (ctx->uslots[i].d_in) cudaFree(ctx->uslots[i].d_in);
+        if (ctx->uslots[i].d_out) cudaFree(ctx->uslots[i].d_out);
+        if (ctx->uslots[i].d_meta) cudaFree(ctx->uslots[i].d_meta);
+        if (ctx->uslots[i].h2d_done) cudaEventDestroy(ctx->uslots[i].h2d_done);
+        if (ctx->uslots[i].compute_done) cudaEventDestroy(ctx->uslots[i].compute_done);
+        if (ctx->uslots[i].d2h_done) cudaEventDestroy(ctx->uslots[i].d2h_done);
         if (ctx->slots[i].h2d_done) cudaEventDestroy(ctx->slots[i].h2d_done);
         if (ctx->slots[i].compute_done) cudaEventDestroy(ctx->slots[i].compute_done);
         if (ctx->slots[i].h_total) cudaFreeHost(ctx->slots[i].h_total);

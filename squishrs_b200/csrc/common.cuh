@@ -45,6 +45,13 @@ struct sq_ctx {
         uint32_t n; uint64_t out_capacity; void *h_out; int busy;
     } slots[2];
     cudaStream_t d2h_stream;
+    // double-buffered unpack pipeline (sq_unpack_submit / sq_unpack_wait): uploads on copy_stream, decode on stream, downloads on d2h_stream
+    struct unpack_slot {
+        void *d_in, *d_out, *d_meta; size_t in_cap, out_cap, meta_cap;
+        cudaEvent_t h2d_done, compute_done, d2h_done;
+        int busy;
+    } uslots[2];
+    int next_uslot;
     cudaStream_t slot_stream[2];   // one compute stream per pipeline slot: the tail of one batch overlaps the head of the next
     cudaEvent_t dedup_done[2];     // K1/K2 of consecutive batches stay ordered across the two slot streams
     int dedup_done_valid[2];

@@ -149,6 +149,55 @@ extern "C" int32_t sq_pack_host(sq_ctx *ctx, const void *h_data, size_t data_len
     return sq_pack_wait(ctx, t, out_used);
 }
 
+// ---- double-buffered unpack pipeline ------------------------------------------------------------------------------
+// submit: payload upload on the copy stream -> K4 on the context stream -> results + decoded bytes download on the
+// d2h stream; returns at once.  With two tickets in flight the upload of batch k+1 and the download of batch k-1
+// overlap the decode of batch k, so unpack runs at the slower of the decoder and the host link.
+static sq_ticket g_utickets[2] = {{0}, {1}};
+
+extern "C" int32_t sq_unpack_submit(sq_ctx *ctx, const void *h_comp, size_t comp_len, const sq_frame *h_frames, uint32_t n, void *h_out,
+                                    size_t out_len, sq_frame_result *h_results, sq_ticket **ticket) {
+    if (!ctx || !ticket) return SQ_ERR_INVALID_ARG;
+    if (n == 0 || !h_comp || !h_frames || !h_results || (!h_out && out_len)) return sq_set_error(ctx, SQ_ERR_INVALID_ARG, "sq_unpack_submit: bad arguments");
+    for (uint32_t i = 0; i < n; i++) {
+        if (h_frames[i].src_off + h_frames[i].src_len > comp_len)
+            return sq_set_error(ctx, SQ_ERR_READER, "frame %u payload outside the compressed buffer", i);
+        if (h_frames[i].dst_off + h_frames[i].capacity > out_len)
+            return sq_set_error(ctx, SQ_ERR_CAPACITY, "frame %u capacity outside the output buffer", i);
+    }
+    const int si = ctx->next_uslot;
+    sq_ctx::unpack_slot &sl = ctx->uslots[si];
+    if (sl.busy) return sq_set_error(ctx, SQ_ERR_OTHER, "sq_unpack_submit: both pipeline slots are in flight; call sq_unpack_wait first");
+    int32_t rc;
+    if ((rc = sq_ensure(ctx, &sl.d_in, &sl.in_cap, comp_len + 64))) return rc;
+    if ((rc = sq_ensure(ctx, &sl.d_out, &sl.out_cap, out_len + 64))) return rc;
+    pack_meta m;
+    if ((rc = meta_layout_in(ctx, &sl.d_meta, &sl.meta_cap, n, &m))) return rc;
+    SQ_CUDA(ctx, cudaMemcpyAsync(sl.d_in, h_comp, comp_len, cudaMemcpyHostToDevice, ctx->copy_stream));
+    SQ_CUDA(ctx, cudaMemcpyAsync(m.frames, h_frames, (size_t)n * sizeof(sq_frame), cudaMemcpyHostToDevice, ctx->copy_stream));
+    SQ_CUDA(ctx, cudaEventRecord(sl.h2d_done, ctx->copy_stream));
+    SQ_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, sl.h2d_done, 0));
+    if ((rc = sq_decode_device(ctx, sl.d_in, m.frames, n, sl.d_out, m.fres, ctx->stream))) return rc;
+    SQ_CUDA(ctx, cudaEventRecord(sl.compute_done, ctx->stream));
+    SQ_CUDA(ctx, cudaStreamWaitEvent(ctx->d2h_stream, sl.compute_done, 0));
+    SQ_CUDA(ctx, cudaMemcpyAsync(h_results, m.fres, (size_t)n * sizeof(sq_frame_result), cudaMemcpyDeviceToHost, ctx->d2h_stream));
+    if (out_len) SQ_CUDA(ctx, cudaMemcpyAsync(h_out, sl.d_out, out_len, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+    SQ_CUDA(ctx, cudaEventRecord(sl.d2h_done, ctx->d2h_stream));
+    sl.busy = 1;
+    ctx->next_uslot = si ^ 1;
+    *ticket = &g_utickets[si];
+    return SQ_OK;
+}
+
+extern "C" int32_t sq_unpack_wait(sq_ctx *ctx, sq_ticket *ticket) {
+    if (!ctx || !ticket) return SQ_ERR_INVALID_ARG;
+    sq_ctx::unpack_slot &sl = ctx->uslots[ticket->slot];
+    if (!sl.busy) return sq_set_error(ctx, SQ_ERR_INVALID_ARG, "sq_unpack_wait: ticket is not in flight");
+    sl.busy = 0;
+    SQ_CUDA(ctx, cudaEventSynchronize(sl.d2h_done));
+    return SQ_OK;
+}
+
 extern "C" int32_t sq_unpack_host(sq_ctx *ctx, const void *h_comp, size_t comp_len, const sq_frame *h_frames, uint32_t n, void *h_out,
                                   size_t out_len, sq_frame_result *h_results) {
     if (!ctx) return SQ_ERR_INVALID_ARG;

@@ -483,45 +483,72 @@ extern "C" int32_t sq_archive_unpack(sq_ctx *ctx, const char *archive_path, cons
     for (auto &r : a.records) total_comp += (r.comp + 15) & ~15ull;
     const uint64_t batch_out = std::min<uint64_t>(2048ull << 20, std::max<uint64_t>(total_out, 1u << 20)),
                    batch_in = std::min<uint64_t>(1024ull << 20, std::max<uint64_t>(total_comp, 1u << 20));
-    Staging comp_stage, out_stage;
+    // Two staging pairs drive the two-slot unpack pipeline (sq_unpack_submit / sq_unpack_wait): while batch k decodes, the
+    // payloads of batch k+1 are gathered and uploaded and the output of batch k-1 is downloaded and copied into the store.
+    struct UnpackBatch {
+        Staging comp, out;
+        std::vector<sq_frame> frames;
+        std::vector<sq_frame_result> fres;
+        size_t first = 0; uint64_t dof = 0, store_off = 0;
+        sq_ticket *ticket = nullptr; bool live = false;
+    } ub[2];
     const bool pin = total_out >= kPinThreshold;
-    if ((rc = comp_stage.alloc(ctx, batch_in + (4u << 20), pin))) { free(store); return rc; }
-    if ((rc = out_stage.alloc(ctx, batch_out + (4u << 20), pin))) { comp_stage.release(ctx); free(store); return rc; }
-    void *h_comp = comp_stage.p, *h_out = out_stage.p;
+    for (int k = 0; k < 2 && !rc; k++) {
+        if ((rc = ub[k].comp.alloc(ctx, batch_in + (4u << 20), pin))) break;
+        if ((rc = ub[k].out.alloc(ctx, batch_out + (4u << 20), pin))) break;
+        ub[k].fres.resize(ctx->max_batch);
+    }
+    if (rc) { for (int k = 0; k < 2; k++) { ub[k].comp.release(ctx); ub[k].out.release(ctx); } free(store); return rc; }
     SQ_T("unpack buffers allocated");
-    std::vector<sq_frame> frames;
-    std::vector<sq_frame_result> fres(ctx->max_batch);
+    auto finish = [&](UnpackBatch &b) -> int32_t {  // wait for the batch, check every payload, move its bytes into the store
+        b.live = false;
+        double td = now_s();
+        int32_t r = sq_unpack_wait(ctx, b.ticket);
+        t_dev += now_s() - td;
+        if (r) return r;
+        for (size_t k = 0; k < b.frames.size(); k++) {
+            if (b.fres[k].status != SQ_OK) return sq_set_error(ctx, SQ_ERR_READER, "Error reading from squish: chunk %zu failed to decode", b.first + k);
+            dec[b.first + k] = {b.store_off + b.frames[k].dst_off, b.fres[k].out_len};
+        }
+        parallel_for(b.frames.size(), threads, [&](size_t k) { memcpy(store + b.store_off + b.frames[k].dst_off, (uint8_t *)b.out.p + b.frames[k].dst_off, b.fres[k].out_len); });
+        return SQ_OK;
+    };
     uint64_t store_off = 0;
     size_t i = 0;
+    int cur = 0;
     while (i < a.records.size() && !rc) {
-        frames.clear();
+        UnpackBatch &b = ub[cur];
+        if (b.live && (rc = finish(b))) break;  // the slot's previous batch must be home before its buffers are reused
+        b.frames.clear();
         uint64_t so = 0, dof = 0;
-        size_t first = i;
-        while (i < a.records.size() && frames.size() < ctx->max_batch) {
+        b.first = i;
+        while (i < a.records.size() && b.frames.size() < ctx->max_batch) {
             const Record &r = a.records[i];
             uint64_t sneed = (r.comp + 15) & ~15ull, dneed = (bound[i] + 15) & ~15ull;
-            if (!frames.empty() && (so + sneed > batch_in || dof + dneed > batch_out)) break;
+            if (!b.frames.empty() && (so + sneed > batch_in || dof + dneed > batch_out)) break;
             if (sneed > batch_in + (4u << 20) || dneed > batch_out + (4u << 20)) { rc = sq_set_error(ctx, SQ_ERR_INVALID_CHUNK_SIZE, "Invalid chunk size: %llu bytes", (unsigned long long)r.orig); break; }
-            frames.push_back({so, dof, (uint32_t)r.comp, (uint32_t)bound[i]});
+            b.frames.push_back({so, dof, (uint32_t)r.comp, (uint32_t)bound[i]});
             so += sneed; dof += dneed;
             i++;
         }
         if (rc) break;
-        parallel_for(frames.size(), threads, [&](size_t k) { memcpy((uint8_t *)h_comp + frames[k].src_off, a.records[first + k].payload, frames[k].src_len); });
+        parallel_for(b.frames.size(), threads, [&](size_t k) { memcpy((uint8_t *)b.comp.p + b.frames[k].src_off, a.records[b.first + k].payload, b.frames[k].src_len); });
         double td = now_s();
-        rc = sq_unpack_host(ctx, h_comp, so, frames.data(), (uint32_t)frames.size(), h_out, dof, fres.data());
+        rc = sq_unpack_submit(ctx, b.comp.p, so, b.frames.data(), (uint32_t)b.frames.size(), b.out.p, dof, b.fres.data(), &b.ticket);
         t_dev += now_s() - td;
         if (rc) break;
-        for (size_t k = 0; k < frames.size(); k++) {
-            if (fres[k].status != SQ_OK) { rc = sq_set_error(ctx, SQ_ERR_READER, "Error reading from squish: chunk %zu failed to decode", first + k); break; }
-            dec[first + k] = {store_off + frames[k].dst_off, fres[k].out_len};
-        }
-        if (rc) break;
-        parallel_for(frames.size(), threads, [&](size_t k) { memcpy(store + store_off + frames[k].dst_off, (uint8_t *)h_out + frames[k].dst_off, fres[k].out_len); });
+        b.live = true; b.dof = dof; b.store_off = store_off;
         store_off += dof;
+        cur ^= 1;
     }
+    for (int k = 0; k < 2; k++) {  // drain, oldest first; on error still wait before the buffers go away
+        UnpackBatch &b = ub[cur ^ k];
+        if (!b.live) continue;
+        if (rc) { sq_unpack_wait(ctx, b.ticket); b.live = false; }
+        else rc = finish(b);
+    }
+    for (int k = 0; k < 2; k++) { ub[k].comp.release(ctx); ub[k].out.release(ctx); }
     SQ_T("all chunks decoded");
-    comp_stage.release(ctx); out_stage.release(ctx);
     if (rc) { free(store); return rc; }
 
     struct Key { uint64_t a, b; bool operator==(const Key &o) const { return a == o.a && b == o.b; } };

@@ -493,3 +493,41 @@ def test_encode_device_on_several_streams(sq, oracle):
         assert int(total.item()) == sum(fl)
         for k, b in enumerate(blobs):
             assert oracle.decompress(o[fo[k]:fo[k] + fl[k]].tobytes(), size) == b, k
+
+
+def test_unpack_pipeline_two_tickets_in_flight(sq, oracle):
+    # sq_unpack_submit / sq_unpack_wait: same bytes as the synchronous sq_unpack_host, two batches in flight, a third refused
+    from squishrs_b200 import _lib as L
+    c = sq.Context()
+    lib = c.lib
+    samples = [s for _, s in corpus_samples(sq)]
+    batches = [samples[0::2], samples[1::2]]
+    staged = []
+    for b in batches:
+        payloads = [oracle.compress(s) for s in b]
+        n = len(payloads)
+        frames = (L.SqFrame * n)()
+        so = do = 0
+        for i, (pl, s) in enumerate(zip(payloads, b)):
+            frames[i].src_off, frames[i].dst_off, frames[i].src_len, frames[i].capacity = so, do, len(pl), len(s)
+            so += (len(pl) + 15) & ~15
+            do += (len(s) + 15) & ~15
+        comp = bytearray(so + 16)
+        for i, pl in enumerate(payloads):
+            comp[frames[i].src_off:frames[i].src_off + len(pl)] = pl
+        staged.append(dict(n=n, frames=frames, comp=(C.c_uint8 * len(comp)).from_buffer(comp), so=so, out=(C.c_uint8 * (do + 16))(), do=do,
+                           res=(L.SqFrameResult * n)(), ticket=C.c_void_p(), expect=b))
+    for st in staged:
+        c.check(lib.sq_unpack_submit(c.h, st["comp"], st["so"], st["frames"], st["n"], st["out"], st["do"], st["res"], C.byref(st["ticket"])))
+    extra = C.c_void_p()
+    st0 = staged[0]
+    assert lib.sq_unpack_submit(c.h, st0["comp"], st0["so"], st0["frames"], st0["n"], st0["out"], st0["do"], st0["res"], C.byref(extra)) != 0  # both slots busy
+    for st in staged:
+        c.check(lib.sq_unpack_wait(c.h, st["ticket"]))
+        mv = memoryview(st["out"])
+        for i, s in enumerate(st["expect"]):
+            assert st["res"][i].status == 0 and st["res"][i].out_len == len(s)
+            assert bytes(mv[st["frames"][i].dst_off:st["frames"][i].dst_off + len(s)]) == s
+    assert lib.sq_unpack_wait(c.h, staged[0]["ticket"]) != 0  # not in flight any more
+    # the slots are free again, and the synchronous call still works on the same context
+    assert c.unpack_batch([oracle.compress(samples[0])], [len(samples[0])]) == [samples[0]]
