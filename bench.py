@@ -541,9 +541,9 @@ def run_ours(args):
         st = np.frombuffer(d_res.cpu().numpy().tobytes(), dtype="<i4").reshape(-1, 2)
         unpack = {"value": len(sel) * CHUNK / (min(t_dec[1:]) * 1e-3) / 1e9, "unit": "GB/s", "frames": int(len(sel)), "what": "K4 decode of one packed batch, device-resident, restored bytes/s",
                   "byte_identical": ok and int((st[:, 1] != 0).sum()) == 0, "algorithmic_gbs": (int(r["len"][sel].sum()) + len(sel) * CHUNK) / (min(t_dec[1:]) * 1e-3) / 1e9}
-        # e2e unpack through the host-buffer C-ABI call (H2D payloads + K4 + D2H restored bytes), <= 1024 frames per call
+        # e2e unpack through the host-buffer C-ABI calls (H2D payloads + K4 + D2H restored bytes), one packed batch (<= 2048 frames) per call
         try:
-            ne = int(min(len(sel), 1024))
+            ne = int(min(len(sel), 2048))
             host_out = d_out[: int(used.value)].cpu().numpy()
             payloads = [host_out[int(r["off"][i]): int(r["off"][i]) + int(r["len"][i])] for i in sel[:ne]]
             hf = (L.SqFrame * ne)()

@@ -94,6 +94,16 @@ ZD_DEV uint32_t br_read(BitReader *b, uint32_t n) {
     return v;
 }
 
+// Unchecked read for a caller that has just refilled: n <= 31 and the window still covers [pos - n, pos).  After br_refill
+// the window holds more than 56 unread bits (or the stream is exhausted and it holds zeros), so a caller may take up to 56
+// bits before the next refill.  Once pos has gone negative (corrupt input) the values are meaningless but the shift stays in
+// range; callers check pos < 0 afterwards.
+ZD_DEV uint32_t br_take(BitReader *b, uint32_t n) {
+    b->pos -= (int32_t)n;
+    const uint32_t sh = (uint32_t)(b->pos - b->wlo) & 63u;
+    return (uint32_t)(b->win >> sh) & ((1u << n) - 1u);
+}
+
 // Forward bit reader (FSE table descriptions)
 struct FwdReader { const uint8_t *p; uint32_t size; uint32_t bit; };
 ZD_DEV uint32_t fr_peek(const FwdReader *r, uint32_t n) {
@@ -410,10 +420,16 @@ ZD_DEV int64_t decode_compressed_block(const uint8_t *src, uint32_t size, uint8_
             int err = 0;
             for (uint32_t k = 0; k < nbatch; k++) {
                 const SeqCell cl = T->ll[s_ll], co = T->of[s_of], cm = T->ml[s_ml];
+                // One refill per sequence covers its extra bits and state transitions in the common case (the window then holds
+                // more than 56 bits); the two further refills only happen for very long offsets / lengths.  All branches are
+                // warp-uniform: every lane walks the same chain.
+                const uint32_t ofb = co.sym /* <= 31, checked when the table was built */, mlb = zc::ZTAB(ML_bits)[cm.sym], llb = zc::ZTAB(LL_bits)[cl.sym];
+                br_refill(&b);
                 // extra bits: offset, match length, literal length
-                const uint32_t ofv = (1u << co.sym) + br_read(&b, co.sym);
-                const uint32_t ml = zc::ZTAB(ML_base)[cm.sym] + br_read(&b, zc::ZTAB(ML_bits)[cm.sym]);
-                const uint32_t ll = zc::ZTAB(LL_base)[cl.sym] + br_read(&b, zc::ZTAB(LL_bits)[cl.sym]);
+                const uint32_t ofv = (1u << ofb) + br_take(&b, ofb);
+                if (ofb + mlb + llb > 56) br_refill(&b);
+                const uint32_t ml = zc::ZTAB(ML_base)[cm.sym] + br_take(&b, mlb);
+                const uint32_t ll = zc::ZTAB(LL_base)[cl.sym] + br_take(&b, llb);
                 uint32_t off;
                 if (ofv > 3) { off = ofv - 3; r2 = r1; r1 = r0; r0 = off; }
                 else {
@@ -426,10 +442,11 @@ ZD_DEV int64_t decode_compressed_block(const uint8_t *src, uint32_t size, uint8_
                         r1 = r0; r0 = off;
                     }
                 }
-                if (i0 + k + 1 < nseq) {  // state updates: LL, ML, OF
-                    s_ll = cl.next_base + br_read(&b, cl.nb_bits);
-                    s_ml = cm.next_base + br_read(&b, cm.nb_bits);
-                    s_of = co.next_base + br_read(&b, co.nb_bits);
+                if (i0 + k + 1 < nseq) {  // state updates: LL, ML, OF (at most 9 + 9 + 8 bits)
+                    if (ofb + mlb + llb > 56 - 26) br_refill(&b);
+                    s_ll = cl.next_base + br_take(&b, cl.nb_bits);
+                    s_ml = cm.next_base + br_take(&b, cm.nb_bits);
+                    s_of = co.next_base + br_take(&b, co.nb_bits);
                 }
                 if (k == ZD_LANE()) { my_ll = ll; my_ml = ml; my_off = off; }
             }

@@ -481,8 +481,8 @@ extern "C" int32_t sq_archive_unpack(sq_ctx *ctx, const char *archive_path, cons
     // a frame decodes on one warp: many frames per call keep the GPU full; pinned staging is sized to the job
     uint64_t total_comp = 0;
     for (auto &r : a.records) total_comp += (r.comp + 15) & ~15ull;
-    const uint64_t batch_out = std::min<uint64_t>(2048ull << 20, std::max<uint64_t>(total_out, 1u << 20)),
-                   batch_in = std::min<uint64_t>(1024ull << 20, std::max<uint64_t>(total_comp, 1u << 20));
+    const uint64_t batch_out = std::min<uint64_t>(4096ull << 20, std::max<uint64_t>(total_out, 1u << 20)),
+                   batch_in = std::min<uint64_t>(2048ull << 20, std::max<uint64_t>(total_comp, 1u << 20));
     // Two staging pairs drive the two-slot unpack pipeline (sq_unpack_submit / sq_unpack_wait): while batch k decodes, the
     // payloads of batch k+1 are gathered and uploaded and the output of batch k-1 is downloaded and copied into the store.
     struct UnpackBatch {
