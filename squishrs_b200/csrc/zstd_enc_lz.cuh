@@ -313,8 +313,8 @@ __global__ void __launch_bounds__(THREADS, SQ_LZ_MINB) lz_search_kernel(const ui
                 if (gfast) {
 #pragma unroll 1
                     for (uint32_t i = lane; i < total; i += 64) {
-                        // two pairs per lane per trip: both candidates' first 8 bytes (two aligned 8-byte loads each) are requested
-                        // before either is examined; pairs that match all 8 fetch bytes 8..23 in ONE further round
+                        // two pairs per lane per trip: both candidates' bytes (four aligned 8-byte loads each, 24 bytes at any
+                        // alignment) are requested before either is examined
                         const bool h1 = i + 32 < total;
                         const uint32_t pr0 = queue[i], pr1 = queue[h1 ? i + 32 : i];
                         const uint32_t l0 = pr0 & 1023u, c0 = pr0 >> 10, l1 = pr1 & 1023u, c1 = pr1 >> 10;
@@ -335,10 +335,10 @@ __global__ void __launch_bounds__(THREADS, SQ_LZ_MINB) lz_search_kernel(const ui
                         uint32_t m0 = x0lo ? 0u : x0hi ? 4u + (uint32_t)(__ffs((int)x0hi) - 1) / 8 : 8u;
                         uint32_t m1 = x1lo ? 0u : x1hi ? 4u + (uint32_t)(__ffs((int)x1hi) - 1) / 8 : 8u;
                         const bool g0 = m0 == 8u, g1 = m1 == 8u;
+                        // bytes 8..23 are requested right away as well (same or next sector as the first 16 bytes): a pair that
+                        // matches all 8 first bytes then needs no second round trip
+                        const uint2 A2 = __ldg(wc0 + 2), A3 = __ldg(wc0 + 3), B2 = __ldg(wc1 + 2), B3 = __ldg(wc1 + 3);
                         if (g0 | g1) {
-                            uint2 A2 = make_uint2(0u, 0u), A3 = A2, B2 = A2, B3 = A2;
-                            if (g0) { A2 = __ldg(wc0 + 2); A3 = __ldg(wc0 + 3); }
-                            if (g1) { B2 = __ldg(wc1 + 2); B3 = __ldg(wc1 + 3); }
                             if (g0) {
                                 const uint32_t a3w = u0 ? A2.x : A1.y, a4w = u0 ? A2.y : A2.x, a5w = u0 ? A3.x : A2.y, a6w = u0 ? A3.y : A3.x;
                                 const uint32_t p3w = wp0[3], p4w = wp0[4], p5w = wp0[5], p6w = wp0[6];
@@ -513,7 +513,7 @@ __global__ void __launch_bounds__(THREADS, SQ_LZ_MINB) lz_search_kernel(const ui
 // ---- kernel B: chase.  One warp per 128 KiB block walks the records from the block start: lanes hold a
 // window of 32 records (one coalesced load), hops inside the window are shuffles, literal runs are skipped
 // with a ballot, capped matches are extended 256 bytes per step by the whole warp. ------------------------
-__device__ __forceinline__ uint32_t warp_extend(const uint8_t *__restrict__ in, uint32_t a, uint32_t b, uint32_t maxlen, uint32_t lane) {
+__device__ __forceinline__ uint32_t warp_extend(const uint8_t *__restrict__ in, uint32_t n, uint32_t a, uint32_t b, uint32_t maxlen, uint32_t lane) {
     // common prefix of in[a..] and in[b..] (b < a), at most maxlen; all lanes return the same value
     uint32_t done = 0;
     while (done < maxlen) {
@@ -521,9 +521,15 @@ __device__ __forceinline__ uint32_t warp_extend(const uint8_t *__restrict__ in, 
         uint32_t m = 8;  // bytes of this lane's 8-byte slot that match (slots past maxlen count as matching)
         if (i < maxlen) {
             const uint32_t lim = min(8u, maxlen - i);
-            m = 0;
-            while (m < lim && in[a + i + m] == in[b + i + m]) m++;
-            if (m == lim) m = 8;
+            if (a + i + 16 <= n) {  // both unaligned 8-byte reads stay inside the chunk
+                const uint64_t x = ld64_unaligned(in, a + i) ^ ld64_unaligned(in, b + i);
+                m = x ? (uint32_t)(__ffsll((long long)x) - 1) / 8 : 8u;
+                if (m >= lim) m = 8;
+            } else {
+                m = 0;
+                while (m < lim && in[a + i + m] == in[b + i + m]) m++;
+                if (m == lim) m = 8;
+            }
         }
         const uint32_t bad = __ballot_sync(0xffffffffu, m != 8);
         if (bad) {
@@ -555,9 +561,16 @@ __global__ void __launch_bounds__(128) lz_chase_kernel(const uint8_t *__restrict
     uint32_t p = bs, anchor = bs, nseq = 0;
     uint32_t r0 = 0, r1 = 0, r2 = 0;  // repeat offsets are unknown at a block start (see file header); the frame's first block knows 1,4,8
     if (b == 0) { r0 = 1; r1 = 4; r2 = 8; }
+    // the window after the current one is requested speculatively: unless a long match jumps over it, its records are
+    // already in registers when the cursor gets there
+    uint32_t pf_base = ~0u, pf = 0;
     while (p < be) {
         const uint32_t base = p & ~31u;
-        const uint32_t mine = (base + lane < be) ? __ldg(rec + base + lane) : 0u;
+        uint32_t mine;
+        if (base == pf_base) mine = pf;
+        else mine = (base + lane < be) ? __ldg(rec + base + lane) : 0u;
+        pf_base = base + 32;
+        pf = (pf_base + lane < be) ? __ldg(rec + pf_base + lane) : 0u;
         uint32_t live = __ballot_sync(0xffffffffu, mine != 0);
         live &= 0xffffffffu << (p - base);  // records at or after the cursor
         while (live) {
@@ -565,7 +578,7 @@ __global__ void __launch_bounds__(128) lz_chase_kernel(const uint8_t *__restrict
             const uint32_t r = __shfl_sync(0xffffffffu, mine, idx);
             p = base + idx;
             uint32_t off = r & 0x1FFFFFu, len = ((r >> 21) & 31u) + 1, back = (r >> 27) & 3u, start = p + (r >> 29);
-            if ((r >> 26 & 1u) && start + len < be) len += warp_extend(in, start + len, start + len - off, be - start - len, lane);
+            if ((r >> 26 & 1u) && start + len < be) len += warp_extend(in, n, start + len, start + len - off, be - start - len, lane);
             if (back > start - anchor) back = start - anchor;
             start -= back; len += back;
             const uint32_t ll = start - anchor;
