@@ -482,7 +482,7 @@ __global__ void __launch_bounds__(THREADS, SQ_LZ_MINB) lz_search_kernel(const ui
                         const uint32_t kb = s_back[start - t0 + HALO];
                         r = pack_rec(s_off[start - t0 + HALO], kb >> 2, s_len[start - t0 + HALO] >= TARGET_LEN, kb & 3u, start - p);
                     }
-                    rec[p] = r;
+                    __stcs(&rec[p], r);  // streamed: written once, read once by the chase kernel
                 }
                 if (first) {
                     first = false;
