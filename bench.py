@@ -481,11 +481,11 @@ def run_ours(args):
     u_stage = stage_new * CHUNK
     alg = {"digest": stage_in, "dedup": stage_steps * B * 48, "encode": u_stage + stage_out}[dom]
     ach = alg / (stage_ms[dom] * 1e-3) / 1e9 if stage_ms[dom] > 0 else 0.0
-    roof = {"bound": "hbm", "kernel": {"digest": "xxh3_128_kernel (K1)", "dedup": "dedup_insert_kernel (K2)", "encode": "zstd encode stages (K3), lz_search_kernel ~80% of it"}[dom],
+    roof = {"bound": "hbm", "kernel": {"digest": "xxh3_128_kernel (K1)", "dedup": "dedup_insert_kernel (K2)", "encode": "zstd encode stages (K3), lz_search_kernel ~78% of it"}[dom],
             "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-            # dram bytes/launch of the dominant kernel: 139 B per unique input byte measured by ncu --set full on lz_search_kernel
-            # (profiles/r1_lz_search_v4_raw.csv: 200.8 GB read + 58.7 GB written for 888 chunks); K1 reads its input once (ncu: 1.00x)
-            "traffic": int(139 * u_stage / stage_steps) if dom == "encode" else (alg // stage_steps if dom == "digest" else None),
+            # dram bytes/launch of the dominant kernel: 142 B per unique input byte measured by ncu --set full on lz_search_kernel
+            # (profiles/r1_enc_final_raw.csv: 205.6 GB read + 58.8 GB written for 888 chunks); K1 reads its input once (ncu: 1.00x)
+            "traffic": int(142 * u_stage / stage_steps) if dom == "encode" else (alg // stage_steps if dom == "digest" else None),
             "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
             "algorithmic_bytes_per_step": alg // stage_steps,
             "timing": ("per-launch CUDA-event durations from a %d-step single-stream pass after the timed region (the timed region itself "
