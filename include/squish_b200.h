@@ -71,8 +71,13 @@ typedef struct {
     uint32_t chunk_size;        /* 0 = SQ_CHUNK_SIZE; must be <= SQ_CHUNK_SIZE */
     uint64_t dedup_capacity;    /* max distinct digests the context will ever hold (0 = 1<<20) */
     uint32_t max_batch_chunks;  /* largest n passed to any batch call (0 = 4096) */
-    uint32_t flags;             /* reserved, 0 */
+    uint32_t flags;             /* SQ_FLAG_* bits, 0 = defaults */
 } sq_config;
+
+/* The encoder's match search normally looks up every second position (the others inherit matches and are
+ * reached through backward extension): about 1.3x faster, +0.3 % bytes on log/JSON/record data, about
+ * +3 % on text and source code.  This flag makes it look up every position. */
+#define SQ_FLAG_DENSE_SEARCH 1u
 
 /* One chunk of a batch: bytes [off, off+len) of the batch buffer.
  * Chunk rule (reference src/archive/writer.rs:240-246): chunk i of a file is

@@ -25,6 +25,7 @@ SQ_ERR_NO_DEVICE = -100
 SQ_ERR_CUDA = -101
 SQ_ERR_INVALID_ARG = -102
 SQ_ERR_CAPACITY = -103
+SQ_FLAG_DENSE_SEARCH = 1
 
 
 class SqConfig(C.Structure):

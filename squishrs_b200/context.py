@@ -22,9 +22,10 @@ COMPRESSION_LEVEL = 12
 class Context:
     """Owns one sq_ctx (one GPU).  Raises SquishError(SQ_ERR_NO_DEVICE) without a CUDA device."""
 
-    def __init__(self, device: int = 0, dedup_capacity: int = 1 << 20, max_batch_chunks: int = 4096):
+    def __init__(self, device: int = 0, dedup_capacity: int = 1 << 20, max_batch_chunks: int = 4096, dense_search: bool = False):
+        """dense_search: look up every position in the encoder's match search (SQ_FLAG_DENSE_SEARCH): slower, smaller frames on text."""
         self.lib = L.load()
-        cfg = L.SqConfig(device, 0, dedup_capacity, max_batch_chunks, 0)
+        cfg = L.SqConfig(device, 0, dedup_capacity, max_batch_chunks, L.SQ_FLAG_DENSE_SEARCH if dense_search else 0)
         h = C.c_void_p()
         rc = self.lib.sq_create(C.byref(cfg), C.byref(h))
         if rc != L.SQ_OK:

@@ -79,6 +79,7 @@ extern "C" int32_t sq_create(const sq_config *cfg, sq_ctx **out) {
     ctx->device = dev;
     ctx->chunk_size = cfg && cfg->chunk_size ? cfg->chunk_size : SQ_CHUNK_SIZE;
     ctx->max_batch = cfg && cfg->max_batch_chunks ? cfg->max_batch_chunks : 4096;
+    ctx->flags = cfg ? cfg->flags : 0;
     ctx->dedup_capacity = cfg && cfg->dedup_capacity ? cfg->dedup_capacity : (1ull << 20);
     int32_t rc = SQ_OK;
     auto fail = [&](int32_t code) { snprintf(g_create_err, sizeof g_create_err, "%s", ctx->err); sq_destroy(ctx); return code; };

@@ -21,6 +21,7 @@ struct sq_ctx {
     int sm_count;
     uint32_t chunk_size;
     uint32_t max_batch;
+    uint32_t flags;           // sq_config.flags
     uint64_t dedup_capacity;
     cudaStream_t stream;      // the context's own stream
     cudaStream_t copy_stream; // second stream for double-buffered uploads

@@ -280,7 +280,14 @@ int32_t sq_encode_device_set(sq_ctx *ctx, int set, const void *d_data, const sq_
     {
         static_assert(sizeof(lz::BlockOut) == sizeof(sq_block_info), "block info layout");
         const uint32_t lz_grid = n < e->lz_ctas ? n : e->lz_ctas;
-        lz::lz_search_kernel<<<lz_grid, lz::THREADS, 0, st>>>((const uint8_t *)d_data, d_spans, d_select, n, e->tab, e->head, e->rec, e->status + 1);
+        // Search stride: 2 by default; SQ_FLAG_DENSE_SEARCH in sq_config.flags (or SQ_LZ_STRIDE=1) searches every position (about 1.3x
+        // slower, ~3 % smaller frames on text and source code).  SQ_LZ_STRIDE=0 picks per tile: stride 2 when at least SQ_LZ_ADAPT of
+        // the previous tile's 1024 positions sat inside a long match (experimental).
+        static const int env_stride = getenv("SQ_LZ_STRIDE") ? atoi(getenv("SQ_LZ_STRIDE")) : -1;
+        static const uint32_t adapt_thr = getenv("SQ_LZ_ADAPT") ? (uint32_t)atoi(getenv("SQ_LZ_ADAPT")) : 384u;
+        const uint32_t stride_mode = env_stride >= 0 && env_stride <= 2 ? (uint32_t)env_stride : (ctx->flags & SQ_FLAG_DENSE_SEARCH) ? 1u : (uint32_t)SQ_LZ_SSTRIDE;
+        lz::lz_search_kernel<<<lz_grid, lz::THREADS, 0, st>>>((const uint8_t *)d_data, d_spans, d_select, n, e->tab, e->head, e->rec, e->status + 1,
+                                                              stride_mode, adapt_thr);
         lz::lz_chase_kernel<<<(n * SQ_MAX_BLOCKS + 3) / 4, 128, 0, st>>>((const uint8_t *)d_data, d_spans, d_select, n, e->rec, e->seqs, e->meta);
         const uint32_t ent_ctas = e->ent_warps / 4;
         lz::entropy_kernel<<<ent_ctas, 128, 0, st>>>((const uint8_t *)d_data, d_spans, d_select, n, e->seqs, e->meta, e->lits, e->bodies,

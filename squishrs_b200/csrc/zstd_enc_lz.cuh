@@ -34,7 +34,10 @@ constexpr uint32_t ROW_LOG = 15, ROWS = 1u << ROW_LOG, ROW_K = 16, TAG_BITS = 10
 constexpr uint32_t TILE = 1024, HALO = 32, RING = TILE + HALO, THREADS = 256, PER_THREAD = TILE / THREADS;
 constexpr uint32_t MIN_MATCH = 6, SEARCH_CAP = 24, TARGET_LEN = 24, DEFER = 20, MAX_LAZY_ITERS = 8;
 constexpr uint32_t LOOKAHEAD = SEARCH_CAP + 16;  // bytes staged past the tile so the p-side of every comparison is in smem
-constexpr int32_t ACCEPT_THR = 8;
+#ifndef SQ_LZ_ACCEPT
+#define SQ_LZ_ACCEPT 8
+#endif
+constexpr int32_t ACCEPT_THR = SQ_LZ_ACCEPT;
 constexpr uint32_t BLOCKS_PER_CHUNK = 16;
 constexpr uint32_t BODY_STRIDE = 2 * Z_BLOCK_MAX;  // per-block body slot: literals + <= 8 bytes per sequence always fit
 constexpr uint32_t SEQ_PER_BLOCK = Z_BLOCK_MAX / MIN_MATCH + 8, MAX_SEQ_PER_CHUNK = BLOCKS_PER_CHUNK * SEQ_PER_BLOCK;
@@ -120,7 +123,9 @@ __device__ __forceinline__ uint32_t stage_word(const uint8_t *__restrict__ in, u
 }
 
 #ifndef SQ_LZ_SSTRIDE
-#define SQ_LZ_SSTRIDE 2  // search stride: 1 = every position reads its row; 2 costs ~0.3 % ratio on the mixed corpus and is ~1.3x faster; 4 costs ~5 %
+#define SQ_LZ_SSTRIDE 2  // default search stride (the kernel takes the mode as an argument): 1 = every position reads its row; 2 = every
+                         // second one (1.3x faster; +0.3 % bytes on the mixed log/JSON/binary corpus, +3 % on real text and code);
+                         // 0 = chosen per tile from the previous tile's share of positions inside long matches (experimental)
 #endif
 #ifndef SQ_LZ_MINB
 #define SQ_LZ_MINB 3  // resident CTAs per SM the register budget is held to
@@ -128,7 +133,7 @@ __device__ __forceinline__ uint32_t stage_word(const uint8_t *__restrict__ in, u
 __global__ void __launch_bounds__(THREADS, SQ_LZ_MINB) lz_search_kernel(const uint8_t *__restrict__ data, const sq_span *__restrict__ spans,
                                                              const uint8_t *__restrict__ select, uint32_t n_chunks,
                                                              uint32_t *__restrict__ tab_all, uint32_t *__restrict__ head_all,
-                                                             uint32_t *__restrict__ rec_all, uint32_t *__restrict__ counter) {
+                                                             uint32_t *__restrict__ rec_all, uint32_t *__restrict__ counter, uint32_t stride_mode, uint32_t adapt_thr) {
     __shared__ __align__(16) uint8_t s_in2[2][SIN];
     __shared__ uint8_t s_len[RING];
     __shared__ uint32_t s_off[RING];
@@ -136,7 +141,7 @@ __global__ void __launch_bounds__(THREADS, SQ_LZ_MINB) lz_search_kernel(const ui
     __shared__ int16_t s_sc[RING];  // lazy score of the position's usable match, -1 = none
     __shared__ __align__(16) uint32_t s_queue[(THREADS / 32) * 32 * ROW_K];  // per warp: compacted (position | candidate << 10) pairs
     __shared__ uint32_t s_best[TILE];                           // per position: (score+9) << 26 | (len-6) << 21 | off  (0 = none)
-    __shared__ uint32_t s_chunk, s_gctr;
+    __shared__ uint32_t s_chunk, s_gctr, s_stride, s_long;
 #ifdef SQ_LZ_TIMERS
     long long tm[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, tc = clock64();
 #define LZ_TICK(i) do { long long now_ = clock64(); tm[i] += now_ - tc; tc = now_; } while (0)
@@ -147,9 +152,12 @@ __global__ void __launch_bounds__(THREADS, SQ_LZ_MINB) lz_search_kernel(const ui
     uint32_t *head = head_all + (size_t)blockIdx.x * ROWS;
     const uint32_t tid = threadIdx.x, wq = tid >> 5, lane = tid & 31;
     uint32_t *queue = s_queue + wq * (32 * ROW_K);
-    // SSTRIDE = 2 (or 4): only every second (fourth) position reads its row; the others live on inherited matches (and on the backward
+    // Search stride 2: only every second position reads its row; the others live on inherited matches (and on the backward
     // extension of their right neighbour's finds).  A group of 32 lanes then spans 64 positions.
-    constexpr uint32_t SSTRIDE = SQ_LZ_SSTRIDE, GSPAN = 32 * SSTRIDE, GROUPS = TILE / GSPAN, TAG_MASK = (1u << TAG_BITS) - 1;
+    // The stride is chosen per tile: where most positions of the previous tile sat inside long matches (repetitive data: logs,
+    // records, padding) the in-between positions have little to add and stride 2 costs almost nothing; elsewhere (text, code)
+    // every position is searched.  adapt_thr = number of such positions (of TILE) from which the next tile runs at stride 2.
+    constexpr uint32_t TAG_MASK = (1u << TAG_BITS) - 1, STAT_LEN = 16;
 
     for (;;) {
         __syncthreads();
@@ -158,6 +166,8 @@ __global__ void __launch_bounds__(THREADS, SQ_LZ_MINB) lz_search_kernel(const ui
             do { c = atomicAdd(counter, 1u); } while (c < n_chunks && select && !select[c]);
             s_chunk = c;
             s_gctr = THREADS / 32;
+            s_stride = stride_mode ? stride_mode : 1u;
+            s_long = 0;
         }
         __syncthreads();
         const uint32_t chunk = s_chunk;
@@ -190,6 +200,7 @@ __global__ void __launch_bounds__(THREADS, SQ_LZ_MINB) lz_search_kernel(const ui
             const uint32_t t0 = t * TILE, t1 = min(n, t0 + TILE);
             const uint32_t be = min(n, (t0 / Z_BLOCK_MAX + 1) * Z_BLOCK_MAX);  // end of the block this tile lies in
             const bool last_tile_of_block = (t1 == be);
+            const uint32_t SSTRIDE = s_stride, GSPAN = 32 * SSTRIDE, GROUPS = TILE / GSPAN;
             const uint8_t *s_in = s_in2[t & 1];
             const uint8_t *s_nx = s_in2[(t + 1) & 1];
             // ---- reserve: ring slots for the next tile's positions (results are consumed after the search) ----
@@ -430,11 +441,14 @@ __global__ void __launch_bounds__(THREADS, SQ_LZ_MINB) lz_search_kernel(const ui
                         s_off[l_e + HALO] = boff_e;
                         s_back[l_e + HALO] = (uint8_t)(bback | known_e << 2);
                     }
+                    if (stride_mode == 0) {  // adaptive stride: positions that sit inside a long match
+                        const uint32_t nl = __popc(__ballot_sync(0xffffffffu, known_e >= STAT_LEN));
+                        if (lane == 0 && nl) atomicAdd(&s_long, nl);
+                    }
                 };
                 emit(li, blen, known, boff);
-#pragma unroll
-                for (uint32_t d = 1; d < SSTRIDE; d++) {
-                    const uint32_t end = win >> 22, gp = SSTRIDE * lane + d;
+                if (SSTRIDE == 2) {
+                    const uint32_t d = 1, end = win >> 22, gp = SSTRIDE * lane + d;
                     uint32_t blen1 = 0, known1 = 0, boff1 = 0;
                     if (end >= gp + MIN_MATCH && p + d + 8 <= n) {
                         known1 = end - gp; boff1 = win & 0x1FFFFFu;
@@ -500,7 +514,10 @@ __global__ void __launch_bounds__(THREADS, SQ_LZ_MINB) lz_search_kernel(const ui
                 dst[tid] = sw0;
                 if (tid < SIN_WORDS - THREADS) dst[THREADS + tid] = sw1;
             }
-            if (tid == 0) s_gctr = THREADS / 32;
+            if (tid == 0) {
+                s_gctr = THREADS / 32;
+                if (stride_mode == 0) { s_stride = s_long >= adapt_thr ? 2u : 1u; s_long = 0; }
+            }
             __syncthreads();
             LZ_TICK(3);
         }

@@ -531,3 +531,19 @@ def test_unpack_pipeline_two_tickets_in_flight(sq, oracle):
     assert lib.sq_unpack_wait(c.h, staged[0]["ticket"]) != 0  # not in flight any more
     # the slots are free again, and the synchronous call still works on the same context
     assert c.unpack_batch([oracle.compress(samples[0])], [len(samples[0])]) == [samples[0]]
+
+
+def test_dense_search_flag_roundtrip_and_ratio(sq, oracle):
+    # SQ_FLAG_DENSE_SEARCH: every position is looked up; frames stay stock-decodable and are not larger on text-like data
+    import glob
+    src = b"".join(open(f, "rb").read() for f in sorted(glob.glob("/usr/lib/python3*/**/*.py", recursive=True))[:300])[:4 * MiB]
+    chunks = [src[i:i + 2 * MiB] for i in range(0, len(src), 2 * MiB)] + [s for k, s in corpus_samples(sq, sizes=(300000,)) if k in (0, 1, 2)]
+    sizes = {}
+    for dense in (False, True):
+        c = sq.Context(dense_search=dense)
+        res = c.pack_batch(chunks)
+        for ch, (_, f) in zip(chunks, res):
+            assert f is not None and oracle.decompress(f, len(ch)) == ch
+        sizes[dense] = sum(len(f) for _, f in res)
+        c.close()
+    assert sizes[True] <= sizes[False] * 1.002, sizes
