@@ -249,6 +249,10 @@ def run_ours(args):
     budget = int(free * 0.55)
     n_batches = int(max(1, min(want_batches, budget // (B * CHUNK))))
     n_slots = n_batches * B
+    if world > 1 and not args.single_stream:
+        # leave two SMs' worth of search-CTA slots free: the digest / exchange kernels of the step after next (and NCCL's copy
+        # kernels) then run beside the encoder instead of waiting for its tail
+        os.environ.setdefault("SQ_LZ_CTAS_TOTAL", str(3 * (torch.cuda.get_device_properties(local).multi_processor_count - 2)))
     ctx = sq.Context(device=local, dedup_capacity=max(1 << 20, 4 * n_slots * max(world, 1) * (args.steps + args.warmup + 4) // max(n_batches, 1) + n_slots * 4),
                      max_batch_chunks=B * max(world, 1))
     ids, klass = corpus_plan(n_slots, first_slot=rank * n_slots, workload=args.workload)
@@ -293,6 +297,53 @@ def run_ours(args):
                          flen=torch.empty(B, dtype=torch.int32, device="cuda"), total=torch.zeros(1, dtype=torch.int64, device="cuda")))
     d_out, d_dig, d_new, d_foff, d_flen, d_total = (bufs[0][k] for k in ("out", "dig", "new", "foff", "flen", "total"))
     last_dedup = [None]
+    # Multi-GPU: digest + digest exchange ("front") of step i+2 run on their own stream while steps i and i+1 encode, so a rank
+    # never waits for its peers inside a step: the all-to-all it needs next was finished one step ago.  Three small
+    # (digest, verdict) sets rotate; the search kernel leaves a few CTA slots free (SQ_LZ_CTAS_TOTAL) so the front kernels and
+    # NCCL's copy kernels can run beside it.
+    ahead = sd is not None and not args.single_stream
+    front_stream = torch.cuda.Stream() if ahead else None
+    fsp = C.c_void_p(front_stream.cuda_stream) if ahead else None
+    fsets = [dict(dig=torch.empty(B * 16, dtype=torch.uint8, device="cuda"), new=torch.empty(B, dtype=torch.uint8, device="cuda")) for _ in range(3)] if ahead else None
+    front_done, enc_done = {}, {}
+
+    def front(i, gidx_base):  # digest + exchange of step i on the front stream
+        fs = fsets[i % 3]
+        base = corpus.data_ptr() + (i % n_batches) * B * CHUNK
+        with torch.cuda.stream(front_stream):
+            if i - 3 in enc_done:  # the set's previous reader
+                front_stream.wait_event(enc_done[i - 3])
+            ctx.check(lib.sq_digest_device(ctx.h, base, d_spans.data_ptr(), B, fs["dig"].data_ptr(), fsp))
+            sd.ops.sp = fsp
+            sd.exchange(fs["dig"], gidx_base, B, fs["new"])
+            e_ = torch.cuda.Event()
+            e_.record(front_stream)
+            front_done[i] = e_
+
+    def back(i, timed):  # encode of step i on its own stream, once its verdicts are there
+        b = i % n_batches
+        st, spx, bf, fs = streams[i % 2], sps[i % 2], bufs[i % 2], fsets[i % 3]
+        base = corpus.data_ptr() + b * B * CHUNK
+        with torch.cuda.stream(st):
+            st.wait_event(front_done[i])
+            ctx.check(lib.sq_encode_device(ctx.h, base, d_spans.data_ptr(), fs["new"].data_ptr(), B, bf["out"].data_ptr(), out_cap,
+                                           bf["foff"].data_ptr(), bf["flen"].data_ptr(), bf["total"].data_ptr(), spx))
+            e_ = torch.cuda.Event()
+            e_.record(st)
+            enc_done[i] = e_
+            tot = (bf["total"].clone(), fs["new"].sum(dtype=torch.int64)) if timed else None
+        return None, tot
+
+    def run_ahead(n_steps, gidx_of, timed):
+        front_done.clear(); enc_done.clear()
+        res = []
+        for j in range(min(2, n_steps)):
+            front(j, gidx_of(j))
+        for i in range(n_steps):
+            res.append(back(i, timed))
+            if i + 2 < n_steps:
+                front(i + 2, gidx_of(i + 2))
+        return res
 
     def step(i, gidx_base, timed):
         b = i % n_batches
@@ -331,8 +382,11 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # warm-up on a throwaway index state
-    for w in range(args.warmup):
-        step(w, w * B * world + rank * B, False)
+    if ahead:
+        run_ahead(args.warmup, lambda w: w * B * world + rank * B, False)
+    else:
+        for w in range(args.warmup):
+            step(w, w * B * world + rank * B, False)
     barrier()
     ctx.dedup_reset()
     launches0 = C.c_uint64()
@@ -345,10 +399,16 @@ def run_ours(args):
     start.record(stream)
     evs = []
     outs = []
-    for k in range(args.steps):
-        e_k, tot_k = step(k, k * B * world + rank * B, True)
-        evs.append(e_k)
-        outs.append(tot_k)  # tiny device-side reads on the step's stream, no sync
+    if ahead:
+        for e_k, tot_k in run_ahead(args.steps, lambda k: k * B * world + rank * B, True):
+            evs.append(e_k)
+            outs.append(tot_k)
+        stream.wait_stream(front_stream)
+    else:
+        for k in range(args.steps):
+            e_k, tot_k = step(k, k * B * world + rank * B, True)
+            evs.append(e_k)
+            outs.append(tot_k)  # tiny device-side reads on the step's stream, no sync
     stream.wait_stream(stream_b)  # the timed region ends when BOTH streams have drained
     stop.record(stream)
     barrier()
