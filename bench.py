@@ -465,6 +465,12 @@ def run_ours(args):
         ctx.dedup_reset()
         n_e2e = max(4, min(args.steps, 8))
         n_warm = 2
+        try:  # every step's input is pinned up front: stay well inside this rank's share of the host memory that is free
+            avail = [int(l.split()[1]) * 1024 for l in open("/proc/meminfo") if l.startswith("MemAvailable:")][0]
+            fit = int(avail * 0.5 / max(world, 1) // (eb * CHUNK)) - n_warm - 2
+            n_e2e = max(2, min(n_e2e, fit))
+        except Exception:
+            pass
         total_steps = n_warm + n_e2e
         # Every step's input sits in its own pinned host buffer BEFORE the clock starts (staging it costs PCIe time that is not
         # part of the workload); outputs and results use a ring of two, like the two pipeline slots.
