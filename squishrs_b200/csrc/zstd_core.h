@@ -295,9 +295,11 @@ ZHDN void fse_build_dtable(FseDCell *t, const int16_t *norm, uint32_t max_sym, u
 // ---- Huffman --------------------------------------------------------------------------------------
 // Code lengths (<= max_bits) for counts[0..255]; lens[s] = 0 for unused symbols.  Needs >= 2 used symbols.
 // Package-free construction: sort, two-queue merge, then repair depths over the limit keeping Kraft equality.
+// huf_build_lengths_sorted: work[0..n) already holds the used symbols in ascending (count, symbol) order and lens[] is zeroed
+// (the GPU entropy stage sorts with all lanes of the warp; the order is the one the stable insertion sort below produces).
+ZHDN uint32_t huf_build_lengths_sorted(uint8_t *lens, const uint32_t *counts, uint32_t max_bits, uint16_t *work /* 1280 u16 */, uint32_t n);
 ZHDN uint32_t huf_build_lengths(uint8_t *lens, const uint32_t *counts, uint32_t max_bits, uint16_t *work /* 1280 u16 */) {
     uint16_t *order = work;          // 256: symbols sorted by ascending count
-    uint16_t *parent = work + 256;   // 512: tree parents (leaves 0..n-1, internal n..2n-2)
     uint32_t n = 0;
     for (uint32_t s = 0; s < 256; s++) { lens[s] = 0; if (counts[s]) order[n++] = (uint16_t)s; }
     if (n < 2) return 0;
@@ -307,6 +309,12 @@ ZHDN uint32_t huf_build_lengths(uint8_t *lens, const uint32_t *counts, uint32_t 
         while (j > 0 && counts[order[j - 1]] > c) { order[j] = order[j - 1]; j--; }
         order[j] = s;
     }
+    return huf_build_lengths_sorted(lens, counts, max_bits, work, n);
+}
+ZHDN uint32_t huf_build_lengths_sorted(uint8_t *lens, const uint32_t *counts, uint32_t max_bits, uint16_t *work /* 1280 u16 */, uint32_t n) {
+    uint16_t *order = work;          // 256: symbols sorted by ascending count
+    uint16_t *parent = work + 256;   // 512: tree parents (leaves 0..n-1, internal n..2n-2)
+    if (n < 2) return 0;
     // two-queue Huffman: leaves in `order`, internal node weights in wq[] (monotone)
     uint32_t *wq = (uint32_t *)(work + 768);  // up to 255 internal weights (needs 510 u16 -> within 1280)
     uint32_t li = 0, qi = 0, qn = 0;

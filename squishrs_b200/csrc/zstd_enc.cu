@@ -206,7 +206,7 @@ static int32_t enc_scratch(sq_ctx *ctx, uint32_t n, int set) {
         SQ_CUDA(ctx, cudaMalloc(&e->head, (size_t)e->lz_ctas * lz::ROWS * sizeof(uint32_t)));
         SQ_CUDA(ctx, cudaMemset(e->head, 0, (size_t)e->lz_ctas * lz::ROWS * sizeof(uint32_t)));
         SQ_CUDA(ctx, cudaMalloc(&e->lits, (size_t)e->ent_warps * (Z_BLOCK_MAX + 64)));
-        SQ_CUDA(ctx, cudaMalloc(&e->sbits, (size_t)e->ent_warps * 4 * lz::SEQ_PER_BLOCK * sizeof(uint32_t)));
+        SQ_CUDA(ctx, cudaMalloc(&e->sbits, (size_t)e->ent_warps * lz::SBITS_STRIDE * sizeof(uint32_t)));
         SQ_CUDA(ctx, cudaMalloc(&e->status, 8 * sizeof(uint32_t)));
         SQ_CUDA(ctx, cudaMemset(e->status, 0, 8 * sizeof(uint32_t)));
     }

@@ -87,17 +87,39 @@ __device__ uint32_t warp_write_literals(uint8_t *dst, const uint8_t *lits, uint3
     __syncwarp();
     for (uint32_t i = lane; i < n; i += 32) atomicAdd(&wk->counts[lits[i]], 1u);
     __syncwarp();
-    // mode decision + tables by one lane
+    // mode decision + tables by one lane; the symbol sort that the Huffman construction starts from is done by the whole warp
+    // (rank = number of used symbols that come before in (count, symbol) order: 8 symbols per lane against all 256)
     enum { M_RAW = 0, M_RLE = 1, M_HUF1 = 2, M_HUF4 = 3 };
     const uint32_t lh = 3 + (n >= 1024) + (n >= 16384);
+    uint32_t used = 0;
+    {
+        uint32_t mine = 0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) mine += wk->counts[lane + 32 * j] != 0;
+        used = mine;
+#pragma unroll
+        for (int d = 16; d; d >>= 1) used += __shfl_xor_sync(0xffffffffu, used, d);
+    }
+    if (used >= 2 && n >= 64) {
+        uint32_t cs[8], rk[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) { cs[j] = wk->counts[lane + 32 * j]; rk[j] = 0; wk->lens[lane + 32 * j] = 0; }
+        for (uint32_t t = 0; t < 256; t++) {
+            const uint32_t ct = wk->counts[t];
+            if (ct == 0) continue;  // warp-uniform
+#pragma unroll
+            for (int j = 0; j < 8; j++) rk[j] += (ct < cs[j] || (ct == cs[j] && t < lane + 32 * j)) ? 1u : 0u;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; j++) if (cs[j]) wk->hwork[rk[j]] = (uint16_t)(lane + 32 * j);
+    }
+    __syncwarp();
     if (lane == 0) {
         uint32_t mode = M_RAW, tree = 0, maxlen = 0;
         if (n > 0) {
-            uint32_t used = 0;
-            for (uint32_t s = 0; s < 256; s++) used += wk->counts[s] != 0;
             if (used == 1) mode = M_RLE;
             else if (n >= 64) {
-                maxlen = zc::huf_build_lengths(wk->lens, wk->counts, Z_HUF_MAXBITS, wk->hwork);
+                maxlen = zc::huf_build_lengths_sorted(wk->lens, wk->counts, Z_HUF_MAXBITS, wk->hwork, used);
                 if (maxlen) {
                     uint64_t bits = 0;
                     for (uint32_t s = 0; s < 256; s++) bits += (uint64_t)wk->counts[s] * wk->lens[s];
@@ -123,8 +145,18 @@ __device__ uint32_t warp_write_literals(uint8_t *dst, const uint8_t *lits, uint3
         const uint32_t s_begin = k * seg4, s_cnt = k < 3 ? seg4 : n - 3 * seg4;
         const uint32_t q = (s_cnt + 7) / 8;
         const uint32_t hi = s_cnt > j * q ? s_cnt - j * q : 0, lo = s_cnt > (j + 1) * q ? s_cnt - (j + 1) * q : 0;  // symbols [lo, hi) of stream k
+        // the literal buffer is read a 32-bit word at a time (each lane walks its own segment; byte loads would cost a
+        // memory round trip per symbol)
+        const uint32_t *lits32 = reinterpret_cast<const uint32_t *>(lits);  // the per-warp literal slot is 64-byte aligned
         uint32_t bits = 0;
-        for (uint32_t i = lo; i < hi; i++) bits += wk->lens[lits[s_begin + i]];
+        {
+            uint32_t cw = 0, cwi = ~0u;
+            for (uint32_t i = lo; i < hi; i++) {
+                const uint32_t a = s_begin + i;
+                if ((a >> 2) != cwi) { cwi = a >> 2; cw = lits32[cwi]; }
+                bits += wk->lens[(cw >> (8 * (a & 3u))) & 0xFFu];
+            }
+        }
         if (j == 7) bits += 1;  // the segment holding symbol 0 ends the stream: sentinel bit
         // prefix within each group of 8 lanes
         uint32_t x = bits;
@@ -152,7 +184,13 @@ __device__ uint32_t warp_write_literals(uint8_t *dst, const uint8_t *lits, uint3
             __syncwarp();
             __threadfence_block();
             if (active) {
-                for (uint32_t i = hi; i > lo; i--) { const uint32_t s = lits[s_begin + i - 1]; seg_put(&w, wk->codes[s], wk->lens[s]); }
+                uint32_t cw = 0, cwi = ~0u;
+                for (uint32_t i = hi; i > lo; i--) {
+                    const uint32_t a = s_begin + i - 1;
+                    if ((a >> 2) != cwi) { cwi = a >> 2; cw = lits32[cwi]; }
+                    const uint32_t s = (cw >> (8 * (a & 3u))) & 0xFFu;
+                    seg_put(&w, wk->codes[s], wk->lens[s]);
+                }
                 if (j == 7) seg_put(&w, 1, 1);
                 seg_finish(&w);
             }
@@ -192,7 +230,10 @@ __device__ uint32_t warp_write_literals(uint8_t *dst, const uint8_t *lits, uint3
 // ---- sequences section ------------------------------------------------------------------------------------------------
 // sbits: per-warp scratch of 4 * nseq u32: state-transition bits | count << 16 for LL, OF, ML, then the packed symbol codes
 // (LL code | OF code << 8 | ML code << 16), computed once by all lanes so that the serial passes never recompute them
-__device__ uint32_t warp_write_sequences(uint8_t *dst, const zc::Seq *seqs, uint32_t nseq, WarpWork *W, uint32_t *sbits, uint32_t lane) {
+// cbytes: per-warp scratch of 3 byte arrays (stride cstride, 16-byte aligned): the LL / OF / ML code of every sequence, the form the
+// serial FSE chains read (16 symbols per load)
+__device__ uint32_t warp_write_sequences(uint8_t *dst, const zc::Seq *seqs, uint32_t nseq, WarpWork *W, uint32_t *sbits, uint8_t *cbytes,
+                                         uint32_t cstride, uint32_t lane) {
     zc::EncWork *wk = &W->wk;
     if (nseq == 0) { if (lane == 0) dst[0] = 0; __syncwarp(); return 1; }
     // code histograms
@@ -206,6 +247,7 @@ __device__ uint32_t warp_write_sequences(uint8_t *dst, const zc::Seq *seqs, uint
         atomicAdd(&wk->hist[1][oc], 1u);
         atomicAdd(&wk->hist[2][mc], 1u);
         codes[i] = lc | oc << 8 | mc << 16;
+        cbytes[i] = (uint8_t)lc; cbytes[cstride + i] = (uint8_t)oc; cbytes[2 * cstride + i] = (uint8_t)mc;
     }
     __syncwarp();
     __threadfence_block();
@@ -232,35 +274,45 @@ __device__ uint32_t warp_write_sequences(uint8_t *dst, const zc::Seq *seqs, uint
         const zc::FseCTable *ct = &wk->ct[lane];
         const bool rle = mode_of_lane[lane] == 1;
         uint32_t *out = sbits + (size_t)lane * nseq;
-        const uint32_t csh = 8 * lane;  // this lane's byte of the packed codes
+        const uint8_t *cb = cbytes + (size_t)lane * cstride;  // this lane's stream of symbol codes
         uint32_t state = 0;
         if (rle) {
             for (uint32_t i = 0; i + 1 < nseq; i++) out[i] = 0;
         } else {
-            state = zc::fse_init_state(ct, codes[nseq - 1] >> csh & 0xFFu);
-            // the chain itself is serial (one shared-memory lookup per symbol depends on the previous state); the symbol codes
-            // and their per-symbol table entries do not, so they are fetched four symbols ahead of the chain
-            uint32_t i = nseq - 1;
-            while (i >= 4) {
-                uint32_t c[4], dn[4]; int32_t df[4];
-#pragma unroll
-                for (int k = 0; k < 4; k++) c[k] = codes[i - 1 - k] >> csh & 0xFFu;
-#pragma unroll
-                for (int k = 0; k < 4; k++) { dn[k] = ct->delta_nb_bits[c[k]]; df[k] = ct->delta_find_state[c[k]]; }
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const uint32_t nb = (state + dn[k]) >> 16;
-                    out[i - 1 - k] = (state & ((1u << nb) - 1)) | nb << 16;
-                    state = ct->next_state[(int32_t)(state >> nb) + df[k]];
-                }
-                i -= 4;
-            }
-            while (i-- > 0) {
-                const uint32_t c = codes[i] >> csh & 0xFFu;
+            state = zc::fse_init_state(ct, cb[nseq - 1]);
+            // The chain itself is serial (one shared-memory lookup per symbol depends on the previous state); the symbol codes and
+            // their per-symbol table entries do not: codes arrive 16 per load, one load ahead, and the table entries of four symbols
+            // are fetched before the four dependent steps.
+            auto step1 = [&](uint32_t i, uint32_t c) {
                 const uint32_t nb = (state + ct->delta_nb_bits[c]) >> 16;
                 out[i] = (state & ((1u << nb) - 1)) | nb << 16;
                 state = ct->next_state[(int32_t)(state >> nb) + ct->delta_find_state[c]];
+            };
+            int32_t i = (int32_t)nseq - 2;  // next symbol to encode
+            while (i >= 0 && (i & 15) != 15) { step1((uint32_t)i, cb[i]); i--; }
+            uint4 nxt = make_uint4(0u, 0u, 0u, 0u);
+            if (i >= 15) nxt = *reinterpret_cast<const uint4 *>(cb + i - 15);
+            while (i >= 15) {
+                const uint4 cur = nxt;
+                if (i >= 31) nxt = *reinterpret_cast<const uint4 *>(cb + i - 31);
+                const uint32_t wv[4] = {cur.w, cur.z, cur.y, cur.x};  // descending symbol order
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    uint32_t c[4], dn[4]; int32_t df[4];
+#pragma unroll
+                    for (int k = 0; k < 4; k++) c[k] = wv[q] >> (8 * (3 - k)) & 0xFFu;
+#pragma unroll
+                    for (int k = 0; k < 4; k++) { dn[k] = ct->delta_nb_bits[c[k]]; df[k] = ct->delta_find_state[c[k]]; }
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const uint32_t nb = (state + dn[k]) >> 16;
+                        out[i - 4 * q - k] = (state & ((1u << nb) - 1)) | nb << 16;
+                        state = ct->next_state[(int32_t)(state >> nb) + df[k]];
+                    }
+                }
+                i -= 16;
             }
+            while (i >= 0) { step1((uint32_t)i, cb[i]); i--; }
         }
         W->scalars[4 + lane] = rle ? 0 : (state & ((1u << ct->tl) - 1)) | ct->tl << 16;  // final state flush
     }

@@ -42,6 +42,9 @@ constexpr uint32_t BLOCKS_PER_CHUNK = 16;
 constexpr uint32_t BODY_STRIDE = 2 * Z_BLOCK_MAX;  // per-block body slot: literals + <= 8 bytes per sequence always fit
 constexpr uint32_t SEQ_PER_BLOCK = Z_BLOCK_MAX / MIN_MATCH + 8, MAX_SEQ_PER_CHUNK = BLOCKS_PER_CHUNK * SEQ_PER_BLOCK;
 constexpr uint32_t REC_PER_CHUNK = 2048u * 1024u, MAX_SHIFT = 7;
+// per entropy warp: 3 x SEQ_PER_BLOCK words of FSE state-transition records, SEQ_PER_BLOCK words of packed symbol codes, then three
+// byte arrays of symbol codes (stride SEQ_CODE_STRIDE)
+constexpr uint32_t SEQ_CODE_STRIDE = (SEQ_PER_BLOCK + 15u) & ~15u, SBITS_STRIDE = (4 * SEQ_PER_BLOCK + 3 * SEQ_CODE_STRIDE / 4 + 3u) & ~3u;
 
 #ifdef SQ_LZ_TIMERS
 __device__ unsigned long long g_lz_timers[12];
@@ -639,7 +642,8 @@ __global__ void __launch_bounds__(128) entropy_kernel(const uint8_t *__restrict_
     const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     ent::WarpWork *W = &s_work[threadIdx.x >> 5];
     uint8_t *lits = lit_all + (size_t)warp_global * (Z_BLOCK_MAX + 64);
-    uint32_t *sbits = sbits_all + (size_t)warp_global * 4 * SEQ_PER_BLOCK;
+    uint32_t *sbits = sbits_all + (size_t)warp_global * SBITS_STRIDE;
+    uint8_t *cbytes = reinterpret_cast<uint8_t *>(sbits + 4 * SEQ_PER_BLOCK);  // 16-byte aligned: 4 * SEQ_PER_BLOCK and SBITS_STRIDE are multiples of 4 words
     for (;;) {
         uint32_t item = 0;
         if (lane == 0) item = atomicAdd(counter, 1u);
@@ -696,7 +700,7 @@ __global__ void __launch_bounds__(128) entropy_kernel(const uint8_t *__restrict_
         if (src_pos + m.last_lits == be && zc::block_body_bound(nlits, m.nseq) <= BODY_STRIDE) {
             uint8_t *dst = bodies + ((size_t)chunk * BLOCKS_PER_CHUNK + b) * (size_t)BODY_STRIDE;
             uint32_t sz = ent::warp_write_literals(dst, lits, nlits, W, lane);
-            sz += ent::warp_write_sequences(dst + sz, seqs, m.nseq, W, sbits, lane);
+            sz += ent::warp_write_sequences(dst + sz, seqs, m.nseq, W, sbits, cbytes, SEQ_CODE_STRIDE, lane);
             if (sz < blen) { out.type = 2; out.body_len = sz; }
         }
         if (lane == 0) blocks[(size_t)chunk * BLOCKS_PER_CHUNK + b] = out;
