@@ -693,7 +693,7 @@ def main():
     ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS))
     ap.add_argument("--batch-chunks", type=int, default=2048)
     ap.add_argument("--corpus-gib", type=int, default=64)
-    ap.add_argument("--e2e-chunks", type=int, default=1024)
+    ap.add_argument("--e2e-chunks", type=int, default=2048)
     ap.add_argument("--ref-chunks", type=int, default=0)
     ap.add_argument("--single-stream", action="store_true", help="run every step on one stream (no overlap between consecutive steps)")
     ap.add_argument("--no-e2e", action="store_true")
