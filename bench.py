@@ -467,7 +467,7 @@ def run_ours(args):
         n_warm = 2
         try:  # every step's input is pinned up front: stay well inside this rank's share of the host memory that is free
             avail = [int(l.split()[1]) * 1024 for l in open("/proc/meminfo") if l.startswith("MemAvailable:")][0]
-            fit = int(avail * 0.5 / max(world, 1) // (eb * CHUNK)) - n_warm - 2
+            fit = int((avail * 0.4 / max(world, 1) - 2 * ocap) // (eb * CHUNK)) - n_warm  # ranks of one box share the host memory
             n_e2e = max(2, min(n_e2e, fit))
         except Exception:
             pass
