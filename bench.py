@@ -471,6 +471,10 @@ def run_ours(args):
             n_e2e = max(2, min(n_e2e, fit))
         except Exception:
             pass
+        if world > 1:  # every rank times the same number of steps
+            t_n = torch.tensor([n_e2e], dtype=torch.int64, device="cuda")
+            dist.all_reduce(t_n, op=dist.ReduceOp.MIN)
+            n_e2e = int(t_n.item())
         total_steps = n_warm + n_e2e
         # Every step's input sits in its own pinned host buffer BEFORE the clock starts (staging it costs PCIe time that is not
         # part of the workload); outputs and results use a ring of two, like the two pipeline slots.
