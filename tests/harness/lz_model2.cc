@@ -1,0 +1,273 @@
+// CPU model of the round-2 K3 parse (dev/test tool, NOT product path): bucketed row search -> rep-blind lazy
+// decide -> chase with repeat-offset scanning, written stage by stage the way the CUDA kernels run it, so the
+// ratio of a parameter set can be measured against libzstd level 12 without a GPU.
+//   g++ -O2 -shared -fPIC -I squishrs_b200/csrc tests/harness/lz_model2.cc -o tests/harness/liblz_model2.so
+#include <stdint.h>
+#include <stdlib.h>
+#include <stdio.h>
+#include <string.h>
+#include <vector>
+#include <algorithm>
+#include "zstd_enc_block.h"
+
+using namespace zc;
+
+struct P2 {
+    int rows_log, K, mm, cap, stride, tile, slot_by_pos;
+    int rep_scan;     // 0 none, 1 rep0 in gaps, 2 rep0+rep1, 3 all three
+    int rep_min;      // minimum length of a rep match taken in a gap
+    int rep_at_start; // compare rep candidates against the found match at its start (zstd gain rule)
+    int accept_thr, target_len, max_shift, back_max;
+    int hash2_log, hash2_K, hash2_bytes;  // optional second table keyed on a longer hash (0 = off)
+    int sel_mul;
+    int lazy_rep;     // decide pass: neighbour-offset rep approximation (0 off)
+    int chain;        // 1: candidates come from a full per-position hash chain (upper bound study), depth = K
+    int short_keep;   // > 0: candidates whose first 8 bytes do not all match ("short") are verified only for the short_keep nearest; 0 = all
+    int tag_bits;     // > 0 (with short_keep): long/short classes come from ptag (5 bits of the row hash) and xtag (tag_bits bits of a hash of bytes 5..7) instead of the bytes
+    int cont;         // continuation filter: 0 off, 1 exact (pair (p-1,c-1) was a candidate pair), 2 previous byte equal; refresh every 16 positions
+};
+
+static inline uint64_t rd64(const uint8_t *p) { uint64_t v; memcpy(&v, p, 8); return v; }
+static inline uint32_t rd32(const uint8_t *p) { uint32_t v; memcpy(&v, p, 4); return v; }
+static inline uint32_t hashN(uint64_t v, int bytes, int hl) {
+    if (bytes == 4) return (uint32_t)((uint32_t)v * 2654435761u) >> (32 - hl);
+    if (bytes == 5) return (uint32_t)(((v << 24) * 889523592379ULL) >> (64 - hl));
+    if (bytes == 6) return (uint32_t)(((v << 16) * 227718039650203ULL) >> (64 - hl));
+    if (bytes == 7) return (uint32_t)(((v << 8) * 58295818150454627ULL) >> (64 - hl));
+    return (uint32_t)((v * 0xCF1BBCDCB7A56463ULL) >> (64 - hl));
+}
+static inline uint32_t match_len(const uint8_t *s, uint32_t a, uint32_t b, uint32_t n) {  // a > b
+    uint32_t l = 0;
+    while (a + l + 8 <= n) {
+        uint64_t x = rd64(s + a + l) ^ rd64(s + b + l);
+        if (x) return l + (__builtin_ctzll(x) >> 3);
+        l += 8;
+    }
+    while (a + l < n && s[a + l] == s[b + l]) l++;
+    return l;
+}
+static inline int32_t lazy_score(uint32_t len, uint32_t off) { return (int32_t)(4 * len) - (int32_t)highbit(off + 3); }
+
+struct Rec { uint32_t off, len, shift, back; bool capped; };
+
+extern "C" long lz_model2_frame(const uint8_t *s, uint32_t n, uint8_t *dst, uint32_t cap_dst, const P2 *Pp, uint64_t *stats) {
+    const P2 P = *Pp;
+    const uint32_t MM = (uint32_t)P.mm, CAP = (uint32_t)P.cap;
+    std::vector<uint32_t> blen(n + 64, 0), boff(n + 64, 0);
+    uint64_t nverify = 0, nrows = 0;
+    // ---- stage S: search ----
+    {
+        const uint32_t rows = 1u << P.rows_log, K = (uint32_t)P.K;
+        std::vector<uint32_t> tab((size_t)rows * K, 0), head(rows, 0);
+        const uint32_t rows2 = P.hash2_log ? 1u << P.hash2_log : 0, K2 = (uint32_t)P.hash2_K;
+        std::vector<uint32_t> tab2((size_t)rows2 * std::max(K2, 1u), 0), head2(std::max(rows2, 1u), 0);
+        std::vector<uint32_t> chain_prev, chain_head;
+        if (P.chain) { chain_prev.assign(n, 0); chain_head.assign(1u << 20, 0); }
+        const uint32_t T = (uint32_t)P.tile;
+        for (uint32_t t0 = 0; t0 < n; t0 += T) {
+            const uint32_t t1 = std::min(n, t0 + T);
+            for (uint32_t p = t0; p < t1 && p + 8 <= n; p++) {
+                const uint32_t h = hashN(rd64(s + p), P.mm, P.rows_log);
+                tab[(size_t)h * K + (P.slot_by_pos ? p % K : head[h]++ % K)] = p + 1;
+                if (rows2) { const uint32_t h2 = hashN(rd64(s + p), P.hash2_bytes, P.hash2_log); tab2[(size_t)h2 * K2 + (P.slot_by_pos ? p % K2 : head2[h2]++ % K2)] = p + 1; }
+                if (P.chain) { const uint32_t hc = hashN(rd64(s + p), P.mm, 20); chain_prev[p] = chain_head[hc]; chain_head[hc] = p + 1; }
+            }
+            std::vector<uint32_t> prevc, curc;
+            for (uint32_t p = t0; p < t1 && p + 8 <= n; p++) {
+                if (p % (uint32_t)P.stride) continue;
+                uint32_t bl = 0, bo = 0; int32_t bs = -1000;
+                prevc.swap(curc); curc.clear(); if (p == t0) prevc.clear();
+                auto consider = [&](uint32_t c) {
+                    if (c >= p) return;
+                    if (rd32(s + c) != rd32(s + p)) return;
+                    if (P.cont) {
+                        if (std::find(curc.begin(), curc.end(), c) != curc.end()) return;  // same candidate from the second table
+                        curc.push_back(c);
+                        if ((p & 15u) != 0 && p > t0 && c > 0) {
+                            if (P.cont == 1 && std::find(prevc.begin(), prevc.end(), c - 1) != prevc.end()) return;
+                            if (P.cont == 2 && s[p - 1] == s[c - 1]) return;
+                        }
+                    }
+                    uint32_t l = match_len(s, p, c, n);
+                    nverify++;
+                    if (l < MM) return;
+                    if (l > CAP) l = CAP;
+                    const uint32_t off = p - c;
+                    const int32_t sc = P.sel_mul * (int32_t)l - (int32_t)highbit(off + 3);
+                    if (sc > bs || (sc == bs && off < bo)) { bs = sc; bl = l; bo = off; }
+                };
+                nrows++;
+                if (P.chain) {
+                    uint32_t e = chain_prev[p]; int depth = P.K;
+                    while (e && depth--) { consider(e - 1); e = chain_prev[e - 1]; }
+                } else {
+                    const uint32_t h = hashN(rd64(s + p), P.mm, P.rows_log);
+                    if (P.short_keep) {
+                        uint32_t shorts[64]; int ns = 0;
+                        for (uint32_t k = 0; k < K; k++) {
+                            const uint32_t e = tab[(size_t)h * K + k];
+                            if (!e || e - 1 >= p) continue;
+                            if (P.tag_bits) {
+                                const uint64_t vc = rd64(s + e - 1), vp = rd64(s + p);
+                                const uint32_t pc = hashN(vc, 5, 19) & 31u, pp = hashN(vp, 5, 19) & 31u;
+                                const uint32_t xc = (uint32_t)(((vc >> 40) * 0x9E3779B1u) & 0xFFFFFFFFu) >> (32 - P.tag_bits), xp = (uint32_t)(((vp >> 40) * 0x9E3779B1u) & 0xFFFFFFFFu) >> (32 - P.tag_bits);
+                                if (pc != pp) continue;
+                                if (xc == xp) consider(e - 1); else shorts[ns++] = e - 1;
+                                continue;
+                            }
+                            if (rd64(s + e - 1) == rd64(s + p)) consider(e - 1);
+                            else if (rd32(s + e - 1) == rd32(s + p) && s[e - 1 + 4] == s[p + 4]) shorts[ns++] = e - 1;
+                        }
+                        std::sort(shorts, shorts + ns);
+                        for (int i = 0; i < P.short_keep && i < ns; i++) consider(shorts[ns - 1 - i]);
+                    } else
+                    for (uint32_t k = 0; k < K; k++) { const uint32_t e = tab[(size_t)h * K + k]; if (e) consider(e - 1); }
+                    if (rows2) {
+                        const uint32_t h2 = hashN(rd64(s + p), P.hash2_bytes, P.hash2_log);
+                        for (uint32_t k = 0; k < K2; k++) { const uint32_t e = tab2[(size_t)h2 * K2 + k]; if (e) consider(e - 1); }
+                    }
+                }
+                blen[p] = bl; boff[p] = bo;
+            }
+        }
+        // inheritance: a match (off, len) at p is a match (off, len-1) at p+1 -- serves un-searched positions and capped matches
+        for (uint32_t p = 1; p < n; p++) {
+            if (blen[p - 1] > MM || (blen[p - 1] >= CAP)) {
+                const uint32_t il = blen[p - 1] >= CAP ? CAP : blen[p - 1] - 1, io = boff[p - 1];
+                // a capped match stays capped while it really continues; the model checks the true length
+                uint32_t tl = il;
+                if (blen[p - 1] >= CAP) { tl = match_len(s, p, p - io, n); if (tl > CAP) tl = CAP; }
+                if (tl >= MM) {
+                    const int32_t si = P.sel_mul * (int32_t)tl - (int32_t)highbit(io + 3);
+                    const int32_t so = blen[p] ? P.sel_mul * (int32_t)blen[p] - (int32_t)highbit(boff[p] + 3) : -1000;
+                    if (si > so) { blen[p] = tl; boff[p] = io; }
+                }
+            }
+        }
+    }
+    // ---- stage D: decide (rep-blind lazy, depth 2) ----
+    std::vector<Rec> rec(n);
+    std::vector<int32_t> sc(n + 8, -1);
+    for (uint32_t p = 0; p < n; p++) if (blen[p] >= MM) { int32_t v = lazy_score(blen[p], boff[p]); sc[p] = v >= P.accept_thr ? v : -1; }
+    for (uint32_t p = 0; p < n; p++) {
+        Rec r = {0, 0, 0, 0, false};
+        const uint32_t be = std::min(n, (p / Z_BLOCK_MAX + 1) * Z_BLOCK_MAX);
+        if (sc[p] >= 0) {
+            uint32_t start = p; int32_t cur = sc[p];
+            while (blen[start] < (uint32_t)P.target_len && start - p + 2 <= (uint32_t)P.max_shift) {
+                const int32_t s1 = start + 1 < be ? sc[start + 1] : -1;
+                if (s1 > cur + 4) { cur = s1; start += 1; continue; }
+                const int32_t s2 = start + 2 < be ? sc[start + 2] : -1;
+                if (s2 > cur + 7) { cur = s2; start += 2; continue; }
+                break;
+            }
+            r.off = boff[start]; r.len = blen[start]; r.shift = start - p; r.capped = blen[start] >= CAP;
+            uint32_t k = 0;
+            while (k < (uint32_t)P.back_max && start > k && start - k > r.off && s[start - k - 1] == s[start - k - 1 - r.off]) k++;
+            r.back = k;
+        }
+        rec[p] = r;
+    }
+    // ---- stage C: chase with repeat-offset scanning, block by block ----
+    uint8_t *o = dst;
+    *o++ = 0x28; *o++ = 0xB5; *o++ = 0x2F; *o++ = 0xFD;
+    if (n <= 255) { *o++ = 0x20; *o++ = (uint8_t)n; }
+    else if (n <= 65791) { *o++ = 0x60; uint32_t v = n - 256; *o++ = (uint8_t)v; *o++ = (uint8_t)(v >> 8); }
+    else { *o++ = 0xA0; for (int i = 0; i < 4; i++) *o++ = (uint8_t)(n >> (8 * i)); }
+    std::vector<Seq> seqs; std::vector<uint8_t> lits, body;
+    EncWork *wk = new EncWork;
+    uint64_t total_seq = 0, rep_seq = 0, total_lit = 0;
+    const uint32_t nblocks = n ? (n + Z_BLOCK_MAX - 1) / Z_BLOCK_MAX : 1;
+    for (uint32_t b = 0; b < nblocks; b++) {
+        const uint32_t bs = b * Z_BLOCK_MAX, be = std::min(n, bs + Z_BLOCK_MAX);
+        seqs.clear(); lits.clear();
+        uint32_t rep[3] = {0, 0, 0};
+        if (b == 0) { rep[0] = 1; rep[1] = 4; rep[2] = 8; }
+        uint32_t p = bs, anchor = bs;
+        auto emit = [&](uint32_t start, uint32_t len, uint32_t off) {
+            const uint32_t ll = start - anchor;
+            uint32_t ob = off + 3;
+            if (ll) { if (off == rep[0]) ob = 1; else if (off == rep[1]) ob = 2; else if (off == rep[2]) ob = 3; }
+            else { if (off == rep[1]) ob = 1; else if (off == rep[2]) ob = 2; else if (rep[0] > 1 && off == rep[0] - 1) ob = 3; }
+            if (ob > 3) { rep[2] = rep[1]; rep[1] = rep[0]; rep[0] = off; }
+            else {
+                const uint32_t ix = ob - 1 + (ll ? 0 : 1);
+                if (ix == 1) std::swap(rep[0], rep[1]);
+                else if (ix == 2) { const uint32_t t = rep[2]; rep[2] = rep[1]; rep[1] = rep[0]; rep[0] = t; }
+                else if (ix == 3) { const uint32_t t = rep[0] - 1; rep[2] = rep[1]; rep[1] = rep[0]; rep[0] = t; }
+            }
+            if (ob <= 3) rep_seq++;
+            lits.insert(lits.end(), s + anchor, s + start);
+            seqs.push_back({ll, len, ob});
+            p = start + len; anchor = p;
+        };
+        // the rep offsets a position g may use cheaply, given the literal run so far
+        auto rep_len_at = [&](uint32_t g, uint32_t *off_out) -> uint32_t {
+            uint32_t bestl = 0, besto = 0;
+            const bool ll0 = g == anchor;
+            uint32_t cand[3]; int nc = 0;
+            if (!ll0) { cand[nc++] = rep[0]; if (P.rep_scan >= 2) cand[nc++] = rep[1]; if (P.rep_scan >= 3) cand[nc++] = rep[2]; }
+            else { cand[nc++] = rep[1]; if (P.rep_scan >= 2) cand[nc++] = rep[2]; if (P.rep_scan >= 3 && rep[0] > 1) cand[nc++] = rep[0] - 1; }
+            for (int i = 0; i < nc; i++) {
+                const uint32_t ofs = cand[i];
+                if (!ofs || ofs > g) continue;
+                if (g + 4 > be) continue;
+                uint32_t l = match_len(s, g, g - ofs, n);
+                if (g + l > be) l = be - g;
+                if (l > bestl) { bestl = l; besto = ofs; }
+            }
+            *off_out = besto;
+            return bestl;
+        };
+        while (p < be) {
+            // next record at or after p
+            uint32_t q = p;
+            while (q < be && rec[q].len == 0) q++;
+            uint32_t mstart = be, mlen = 0, moff = 0;
+            if (q < be) {
+                const Rec &r = rec[q];
+                mstart = q + r.shift; mlen = r.len; moff = r.off;
+                if (r.capped) mlen = match_len(s, mstart, mstart - moff, n);
+                if (mstart + mlen > be) mlen = be - mstart;
+                uint32_t back = std::min(r.back, mstart - anchor);
+                // backward extension must not cross the cursor's literal run start
+                mstart -= back; mlen += back;
+            }
+            // scan the literal gap [p, mstart) for rep matches
+            bool took = false;
+            if (P.rep_scan) {
+                for (uint32_t g = p; g < mstart && g + 4 <= be; g++) {
+                    uint32_t ro; const uint32_t rl = rep_len_at(g, &ro);
+                    if (rl >= (uint32_t)P.rep_min) { emit(g, rl, ro); took = true; break; }
+                }
+            }
+            if (took) continue;
+            if (mstart >= be || mlen < 3) { p = be; break; }
+            if (P.rep_at_start) {
+                uint32_t ro; const uint32_t rl = rep_len_at(mstart, &ro);
+                // zstd's rule of thumb: a rep match wins if 3*rl > 3*ml - log2(off) + 1
+                if (rl >= 3 && ro != moff && (int32_t)(3 * rl) > (int32_t)(3 * mlen) - (int32_t)highbit(moff + 3) + 1) { emit(mstart, rl, ro); continue; }
+            }
+            emit(mstart, mlen, moff);
+        }
+        lits.insert(lits.end(), s + anchor, s + be);
+        body.resize(block_body_bound((uint32_t)lits.size(), (uint32_t)seqs.size()) + 64);
+        const uint32_t bl = write_block_body(body.data(), lits.data(), (uint32_t)lits.size(), seqs.data(), (uint32_t)seqs.size(), wk);
+        const uint32_t blen_b = be - bs;
+        const bool last = b + 1 == nblocks;
+        if ((size_t)(o - dst) + 3 + std::max(bl, blen_b) > cap_dst) { delete wk; return -1; }
+        if (bl >= blen_b || blen_b == 0) {
+            const uint32_t h = (last ? 1u : 0u) | 0u << 1 | blen_b << 3;
+            *o++ = (uint8_t)h; *o++ = (uint8_t)(h >> 8); *o++ = (uint8_t)(h >> 16);
+            memcpy(o, s + bs, blen_b); o += blen_b;
+        } else {
+            const uint32_t h = (last ? 1u : 0u) | 2u << 1 | bl << 3;
+            *o++ = (uint8_t)h; *o++ = (uint8_t)(h >> 8); *o++ = (uint8_t)(h >> 16);
+            memcpy(o, body.data(), bl); o += bl;
+            total_seq += seqs.size(); total_lit += lits.size();
+        }
+    }
+    delete wk;
+    if (stats) { stats[0] = total_seq; stats[1] = total_lit; stats[2] = rep_seq; stats[3] = nverify; stats[4] = nrows; }
+    return o - dst;
+}
