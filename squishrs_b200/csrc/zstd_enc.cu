@@ -13,6 +13,7 @@
 #include <stdlib.h>
 #include "common.cuh"
 #include "zstd_enc_lz.cuh"
+#include "zstd_enc_lz2.cuh"
 
 #define SQ_BLOCK_MAX (128u * 1024u)  // zstd Block_Maximum_Size
 #define SQ_MAX_BLOCKS 16u            // 2 MiB / 128 KiB
@@ -29,10 +30,11 @@ struct sq_enc_scratch {
     zc::Seq *seqs;           // [cap_chunks * lz::MAX_SEQ_PER_CHUNK] parsed sequences
     lz::BlockMeta *meta;     // [cap_chunks * SQ_MAX_BLOCKS]
     uint32_t *rec;           // [cap_chunks * lz::REC_PER_CHUNK] per-position parse records
-    uint32_t *tab, *head;    // per resident lz CTA: bucketed hash table (never cleared between chunks)
     uint8_t *lits;           // per entropy warp: gathered literals
     uint32_t *sbits;         // per entropy warp: FSE state-transition records + packed symbol codes, 4 x SEQ_PER_BLOCK
-    uint32_t lz_ctas, ent_warps;
+    uint32_t ent_warps;
+    uint32_t *tab2, *head2;  // round-2 search: one table (2 MB) + ring heads per resident CLUSTER
+    uint32_t lz2_clusters; int lz2_cfg;
     uint32_t cap_chunks;
     uint32_t *status;        // [0] != 0 => capacity overflow; [1],[2] work counters
 };
@@ -172,39 +174,77 @@ __global__ void __launch_bounds__(256) enc_emit_kernel(const uint8_t *__restrict
 
 }  // namespace
 
+
+// ---- round-2 search kernel: launch configurations (cluster size, threads, positions per CTA and step, CTAs per SM) ----
+namespace {
+struct Lz2Cfg { int g, threads, sub, minb; };
+constexpr Lz2Cfg LZ2_CFGS[] = {{8, 256, 256, 2}, {8, 512, 512, 1}, {8, 256, 512, 2}, {4, 256, 256, 2}, {4, 512, 512, 1}, {1, 256, 256, 2}, {8, 256, 256, 1}, {2, 256, 256, 2}, {8, 512, 512, 2}};
+constexpr int LZ2_NCFG = sizeof(LZ2_CFGS) / sizeof(LZ2_CFGS[0]);
+
+template <int G, int T, int SUB, int MINB>
+cudaError_t lz2_launch(int clusters_or_query, int *max_clusters, cudaStream_t st, const uint8_t *data, const sq_span *spans, const uint8_t *select,
+                       uint32_t n, uint32_t *tab, uint32_t *head, uint32_t *rec, uint32_t *counter) {
+    auto kern = lz2::search_kernel<G, T, SUB, MINB>;
+    const size_t smem = lz2::SearchSmem<T, SUB>::BYTES;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.blockDim = dim3(T, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = G; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (max_clusters) {  // query: how many clusters of this shape are resident at once
+        cfg.gridDim = dim3(G * 1024, 1, 1);
+        return cudaOccupancyMaxActiveClusters(max_clusters, kern, &cfg);
+    }
+    cfg.gridDim = dim3((unsigned)(clusters_or_query * G), 1, 1);
+    return cudaLaunchKernelEx(&cfg, kern, data, spans, select, n, tab, head, rec, counter);
+}
+
+cudaError_t lz2_dispatch(int c, int clusters, int *max_clusters, cudaStream_t st, const uint8_t *data, const sq_span *spans, const uint8_t *select,
+                         uint32_t n, uint32_t *tab, uint32_t *head, uint32_t *rec, uint32_t *counter) {
+#define LZ2_CASE(i)                                                                                                                     \
+    case i: return lz2_launch<LZ2_CFGS[i].g, LZ2_CFGS[i].threads, LZ2_CFGS[i].sub, LZ2_CFGS[i].minb>(clusters, max_clusters, st, data, spans, select, n, tab, \
+                                                                                                   head, rec, counter);
+    switch (c) {
+        LZ2_CASE(0) LZ2_CASE(1) LZ2_CASE(2) LZ2_CASE(3) LZ2_CASE(4) LZ2_CASE(5) LZ2_CASE(6) LZ2_CASE(7) LZ2_CASE(8)
+    }
+#undef LZ2_CASE
+    return cudaErrorInvalidValue;
+}
+}  // namespace
+
 static int32_t enc_scratch(sq_ctx *ctx, uint32_t n, int set) {
     if (!ctx->enc_sets[set]) {
         ctx->enc_sets[set] = new sq_enc_scratch();
         memset(ctx->enc_sets[set], 0, sizeof(sq_enc_scratch));
     }
     sq_enc_scratch *e = ctx->enc_sets[set];
-    if (!e->tab) {  // per-resident-worker state, sized once from the SM count
-        {   // The search kernel leans on L1 for candidate bytes: give shared memory only what the resident CTAs need.
-            cudaFuncAttributes fa;
-            SQ_CUDA(ctx, cudaFuncGetAttributes(&fa, lz::lz_search_kernel));
-            const char *ov = getenv("SQ_LZ_CTAS_PER_SM");
-            const int per_sm = ov && atoi(ov) > 0 ? atoi(ov) : 3;
-            int carve = (int)((per_sm * (fa.sharedSizeBytes + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024));
-            if (const char *cv = getenv("SQ_LZ_CARVEOUT")) carve = atoi(cv);
-            if (carve > 100) carve = 100;
-            SQ_CUDA(ctx, cudaFuncSetAttribute(lz::lz_search_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
-        }
-        {
-            const char *ov = getenv("SQ_LZ_CTAS_PER_SM");  // tuning knob; default = what the register budget allows
-            const uint32_t per_sm = ov && atoi(ov) > 0 ? (uint32_t)atoi(ov) : 3u;
-            e->lz_ctas = (uint32_t)ctx->sm_count * per_sm;
-            const char *tot = getenv("SQ_LZ_CTAS_TOTAL");  // experiment knob: cap the number of chunks in flight
-            if (tot && atoi(tot) > 0) e->lz_ctas = (uint32_t)atoi(tot);
-        }
+    if (!e->tab2) {  // per-resident-worker state, sized once from the SM count
         {   // entropy stage: one warp per block, 4 warps per CTA; shared memory (42.8 KB per CTA) allows 5 CTAs per SM
             const char *ov = getenv("SQ_ENT_WARPS_PER_SM");
             e->ent_warps = (uint32_t)ctx->sm_count * (ov && atoi(ov) > 0 ? (uint32_t)atoi(ov) : 20u);
             SQ_CUDA(ctx, cudaFuncSetAttribute(lz::entropy_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         }
-        SQ_CUDA(ctx, cudaMalloc(&e->tab, (size_t)e->lz_ctas * lz::ROWS * lz::ROW_K * sizeof(uint32_t)));
-        SQ_CUDA(ctx, cudaMemset(e->tab, 0, (size_t)e->lz_ctas * lz::ROWS * lz::ROW_K * sizeof(uint32_t)));
-        SQ_CUDA(ctx, cudaMalloc(&e->head, (size_t)e->lz_ctas * lz::ROWS * sizeof(uint32_t)));
-        SQ_CUDA(ctx, cudaMemset(e->head, 0, (size_t)e->lz_ctas * lz::ROWS * sizeof(uint32_t)));
+        {   // round-2 search: tables per resident cluster
+            static const int env_cfg = getenv("SQ_LZ2_CFG") ? atoi(getenv("SQ_LZ2_CFG")) : 0;
+            e->lz2_cfg = env_cfg >= 0 && env_cfg < LZ2_NCFG ? env_cfg : 0;
+            int maxc = 0;
+            SQ_CUDA(ctx, lz2_dispatch(e->lz2_cfg, 0, &maxc, 0, nullptr, nullptr, nullptr, 0, nullptr, nullptr, nullptr, nullptr));
+            if (maxc < 1) return sq_set_error(ctx, SQ_ERR_CUDA, "search kernel: no cluster of %d CTAs fits this device", LZ2_CFGS[e->lz2_cfg].g);
+            if (const char *cv = getenv("SQ_LZ2_CLUSTERS")) if (atoi(cv) > 0 && atoi(cv) < maxc) maxc = atoi(cv);
+            e->lz2_clusters = (uint32_t)maxc;
+            if (getenv("SQ_TIMING")) fprintf(stderr, "[sq] search kernel cfg %d: cluster %d x %d threads, %d positions per CTA and step, %d clusters resident\n", e->lz2_cfg,
+                                             LZ2_CFGS[e->lz2_cfg].g, LZ2_CFGS[e->lz2_cfg].threads, LZ2_CFGS[e->lz2_cfg].sub, maxc);
+            SQ_CUDA(ctx, cudaMalloc(&e->tab2, (size_t)maxc * lz2::ROWS * lz2::ROW_K * sizeof(uint32_t)));
+            SQ_CUDA(ctx, cudaMalloc(&e->head2, (size_t)maxc * lz2::ROWS * sizeof(uint32_t)));
+            SQ_CUDA(ctx, cudaMemset(e->head2, 0, (size_t)maxc * lz2::ROWS * sizeof(uint32_t)));
+        }
         SQ_CUDA(ctx, cudaMalloc(&e->lits, (size_t)e->ent_warps * (Z_BLOCK_MAX + 64)));
         SQ_CUDA(ctx, cudaMalloc(&e->sbits, (size_t)e->ent_warps * lz::SBITS_STRIDE * sizeof(uint32_t)));
         SQ_CUDA(ctx, cudaMalloc(&e->status, 8 * sizeof(uint32_t)));
@@ -231,7 +271,7 @@ void sq_enc_destroy(sq_ctx *ctx) {
         sq_enc_scratch *e = ctx->enc_sets[set];
         if (!e) continue;
         cudaFree(e->blocks); cudaFree(e->frame_len); cudaFree(e->bodies); cudaFree(e->status); cudaFree(e->seqs); cudaFree(e->meta); cudaFree(e->rec);
-        cudaFree(e->tab); cudaFree(e->head); cudaFree(e->lits); cudaFree(e->sbits);
+        cudaFree(e->tab2); cudaFree(e->head2); cudaFree(e->lits); cudaFree(e->sbits);
         delete e;
         ctx->enc_sets[set] = nullptr;
         if (ctx->enc_set_done[set]) cudaEventDestroy(ctx->enc_set_done[set]);
@@ -279,16 +319,10 @@ int32_t sq_encode_device_set(sq_ctx *ctx, int set, const void *d_data, const sq_
     SQ_CUDA(ctx, cudaMemsetAsync(e->status + 1, 0, 2 * sizeof(uint32_t), st));
     {
         static_assert(sizeof(lz::BlockOut) == sizeof(sq_block_info), "block info layout");
-        const uint32_t lz_grid = n < e->lz_ctas ? n : e->lz_ctas;
-        // Search stride: 2 by default; SQ_FLAG_DENSE_SEARCH in sq_config.flags (or SQ_LZ_STRIDE=1) searches every position (about 1.3x
-        // slower, ~3 % smaller frames on text and source code).  SQ_LZ_STRIDE=0 picks per tile: stride 2 when at least SQ_LZ_ADAPT of
-        // the previous tile's 1024 positions sat inside a long match (experimental).
-        static const int env_stride = getenv("SQ_LZ_STRIDE") ? atoi(getenv("SQ_LZ_STRIDE")) : -1;
-        static const uint32_t adapt_thr = getenv("SQ_LZ_ADAPT") ? (uint32_t)atoi(getenv("SQ_LZ_ADAPT")) : 384u;
-        const uint32_t stride_mode = env_stride >= 0 && env_stride <= 2 ? (uint32_t)env_stride : (ctx->flags & SQ_FLAG_DENSE_SEARCH) ? 1u : (uint32_t)SQ_LZ_SSTRIDE;
-        lz::lz_search_kernel<<<lz_grid, lz::THREADS, 0, st>>>((const uint8_t *)d_data, d_spans, d_select, n, e->tab, e->head, e->rec, e->status + 1,
-                                                              stride_mode, adapt_thr);
-        lz::lz_chase_kernel<<<(n * SQ_MAX_BLOCKS + 3) / 4, 128, 0, st>>>((const uint8_t *)d_data, d_spans, d_select, n, e->rec, e->seqs, e->meta);
+        // search: one cluster per chunk in flight (tables L2-resident), then the parse (lazy choice + repeat offsets) per block
+        const uint32_t clusters = n < e->lz2_clusters ? n : e->lz2_clusters;
+        SQ_CUDA(ctx, lz2_dispatch(e->lz2_cfg, (int)clusters, nullptr, st, (const uint8_t *)d_data, d_spans, d_select, n, e->tab2, e->head2, e->rec, e->status + 1));
+        lz2::chase_kernel<<<(n * SQ_MAX_BLOCKS + 3) / 4, 128, 0, st>>>((const uint8_t *)d_data, d_spans, d_select, n, e->rec, e->seqs, e->meta);
         const uint32_t ent_ctas = e->ent_warps / 4;
         lz::entropy_kernel<<<ent_ctas, 128, 0, st>>>((const uint8_t *)d_data, d_spans, d_select, n, e->seqs, e->meta, e->lits, e->bodies,
                                                      reinterpret_cast<lz::BlockOut *>(e->blocks), e->sbits, e->status + 2);

@@ -24,6 +24,7 @@ struct P2 {
     int chain;        // 1: candidates come from a full per-position hash chain (upper bound study), depth = K
     int short_keep;   // > 0: candidates whose first 8 bytes do not all match ("short") are verified only for the short_keep nearest; 0 = all
     int tag_bits;     // > 0 (with short_keep): long/short classes come from ptag (5 bits of the row hash) and xtag (tag_bits bits of a hash of bytes 5..7) instead of the bytes
+    int long_cap;     // > 0: at most this many long candidates per position enter the pair queue (slot order)
     int cont;         // continuation filter: 0 off, 1 exact (pair (p-1,c-1) was a candidate pair), 2 previous byte equal; refresh every 16 positions
 };
 
@@ -54,7 +55,7 @@ extern "C" long lz_model2_frame(const uint8_t *s, uint32_t n, uint8_t *dst, uint
     const P2 P = *Pp;
     const uint32_t MM = (uint32_t)P.mm, CAP = (uint32_t)P.cap;
     std::vector<uint32_t> blen(n + 64, 0), boff(n + 64, 0);
-    uint64_t nverify = 0, nrows = 0;
+    uint64_t nverify = 0, nrows = 0, nlong = 0;
     // ---- stage S: search ----
     {
         const uint32_t rows = 1u << P.rows_log, K = (uint32_t)P.K;
@@ -103,7 +104,8 @@ extern "C" long lz_model2_frame(const uint8_t *s, uint32_t n, uint8_t *dst, uint
                 } else {
                     const uint32_t h = hashN(rd64(s + p), P.mm, P.rows_log);
                     if (P.short_keep) {
-                        uint32_t shorts[64]; int ns = 0;
+                        uint32_t shorts[64]; int ns = 0, nl = 0;
+                        auto consider_long = [&](uint32_t c) { nlong++; if (P.long_cap && nl >= P.long_cap) return; nl++; consider(c); };
                         for (uint32_t k = 0; k < K; k++) {
                             const uint32_t e = tab[(size_t)h * K + k];
                             if (!e || e - 1 >= p) continue;
@@ -112,7 +114,7 @@ extern "C" long lz_model2_frame(const uint8_t *s, uint32_t n, uint8_t *dst, uint
                                 const uint32_t pc = hashN(vc, 5, 19) & 31u, pp = hashN(vp, 5, 19) & 31u;
                                 const uint32_t xc = (uint32_t)(((vc >> 40) * 0x9E3779B1u) & 0xFFFFFFFFu) >> (32 - P.tag_bits), xp = (uint32_t)(((vp >> 40) * 0x9E3779B1u) & 0xFFFFFFFFu) >> (32 - P.tag_bits);
                                 if (pc != pp) continue;
-                                if (xc == xp) consider(e - 1); else shorts[ns++] = e - 1;
+                                if (xc == xp) consider_long(e - 1); else shorts[ns++] = e - 1;
                                 continue;
                             }
                             if (rd64(s + e - 1) == rd64(s + p)) consider(e - 1);
@@ -268,6 +270,6 @@ extern "C" long lz_model2_frame(const uint8_t *s, uint32_t n, uint8_t *dst, uint
         }
     }
     delete wk;
-    if (stats) { stats[0] = total_seq; stats[1] = total_lit; stats[2] = rep_seq; stats[3] = nverify; stats[4] = nrows; }
+    if (stats) { stats[0] = total_seq; stats[1] = total_lit; stats[2] = rep_seq; stats[3] = nverify; stats[4] = nrows; stats[5] = nlong; }
     return o - dst;
 }
