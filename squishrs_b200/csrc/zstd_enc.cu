@@ -178,12 +178,13 @@ __global__ void __launch_bounds__(256) enc_emit_kernel(const uint8_t *__restrict
 // ---- round-2 search kernel: launch configurations (cluster size, threads, positions per CTA and step, CTAs per SM) ----
 namespace {
 struct Lz2Cfg { int g, threads, sub, minb; };
-constexpr Lz2Cfg LZ2_CFGS[] = {{8, 256, 256, 2}, {8, 512, 512, 1}, {8, 256, 512, 2}, {4, 256, 256, 2}, {4, 512, 512, 1}, {1, 256, 256, 2}, {8, 256, 256, 1}, {2, 256, 256, 2}, {8, 512, 512, 2}};
+constexpr Lz2Cfg LZ2_CFGS[] = {{8, 256, 256, 2}, {8, 512, 512, 1}, {8, 256, 512, 2}, {4, 256, 256, 2}, {4, 512, 512, 1}, {1, 256, 256, 2}, {8, 256, 256, 1}, {2, 256, 256, 2}, {4, 256, 512, 2}};
 constexpr int LZ2_NCFG = sizeof(LZ2_CFGS) / sizeof(LZ2_CFGS[0]);
 
 template <int G, int T, int SUB, int MINB>
 cudaError_t lz2_launch(int clusters_or_query, int *max_clusters, cudaStream_t st, const uint8_t *data, const sq_span *spans, const uint8_t *select,
                        uint32_t n, uint32_t *tab, uint32_t *head, uint32_t *rec, uint32_t *counter) {
+    static const uint32_t dbg = getenv("SQ_LZ2_DBG") ? (uint32_t)atoi(getenv("SQ_LZ2_DBG")) : 0u;
     auto kern = lz2::search_kernel<G, T, SUB, MINB>;
     const size_t smem = lz2::SearchSmem<T, SUB>::BYTES;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -203,7 +204,7 @@ cudaError_t lz2_launch(int clusters_or_query, int *max_clusters, cudaStream_t st
         return cudaOccupancyMaxActiveClusters(max_clusters, kern, &cfg);
     }
     cfg.gridDim = dim3((unsigned)(clusters_or_query * G), 1, 1);
-    return cudaLaunchKernelEx(&cfg, kern, data, spans, select, n, tab, head, rec, counter);
+    return cudaLaunchKernelEx(&cfg, kern, data, spans, select, n, tab, head, rec, counter, dbg);
 }
 
 cudaError_t lz2_dispatch(int c, int clusters, int *max_clusters, cudaStream_t st, const uint8_t *data, const sq_span *spans, const uint8_t *select,
@@ -322,7 +323,9 @@ int32_t sq_encode_device_set(sq_ctx *ctx, int set, const void *d_data, const sq_
         // search: one cluster per chunk in flight (tables L2-resident), then the parse (lazy choice + repeat offsets) per block
         const uint32_t clusters = n < e->lz2_clusters ? n : e->lz2_clusters;
         SQ_CUDA(ctx, lz2_dispatch(e->lz2_cfg, (int)clusters, nullptr, st, (const uint8_t *)d_data, d_spans, d_select, n, e->tab2, e->head2, e->rec, e->status + 1));
-        lz2::chase_kernel<<<(n * SQ_MAX_BLOCKS + 3) / 4, 128, 0, st>>>((const uint8_t *)d_data, d_spans, d_select, n, e->rec, e->seqs, e->meta);
+        static const bool chase_thread = getenv("SQ_LZ2_DBG") && (atoi(getenv("SQ_LZ2_DBG")) & 4);  // debugging reference: the scalar parse, one thread per block
+        if (chase_thread) lz2::chase_thread_kernel<<<(n * SQ_MAX_BLOCKS + 63) / 64, 64, 0, st>>>((const uint8_t *)d_data, d_spans, d_select, n, e->rec, e->seqs, e->meta);
+        else lz2::chase_kernel<<<(n * SQ_MAX_BLOCKS + 3) / 4, 128, 0, st>>>((const uint8_t *)d_data, d_spans, d_select, n, e->rec, e->seqs, e->meta);
         const uint32_t ent_ctas = e->ent_warps / 4;
         lz::entropy_kernel<<<ent_ctas, 128, 0, st>>>((const uint8_t *)d_data, d_spans, d_select, n, e->seqs, e->meta, e->lits, e->bodies,
                                                      reinterpret_cast<lz::BlockOut *>(e->blocks), e->sbits, e->status + 2);

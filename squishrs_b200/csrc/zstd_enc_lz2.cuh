@@ -39,6 +39,7 @@
 #pragma once
 #include <cooperative_groups.h>
 #include "zstd_enc_lz.cuh"
+#include "zstd_enc_parse.h"
 
 namespace lz2 {
 namespace cg = cooperative_groups;
@@ -46,8 +47,8 @@ namespace cg = cooperative_groups;
 constexpr uint32_t ROW_LOG = 14, ROWS = 1u << ROW_LOG, ROW_K = 32;
 constexpr uint32_t POS_BITS = 21, POS_MASK = (1u << POS_BITS) - 1, PTAG_BITS = 5, PFX_MASK = (1u << (POS_BITS + PTAG_BITS)) - 1;
 constexpr uint32_t EMPTY = 0xFFFFFFFFu;
-constexpr uint32_t MIN_MATCH = 5, CAP = 32, TARGET_LEN = 32, MAX_SHIFT = 7, REP_MIN = 3;
-constexpr int32_t ACCEPT_THR = 6;
+constexpr uint32_t MIN_MATCH = zparse::MIN_MATCH, CAP = zparse::CAP, MAX_SHIFT = zparse::MAX_SHIFT, REP_MIN = zparse::REP_MIN;
+constexpr int32_t ACCEPT_THR = zparse::ACCEPT_THR;
 constexpr uint32_t LOOKAHEAD = CAP + 16;
 constexpr uint32_t QUEUE_WORDS = 32 * ROW_K + 32;  // per warp: every entry of every row could be a long candidate, plus one short per position
 constexpr uint32_t SEQ_PER_BLOCK = lz::SEQ_PER_BLOCK, MAX_SEQ_PER_CHUNK = lz::MAX_SEQ_PER_CHUNK, BLOCKS_PER_CHUNK = lz::BLOCKS_PER_CHUNK;
@@ -69,30 +70,50 @@ __device__ __forceinline__ uint32_t pack_rec(uint32_t off, uint32_t len, uint32_
 template <int G> __device__ __forceinline__ void group_sync() {
     if (G > 1) cg::this_cluster().sync(); else __syncthreads();
 }
+// split-phase cluster barrier: arrive (release) early, wait (acquire) late
+template <int G> __device__ __forceinline__ void cl_arrive() { if (G > 1) asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+template <int G> __device__ __forceinline__ void cl_wait() { if (G > 1) asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+
+// 8 bytes at position p of the chunk, straight from global memory (any alignment)
+__device__ __forceinline__ uint64_t gld8(const uint8_t *__restrict__ in, uint32_t p, uint32_t n) {
+    if (p + 12 <= n) return lz::ld8(in, p);
+    uint64_t v = 0;
+    for (uint32_t k = 0; k < 8 && p + k < n; k++) v |= (uint64_t)in[p + k] << (8 * k);
+    return v;
+}
 
 // ---- search -----------------------------------------------------------------------------------------------------------
+// Step pipeline of one CTA (rank r of a cluster of G); step s covers positions [(s G + r) SUB, + SUB) of the chunk:
+//     reserve   ring slots (atomicAdd on the row heads) for my positions of step s+1: the round trips hide behind the search
+//     stage     bytes of my sub-tile of step s+1 -> the free half of the stage buffer
+//     search    step s (every CTA's entries of steps <= s are in the table)
+//     publish   my entries of step s+1 into the reserved slots
+//     barrier   cluster-wide (release / acquire): all entries of step s+1 are visible
+// A measured alternative -- publish two steps ahead, arrive at the top of the iteration and wait at the bottom, so that a CTA
+// only ever waits for one that has not even started the same step -- was 14 % faster but cost 1.2 % of ratio on real files
+// (entries of later positions are never candidates, but they take ring slots early); the tolerance decides.
 template <int THREADS, int SUB> struct SearchSmem {
     static constexpr uint32_t WARPS = THREADS / 32, SIN = SUB + LOOKAHEAD + 32;
     static constexpr uint32_t OFF_IN = 0, OFF_QUEUE = OFF_IN + 2 * SIN, OFF_CONT = OFF_QUEUE + WARPS * QUEUE_WORDS * 4,
-                              OFF_BEST = OFF_CONT + WARPS * 1024 * 2, BYTES = OFF_BEST + SUB * 4;
+                              OFF_BEST = OFF_CONT + WARPS * 1024 * 4, BYTES = OFF_BEST + SUB * 4;
     static_assert(SIN % 16 == 0, "stage buffer shape");
 };
 
 template <int G, int THREADS, int SUB, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB) search_kernel(const uint8_t *__restrict__ data, const sq_span *__restrict__ spans,
-                                                            const uint8_t *__restrict__ select, uint32_t n_chunks,
-                                                            uint32_t *__restrict__ tab_all, uint32_t *__restrict__ head_all,
-                                                            uint32_t *__restrict__ rec_all, uint32_t *__restrict__ counter) {
+                                                               const uint8_t *__restrict__ select, uint32_t n_chunks,
+                                                               uint32_t *__restrict__ tab_all, uint32_t *__restrict__ head_all,
+                                                               uint32_t *__restrict__ rec_all, uint32_t *__restrict__ counter, uint32_t dbg) {
     constexpr uint32_t WARPS = THREADS / 32, PER_THREAD = SUB / THREADS, GROUPS = SUB / 32;
     using L = SearchSmem<THREADS, SUB>;
     constexpr uint32_t SIN = L::SIN, SIN_WORDS = SIN / 4;
-    static_assert(SUB % THREADS == 0 && SIN_WORDS <= 2 * THREADS && SUB <= 1024, "tile shape");
+    static_assert(SUB % THREADS == 0 && SUB <= 1024, "tile shape");
     extern __shared__ __align__(16) uint8_t s_dyn[];
     uint8_t (*s_in2)[SIN] = reinterpret_cast<uint8_t (*)[SIN]>(s_dyn + L::OFF_IN);
     uint32_t *s_queue = reinterpret_cast<uint32_t *>(s_dyn + L::OFF_QUEUE);
-    uint16_t *s_cont = reinterpret_cast<uint16_t *>(s_dyn + L::OFF_CONT);
+    uint32_t *s_cont = reinterpret_cast<uint32_t *>(s_dyn + L::OFF_CONT);
     uint32_t *s_best = reinterpret_cast<uint32_t *>(s_dyn + L::OFF_BEST);
-    __shared__ uint32_t s_chunk, s_gctr;
+    __shared__ uint32_t s_chunk, s_gctr[2];  // group counters alternate by step parity
 
     const uint32_t tid = threadIdx.x, wq = tid >> 5, lane = tid & 31;
     uint32_t rank = 0;
@@ -101,8 +122,9 @@ __global__ void __launch_bounds__(THREADS, MINB) search_kernel(const uint8_t *__
     uint32_t *tab = tab_all + (size_t)cid * ROWS * ROW_K;
     uint32_t *head = head_all + (size_t)cid * ROWS;
     uint32_t *queue = s_queue + wq * QUEUE_WORDS;
-    uint16_t *T = s_cont + wq * 1024;
+    uint32_t *T = s_cont + wq * 1024;  // continuation keys: (pair | epoch << 26), never cleared (the epoch changes with every group)
     const uint32_t sub = lane >> 2, part = lane & 3u;
+    uint32_t epoch = 0;
 
     for (;;) {
         // ---- the cluster takes the next selected chunk ----
@@ -112,8 +134,8 @@ __global__ void __launch_bounds__(THREADS, MINB) search_kernel(const uint8_t *__
             if (G > 1) { for (uint32_t r = 0; r < (uint32_t)G; r++) *cg::this_cluster().map_shared_rank(&s_chunk, r) = c; }
             else s_chunk = c;
         }
-        if (tid == 0) s_gctr = WARPS;
-        group_sync<G>();
+        if (tid == 0) { s_gctr[0] = WARPS; s_gctr[1] = WARPS; }
+        group_sync<G>();  // also: every CTA is done with the previous chunk's table
         const uint32_t chunk = s_chunk;
         if (chunk >= n_chunks) break;
         const uint8_t *in = data + spans[chunk].off;
@@ -127,79 +149,70 @@ __global__ void __launch_bounds__(THREADS, MINB) search_kernel(const uint8_t *__
             for (uint32_t i = tid; i < SLICE4; i += THREADS) __stcg(t4 + i, make_uint4(EMPTY, EMPTY, EMPTY, EMPTY));
         }
         const uint32_t n_steps = (n + G * SUB - 1) / (G * SUB);
-        // prologue: stage my sub-tiles of steps 0 and 1; after the clear is visible everywhere, insert step 0
-        for (uint32_t i = tid; i < 2 * SIN_WORDS; i += THREADS) {
-            const uint32_t b = i >= SIN_WORDS ? 1u : 0u, w = i - b * SIN_WORDS;
-            reinterpret_cast<uint32_t *>(s_in2[b])[w] = lz::stage_word(in, (b * G + rank) * SUB + w * 4, n, aligned);
-        }
-        group_sync<G>();
-#pragma unroll
-        for (uint32_t k = 0; k < PER_THREAD; k++) {
-            const uint32_t li = tid + k * THREADS, p = rank * SUB + li;
-            if (p + 8 <= n) {
-                const uint64_t v = lz::smem_u64(s_in2[0], li);
-                const uint32_t hv = hash_row_ptag(v), row = hv >> PTAG_BITS;
-                const uint32_t slot = atomicAdd(&head[row], 1u) & (ROW_K - 1);
-                __stcg(&tab[row * ROW_K + slot], p | tag_word(hv, v));
-            }
-        }
-        group_sync<G>();
-
-        for (uint32_t s = 0; s < n_steps; s++) {
-            const uint32_t t0 = (s * G + rank) * SUB, t1 = min(n, t0 + SUB);
-            const uint32_t tn = ((s + 1) * G + rank) * SUB;  // my sub-tile of the next step
-            const uint8_t *s_in = s_in2[s & 1];
-            const uint8_t *s_nx = s_in2[(s + 1) & 1];
-            // ---- reserve ring slots for the next step's positions: the atomics' round trips hide behind this step's search ----
-            uint32_t slot_raw[PER_THREAD];
+        for (uint32_t i = tid; i < SIN_WORDS; i += THREADS)
+            reinterpret_cast<uint32_t *>(s_in2[0])[i] = lz::stage_word(in, rank * SUB + i * 4, n, aligned);
+        group_sync<G>();  // the clear is visible everywhere
+        // ring-slot reservation and entry store for my positions of one step
+        uint32_t r_ent[PER_THREAD], r_idx[PER_THREAD], r_slot[PER_THREAD];
+        auto reserve = [&](uint32_t step) {
 #pragma unroll
             for (uint32_t k = 0; k < PER_THREAD; k++) {
-                const uint32_t li = tid + k * THREADS, p = tn + li;
-                slot_raw[k] = 0;
-                if (p + 8 <= n) slot_raw[k] = atomicAdd(&head[hash_row_ptag(lz::smem_u64(s_nx, li)) >> PTAG_BITS], 1u);
-            }
-            // ---- prefetch the bytes of my sub-tile two steps ahead (stored once this step's buffer is free) ----
-            uint32_t sw0 = 0, sw1 = 0;
-            {
-                const uint32_t g2 = ((s + 2) * G + rank) * SUB;
-                if (g2 < n) {
-                    if (tid < SIN_WORDS) sw0 = lz::stage_word(in, g2 + tid * 4, n, aligned);
-                    if (tid + THREADS < SIN_WORDS) sw1 = lz::stage_word(in, g2 + (THREADS + tid) * 4, n, aligned);
+                const uint32_t p = (step * G + rank) * SUB + tid + k * THREADS;
+                r_ent[k] = EMPTY; r_idx[k] = 0; r_slot[k] = 0;
+                if (p + 8 <= n) {
+                    const uint64_t v = gld8(in, p, n);
+                    const uint32_t hv = hash_row_ptag(v);
+                    r_ent[k] = p | tag_word(hv, v);
+                    r_idx[k] = (hv >> PTAG_BITS) * ROW_K;
+                    r_slot[k] = atomicAdd(&head[hv >> PTAG_BITS], 1u);
                 }
+            }
+        };
+        auto publish = [&]() {
+#pragma unroll
+            for (uint32_t k = 0; k < PER_THREAD; k++)
+                if (r_ent[k] != EMPTY) __stcg(&tab[r_idx[k] + (r_slot[k] & (ROW_K - 1))], r_ent[k]);
+        };
+        reserve(0); publish();
+        group_sync<G>();  // step 0 is in the table
+
+        for (uint32_t s = 0; s < n_steps; s++) {
+            reserve(s + 1);  // ring slots for my positions of the next step: the atomics' round trips hide behind this step's search
+            const uint32_t t0 = (s * G + rank) * SUB, t1 = min(n, t0 + SUB);
+            const uint8_t *s_in = s_in2[s & 1];
+            {   // stage my sub-tile of the next step
+                const uint32_t g1 = ((s + 1) * G + rank) * SUB;
+                uint32_t *dst = reinterpret_cast<uint32_t *>(s_in2[(s + 1) & 1]);
+                if (g1 < n) for (uint32_t i = tid; i < SIN_WORDS; i += THREADS) dst[i] = lz::stage_word(in, g1 + i * 4, n, aligned);
             }
             // ---- search: warps take groups of 32 positions ----
             uint32_t g = wq;
 #pragma unroll 1
             while (g < GROUPS && t0 + g * 32 < n) {
-                const uint32_t gl = g * 32, li = gl + lane, p = t0 + li;
+                const uint32_t gl = g * 32, li = gl + lane, p = t0 + li, pg = t0 + gl;
                 const bool searchable = p + 8 <= n;
-                const bool gfast = t0 + gl + 32 + CAP + 16 <= n;
+                const bool gfast = pg + 32 + CAP + 16 <= n;
                 const uint64_t v_own = lz::smem_u64(s_in, li);
                 const uint32_t hv_own = hash_row_ptag(v_own);
                 const uint32_t T_own = tag_word(hv_own, v_own);
-                // rows: pass k serves position 8 k + sub; this lane reads entries [8 part, 8 part + 8) of that row
+                epoch = (epoch + 1u) & 63u;
+                // rows: pass k serves position 8 k + sub; this lane reads entries [4 part, +4) and [16 + 4 part, +4) of that row
                 uint4 ea[4], eb[4];
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
                     const uint32_t hk = __shfl_sync(0xffffffffu, hv_own, 8 * k + sub);
-                    const uint4 *rp = reinterpret_cast<const uint4 *>(tab + (hk >> PTAG_BITS) * ROW_K) + 2 * part;
-                    ea[k] = __ldcg(rp); eb[k] = __ldcg(rp + 1);
+                    const uint4 *rp = reinterpret_cast<const uint4 *>(tab + (hk >> PTAG_BITS) * ROW_K) + part;
+                    ea[k] = __ldcg(rp); eb[k] = __ldcg(rp + 4);
                 }
                 s_best[li] = 0u;
-                // cleared while the rows are in flight
-                {
-                    uint4 *Tz = reinterpret_cast<uint4 *>(T);
-#pragma unroll
-                    for (int z = 0; z < 4; z++) Tz[lane + 32 * z] = make_uint4(0u, 0u, 0u, 0u);
-                }
-                // filter
+                // filter: long candidates (all tag bits agree, before the position) and the nearest short one (ptag only)
                 uint32_t lmask = 0, smax[4];
                 uint32_t xs[32];
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
                     const uint32_t src = 8 * k + sub;
                     const uint32_t Tk = __shfl_sync(0xffffffffu, T_own, src);
-                    const uint32_t pk = t0 + gl + src;
+                    const uint32_t pk = pg + src;
                     const uint32_t plim = pk + 8 <= n ? pk : 0u;
                     const uint32_t e[8] = {ea[k].x, ea[k].y, ea[k].z, ea[k].w, eb[k].x, eb[k].y, eb[k].z, eb[k].w};
                     uint32_t sm = 0;
@@ -207,38 +220,38 @@ __global__ void __launch_bounds__(THREADS, MINB) search_kernel(const uint8_t *__
                     for (int m = 0; m < 8; m++) {
                         const uint32_t x = e[m] ^ Tk, z = x & PFX_MASK;
                         xs[8 * k + m] = x;
-                        lmask |= (x < plim ? 1u : 0u) << (8 * k + m);
-                        const uint32_t w = (z < plim && x != z) ? z + 1u : 0u;  // nearest short candidate, + 1 (0 = none)
-                        sm = max(sm, w);
+                        if (x < plim) lmask |= 1u << (8 * k + m);
+                        sm = max(sm, (z < plim && x != z) ? z : 0u);  // candidate position 0 is not worth a special case
                     }
                     sm = max(sm, __shfl_xor_sync(0xffffffffu, sm, 1));
                     sm = max(sm, __shfl_xor_sync(0xffffffffu, sm, 2));
                     smax[k] = sm;
                 }
-                // long pairs -> queue as (group column | offset << 10)
+                // long pairs -> queue as (candidate position | group column << 21)
                 uint32_t nlong;
                 uint32_t wpos = ent::warp_excl_scan(__popc(lmask), lane, &nlong);
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
-                    const uint32_t col = 8 * k + sub, pk = t0 + gl + col;
+                    const uint32_t colsh = (8 * k + sub) << POS_BITS;
 #pragma unroll
                     for (int m = 0; m < 8; m++)
-                        if (lmask >> (8 * k + m) & 1) queue[wpos++] = col | (pk - xs[8 * k + m]) << 10;
+                        if (lmask >> (8 * k + m) & 1) queue[wpos++] = xs[8 * k + m] | colsh;
                 }
                 __syncwarp();
-                // ---- continuation filter in pair space ----
+                // ---- continuation filter in pair space: (col, c) is dropped when (col - 1, c - 1) is a pair too ----
+                const uint32_t ep = epoch << 26;
                 for (uint32_t i = lane; i < nlong; i += 32) {
-                    const uint32_t pr = queue[i], col = pr & 31u, o = pr >> 10;
-                    T[(o & 31u) * 32u + ((col + (o & 30u)) & 31u)] = (uint16_t)((o >> 5) + 1u);
+                    const uint32_t pr = queue[i], col = pr >> POS_BITS, o = pg + col - (pr & POS_MASK);
+                    T[(o * 37u + col) & 1023u] = pr | ep;
                 }
                 __syncwarp();
                 uint32_t total = 0;
                 for (uint32_t base = 0; base < nlong; base += 32) {
                     const uint32_t i = base + lane;
                     const bool valid = i < nlong;
-                    const uint32_t pr = valid ? queue[i] : 0u, col = pr & 31u, o = pr >> 10;
-                    const bool hit = (col & 15u) != 0 && T[(o & 31u) * 32u + ((col - 1u + (o & 30u)) & 31u)] == (uint16_t)((o >> 5) + 1u);
-                    const bool keep = valid && !hit;
+                    const uint32_t pr = valid ? queue[i] : 0u, col = pr >> POS_BITS, o = pg + col - (pr & POS_MASK);
+                    const bool hit = T[(o * 37u + col - 1u) & 1023u] == ((pr - (1u << POS_BITS) - 1u) | ep);  // col 0 keeps everything: its key would wrap
+                    const bool keep = valid && !(hit && col != 0 && !((dbg & 1u) && col == 16));
                     const uint32_t b = __ballot_sync(0xffffffffu, keep);
                     __syncwarp();
                     if (keep) queue[total + __popc(b & ((1u << lane) - 1u))] = pr;
@@ -254,7 +267,7 @@ __global__ void __launch_bounds__(THREADS, MINB) search_kernel(const uint8_t *__
                     }
                     const bool has = sm != 0;
                     const uint32_t b = __ballot_sync(0xffffffffu, has);
-                    if (has) queue[total + __popc(b & ((1u << lane) - 1u))] = lane | (p - (sm - 1u)) << 10;
+                    if (has) queue[total + __popc(b & ((1u << lane) - 1u))] = sm | lane << POS_BITS;
                     total += __popc(b);
                 }
                 __syncwarp();
@@ -262,7 +275,7 @@ __global__ void __launch_bounds__(THREADS, MINB) search_kernel(const uint8_t *__
                 if (gfast) {
 #pragma unroll 1
                     for (uint32_t i = lane; i < total; i += 32) {
-                        const uint32_t pr = queue[i], l0 = gl + (pr & 31u), o = pr >> 10, c0 = t0 + l0 - o;
+                        const uint32_t pr = queue[i], l0 = gl + (pr >> POS_BITS), c0 = pr & POS_MASK, o = t0 + l0 - c0;
                         const uint32_t *wp = reinterpret_cast<const uint32_t *>(s_in) + (l0 >> 2);
                         const uintptr_t ga = reinterpret_cast<uintptr_t>(in + c0);
                         const uint2 *wc = reinterpret_cast<const uint2 *>(ga & ~(uintptr_t)7);
@@ -275,19 +288,21 @@ __global__ void __launch_bounds__(THREADS, MINB) search_kernel(const uint8_t *__
                         uint32_t cw[9];
                         cw[0] = up ? A0.y : A0.x; cw[1] = up ? A1.x : A0.y; cw[2] = up ? A1.y : A1.x; cw[3] = up ? A2.x : A1.y; cw[4] = up ? A2.y : A2.x;
                         cw[5] = up ? A3.x : A2.y; cw[6] = up ? A3.y : A3.x; cw[7] = up ? A4.x : A3.y; cw[8] = up ? A4.y : A4.x;
-                        uint32_t m = CAP;
+                        uint64_t d[4];
 #pragma unroll
-                        for (int j = 7; j >= 0; j--) {
-                            const uint32_t d = __funnelshift_r(pw[j], pw[j + 1], sp) ^ __funnelshift_r(cw[j], cw[j + 1], sc);
-                            if (d) m = 4u * j + ((uint32_t)(__ffs((int)d) - 1) >> 3);
-                        }
+                        for (int j = 0; j < 4; j++)
+                            d[j] = (uint64_t)(__funnelshift_r(pw[2 * j + 1], pw[2 * j + 2], sp) ^ __funnelshift_r(cw[2 * j + 1], cw[2 * j + 2], sc)) << 32 |
+                                   (__funnelshift_r(pw[2 * j], pw[2 * j + 1], sp) ^ __funnelshift_r(cw[2 * j], cw[2 * j + 1], sc));
+                        uint64_t x = d[0]; uint32_t mb = 0;
+                        if (!x) { x = d[1]; mb = 8; if (!x) { x = d[2]; mb = 16; if (!x) { x = d[3]; mb = 24; } } }
+                        const uint32_t m = x ? mb + ((uint32_t)(__ffsll((long long)x) - 1) >> 3) : CAP;
                         if (m >= MIN_MATCH)
                             atomicMax(&s_best[l0], (uint32_t)((int32_t)(2 * m) - (int32_t)zc::highbit(o + 3) + 12) << POS_BITS | (POS_MASK - o));
                     }
                 } else {  // the last bytes of the chunk: careful scalar comparison
 #pragma unroll 1
                     for (uint32_t i = lane; i < total; i += 32) {
-                        const uint32_t pr = queue[i], l0 = gl + (pr & 31u), o = pr >> 10, pp = t0 + l0;
+                        const uint32_t pr = queue[i], l0 = gl + (pr >> POS_BITS), pp = t0 + l0, o = pp - (pr & POS_MASK);
                         const uint32_t m = lz::match_length(in, pp, pp - o, min(n - pp, CAP), n);
                         if (m >= MIN_MATCH)
                             atomicMax(&s_best[l0], (uint32_t)((int32_t)(2 * m) - (int32_t)zc::highbit(o + 3) + 12) << POS_BITS | (POS_MASK - o));
@@ -337,31 +352,17 @@ __global__ void __launch_bounds__(THREADS, MINB) search_kernel(const uint8_t *__
                     }
                     __stcs(&rec[p], r);
                 }
-                if (lane == 0) g = atomicAdd(&s_gctr, 1u);
+                if (lane == 0) g = atomicAdd(&s_gctr[s & 1], 1u);
                 g = __shfl_sync(0xffffffffu, g, 0);
             }
-            // ---- publish the next step's entries into the slots reserved above ----
+            // ---- publish the next step's entries into the slots reserved above; every CTA's entries of step s+1 are visible after the barrier ----
 #pragma unroll
-            for (uint32_t k = 0; k < PER_THREAD; k++) asm volatile("" : "+r"(slot_raw[k]) :: "memory");
-            asm volatile("" : "+r"(sw0), "+r"(sw1) :: "memory");
-#pragma unroll
-            for (uint32_t k = 0; k < PER_THREAD; k++) {
-                const uint32_t li = tid + k * THREADS, p = tn + li;
-                if (p + 8 <= n) {
-                    const uint64_t v = lz::smem_u64(s_nx, li);
-                    const uint32_t hv = hash_row_ptag(v);
-                    __stcg(&tab[(hv >> PTAG_BITS) * ROW_K + (slot_raw[k] & (ROW_K - 1))], p | tag_word(hv, v));
-                }
-            }
+            for (uint32_t k = 0; k < PER_THREAD; k++) asm volatile("" : "+r"(r_slot[k]) :: "memory");
+            publish();
+            cl_arrive<G>();
+            cl_wait<G>();
+            if (tid == 0) s_gctr[(s + 1) & 1] = WARPS;  // nobody touches the other parity's counter during this iteration
             __syncthreads();
-            // this step's stage buffer is free now: it receives my sub-tile of step s + 2
-            {
-                uint32_t *dst = reinterpret_cast<uint32_t *>(s_in2[s & 1]);
-                if (tid < SIN_WORDS) dst[tid] = sw0;
-                if (tid + THREADS < SIN_WORDS) dst[THREADS + tid] = sw1;
-            }
-            if (tid == 0) s_gctr = WARPS;
-            group_sync<G>();
         }
     }
 }
@@ -415,48 +416,52 @@ __global__ void __launch_bounds__(128) chase_kernel(const uint8_t *__restrict__ 
         p = start + len;
         anchor = p;
     };
-    // the longest repeat-offset match at g (>= 3 bytes), 0 if none; the candidates depend on whether g starts a sequence with no literals
-    auto rep_at = [&](uint32_t g, uint32_t *off_out) -> uint32_t {
-        const bool ll0 = g == anchor;
-        const uint32_t c0 = ll0 ? r1 : r0, c1 = ll0 ? r2 : r1, c2 = ll0 ? (r0 > 1 ? r0 - 1 : 0u) : r2;
-        const uint32_t mine = lane == 0 ? c0 : lane == 1 ? c1 : c2;
-        bool f = false;
-        if (lane < 3 && mine && mine <= g && g + 4 <= be) f = ((load4(in, g, n) ^ load4(in, g - mine, n)) & 0xFFFFFFu) == 0;
-        uint32_t fm = __ballot_sync(0xffffffffu, f), bl = 0, bo = 0;
-        while (fm) {
-            const uint32_t i = __ffs((int)fm) - 1;
-            fm &= fm - 1;
-            const uint32_t o = i == 0 ? c0 : i == 1 ? c1 : c2;
-            const uint32_t l = lz::warp_extend(in, n, g, g - o, be - g, lane);
-            if (l > bl) { bl = l; bo = o; }
-        }
-        *off_out = bo;
-        return bl;
-    };
-    // first literal position in [lo, hi) where a repeat offset matches >= REP_MIN bytes: emits that sequence and returns true
-    auto scan_reps = [&](uint32_t lo, uint32_t hi) -> bool {
+    // One pass over the literal positions [lo, hi) in front of a match -- and, with `with_start`, over the match start hi itself --
+    // for repeat-offset matches (>= 3 bytes): lane j tests position lo + j against the three offsets that are cheap THERE (they
+    // differ when the position follows a match directly).  The first position that matches anything wins; its longest candidate is
+    // extended by the whole warp only if more than 3 bytes agree.  In the gap a hit is taken at once; at the match start it has to
+    // beat the match by zstd's rule of thumb (3 rl > 3 len - log2(offset) + 1).  Returns true if a sequence was emitted.
+    auto scan = [&](uint32_t lo, uint32_t hi, bool with_start, uint32_t mlen, uint32_t moff) -> bool {
         if (!(r0 | r1 | r2)) return false;
-        for (uint32_t gb = lo; gb < hi; gb += 32) {
+        const uint32_t end = with_start ? hi + 1 : hi;
+        for (uint32_t gb = lo; gb < end; gb += 32) {
             const uint32_t g = gb + lane;
-            const bool active = g < hi && g + 4 <= be;
             const bool ll0 = g == anchor;
             const uint32_t c0 = ll0 ? r1 : r0, c1 = ll0 ? r2 : r1, c2 = ll0 ? (r0 > 1 ? r0 - 1 : 0u) : r2;
-            bool f = false;
-            if (active) {
+            uint32_t fl = 0;  // per candidate 2 bits: 0 = no match, 1 = exactly 3 bytes, 2 = 4 or more
+            if (g < end && g + 4 <= be) {
                 const uint32_t v = load4(in, g, n);
-                if (c0 && c0 <= g) f |= ((load4(in, g - c0, n) ^ v) & 0xFFFFFFu) == 0;
-                if (c1 && c1 <= g) f |= ((load4(in, g - c1, n) ^ v) & 0xFFFFFFu) == 0;
-                if (c2 && c2 <= g) f |= ((load4(in, g - c2, n) ^ v) & 0xFFFFFFu) == 0;
+                if (c0 && c0 <= g) { const uint32_t x = load4(in, g - c0, n) ^ v; if (!(x & 0xFFFFFFu)) fl |= x ? 1u : 2u; }
+                if (c1 && c1 <= g) { const uint32_t x = load4(in, g - c1, n) ^ v; if (!(x & 0xFFFFFFu)) fl |= (x ? 1u : 2u) << 2; }
+                if (c2 && c2 <= g) { const uint32_t x = load4(in, g - c2, n) ^ v; if (!(x & 0xFFFFFFu)) fl |= (x ? 1u : 2u) << 4; }
             }
-            const uint32_t any = __ballot_sync(0xffffffffu, f);
-            if (any) {
-                const uint32_t gs = gb + (uint32_t)__ffs((int)any) - 1;
-                uint32_t ro;
-                const uint32_t rl = rep_at(gs, &ro);
-                if (rl >= REP_MIN) { emit(gs, rl, ro); return true; }
+            const uint32_t any = __ballot_sync(0xffffffffu, fl != 0);
+            if (!any) continue;
+            const uint32_t j = (uint32_t)__ffs((int)any) - 1, gs = gb + j;
+            const uint32_t F = __shfl_sync(0xffffffffu, fl, j);
+            const uint32_t C0 = __shfl_sync(0xffffffffu, c0, j), C1 = __shfl_sync(0xffffffffu, c1, j), C2 = __shfl_sync(0xffffffffu, c2, j);
+            uint32_t rl = 0, ro = 0;
+#pragma unroll
+            for (int i = 0; i < 3; i++) {
+                const uint32_t f = F >> (2 * i) & 3u, o = i == 0 ? C0 : i == 1 ? C1 : C2;
+                if (!f) continue;
+                uint32_t l = 3;
+                if (f == 2) l = 4 + (gs + 4 < be ? lz::warp_extend(in, n, gs + 4, gs + 4 - o, be - gs - 4, lane) : 0u);
+                if (l > rl) { rl = l; ro = o; }
             }
+            if (gs < hi) { emit(gs, rl, ro); return true; }
+            // the match start itself
+            if (ro != moff && (int32_t)(3 * rl) > (int32_t)(3 * mlen) - (int32_t)zc::highbit(moff + 3) + 1) { emit(gs, rl, ro); return true; }
+            return false;
         }
         return false;
+    };
+    // lazy score of a record (what the parser gains by taking it), -1 = unusable
+    auto score_of = [&](uint32_t r) -> int32_t {
+        if (!r) return -1;
+        const uint32_t sl = (r >> 26 & 1u) ? CAP : ((r >> 21) & 31u) + MIN_MATCH;
+        const int32_t sc = (int32_t)(4 * sl) - (int32_t)zc::highbit((r & POS_MASK) + 3);
+        return sc >= ACCEPT_THR ? sc : -1;
     };
 
     uint32_t base = ~0u - 63u, w0 = 0, w1 = 0;
@@ -465,42 +470,31 @@ __global__ void __launch_bounds__(128) chase_kernel(const uint8_t *__restrict__ 
         if (nb != base) {
             if (nb == base + 32) w0 = w1;
             else w0 = (nb + lane < be) ? __ldg(rec + nb + lane) : 0u;
-            w1 = (nb + 32 + lane < be) ? __ldg(rec + nb + 32 + lane) : 0u;
+            w1 = (nb + 32 + lane < be) ? __ldg(rec + nb + 32 + lane) : 0u;  // requested now, first touched when the cursor gets near it
             base = nb;
         }
-        // lazy score of each record (what the parser gains by taking it), -1 = unusable
-        auto score_of = [&](uint32_t r) -> int32_t {
-            if (!r) return -1;
-            const uint32_t sl = (r >> 26 & 1u) ? CAP : ((r >> 21) & 31u) + MIN_MATCH;
-            const int32_t sc = (int32_t)(4 * sl) - (int32_t)zc::highbit((r & POS_MASK) + 3);
-            return sc >= ACCEPT_THR ? sc : -1;
-        };
-        const int32_t sc0 = score_of(w0), sc1 = score_of(w1);
-        const uint32_t usable = __ballot_sync(0xffffffffu, sc0 >= 0) & (0xffffffffu << (p - base));
+        const uint32_t usable = __ballot_sync(0xffffffffu, score_of(w0) >= 0) & (0xffffffffu << (p - base));
         if (!usable) {  // literals up to the end of this window (unless a repeat offset matches)
             const uint32_t ge = min(be, base + 32);
-            if (!scan_reps(p, ge)) p = ge;
+            if (!scan(p, ge, false, 0, 0)) p = ge;
             continue;
         }
         const uint32_t q = base + (uint32_t)__ffs((int)usable) - 1;
-        auto sc_at = [&](uint32_t x) -> int32_t {
+        auto rec_at = [&](uint32_t x) -> uint32_t {  // warp-uniform x in [base, base + 64)
             const uint32_t d = x - base;
-            const int32_t a = __shfl_sync(0xffffffffu, sc0, d & 31u), c = __shfl_sync(0xffffffffu, sc1, d & 31u);
-            return x < be ? (d < 32 ? a : c) : -1;
-        };
-        auto rec_at = [&](uint32_t x) -> uint32_t {
-            const uint32_t d = x - base;
-            const uint32_t a = __shfl_sync(0xffffffffu, w0, d & 31u), c = __shfl_sync(0xffffffffu, w1, d & 31u);
-            return d < 32 ? a : c;
+            if (x >= be) return 0u;
+            return d < 32 ? __shfl_sync(0xffffffffu, w0, d) : __shfl_sync(0xffffffffu, w1, d - 32);
         };
         uint32_t start = q;
-        int32_t cur = sc_at(q);
         uint32_t r = rec_at(q);
+        int32_t cur = score_of(r);
         while (!(r >> 26 & 1u) && start - q + 2 <= MAX_SHIFT) {
-            const int32_t s1 = sc_at(start + 1);
-            if (s1 > cur + 4) { cur = s1; start += 1; r = rec_at(start); continue; }
-            const int32_t s2 = sc_at(start + 2);
-            if (s2 > cur + 7) { cur = s2; start += 2; r = rec_at(start); continue; }
+            const uint32_t ra = rec_at(start + 1);
+            const int32_t s1 = score_of(ra);
+            if (s1 > cur + 4) { cur = s1; start += 1; r = ra; continue; }
+            const uint32_t rb = rec_at(start + 2);
+            const int32_t s2 = score_of(rb);
+            if (s2 > cur + 7) { cur = s2; start += 2; r = rb; continue; }
             break;
         }
         const uint32_t off = r & POS_MASK;
@@ -508,13 +502,7 @@ __global__ void __launch_bounds__(128) chase_kernel(const uint8_t *__restrict__ 
         if ((r >> 26 & 1u) && start + len < be) len += lz::warp_extend(in, n, start + len, start + len - off, be - start - len, lane);
         if (back > start - anchor) back = start - anchor;
         start -= back; len += back;
-        if (start > p && scan_reps(p, start)) continue;
-        {
-            uint32_t ro;
-            const uint32_t rl = rep_at(start, &ro);
-            // zstd's rule of thumb: a repeat-offset match wins when 3 rl > 3 len - log2(offset) + 1
-            if (rl >= 3 && ro != off && (int32_t)(3 * rl) > (int32_t)(3 * len) - (int32_t)zc::highbit(off + 3) + 1) { emit(start, rl, ro); continue; }
-        }
+        if (scan(min(p, start), start, true, len, off)) continue;
         emit(start, len, off);
     }
     if (lane == 0) {
@@ -522,6 +510,28 @@ __global__ void __launch_bounds__(128) chase_kernel(const uint8_t *__restrict__ 
         m.seq_start = b * SEQ_PER_BLOCK; m.nseq = nseq; m.last_lits = be - anchor; m.reserved = 0;
         meta_all[(size_t)chunk * BLOCKS_PER_CHUNK + b] = m;
     }
+}
+
+// ---- the same parse with ONE THREAD per block (zstd_enc_parse.h, the function the CPU model runs): a debugging reference for
+// the warp kernel above (SQ_LZ2_DBG & 4), far too slow to ship -- a lone thread's dependent chain runs at a few hundred cycles per step
+__global__ void __launch_bounds__(64) chase_thread_kernel(const uint8_t *__restrict__ data, const sq_span *__restrict__ spans,
+                                                    const uint8_t *__restrict__ select, uint32_t n_chunks,
+                                                    const uint32_t *__restrict__ rec_all, zc::Seq *__restrict__ seqs_all,
+                                                    lz::BlockMeta *__restrict__ meta_all) {
+    const uint32_t item = blockIdx.x * blockDim.x + threadIdx.x;
+    if (item >= n_chunks * BLOCKS_PER_CHUNK) return;
+    const uint32_t chunk = item / BLOCKS_PER_CHUNK, b = item % BLOCKS_PER_CHUNK;
+    if (select && !select[chunk]) return;
+    const uint32_t n = spans[chunk].len;
+    const uint32_t bs = b * Z_BLOCK_MAX;
+    if (bs >= n) return;
+    const uint32_t be = min(n, bs + Z_BLOCK_MAX);
+    uint32_t last_lits;
+    const uint32_t nseq = zparse::chase_block(data + spans[chunk].off, n, rec_all + (size_t)chunk * REC_PER_CHUNK, bs, be, b == 0,
+                                              seqs_all + (size_t)chunk * MAX_SEQ_PER_CHUNK + (size_t)b * SEQ_PER_BLOCK, SEQ_PER_BLOCK, &last_lits);
+    lz::BlockMeta m;
+    m.seq_start = b * SEQ_PER_BLOCK; m.nseq = nseq; m.last_lits = last_lits; m.reserved = 0;
+    meta_all[(size_t)chunk * BLOCKS_PER_CHUNK + b] = m;
 }
 
 }  // namespace lz2

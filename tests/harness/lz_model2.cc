@@ -9,15 +9,13 @@
 #include <vector>
 #include <algorithm>
 #include "zstd_enc_block.h"
+#include "zstd_enc_parse.h"
 
 using namespace zc;
 
 struct P2 {
     int rows_log, K, mm, cap, stride, tile, slot_by_pos;
-    int rep_scan;     // 0 none, 1 rep0 in gaps, 2 rep0+rep1, 3 all three
-    int rep_min;      // minimum length of a rep match taken in a gap
-    int rep_at_start; // compare rep candidates against the found match at its start (zstd gain rule)
-    int accept_thr, target_len, max_shift, back_max;
+    int rep_scan, rep_min, rep_at_start, accept_thr, target_len, max_shift, back_max;  // (round-2 exploration knobs; the parse is zstd_enc_parse.h now)
     int hash2_log, hash2_K, hash2_bytes;  // optional second table keyed on a longer hash (0 = off)
     int sel_mul;
     int lazy_rep;     // decide pass: neighbour-offset rep approximation (0 off)
@@ -25,6 +23,8 @@ struct P2 {
     int short_keep;   // > 0: candidates whose first 8 bytes do not all match ("short") are verified only for the short_keep nearest; 0 = all
     int tag_bits;     // > 0 (with short_keep): long/short classes come from ptag (5 bits of the row hash) and xtag (tag_bits bits of a hash of bytes 5..7) instead of the bytes
     int long_cap;     // > 0: at most this many long candidates per position enter the pair queue (slot order)
+    int skip_capped;  // > 0: positions p with p % skip_capped != 0 are not searched when their anchor (p rounded down) found a match still >= CAP long at p
+    int ins_stride;   // > 1: only positions p % ins_stride == 0 enter the table (every position is still searched; continuation = same pair ins_stride positions earlier)
     int cont;         // continuation filter: 0 off, 1 exact (pair (p-1,c-1) was a candidate pair), 2 previous byte equal; refresh every 16 positions
 };
 
@@ -47,15 +47,12 @@ static inline uint32_t match_len(const uint8_t *s, uint32_t a, uint32_t b, uint3
     while (a + l < n && s[a + l] == s[b + l]) l++;
     return l;
 }
-static inline int32_t lazy_score(uint32_t len, uint32_t off) { return (int32_t)(4 * len) - (int32_t)highbit(off + 3); }
-
-struct Rec { uint32_t off, len, shift, back; bool capped; };
 
 extern "C" long lz_model2_frame(const uint8_t *s, uint32_t n, uint8_t *dst, uint32_t cap_dst, const P2 *Pp, uint64_t *stats) {
     const P2 P = *Pp;
     const uint32_t MM = (uint32_t)P.mm, CAP = (uint32_t)P.cap;
     std::vector<uint32_t> blen(n + 64, 0), boff(n + 64, 0);
-    uint64_t nverify = 0, nrows = 0, nlong = 0;
+    uint64_t nverify = 0, nrows = 0, nlong = 0, nskipped = 0;
     // ---- stage S: search ----
     {
         const uint32_t rows = 1u << P.rows_log, K = (uint32_t)P.K;
@@ -68,16 +65,24 @@ extern "C" long lz_model2_frame(const uint8_t *s, uint32_t n, uint8_t *dst, uint
         for (uint32_t t0 = 0; t0 < n; t0 += T) {
             const uint32_t t1 = std::min(n, t0 + T);
             for (uint32_t p = t0; p < t1 && p + 8 <= n; p++) {
+                if (P.ins_stride > 1 && p % (uint32_t)P.ins_stride) continue;
                 const uint32_t h = hashN(rd64(s + p), P.mm, P.rows_log);
                 tab[(size_t)h * K + (P.slot_by_pos ? p % K : head[h]++ % K)] = p + 1;
                 if (rows2) { const uint32_t h2 = hashN(rd64(s + p), P.hash2_bytes, P.hash2_log); tab2[(size_t)h2 * K2 + (P.slot_by_pos ? p % K2 : head2[h2]++ % K2)] = p + 1; }
                 if (P.chain) { const uint32_t hc = hashN(rd64(s + p), P.mm, 20); chain_prev[p] = chain_head[hc]; chain_head[hc] = p + 1; }
             }
-            std::vector<uint32_t> prevc, curc;
+            std::vector<uint32_t> prevc, curc, hist[4];
+            for (int phase = 0; phase < (P.skip_capped ? 2 : 1); phase++)
             for (uint32_t p = t0; p < t1 && p + 8 <= n; p++) {
                 if (p % (uint32_t)P.stride) continue;
+                if (P.skip_capped) {
+                    const uint32_t a = p - p % (uint32_t)P.skip_capped;
+                    if ((phase == 0) != (a == p)) continue;
+                    if (a != p && blen[a] >= CAP && match_len(s, p, p - boff[a], n) >= CAP) { blen[p] = CAP; boff[p] = boff[a]; nskipped++; continue; }
+                }
                 uint32_t bl = 0, bo = 0; int32_t bs = -1000;
-                prevc.swap(curc); curc.clear(); if (p == t0) prevc.clear();
+                if (P.ins_stride > 1) { hist[p & 3] = curc; prevc = hist[(p + 4 - P.ins_stride) & 3]; if (p < t0 + (uint32_t)P.ins_stride) prevc.clear(); curc.clear(); }
+                else { prevc.swap(curc); curc.clear(); if (p == t0) prevc.clear(); }
                 auto consider = [&](uint32_t c) {
                     if (c >= p) return;
                     if (rd32(s + c) != rd32(s + p)) return;
@@ -85,7 +90,8 @@ extern "C" long lz_model2_frame(const uint8_t *s, uint32_t n, uint8_t *dst, uint
                         if (std::find(curc.begin(), curc.end(), c) != curc.end()) return;  // same candidate from the second table
                         curc.push_back(c);
                         if ((p & 15u) != 0 && p > t0 && c > 0) {
-                            if (P.cont == 1 && std::find(prevc.begin(), prevc.end(), c - 1) != prevc.end()) return;
+                            const uint32_t st = P.ins_stride > 1 ? (uint32_t)P.ins_stride : 1u;
+                            if (P.cont == 1 && c >= st && std::find(prevc.begin(), prevc.end(), c - st) != prevc.end()) return;
                             if (P.cont == 2 && s[p - 1] == s[c - 1]) return;
                         }
                     }
@@ -147,114 +153,39 @@ extern "C" long lz_model2_frame(const uint8_t *s, uint32_t n, uint8_t *dst, uint
             }
         }
     }
-    // ---- stage D: decide (rep-blind lazy, depth 2) ----
-    std::vector<Rec> rec(n);
-    std::vector<int32_t> sc(n + 8, -1);
-    for (uint32_t p = 0; p < n; p++) if (blen[p] >= MM) { int32_t v = lazy_score(blen[p], boff[p]); sc[p] = v >= P.accept_thr ? v : -1; }
+    // ---- records exactly as the search kernel writes them, then the shipped parse (zstd_enc_parse.h) block by block ----
+    std::vector<uint32_t> rec(n + 8, 0);
     for (uint32_t p = 0; p < n; p++) {
-        Rec r = {0, 0, 0, 0, false};
+        uint32_t l = blen[p], capped = l >= CAP ? 1u : 0u;
+        if (!l) continue;
+        if (l > CAP) l = CAP;
         const uint32_t be = std::min(n, (p / Z_BLOCK_MAX + 1) * Z_BLOCK_MAX);
-        if (sc[p] >= 0) {
-            uint32_t start = p; int32_t cur = sc[p];
-            while (blen[start] < (uint32_t)P.target_len && start - p + 2 <= (uint32_t)P.max_shift) {
-                const int32_t s1 = start + 1 < be ? sc[start + 1] : -1;
-                if (s1 > cur + 4) { cur = s1; start += 1; continue; }
-                const int32_t s2 = start + 2 < be ? sc[start + 2] : -1;
-                if (s2 > cur + 7) { cur = s2; start += 2; continue; }
-                break;
-            }
-            r.off = boff[start]; r.len = blen[start]; r.shift = start - p; r.capped = blen[start] >= CAP;
-            uint32_t k = 0;
-            while (k < (uint32_t)P.back_max && start > k && start - k > r.off && s[start - k - 1] == s[start - k - 1 - r.off]) k++;
-            r.back = k;
-        }
-        rec[p] = r;
+        if (p + l > be) { l = be - p; capped = 0; }
+        if (l < MM) continue;
+        uint32_t k = 0;
+        const uint32_t c = p - boff[p];
+        while (k < 3 && p > k && c > k && s[p - k - 1] == s[c - k - 1]) k++;
+        rec[p] = boff[p] | (l - MM) << 21 | capped << 26 | k << 27;
     }
-    // ---- stage C: chase with repeat-offset scanning, block by block ----
     uint8_t *o = dst;
     *o++ = 0x28; *o++ = 0xB5; *o++ = 0x2F; *o++ = 0xFD;
     if (n <= 255) { *o++ = 0x20; *o++ = (uint8_t)n; }
     else if (n <= 65791) { *o++ = 0x60; uint32_t v = n - 256; *o++ = (uint8_t)v; *o++ = (uint8_t)(v >> 8); }
     else { *o++ = 0xA0; for (int i = 0; i < 4; i++) *o++ = (uint8_t)(n >> (8 * i)); }
-    std::vector<Seq> seqs; std::vector<uint8_t> lits, body;
+    std::vector<Seq> seqs(Z_BLOCK_MAX / 3 + 8); std::vector<uint8_t> lits, body;
     EncWork *wk = new EncWork;
     uint64_t total_seq = 0, rep_seq = 0, total_lit = 0;
     const uint32_t nblocks = n ? (n + Z_BLOCK_MAX - 1) / Z_BLOCK_MAX : 1;
     for (uint32_t b = 0; b < nblocks; b++) {
         const uint32_t bs = b * Z_BLOCK_MAX, be = std::min(n, bs + Z_BLOCK_MAX);
-        seqs.clear(); lits.clear();
-        uint32_t rep[3] = {0, 0, 0};
-        if (b == 0) { rep[0] = 1; rep[1] = 4; rep[2] = 8; }
-        uint32_t p = bs, anchor = bs;
-        auto emit = [&](uint32_t start, uint32_t len, uint32_t off) {
-            const uint32_t ll = start - anchor;
-            uint32_t ob = off + 3;
-            if (ll) { if (off == rep[0]) ob = 1; else if (off == rep[1]) ob = 2; else if (off == rep[2]) ob = 3; }
-            else { if (off == rep[1]) ob = 1; else if (off == rep[2]) ob = 2; else if (rep[0] > 1 && off == rep[0] - 1) ob = 3; }
-            if (ob > 3) { rep[2] = rep[1]; rep[1] = rep[0]; rep[0] = off; }
-            else {
-                const uint32_t ix = ob - 1 + (ll ? 0 : 1);
-                if (ix == 1) std::swap(rep[0], rep[1]);
-                else if (ix == 2) { const uint32_t t = rep[2]; rep[2] = rep[1]; rep[1] = rep[0]; rep[0] = t; }
-                else if (ix == 3) { const uint32_t t = rep[0] - 1; rep[2] = rep[1]; rep[1] = rep[0]; rep[0] = t; }
-            }
-            if (ob <= 3) rep_seq++;
-            lits.insert(lits.end(), s + anchor, s + start);
-            seqs.push_back({ll, len, ob});
-            p = start + len; anchor = p;
-        };
-        // the rep offsets a position g may use cheaply, given the literal run so far
-        auto rep_len_at = [&](uint32_t g, uint32_t *off_out) -> uint32_t {
-            uint32_t bestl = 0, besto = 0;
-            const bool ll0 = g == anchor;
-            uint32_t cand[3]; int nc = 0;
-            if (!ll0) { cand[nc++] = rep[0]; if (P.rep_scan >= 2) cand[nc++] = rep[1]; if (P.rep_scan >= 3) cand[nc++] = rep[2]; }
-            else { cand[nc++] = rep[1]; if (P.rep_scan >= 2) cand[nc++] = rep[2]; if (P.rep_scan >= 3 && rep[0] > 1) cand[nc++] = rep[0] - 1; }
-            for (int i = 0; i < nc; i++) {
-                const uint32_t ofs = cand[i];
-                if (!ofs || ofs > g) continue;
-                if (g + 4 > be) continue;
-                uint32_t l = match_len(s, g, g - ofs, n);
-                if (g + l > be) l = be - g;
-                if (l > bestl) { bestl = l; besto = ofs; }
-            }
-            *off_out = besto;
-            return bestl;
-        };
-        while (p < be) {
-            // next record at or after p
-            uint32_t q = p;
-            while (q < be && rec[q].len == 0) q++;
-            uint32_t mstart = be, mlen = 0, moff = 0;
-            if (q < be) {
-                const Rec &r = rec[q];
-                mstart = q + r.shift; mlen = r.len; moff = r.off;
-                if (r.capped) mlen = match_len(s, mstart, mstart - moff, n);
-                if (mstart + mlen > be) mlen = be - mstart;
-                uint32_t back = std::min(r.back, mstart - anchor);
-                // backward extension must not cross the cursor's literal run start
-                mstart -= back; mlen += back;
-            }
-            // scan the literal gap [p, mstart) for rep matches
-            bool took = false;
-            if (P.rep_scan) {
-                for (uint32_t g = p; g < mstart && g + 4 <= be; g++) {
-                    uint32_t ro; const uint32_t rl = rep_len_at(g, &ro);
-                    if (rl >= (uint32_t)P.rep_min) { emit(g, rl, ro); took = true; break; }
-                }
-            }
-            if (took) continue;
-            if (mstart >= be || mlen < 3) { p = be; break; }
-            if (P.rep_at_start) {
-                uint32_t ro; const uint32_t rl = rep_len_at(mstart, &ro);
-                // zstd's rule of thumb: a rep match wins if 3*rl > 3*ml - log2(off) + 1
-                if (rl >= 3 && ro != moff && (int32_t)(3 * rl) > (int32_t)(3 * mlen) - (int32_t)highbit(moff + 3) + 1) { emit(mstart, rl, ro); continue; }
-            }
-            emit(mstart, mlen, moff);
-        }
-        lits.insert(lits.end(), s + anchor, s + be);
-        body.resize(block_body_bound((uint32_t)lits.size(), (uint32_t)seqs.size()) + 64);
-        const uint32_t bl = write_block_body(body.data(), lits.data(), (uint32_t)lits.size(), seqs.data(), (uint32_t)seqs.size(), wk);
+        uint32_t last_lits = be - bs, ns = 0;
+        if (be > bs) ns = zparse::chase_block(s, n, rec.data(), bs, be, b == 0, seqs.data(), Z_BLOCK_MAX / 6 + 8, &last_lits);
+        lits.clear();
+        uint32_t pos = bs;
+        for (uint32_t i = 0; i < ns; i++) { lits.insert(lits.end(), s + pos, s + pos + seqs[i].ll); pos += seqs[i].ll + seqs[i].ml; if (seqs[i].off_base <= 3) rep_seq++; }
+        lits.insert(lits.end(), s + pos, s + be);
+        body.resize(block_body_bound((uint32_t)lits.size(), ns) + 64);
+        const uint32_t bl = write_block_body(body.data(), lits.data(), (uint32_t)lits.size(), seqs.data(), ns, wk);
         const uint32_t blen_b = be - bs;
         const bool last = b + 1 == nblocks;
         if ((size_t)(o - dst) + 3 + std::max(bl, blen_b) > cap_dst) { delete wk; return -1; }
@@ -266,10 +197,10 @@ extern "C" long lz_model2_frame(const uint8_t *s, uint32_t n, uint8_t *dst, uint
             const uint32_t h = (last ? 1u : 0u) | 2u << 1 | bl << 3;
             *o++ = (uint8_t)h; *o++ = (uint8_t)(h >> 8); *o++ = (uint8_t)(h >> 16);
             memcpy(o, body.data(), bl); o += bl;
-            total_seq += seqs.size(); total_lit += lits.size();
+            total_seq += ns; total_lit += lits.size();
         }
     }
     delete wk;
-    if (stats) { stats[0] = total_seq; stats[1] = total_lit; stats[2] = rep_seq; stats[3] = nverify; stats[4] = nrows; stats[5] = nlong; }
+    if (stats) { stats[0] = total_seq; stats[1] = total_lit; stats[2] = rep_seq; stats[3] = nverify; stats[4] = nrows; stats[5] = nlong; stats[6] = nskipped; }
     return o - dst;
 }
