@@ -47,24 +47,25 @@ namespace cg = cooperative_groups;
 constexpr uint32_t ROW_LOG = 14, ROWS = 1u << ROW_LOG, ROW_K = 32;
 constexpr uint32_t POS_BITS = 21, POS_MASK = (1u << POS_BITS) - 1, PTAG_BITS = 5, PFX_MASK = (1u << (POS_BITS + PTAG_BITS)) - 1;
 constexpr uint32_t EMPTY = 0xFFFFFFFFu;
-constexpr uint32_t MIN_MATCH = zparse::MIN_MATCH, CAP = zparse::CAP, MAX_SHIFT = zparse::MAX_SHIFT, REP_MIN = zparse::REP_MIN;
+constexpr uint32_t LEN_BASE = zparse::LEN_BASE, CAP = zparse::CAP, MAX_SHIFT = zparse::MAX_SHIFT, REP_MIN = zparse::REP_MIN;
+constexpr uint32_t SMALL_CHUNK = 128u * 1024u;  // up to here matches of 4 bytes are searched (hash of 4 bytes), above 5: libzstd's level-12 parameters make the same switch
 constexpr int32_t ACCEPT_THR = zparse::ACCEPT_THR;
 constexpr uint32_t LOOKAHEAD = CAP + 16;
 constexpr uint32_t QUEUE_WORDS = 32 * ROW_K + 32;  // per warp: every entry of every row could be a long candidate, plus one short per position
 constexpr uint32_t SEQ_PER_BLOCK = lz::SEQ_PER_BLOCK, MAX_SEQ_PER_CHUNK = lz::MAX_SEQ_PER_CHUNK, BLOCKS_PER_CHUNK = lz::BLOCKS_PER_CHUNK;
 constexpr uint32_t REC_PER_CHUNK = lz::REC_PER_CHUNK;
 
-// row index (14 bits) and ptag (5 bits) from a hash of the first five bytes; xtag from bytes 5..7
-__device__ __forceinline__ uint32_t hash_row_ptag(uint64_t v) { return (uint32_t)(((v << 24) * 889523592379ULL) >> (64 - (ROW_LOG + PTAG_BITS))); }
+// row index (14 bits) and ptag (5 bits) from a hash of the first five bytes (hshift = 24) or four (hshift = 32); xtag from bytes 5..7
+__device__ __forceinline__ uint32_t hash_row_ptag(uint64_t v, uint32_t hshift) { return (uint32_t)(((v << hshift) * 889523592379ULL) >> (64 - (ROW_LOG + PTAG_BITS))); }
 __device__ __forceinline__ uint32_t tag_word(uint32_t hv, uint64_t v) {
     const uint32_t xt = ((uint32_t)(v >> 40) * 0x9E3779B1u) >> 26;
     return (hv & ((1u << PTAG_BITS) - 1)) << POS_BITS | xt << (POS_BITS + PTAG_BITS);
 }
 
 // Per-position search record (4 bytes, HBM), 0 = no match at this position:
-//   bits 0-20 offset   bits 21-25 verified length - MIN_MATCH   bit 26 "may be longer" (the chase extends it)   bits 27-28 backward extension (<= 3)
+//   bits 0-20 offset   bits 21-25 verified length - LEN_BASE   bit 26 "may be longer" (the chase extends it)   bits 27-28 backward extension (<= 3)
 __device__ __forceinline__ uint32_t pack_rec(uint32_t off, uint32_t len, uint32_t capped, uint32_t back) {
-    return off | (len - MIN_MATCH) << 21 | capped << 26 | back << 27;
+    return off | (len - LEN_BASE) << 21 | capped << 26 | back << 27;
 }
 
 template <int G> __device__ __forceinline__ void group_sync() {
@@ -142,6 +143,7 @@ __global__ void __launch_bounds__(THREADS, MINB) search_kernel(const uint8_t *__
         const uint32_t n = spans[chunk].len;
         uint32_t *rec = rec_all + (size_t)chunk * REC_PER_CHUNK;
         const bool aligned = (reinterpret_cast<uintptr_t>(in) & 7) == 0;
+        const uint32_t MIN_MATCH = n <= SMALL_CHUNK ? 4u : 5u, hshift = n <= SMALL_CHUNK ? 32u : 24u;
         // every CTA clears its slice of the table (entries only: a ring head may start anywhere)
         {
             constexpr uint32_t SLICE4 = ROWS * ROW_K / 4 / G;
@@ -161,7 +163,10 @@ __global__ void __launch_bounds__(THREADS, MINB) search_kernel(const uint8_t *__
                 r_ent[k] = EMPTY; r_idx[k] = 0; r_slot[k] = 0;
                 if (p + 8 <= n) {
                     const uint64_t v = gld8(in, p, n);
-                    const uint32_t hv = hash_row_ptag(v);
+                    // inside a run of one byte (the five bytes here are the five bytes one position earlier) nothing is inserted: the run's
+                    // first position stands for it, and a hot row is not flooded with interchangeable entries
+                    if (p > 0 && (v & 0xFFFFFFFFFFull) == (uint64_t)in[p - 1] * 0x0101010101ull) continue;
+                    const uint32_t hv = hash_row_ptag(v, hshift);
                     r_ent[k] = p | tag_word(hv, v);
                     r_idx[k] = (hv >> PTAG_BITS) * ROW_K;
                     r_slot[k] = atomicAdd(&head[hv >> PTAG_BITS], 1u);
@@ -193,7 +198,7 @@ __global__ void __launch_bounds__(THREADS, MINB) search_kernel(const uint8_t *__
                 const bool searchable = p + 8 <= n;
                 const bool gfast = pg + 32 + CAP + 16 <= n;
                 const uint64_t v_own = lz::smem_u64(s_in, li);
-                const uint32_t hv_own = hash_row_ptag(v_own);
+                const uint32_t hv_own = hash_row_ptag(v_own, hshift);
                 const uint32_t T_own = tag_word(hv_own, v_own);
                 epoch = (epoch + 1u) & 63u;
                 // rows: pass k serves position 8 k + sub; this lane reads entries [4 part, +4) and [16 + 4 part, +4) of that row
@@ -369,7 +374,7 @@ __global__ void __launch_bounds__(THREADS, MINB) search_kernel(const uint8_t *__
 
 // ---- chase: lazy decision + repeat offsets + sequence emission, one warp per block ------------------------------------
 __device__ __forceinline__ uint32_t load4(const uint8_t *__restrict__ in, uint32_t pos, uint32_t n) {
-    if (pos + 8 <= n) {
+    if (pos + 8 <= n) {  // n = ~0u: the caller knows every read of this block stays 8 bytes inside the chunk
         const uintptr_t a = reinterpret_cast<uintptr_t>(in + pos);
         const uint32_t *w = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
         return __funnelshift_r(__ldg(w), __ldg(w + 1), (uint32_t)(a & 3u) * 8);
@@ -395,6 +400,7 @@ __global__ void __launch_bounds__(128) chase_kernel(const uint8_t *__restrict__ 
     const uint8_t *in = data + spans[chunk].off;
     const uint32_t *rec = rec_all + (size_t)chunk * REC_PER_CHUNK;
     zc::Seq *seqs = seqs_all + (size_t)chunk * MAX_SEQ_PER_CHUNK + (size_t)b * SEQ_PER_BLOCK;
+    const uint32_t nl = be + 8 <= n ? ~0u : n;  // bound handed to load4: no per-load check except in the chunk's last block
     uint32_t p = bs, anchor = bs, nseq = 0;
     uint32_t r0 = 0, r1 = 0, r2 = 0;  // repeat offsets are unknown at a block start (a raw block must not desynchronise the decoder); the frame's first block knows 1,4,8
     if (b == 0) { r0 = 1; r1 = 4; r2 = 8; }
@@ -430,10 +436,10 @@ __global__ void __launch_bounds__(128) chase_kernel(const uint8_t *__restrict__ 
             const uint32_t c0 = ll0 ? r1 : r0, c1 = ll0 ? r2 : r1, c2 = ll0 ? (r0 > 1 ? r0 - 1 : 0u) : r2;
             uint32_t fl = 0;  // per candidate 2 bits: 0 = no match, 1 = exactly 3 bytes, 2 = 4 or more
             if (g < end && g + 4 <= be) {
-                const uint32_t v = load4(in, g, n);
-                if (c0 && c0 <= g) { const uint32_t x = load4(in, g - c0, n) ^ v; if (!(x & 0xFFFFFFu)) fl |= x ? 1u : 2u; }
-                if (c1 && c1 <= g) { const uint32_t x = load4(in, g - c1, n) ^ v; if (!(x & 0xFFFFFFu)) fl |= (x ? 1u : 2u) << 2; }
-                if (c2 && c2 <= g) { const uint32_t x = load4(in, g - c2, n) ^ v; if (!(x & 0xFFFFFFu)) fl |= (x ? 1u : 2u) << 4; }
+                const uint32_t v = load4(in, g, nl);
+                if (c0 && c0 <= g) { const uint32_t x = load4(in, g - c0, nl) ^ v; if (!(x & 0xFFFFFFu)) fl |= x ? 1u : 2u; }
+                if (c1 && c1 <= g) { const uint32_t x = load4(in, g - c1, nl) ^ v; if (!(x & 0xFFFFFFu)) fl |= (x ? 1u : 2u) << 2; }
+                if (c2 && c2 <= g) { const uint32_t x = load4(in, g - c2, nl) ^ v; if (!(x & 0xFFFFFFu)) fl |= (x ? 1u : 2u) << 4; }
             }
             const uint32_t any = __ballot_sync(0xffffffffu, fl != 0);
             if (!any) continue;
@@ -459,12 +465,12 @@ __global__ void __launch_bounds__(128) chase_kernel(const uint8_t *__restrict__ 
     // lazy score of a record (what the parser gains by taking it), -1 = unusable
     auto score_of = [&](uint32_t r) -> int32_t {
         if (!r) return -1;
-        const uint32_t sl = (r >> 26 & 1u) ? CAP : ((r >> 21) & 31u) + MIN_MATCH;
+        const uint32_t sl = (r >> 26 & 1u) ? CAP : ((r >> 21) & 31u) + LEN_BASE;
         const int32_t sc = (int32_t)(4 * sl) - (int32_t)zc::highbit((r & POS_MASK) + 3);
         return sc >= ACCEPT_THR ? sc : -1;
     };
 
-    uint32_t base = ~0u - 63u, w0 = 0, w1 = 0;
+    uint32_t base = ~0u - 63u, w0 = 0, w1 = 0, umask = 0;
     while (p < be && nseq < SEQ_PER_BLOCK) {
         const uint32_t nb = p & ~31u;
         if (nb != base) {
@@ -472,8 +478,9 @@ __global__ void __launch_bounds__(128) chase_kernel(const uint8_t *__restrict__ 
             else w0 = (nb + lane < be) ? __ldg(rec + nb + lane) : 0u;
             w1 = (nb + 32 + lane < be) ? __ldg(rec + nb + 32 + lane) : 0u;  // requested now, first touched when the cursor gets near it
             base = nb;
+            umask = __ballot_sync(0xffffffffu, score_of(w0) >= 0);  // usable records of this window, once per window
         }
-        const uint32_t usable = __ballot_sync(0xffffffffu, score_of(w0) >= 0) & (0xffffffffu << (p - base));
+        const uint32_t usable = umask & (0xffffffffu << (p - base));
         if (!usable) {  // literals up to the end of this window (unless a repeat offset matches)
             const uint32_t ge = min(be, base + 32);
             if (!scan(p, ge, false, 0, 0)) p = ge;
@@ -498,7 +505,7 @@ __global__ void __launch_bounds__(128) chase_kernel(const uint8_t *__restrict__ 
             break;
         }
         const uint32_t off = r & POS_MASK;
-        uint32_t len = ((r >> 21) & 31u) + MIN_MATCH, back = (r >> 27) & 3u;
+        uint32_t len = ((r >> 21) & 31u) + LEN_BASE, back = (r >> 27) & 3u;
         if ((r >> 26 & 1u) && start + len < be) len += lz::warp_extend(in, n, start + len, start + len - off, be - start - len, lane);
         if (back > start - anchor) back = start - anchor;
         start -= back; len += back;

@@ -6,8 +6,9 @@
 // round-2 version: 95 M warp instructions per chunk, a third of the search kernel's time).  With a thread per block the same
 // instructions serve 32 blocks at once.
 //
-// Search record (one u32 per position, 0 = no match): bits 0-20 offset, 21-25 verified length - 5, 26 "may be longer",
+// Search record (one u32 per position, 0 = no match): bits 0-20 offset, 21-25 verified length - 4, 26 "may be longer",
 // 27-28 backward extension available (<= 3).
+// The shortest match the search reports is 5 bytes (4 in chunks of at most 128 KiB, like libzstd's parameters for small inputs).
 #pragma once
 #include "zstd_enc_block.h"
 #if defined(__CUDACC__)
@@ -18,7 +19,7 @@
 
 namespace zparse {
 
-constexpr uint32_t MIN_MATCH = 5, CAP = 32, MAX_SHIFT = 7, REP_MIN = 3, POS_MASK = (1u << 21) - 1;
+constexpr uint32_t LEN_BASE = 4, CAP = 32, MAX_SHIFT = 7, REP_MIN = 3, POS_MASK = (1u << 21) - 1;  // record length field = length - LEN_BASE
 constexpr int32_t ACCEPT_THR = 6;
 
 ZHD uint32_t ld32(const uint8_t *in, uint32_t pos, uint32_t n) {  // 4 bytes at any alignment; bytes past n read as 0
@@ -56,7 +57,7 @@ ZHD uint32_t common_len(const uint8_t *in, uint32_t n, uint32_t a, uint32_t b, u
 
 ZHD int32_t rec_score(uint32_t r) {  // what the parser gains by taking this record's match; -1 = unusable
     if (!r) return -1;
-    const uint32_t sl = (r >> 26 & 1u) ? CAP : ((r >> 21) & 31u) + MIN_MATCH;
+    const uint32_t sl = (r >> 26 & 1u) ? CAP : ((r >> 21) & 31u) + LEN_BASE;
     const int32_t sc = (int32_t)(4 * sl) - (int32_t)zc::highbit((r & POS_MASK) + 3);
     return sc >= ACCEPT_THR ? sc : -1;
 }
@@ -139,7 +140,7 @@ ZHDN uint32_t chase_block(const uint8_t *in, uint32_t n, const uint32_t *rec, ui
             break;
         }
         const uint32_t off = r & POS_MASK;
-        uint32_t len = ((r >> 21) & 31u) + MIN_MATCH, back = (r >> 27) & 3u;
+        uint32_t len = ((r >> 21) & 31u) + LEN_BASE, back = (r >> 27) & 3u;
         if ((r >> 26 & 1u) && start + len < be) len += common_len(in, n, start + len, start + len - off, be - start - len);
         if (back > start - P.anchor) back = start - P.anchor;
         start -= back; len += back;

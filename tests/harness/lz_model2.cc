@@ -25,26 +25,27 @@ struct P2 {
     int long_cap;     // > 0: at most this many long candidates per position enter the pair queue (slot order)
     int skip_capped;  // > 0: positions p with p % skip_capped != 0 are not searched when their anchor (p rounded down) found a match still >= CAP long at p
     int ins_stride;   // > 1: only positions p % ins_stride == 0 enter the table (every position is still searched; continuation = same pair ins_stride positions earlier)
+    int skip_runs;    // 1: a position whose 5-byte prefix equals the previous position's (inside a run of one byte) is not inserted
     int cont;         // continuation filter: 0 off, 1 exact (pair (p-1,c-1) was a candidate pair), 2 previous byte equal; refresh every 16 positions
 };
 
 static inline uint64_t rd64(const uint8_t *p) { uint64_t v; memcpy(&v, p, 8); return v; }
 static inline uint32_t rd32(const uint8_t *p) { uint32_t v; memcpy(&v, p, 4); return v; }
 static inline uint32_t hashN(uint64_t v, int bytes, int hl) {
-    if (bytes == 4) return (uint32_t)((uint32_t)v * 2654435761u) >> (32 - hl);
+    if (bytes == 4) return (uint32_t)(((v << 32) * 889523592379ULL) >> (64 - hl));
     if (bytes == 5) return (uint32_t)(((v << 24) * 889523592379ULL) >> (64 - hl));
     if (bytes == 6) return (uint32_t)(((v << 16) * 227718039650203ULL) >> (64 - hl));
     if (bytes == 7) return (uint32_t)(((v << 8) * 58295818150454627ULL) >> (64 - hl));
     return (uint32_t)((v * 0xCF1BBCDCB7A56463ULL) >> (64 - hl));
 }
-static inline uint32_t match_len(const uint8_t *s, uint32_t a, uint32_t b, uint32_t n) {  // a > b
+static inline uint32_t match_len(const uint8_t *s, uint32_t a, uint32_t b, uint32_t n, uint32_t lim = ~0u) {  // a > b; stops counting at lim
     uint32_t l = 0;
-    while (a + l + 8 <= n) {
+    while (a + l + 8 <= n && l < lim) {
         uint64_t x = rd64(s + a + l) ^ rd64(s + b + l);
         if (x) return l + (__builtin_ctzll(x) >> 3);
         l += 8;
     }
-    while (a + l < n && s[a + l] == s[b + l]) l++;
+    while (a + l < n && l < lim && s[a + l] == s[b + l]) l++;
     return l;
 }
 
@@ -66,6 +67,7 @@ extern "C" long lz_model2_frame(const uint8_t *s, uint32_t n, uint8_t *dst, uint
             const uint32_t t1 = std::min(n, t0 + T);
             for (uint32_t p = t0; p < t1 && p + 8 <= n; p++) {
                 if (P.ins_stride > 1 && p % (uint32_t)P.ins_stride) continue;
+                if (P.skip_runs && p > 0 && ((rd64(s + p) ^ rd64(s + p - 1)) & 0xFFFFFFFFFFull) == 0) continue;
                 const uint32_t h = hashN(rd64(s + p), P.mm, P.rows_log);
                 tab[(size_t)h * K + (P.slot_by_pos ? p % K : head[h]++ % K)] = p + 1;
                 if (rows2) { const uint32_t h2 = hashN(rd64(s + p), P.hash2_bytes, P.hash2_log); tab2[(size_t)h2 * K2 + (P.slot_by_pos ? p % K2 : head2[h2]++ % K2)] = p + 1; }
@@ -78,7 +80,7 @@ extern "C" long lz_model2_frame(const uint8_t *s, uint32_t n, uint8_t *dst, uint
                 if (P.skip_capped) {
                     const uint32_t a = p - p % (uint32_t)P.skip_capped;
                     if ((phase == 0) != (a == p)) continue;
-                    if (a != p && blen[a] >= CAP && match_len(s, p, p - boff[a], n) >= CAP) { blen[p] = CAP; boff[p] = boff[a]; nskipped++; continue; }
+                    if (a != p && blen[a] >= CAP && match_len(s, p, p - boff[a], n, CAP) >= CAP) { blen[p] = CAP; boff[p] = boff[a]; nskipped++; continue; }
                 }
                 uint32_t bl = 0, bo = 0; int32_t bs = -1000;
                 if (P.ins_stride > 1) { hist[p & 3] = curc; prevc = hist[(p + 4 - P.ins_stride) & 3]; if (p < t0 + (uint32_t)P.ins_stride) prevc.clear(); curc.clear(); }
@@ -95,7 +97,7 @@ extern "C" long lz_model2_frame(const uint8_t *s, uint32_t n, uint8_t *dst, uint
                             if (P.cont == 2 && s[p - 1] == s[c - 1]) return;
                         }
                     }
-                    uint32_t l = match_len(s, p, c, n);
+                    uint32_t l = match_len(s, p, c, n, CAP);
                     nverify++;
                     if (l < MM) return;
                     if (l > CAP) l = CAP;
@@ -117,7 +119,7 @@ extern "C" long lz_model2_frame(const uint8_t *s, uint32_t n, uint8_t *dst, uint
                             if (!e || e - 1 >= p) continue;
                             if (P.tag_bits) {
                                 const uint64_t vc = rd64(s + e - 1), vp = rd64(s + p);
-                                const uint32_t pc = hashN(vc, 5, 19) & 31u, pp = hashN(vp, 5, 19) & 31u;
+                                const uint32_t pc = hashN(vc, P.mm, 19) & 31u, pp = hashN(vp, P.mm, 19) & 31u;
                                 const uint32_t xc = (uint32_t)(((vc >> 40) * 0x9E3779B1u) & 0xFFFFFFFFu) >> (32 - P.tag_bits), xp = (uint32_t)(((vp >> 40) * 0x9E3779B1u) & 0xFFFFFFFFu) >> (32 - P.tag_bits);
                                 if (pc != pp) continue;
                                 if (xc == xp) consider_long(e - 1); else shorts[ns++] = e - 1;
@@ -144,7 +146,7 @@ extern "C" long lz_model2_frame(const uint8_t *s, uint32_t n, uint8_t *dst, uint
                 const uint32_t il = blen[p - 1] >= CAP ? CAP : blen[p - 1] - 1, io = boff[p - 1];
                 // a capped match stays capped while it really continues; the model checks the true length
                 uint32_t tl = il;
-                if (blen[p - 1] >= CAP) { tl = match_len(s, p, p - io, n); if (tl > CAP) tl = CAP; }
+                if (blen[p - 1] >= CAP) { tl = match_len(s, p, p - io, n, CAP); if (tl > CAP) tl = CAP; }
                 if (tl >= MM) {
                     const int32_t si = P.sel_mul * (int32_t)tl - (int32_t)highbit(io + 3);
                     const int32_t so = blen[p] ? P.sel_mul * (int32_t)blen[p] - (int32_t)highbit(boff[p] + 3) : -1000;
@@ -165,7 +167,7 @@ extern "C" long lz_model2_frame(const uint8_t *s, uint32_t n, uint8_t *dst, uint
         uint32_t k = 0;
         const uint32_t c = p - boff[p];
         while (k < 3 && p > k && c > k && s[p - k - 1] == s[c - k - 1]) k++;
-        rec[p] = boff[p] | (l - MM) << 21 | capped << 26 | k << 27;
+        rec[p] = boff[p] | (l - zparse::LEN_BASE) << 21 | capped << 26 | k << 27;
     }
     uint8_t *o = dst;
     *o++ = 0x28; *o++ = 0xB5; *o++ = 0x2F; *o++ = 0xFD;
@@ -203,4 +205,15 @@ extern "C" long lz_model2_frame(const uint8_t *s, uint32_t n, uint8_t *dst, uint
     delete wk;
     if (stats) { stats[0] = total_seq; stats[1] = total_lit; stats[2] = rep_seq; stats[3] = nverify; stats[4] = nrows; stats[5] = nlong; stats[6] = nskipped; }
     return o - dst;
+}
+
+// The parameters the GPU ships (zstd_enc_lz2.cuh): 2^14 rows x 32 entries, 5 + 6 tag bits, nearest short candidate only, exact
+// continuation filter, one step of 2048 positions inserted before it is searched, 5-byte matches (4 in chunks <= 128 KiB), no
+// inserts inside runs of one byte.
+extern "C" long lz_model2_shipped(const uint8_t *s, uint32_t n, uint8_t *dst, uint32_t cap_dst) {
+    P2 P;
+    memset(&P, 0, sizeof P);
+    P.rows_log = 14; P.K = 32; P.mm = n <= 128u * 1024u ? 4 : 5; P.cap = 32; P.stride = 1; P.tile = 2048; P.sel_mul = 2;
+    P.short_keep = 1; P.tag_bits = 6; P.cont = 1; P.skip_runs = 1;
+    return lz_model2_frame(s, n, dst, cap_dst, &P, nullptr);
 }

@@ -35,23 +35,18 @@ def dec():
     return run
 
 
-class _Params(C.Structure):
-    _fields_ = [(n, C.c_int) for n in ("hash_log", "row_entries", "min_match", "lazy_depth", "rep_mode", "tile", "target_len", "alt_window",
-                                        "sel_mul", "accept_thr", "skip_stride", "skip_min", "precheck")]
-
-
 @pytest.fixture(scope="module")
 def enc():
-    lib = _build("enc_model")
-    lib.enc_model_frame.restype = C.c_long
-    lib.enc_model_frame.argtypes = [C.c_char_p, C.c_uint32, C.c_char_p, C.c_uint32, C.POINTER(_Params), C.POINTER(C.c_uint32)]
-    P = _Params(15, 16, 6, 2, 6, 1024, 64, 0, 2, 8, 0, 0, 0)  # the shipped K3 parameters
+    """the CPU model of the shipped K3 parse (tests/harness/lz_model2.cc): same table shape and candidate rules as the search
+    kernel, and the very parse function (zstd_enc_parse.h) and block writer (zstd_enc_block.h) the GPU compiles"""
+    lib = _build("lz_model2")
+    lib.lz_model2_shipped.restype = C.c_long
+    lib.lz_model2_shipped.argtypes = [C.c_char_p, C.c_uint32, C.c_char_p, C.c_uint32]
 
     def run(data: bytes):
         cap = len(data) + 4096
         dst = C.create_string_buffer(cap)
-        st = (C.c_uint32 * 8)()
-        n = lib.enc_model_frame(data, len(data), dst, cap, C.byref(P), st)
+        n = lib.lz_model2_shipped(data, len(data), dst, cap)
         assert n > 0
         return dst.raw[:n]
     return run
