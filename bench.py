@@ -1,14 +1,17 @@
 #!/usr/bin/env python
-"""bench.py — device-resident pack throughput of the squishRS data path on B200.
+"""bench.py -- pack / unpack throughput of the squishRS data path on B200.
 
-Workload (BASELINE.json configs[1]): synthetic mixed corpus (40% log lines / 30% JSON / 30% binary
-records by 2 MiB slot, 20% duplicate slots), 64 GiB per GPU when it fits, packed in batches of
-`--batch-chunks` 2 MiB chunk slots.  One "step" = one pass of the hot path (K1 digest -> K2 dedup
-[-> digest all-to-all at N>1] -> K3 zstd encode of the winners) over one batch that is already
-resident in HBM.  `value` = input GB/s over all ranks; `e2e` = the same through the host-buffer
-C-ABI call sq_pack_host (H2D + kernels + D2H inside the timed region).
+Pack workloads (BASELINE.json configs[1..3]; default configs[1]): a synthetic corpus of 2 MiB slots, resident in HBM, packed in
+steps of `--batch-chunks` slots.  One "step" = one pass of the hot path (K1 digest -> K2 dedup [-> digest all-to-all at N>1] ->
+K3 zstd encode of the winners) over one batch.  `value` = input GB/s over all ranks; `e2e` = the same through the host-buffer
+C-ABI calls sq_pack_submit / sq_pack_wait (H2D + kernels + D2H inside the timed region).  A corpus pass never wraps inside one
+dedup index: when --steps exceeds the resident batches the index is reset at the pass boundary (a new job over the same bytes),
+and the line fails if the measured unique fraction is not the planned one.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+Unpack workload (`--workload config5`, configs[4]): frames written by the ORACLE (libzstd level 12) for small files of
+4..64 KiB, decoded by K4; `value` = restored GB/s device-resident, `e2e` through sq_unpack_submit / sq_unpack_wait.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload config2|config3|config4|config5]
 
 One JSON line on stdout (rank 0).  Everything else goes to stderr.
 """
@@ -60,6 +63,7 @@ WORKLOADS = {
     "config2": "configs[1]: mixed logs/JSON/binary corpus, 20% duplicate 2 MiB slots, device-resident pack",
     "config3": "configs[2]: VM-image-like corpus (35% zero / 45% fs-like mixed / 20% random slots, ~70% duplicate slots), device-resident pack",
     "config4": "configs[3]: incompressible random corpus, 0% duplicates (raw-block fallback, hash/dedup ceiling)",
+    "config5": "configs[4]: unpack-only, oracle-written (libzstd level 12) frames of small files (4-64 KiB, 50% text / 50% JSON)",
 }
 
 
@@ -95,6 +99,18 @@ def corpus_plan(n_slots: int, first_slot: int = 0, dup_frac: float = 0.2, seed: 
 def expected_unique(ids) -> int:
     import numpy as np
     return int(len(np.unique(ids)))
+
+
+def planned_new(workload: str, world: int, n_slots: int, B: int, steps: int, n_batches: int) -> int:
+    """How many chunks of the timed region are first occurrences: steps are processed in order, ranks within a step in rank
+    order, and the dedup index is reset at every corpus pass boundary (each pass is a fresh job)."""
+    import numpy as np
+    per_rank = [corpus_plan(n_slots, first_slot=r * n_slots, workload=workload)[0] for r in range(world)]
+    new = 0
+    for p0 in range(0, steps, n_batches):
+        order = [per_rank[r][(k % n_batches) * B:(k % n_batches + 1) * B] for k in range(p0, min(steps, p0 + n_batches)) for r in range(world)]
+        new += len(np.unique(np.concatenate(order)))
+    return new
 
 
 # --------------------------------------------------------------------------- clocks sampler
@@ -145,16 +161,19 @@ def load_oracle():
     return Oracle()
 
 
-def host_corpus(lib, ids, klass):
-    """Generate slots on the host (same generator as the device) into one contiguous buffer."""
+def host_corpus(oracle, ids, klass):
+    """Generate slots on the host into one contiguous buffer, with the ORACLE's build of the generator (oracle/corpus_gen.cc
+    compiles the same header as the device kernel; tests pin the two byte for byte), so the reference arm loads no product code."""
     n = len(ids)
     buf = C.create_string_buffer(n * CHUNK)
     base = C.addressof(buf)
     nthreads = min(os.cpu_count() or 1, 32)
+    fill = oracle.L.sqo_corpus_fill
+    fill.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32]
 
     def work(t):
         for i in range(t, n, nthreads):
-            lib.sq_corpus_fill_host(C.c_void_p(base + i * CHUNK), CHUNK, SEED, int(ids[i]), int(klass[i]))
+            fill(C.c_void_p(base + i * CHUNK), CHUNK, SEED, int(ids[i]), int(klass[i]))
     ths = [threading.Thread(target=work, args=(t,)) for t in range(nthreads)]
     [t.start() for t in ths]
     [t.join() for t in ths]
@@ -194,17 +213,100 @@ def cpu_pack(oracle, buf, n_slots: int, threads: int, files: int = 0):
     return dt, st
 
 
+def small_files(oracle, n_files: int, seed: int = 0x51510005):
+    """configs[4] inputs: n_files payloads of uniform size in [4096, 65536], 50 % text / 50 % JSON, 0 % duplicates."""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    sizes = rng.integers(4096, 65537, n_files)
+    klass = np.where(rng.random(n_files) < 0.5, 0, 2)
+    fill = oracle.L.sqo_corpus_fill
+    fill.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32]
+    offs = np.concatenate([[0], np.cumsum((sizes + 15) & ~15)]).astype(np.int64)
+    buf = C.create_string_buffer(int(offs[-1]) + 64)
+    base = C.addressof(buf)
+    nthreads = min(os.cpu_count() or 1, 32)
+
+    def work(t):
+        for i in range(t, n_files, nthreads):
+            fill(C.c_void_p(base + int(offs[i])), int(sizes[i]), seed, 1 + i, int(klass[i]))
+    ths = [threading.Thread(target=work, args=(t,)) for t in range(nthreads)]
+    [t.start() for t in ths]
+    [t.join() for t in ths]
+    return buf, offs, sizes
+
+
+def oracle_frames(oracle, buf, offs, sizes, level: int = 12):
+    """zstd frames of every payload, written by the oracle (stock libzstd) on all host cores."""
+    n = len(sizes)
+    base = C.addressof(buf)
+    out = [None] * n
+    nthreads = min(os.cpu_count() or 1, 32)
+    comp = oracle.L.sqo_zstd_compress
+    comp.argtypes = [C.c_void_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_int]
+
+    def work(t):
+        scratch = C.create_string_buffer(int(oracle.L.sqo_zstd_bound(int(max(sizes)))))
+        for i in range(t, n, nthreads):
+            m = comp(C.c_void_p(base + int(offs[i])), int(sizes[i]), scratch, len(scratch), level)
+            out[i] = scratch.raw[:m]
+    ths = [threading.Thread(target=work, args=(t,)) for t in range(nthreads)]
+    [t.start() for t in ths]
+    [t.join() for t in ths]
+    return out
+
+
+def cpu_decode(oracle, frames, caps, threads: int):
+    """stock ZSTD_decompress of every frame on `threads` host threads (1 = what the reference's read_chunks does)."""
+    dec = oracle.L.sqo_zstd_decompress
+    dec.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t]
+    n = len(frames)
+    ok = [True] * threads
+
+    def work(t):
+        scratch = C.create_string_buffer(int(max(caps)))
+        for i in range(t, n, threads):
+            if dec(frames[i], len(frames[i]), scratch, int(caps[i])) != int(caps[i]):
+                ok[t] = False
+    t0 = time.perf_counter()
+    ths = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
+    [t.start() for t in ths]
+    [t.join() for t in ths]
+    dt = time.perf_counter() - t0
+    assert all(ok), "oracle decode failed"
+    return dt
+
+
 def run_reference(args):
+    """The reference's CPU implementation of the path (the oracle port: the reference is Rust and cannot be built here) on this
+    box's host cores, on a bounded sample per step.  Loads oracle/ only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import squishrs_b200 as sq
-    lib = sq.load()
     oracle = load_oracle()
     cores = os.cpu_count() or 1
+    if args.workload == "config5":
+        n = args.ref_chunks or 20000
+        buf, offs, sizes = small_files(oracle, n)
+        frames = oracle_frames(oracle, buf, offs, sizes)
+        restored = int(sizes.sum())
+        for _ in range(args.warmup):
+            cpu_decode(oracle, frames[: n // 8], sizes[: n // 8], 1)
+        t1 = sum(cpu_decode(oracle, frames, sizes, 1) for _ in range(args.steps))
+        tp = sum(cpu_decode(oracle, frames, sizes, cores) for _ in range(args.steps))
+        gbs = args.steps * restored / t1 / 1e9
+        line = {"impl": "reference", "metric": "unpack_gb_per_s", "value": gbs, "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": t1 / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "u8", "data": "synthetic",
+                "config": {"workload": WORKLOADS[args.workload] + " (CPU sample)", "frames": n, "restored_bytes": restored, "libzstd": oracle.L.sqo_zstd_version()},
+                "cpu_baseline": {"value": gbs, "unit": "GB/s", "cores": 1, "kind": "port",
+                                 "sample": f"{n} oracle-written level-12 frames per step, serial decode on one thread as reader.rs:276-311 does",
+                                 "parallel_decode": {"value": args.steps * restored / tp / 1e9, "cores": cores}},
+                "e2e": {"value": gbs, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        emit(line)
+        return
     n = args.ref_chunks or max(64, min(2048, cores * 16))
     ids, klass = corpus_plan(n, workload=args.workload)
-    buf = host_corpus(lib, ids, klass)
+    buf = host_corpus(oracle, ids, klass)
     for _ in range(args.warmup):
         cpu_pack(oracle, buf, min(n, max(8, cores)), cores)
     t = 0.0
@@ -213,16 +315,174 @@ def run_reference(args):
         dt, stats = cpu_pack(oracle, buf, n, cores)
         t += dt
     gbs = args.steps * n * CHUNK / t / 1e9
+    dt25, _ = cpu_pack(oracle, buf, n, 25)  # the reference's default -j (src/cmd/mod.rs:16)
     line = {"impl": "reference", "metric": "pack_gb_per_s", "value": gbs, "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": t / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic",
             "config": {"workload": WORKLOADS[args.workload] + " (CPU sample)", "sample_chunks": n, "chunk_bytes": CHUNK,
                        "zstd_level": 12, "libzstd": oracle.L.sqo_zstd_version()},
             "cpu_baseline": {"value": gbs, "unit": "GB/s", "cores": cores, "kind": "port",
-                             "sample": f"{n} x 2 MiB slots of the configs[1] stream per step, in memory, archive to /dev/shm"},
+                             "sample": f"{n} x 2 MiB slots of the {args.workload} stream per step, in memory, archive to /dev/shm",
+                             "j25": {"value": n * CHUNK / dt25 / 1e9, "threads": 25, "note": "the reference's default -j 25 on this box's cores"}},
             "e2e": {"value": gbs, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "ratio": stats.payload_bytes / (stats.unique_chunks * CHUNK) if stats and stats.unique_chunks else None}
     emit(line)
+
+
+def real_data_ratio(ctx, oracle, limit=4 * MiB):
+    """GPU frames against libzstd level 12 on real files of this image (the same files on the GPU box): per corpus, 2 MiB chunks,
+    plus 24 KB pieces of all three.  Returns {corpus: delta in percent}."""
+    import glob
+    import sysconfig
+
+    def blob(pattern):
+        out = bytearray()
+        for f in sorted(glob.glob(pattern, recursive=True)):
+            try:
+                out += open(f, "rb").read()
+            except OSError:
+                continue
+            if len(out) >= limit:
+                break
+        return bytes(out[:limit])
+    sets = {"python sources": blob("/usr/lib/python3*/**/*.py"), "shared libraries": blob("/usr/lib/x86_64-linux-gnu/*.so*"),
+            "site-packages": blob(sysconfig.get_paths()["purelib"] + "/**/*.py")}
+    cases = {k: [v[i:i + CHUNK] for i in range(0, len(v), CHUNK)] for k, v in sets.items() if len(v) >= MiB}
+    cases["24 KB pieces"] = [v[i:i + 24000] for v in sets.values() for i in range(0, min(len(v), MiB), 24000)]
+    out = {}
+    for name, chunks in cases.items():
+        ctx.dedup_reset()
+        res = ctx.pack_batch(chunks)
+        gpu = sum(len(f) for _, f in res if f is not None)
+        cpu = sum(len(oracle.compress(c, 12)) for c, (_, f) in zip(chunks, res) if f is not None)
+        out[name] = (gpu / cpu - 1) * 100 if cpu else None
+    ctx.dedup_reset()
+    return out
+
+
+def pack_frames(frames, caps):
+    """Lay frames out back to back (16-byte aligned) with their sq_frame table: (comp bytes, frame table, comp size, restored size)."""
+    import numpy as np
+    n = len(frames)
+    lens = np.fromiter((len(f) for f in frames), dtype=np.int64, count=n)
+    caps = np.asarray(caps, dtype=np.int64)
+    src_off = np.concatenate([[0], np.cumsum((lens + 15) & ~15)])
+    dst_off = np.concatenate([[0], np.cumsum((caps + 15) & ~15)])
+    so, do = int(src_off[-1]), int(dst_off[-1])
+    comp = np.zeros(so + 64, dtype=np.uint8)
+    for i, f in enumerate(frames):
+        comp[src_off[i]: src_off[i] + len(f)] = np.frombuffer(f, dtype=np.uint8)
+    fr = np.zeros(n, dtype=np.dtype([("src", "<u8"), ("dst", "<u8"), ("len", "<u4"), ("cap", "<u4")]))
+    fr["src"], fr["dst"], fr["len"], fr["cap"] = src_off[:-1], dst_off[:-1], lens, caps
+    return comp, fr, so, do
+
+
+def decode_frames_device(ctx, lib, L, frames, caps, sp, stream, reps=4, check=None):
+    """K4 on a list of frames (bytes) already resident in HBM: best-of-reps device time in ms, and whether every frame decoded."""
+    import numpy as np
+    import torch
+    n = len(frames)
+    comp, fr, so, do = pack_frames(frames, caps)
+    dst_off = fr["dst"].astype(np.int64)
+    d_comp = torch.from_numpy(comp).cuda()
+    d_fr = torch.frombuffer(bytearray(fr.tobytes()), dtype=torch.uint8).cuda()
+    dec = torch.empty(do + 64, dtype=torch.uint8, device="cuda")
+    d_res = torch.empty(n * 8, dtype=torch.uint8, device="cuda")
+    ts = []
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        ctx.check(lib.sq_decode_device(ctx.h, d_comp.data_ptr(), d_fr.data_ptr(), n, dec.data_ptr(), d_res.data_ptr(), sp))
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    st = np.frombuffer(d_res.cpu().numpy().tobytes(), dtype="<i4").reshape(-1, 2)
+    ok = int((st[:, 1] != 0).sum()) == 0 and bool((st[:, 0] == np.asarray(caps)).all())
+    if check is not None and ok:
+        host = dec.cpu().numpy()
+        ok = all(host[dst_off[i]: dst_off[i] + int(caps[i])].tobytes() == check(i) for i in range(0, n, max(1, n // 64)))
+    return min(ts[1:]) if len(ts) > 1 else ts[0], ok, so, do, (comp, fr)
+
+
+def unpack_e2e(ctx, lib, L, comp, fr, so, do, n, steps=6, warm=2):
+    """sq_unpack_submit / sq_unpack_wait as a rolling two-slot pipeline over pinned host buffers: every step uploads the payloads
+    and downloads the restored bytes.  Returns restored GB/s."""
+    import numpy as np
+    hc = C.c_void_p()
+    hds = [C.c_void_p(), C.c_void_p()]
+    ctx.check(lib.sq_host_alloc(ctx.h, so + 64, C.byref(hc)))
+    for hd_ in hds:
+        ctx.check(lib.sq_host_alloc(ctx.h, do + 64, C.byref(hd_)))
+    np.frombuffer((C.c_uint8 * (so + 64)).from_address(hc.value), dtype=np.uint8)[:] = comp[: so + 64]
+    hf = (L.SqFrame * n)()
+    for k in range(n):
+        hf[k].src_off, hf[k].dst_off, hf[k].src_len, hf[k].capacity = int(fr["src"][k]), int(fr["dst"][k]), int(fr["len"][k]), int(fr["cap"][k])
+    hress = [(L.SqFrameResult * n)(), (L.SqFrameResult * n)()]
+    utk = [None, None]
+
+    def usubmit(k):
+        t = C.c_void_p()
+        ctx.check(lib.sq_unpack_submit(ctx.h, hc, so + 64, hf, n, hds[k % 2], do + 64, hress[k % 2], C.byref(t)))
+        utk[k % 2] = t
+    total = steps + warm
+    usubmit(0); usubmit(1)
+    t0 = None
+    for k in range(total):
+        ctx.check(lib.sq_unpack_wait(ctx.h, utk[k % 2]))
+        if k == warm - 1:
+            t0 = time.perf_counter()
+        if k + 2 < total:
+            usubmit(k + 2)
+    dt = time.perf_counter() - t0
+    ok = all(hress[j][k].status == 0 for j in range(2) for k in range(n))
+    restored = int(np.asarray(fr["cap"], dtype=np.int64).sum())
+    for h_ in [hc] + hds:
+        lib.sq_host_free(ctx.h, h_)
+    return steps * restored / dt / 1e9, ok, restored
+
+
+def unpack_section(ctx, lib, L, oracle, corpus, sp, stream, args):
+    """K4 on reference-written frames (what configs[4] asks for; the reference writes libzstd level-12 frames): (a) 2 MiB chunks of
+    the corpus, (b) small files of 4-64 KiB.  Device-resident and end to end, with the CPU decoding the same frames beside it."""
+    import numpy as np
+    cores = os.cpu_count() or 1
+    out = {}
+    # (a) 2 MiB frames
+    n_big = min(args.unpack_chunks, corpus.numel() // CHUNK)
+    host = corpus[: n_big * CHUNK].cpu().numpy()
+    buf = (C.c_uint8 * (n_big * CHUNK)).from_buffer(host)
+    offs = np.arange(n_big + 1, dtype=np.int64) * CHUNK
+    sizes = np.full(n_big, CHUNK, dtype=np.int64)
+    frames = oracle_frames(oracle, buf, offs, sizes)
+    ms, ok, so, do, (comp, fr) = decode_frames_device(ctx, lib, L, frames, sizes, sp, stream, check=lambda i: host[i * CHUNK:(i + 1) * CHUNK].tobytes())
+    e2e_v, ok_e, restored = unpack_e2e(ctx, lib, L, comp, fr, so, do, n_big)
+    t1 = cpu_decode(oracle, frames[: min(n_big, 96)], sizes[: min(n_big, 96)], 1)
+    tp = cpu_decode(oracle, frames, sizes, cores)
+    out.update({"value": restored / (ms * 1e-3) / 1e9, "unit": "GB/s", "frames": int(n_big),
+                "what": "K4 decode of oracle-written (libzstd level 12) frames of 2 MiB corpus chunks, device-resident, restored bytes/s",
+                "byte_identical": bool(ok), "algorithmic_gbs": (sum(len(f) for f in frames) + restored) / (ms * 1e-3) / 1e9,
+                "e2e": {"value": e2e_v, "unit": "GB/s", "byte_identical": bool(ok_e), "h2d_bytes_per_step": so, "d2h_bytes_per_step": do,
+                        "api": "sq_unpack_submit/sq_unpack_wait, rolling two-slot pipeline, pinned host buffers"},
+                "cpu_baseline": {"value": min(n_big, 96) * CHUNK / t1 / 1e9, "unit": "GB/s", "cores": 1, "kind": "port",
+                                 "sample": "the same frames, stock libzstd on one thread (the reference's serial read_chunks)",
+                                 "parallel_decode": {"value": restored / tp / 1e9, "cores": cores}}})
+    # (b) small files
+    n_small = args.unpack_small
+    sbuf, soffs, ssizes = small_files(oracle, n_small)
+    sframes = oracle_frames(oracle, sbuf, soffs, ssizes)
+    raw = bytes(sbuf)
+    ms, ok, so, do, (comp, fr) = decode_frames_device(ctx, lib, L, sframes, ssizes, sp, stream,
+                                                      check=lambda i: raw[int(soffs[i]): int(soffs[i]) + int(ssizes[i])])
+    e2e_v, ok_e, restored = unpack_e2e(ctx, lib, L, comp, fr, so, do, n_small)
+    t1 = cpu_decode(oracle, sframes, ssizes, 1)
+    tp = cpu_decode(oracle, sframes, ssizes, cores)
+    out["small_files"] = {"value": restored / (ms * 1e-3) / 1e9, "unit": "GB/s", "frames": int(n_small), "restored_bytes": restored,
+                          "what": "K4 decode of oracle-written level-12 frames of 4-64 KiB files (configs[4] shape), device-resident",
+                          "byte_identical": bool(ok),
+                          "e2e": {"value": e2e_v, "unit": "GB/s", "byte_identical": bool(ok_e), "h2d_bytes_per_step": so, "d2h_bytes_per_step": do},
+                          "cpu_baseline": {"value": restored / t1 / 1e9, "unit": "GB/s", "cores": 1, "kind": "port",
+                                           "parallel_decode": {"value": restored / tp / 1e9, "cores": cores}}}
+    return out
 
 
 # --------------------------------------------------------------------------- our arm (GPU)
@@ -249,12 +509,8 @@ def run_ours(args):
     budget = int(free * 0.55)
     n_batches = int(max(1, min(want_batches, budget // (B * CHUNK))))
     n_slots = n_batches * B
-    if world > 1 and not args.single_stream:
-        # leave two SMs' worth of search-CTA slots free: the digest / exchange kernels of the step after next (and NCCL's copy
-        # kernels) then run beside the encoder instead of waiting for its tail
-        os.environ.setdefault("SQ_LZ_CTAS_TOTAL", str(3 * (torch.cuda.get_device_properties(local).multi_processor_count - 2)))
-    ctx = sq.Context(device=local, dedup_capacity=max(1 << 20, 4 * n_slots * max(world, 1) * (args.steps + args.warmup + 4) // max(n_batches, 1) + n_slots * 4),
-                     max_batch_chunks=B * max(world, 1))
+    ctx = sq.Context(device=local, dedup_capacity=max(1 << 20, 4 * n_slots * max(world, 1) + n_slots * 4),
+                     max_batch_chunks=B * max(world, 1), stage_timing=True)
     ids, klass = corpus_plan(n_slots, first_slot=rank * n_slots, workload=args.workload)
     corpus = torch.empty(n_slots * CHUNK, dtype=torch.uint8, device="cuda")
     d_ids = torch.from_numpy(ids.astype(np.int64)).cuda()
@@ -334,16 +590,25 @@ def run_ours(args):
             tot = (bf["total"].clone(), fs["new"].sum(dtype=torch.int64)) if timed else None
         return None, tot
 
-    def run_ahead(n_steps, gidx_of, timed):
+    def run_ahead(n_steps, gidx_of, timed, first=0):
         front_done.clear(); enc_done.clear()
         res = []
         for j in range(min(2, n_steps)):
-            front(j, gidx_of(j))
+            front(first + j, gidx_of(j))
         for i in range(n_steps):
-            res.append(back(i, timed))
+            res.append(back(first + i, timed))
             if i + 2 < n_steps:
-                front(i + 2, gidx_of(i + 2))
+                front(first + i + 2, gidx_of(i + 2))
         return res
+
+    def pass_reset():
+        """The resident corpus has been packed once: what follows is a NEW job over the same bytes, so the dedup index starts
+        empty again (inside the timed region: both streams drain, the index is cleared, the pipeline restarts)."""
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ctx.dedup_reset()
+        last_dedup[0] = None
 
     def step(i, gidx_base, timed):
         b = i % n_batches
@@ -400,12 +665,17 @@ def run_ours(args):
     evs = []
     outs = []
     if ahead:
-        for e_k, tot_k in run_ahead(args.steps, lambda k: k * B * world + rank * B, True):
-            evs.append(e_k)
-            outs.append(tot_k)
+        for p0 in range(0, args.steps, n_batches):  # one pipeline per corpus pass; the index is reset between passes
+            if p0:
+                pass_reset()
+            for e_k, tot_k in run_ahead(min(n_batches, args.steps - p0), lambda k: (p0 + k) * B * world + rank * B, True, first=p0):
+                evs.append(e_k)
+                outs.append(tot_k)
         stream.wait_stream(front_stream)
     else:
         for k in range(args.steps):
+            if k and k % n_batches == 0:
+                pass_reset()
             e_k, tot_k = step(k, k * B * world + rank * B, True)
             evs.append(e_k)
             outs.append(tot_k)  # tiny device-side reads on the step's stream, no sync
@@ -419,21 +689,26 @@ def run_ours(args):
     rc = lib.sq_encode_status(ctx.h)
     if rc != 0:
         raise SystemExit(f"encode overflow: {rc}")
-    # Per-stage durations for the roofline: with two streams the launches of consecutive steps overlap on the device, so their
-    # event durations double-count.  A short single-stream pass on fresh dedup state (same batches, same kernels, CUDA events on
-    # the launching stream) gives clean per-launch times; the headline value above is untouched by it.
-    overlapped = not args.single_stream
-    if overlapped:
-        ctx.dedup_reset()
-        last_dedup[0] = None
-        save_streams, save_sps = list(streams), list(sps)
-        streams[1], sps[1] = streams[0], sps[0]
-        prof = [step(k, k * B * world + rank * B, True) for k in range(min(args.steps, 3))]
-        barrier()
-        streams[:], sps[:] = save_streams, save_sps
-        stage_evs, stage_outs, stage_steps = [p[0] for p in prof], [p[1] for p in prof], len(prof)
-    else:
-        stage_evs, stage_outs, stage_steps = evs, outs, args.steps
+    # Per-stage / per-kernel durations for the roofline: with two streams the launches of consecutive steps overlap on the device, so
+    # their event durations double-count.  A short single-stream pass on fresh dedup state (same batches, same kernels, CUDA events
+    # on the launching stream; the encoder's own kernels through sq_encode_stage_ms) gives clean per-launch times; the headline value
+    # above is untouched by it.
+    ctx.dedup_reset()
+    last_dedup[0] = None
+    save_streams, save_sps = list(streams), list(sps)
+    streams[1], sps[1] = streams[0], sps[0]
+    kern_ms = {"search": 0.0, "chase": 0.0, "entropy": 0.0, "emit": 0.0}
+    prof = []
+    for k in range(min(args.steps, n_batches, 3)):
+        prof.append(step(k, k * B * world + rank * B, True))
+        k4 = (C.c_float * 4)()
+        ctx.check(lib.sq_encode_stage_ms(ctx.h, sps[0], k4))
+        for name, v in zip(kern_ms, k4):
+            kern_ms[name] += float(v)
+    barrier()
+    streams[:], sps[:] = save_streams, save_sps
+    stage_evs, stage_outs, stage_steps = [p[0] for p in prof], [p[1] for p in prof], len(prof)
+    overlapped = True
     for e in stage_evs:
         stage_ms["digest"] += e[0].elapsed_time(e[1])
         stage_ms["dedup"] += e[1].elapsed_time(e[2])
@@ -454,6 +729,17 @@ def run_ours(args):
     elapsed_ms = float(t.item())
     in_bytes, out_bytes, n_new = (float(x) for x in agg.tolist())
     value = in_bytes / (elapsed_ms * 1e-3) / 1e9
+    plan_new = planned_new(args.workload, world, n_slots, B, args.steps, n_batches)
+    if abs(n_new - plan_new) > 0.01 * max(plan_new, 1):
+        raise SystemExit(f"unique chunks in the timed region: measured {n_new:.0f}, planned {plan_new}: work was skipped or repeated")
+    # scaling diagnostics: per-rank stage times of the single-stream pass (the digest exchange is the 'dedup' stage at N > 1)
+    diag = torch.tensor([stage_ms["digest"], stage_ms["dedup"], stage_ms["encode"]], dtype=torch.float64, device="cuda") / max(stage_steps, 1)
+    diag_all = [torch.zeros_like(diag) for _ in range(world)]
+    if world > 1:
+        dist.all_gather(diag_all, diag)
+    else:
+        diag_all = [diag]
+    per_rank = [[float(x) for x in d.tolist()] for d in diag_all]
 
     # ---- e2e through the host-buffer C-ABI call (rank-local; pinned input, H2D + kernels + D2H) ----
     e2e = None
@@ -539,34 +825,59 @@ def run_ours(args):
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel (the stage with the most time) ----
+    # ---- roofline: the dominant kernel, the K3 stage, and the whole pack ----
     peaks = {}
     try:
         peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    dom = max(stage_ms, key=stage_ms.get)
     local_in, local_out, local_new = totals["in"], totals["out"], totals["new"]
-    u_stage = stage_new * CHUNK
-    alg = {"digest": stage_in, "dedup": stage_steps * B * 48, "encode": u_stage + stage_out}[dom]
-    ach = alg / (stage_ms[dom] * 1e-3) / 1e9 if stage_ms[dom] > 0 else 0.0
-    roof = {"bound": "hbm", "kernel": {"digest": "xxh3_128_kernel (K1)", "dedup": "dedup_insert_kernel (K2)", "encode": "zstd encode stages (K3), lz_search_kernel ~78% of it"}[dom],
-            "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-            # dram bytes/launch of the dominant kernel: 142 B per unique input byte measured by ncu --set full on lz_search_kernel
-            # (profiles/r1_enc_final_raw.csv: 205.6 GB read + 58.8 GB written for 888 chunks); K1 reads its input once (ncu: 1.00x)
-            "traffic": int(142 * u_stage / stage_steps) if dom == "encode" else (alg // stage_steps if dom == "digest" else None),
+    u_stage = stage_new * CHUNK                       # unique input bytes of the single-stream pass
+    a_k3 = u_stage + stage_out                        # K3 algorithmic bytes: u B read + u r B written
+    a_pack = stage_in + a_k3                          # A_pack = B (1 + u (1 + r)): digest reads B, encode reads u B and writes u r B
+    pack_ms = stage_ms["digest"] + stage_ms["dedup"] + stage_ms["encode"]
+    gbs = lambda bytes_, ms: bytes_ / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+    encode_dominates = stage_ms["encode"] >= stage_ms["digest"]
+    dom_kernel = max(kern_ms, key=kern_ms.get) if encode_dominates else "digest"
+    dom_names = {"search": "lz2::search_kernel (K3 match search, one cluster per chunk)", "chase": "lz2::chase_kernel (K3 parse)",
+                 "entropy": "lz::entropy_kernel (K3)", "emit": "K3 frame sizing/emission", "digest": "xxh3_128_kernel (K1)"}
+    dom_ms = kern_ms[dom_kernel] if encode_dominates else stage_ms["digest"]
+    dom_alg = a_k3 if encode_dominates else stage_in
+    traffic = None
+    try:  # DRAM bytes per launch of the dominant kernel: per-unique-byte figure of the committed ncu capture x this run's bytes
+        tj = json.loads((ROOT / "profiles" / "r2_search_traffic.json").read_text())
+        if dom_kernel == "search":
+            traffic = int(float(tj["dram_bytes_per_unique_input_byte"]) * u_stage / stage_steps)
+    except Exception:
+        tj = None
+    if dom_kernel == "digest":
+        traffic = stage_in // stage_steps  # ncu: K1 reads its input exactly once (profiles/r1_k1_xxh3_raw.csv)
+    roof = {"bound": "hbm", "kernel": dom_names[dom_kernel], "achieved": gbs(dom_alg, dom_ms), "peak": peak, "unit": "GB/s",
+            "frac": gbs(dom_alg, dom_ms) / peak, "traffic": traffic,
+            "traffic_source": (tj or {}).get("source") if dom_kernel == "search" else None,
             "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
-            "algorithmic_bytes_per_step": alg // stage_steps,
-            "timing": ("per-launch CUDA-event durations from a %d-step single-stream pass after the timed region (the timed region itself "
-                       "overlaps consecutive steps on two streams)" % stage_steps) if overlapped else "CUDA events over the timed region",
+            "algorithmic_bytes_per_launch": dom_alg // stage_steps,
+            "launch_ms": dom_ms / stage_steps,
+            "timing": "CUDA events on the launching stream, %d-step single-stream pass after the timed region (the timed region overlaps "
+                      "consecutive steps on two streams); the encoder's kernels through sq_encode_stage_ms" % stage_steps,
+            "k3_stage": {"achieved": gbs(a_k3, stage_ms["encode"]), "frac": gbs(a_k3, stage_ms["encode"]) / peak, "ms_per_step": stage_ms["encode"] / stage_steps},
+            "pack": {"achieved": gbs(a_pack, pack_ms), "frac": gbs(a_pack, pack_ms) / peak, "ms_per_step": pack_ms / stage_steps,
+                     "what": "A_pack = B (1 + u (1 + r)) over digest + dedup + encode"},
+            "kernel_ms_per_step": {k: v / stage_steps for k, v in kern_ms.items()},
             "stage_ms_per_step": {k: v / stage_steps for k, v in stage_ms.items()},
-            "stage_achieved_gbs": {"digest": stage_in / (stage_ms["digest"] * 1e-3) / 1e9 if stage_ms["digest"] else None,
-                                   "encode": (u_stage + stage_out) / (stage_ms["encode"] * 1e-3) / 1e9 if stage_ms["encode"] else None}}
+            "digest_achieved_gbs": gbs(stage_in, stage_ms["digest"])}
+    scaling_diag = None
+    if world > 1:
+        scaling_diag = {"exchange_ms_per_step": {"min": min(r[1] for r in per_rank), "max": max(r[1] for r in per_rank)},
+                        "encode_ms_per_step": {"min": min(r[2] for r in per_rank), "max": max(r[2] for r in per_rank)},
+                        "digest_ms_per_step": {"min": min(r[0] for r in per_rank), "max": max(r[0] for r in per_rank)},
+                        "what": "per-rank CUDA-event stage times of the single-stream pass; 'exchange' = route + 2 x all_to_all_single + owner insert + unroute"}
 
     # ---- CPU baseline: the oracle timed on this box's host cores on a bounded sample ----
     cpu = None
     cpu_n = 0
+    oracle = None
     if not args.no_cpu:
         try:
             oracle = load_oracle()
@@ -577,99 +888,38 @@ def run_ours(args):
             sample = corpus[: n * CHUNK].cpu().numpy()
             buf = (C.c_uint8 * (n * CHUNK)).from_buffer(sample)
             dt, st = cpu_pack(oracle, buf, n, cores)
+            dt25, _ = cpu_pack(oracle, buf, n, 25)
             cpu = {"value": n * CHUNK / dt / 1e9, "unit": "GB/s", "cores": cores, "kind": "port",
                    "sample": f"first {n} x 2 MiB slots of this rank's corpus, in memory, {cores} threads, archive to /dev/shm",
+                   "j25": {"value": n * CHUNK / dt25 / 1e9, "threads": 25, "note": "the reference's default -j 25 (src/cmd/mod.rs:16) on this box's cores"},
                    "ratio": st.payload_bytes / (st.unique_chunks * CHUNK) if st.unique_chunks else None,
                    "libzstd": oracle.L.sqo_zstd_version()}
         except Exception as e:  # the baseline is a report, never a reason to lose the bench line
             log("cpu_baseline failed:", repr(e))
 
-    # ---- unpack (K4) on the frames of one packed batch, device-resident, + same-sample ratio vs the oracle ----
-    unpack = None
+    # ---- ratio: the same sample through the GPU, and REAL files of this image against libzstd level 12 ----
     try:
-        uctx = ctx  # reuse the main context (and its scratch) with a fresh dedup index
-        uctx.dedup_reset()
-        res = torch.empty(B * 32, dtype=torch.uint8, device="cuda")
-        used = C.c_uint64()
-        uctx.check(lib.sq_pack_device(uctx.h, corpus.data_ptr(), d_spans.data_ptr(), B, 0, res.data_ptr(), d_out.data_ptr(), out_cap - 64, C.byref(used), sp))
-        r = np.frombuffer(res.cpu().numpy().tobytes(), dtype=np.dtype([("d", "u1", 16), ("off", "<u8"), ("len", "<u4"), ("new", "u1"), ("pad", "u1", 3)]))
-        sel = np.nonzero(r["new"])[0]
-        fr = np.zeros(len(sel), dtype=np.dtype([("src", "<u8"), ("dst", "<u8"), ("len", "<u4"), ("cap", "<u4")]))
-        fr["src"], fr["dst"], fr["len"], fr["cap"] = r["off"][sel], np.arange(len(sel)) * CHUNK, r["len"][sel], CHUNK
-        d_fr = torch.frombuffer(bytearray(fr.tobytes()), dtype=torch.uint8).cuda()
-        dec = torch.empty(len(sel) * CHUNK, dtype=torch.uint8, device="cuda")
-        d_res = torch.empty(len(sel) * 8, dtype=torch.uint8, device="cuda")
-        t_dec = []
-        for _ in range(4):
-            e0, e1 = ev(), ev()
-            e0.record(stream)
-            uctx.check(lib.sq_decode_device(uctx.h, d_out.data_ptr(), d_fr.data_ptr(), len(sel), dec.data_ptr(), d_res.data_ptr(), sp))
-            e1.record(stream)
-            torch.cuda.synchronize()
-            t_dec.append(e0.elapsed_time(e1))
-        ok = all(bool(torch.equal(dec[k * CHUNK:(k + 1) * CHUNK], corpus[int(i) * CHUNK:(int(i) + 1) * CHUNK])) for k, i in enumerate(sel[:64]))
-        st = np.frombuffer(d_res.cpu().numpy().tobytes(), dtype="<i4").reshape(-1, 2)
-        unpack = {"value": len(sel) * CHUNK / (min(t_dec[1:]) * 1e-3) / 1e9, "unit": "GB/s", "frames": int(len(sel)), "what": "K4 decode of one packed batch, device-resident, restored bytes/s",
-                  "byte_identical": ok and int((st[:, 1] != 0).sum()) == 0, "algorithmic_gbs": (int(r["len"][sel].sum()) + len(sel) * CHUNK) / (min(t_dec[1:]) * 1e-3) / 1e9}
-        # e2e unpack through the host-buffer C-ABI calls (H2D payloads + K4 + D2H restored bytes), one packed batch (<= 2048 frames) per call
-        try:
-            ne = int(min(len(sel), 2048))
-            host_out = d_out[: int(used.value)].cpu().numpy()
-            payloads = [host_out[int(r["off"][i]): int(r["off"][i]) + int(r["len"][i])] for i in sel[:ne]]
-            hf = (L.SqFrame * ne)()
-            so = 0
-            for k, pl in enumerate(payloads):
-                hf[k].src_off, hf[k].dst_off, hf[k].src_len, hf[k].capacity = so, k * CHUNK, len(pl), CHUNK
-                so += (len(pl) + 15) & ~15
-            hc = C.c_void_p(); hds = [C.c_void_p(), C.c_void_p()]
-            ctx.check(lib.sq_host_alloc(ctx.h, so + 64, C.byref(hc)))
-            for hd_ in hds:
-                ctx.check(lib.sq_host_alloc(ctx.h, ne * CHUNK, C.byref(hd_)))
-            stage = np.frombuffer((C.c_uint8 * (so + 64)).from_address(hc.value), dtype=np.uint8)
-            for k, pl in enumerate(payloads):
-                stage[hf[k].src_off: hf[k].src_off + len(pl)] = pl
-            hress = [(L.SqFrameResult * ne)(), (L.SqFrameResult * ne)()]
-            # rolling two-slot pipeline (wait k, submit k+2): every step uploads the payloads and downloads the restored bytes
-            n_u, n_uwarm = 8, 2
-            utk = [None, None]
-
-            def usubmit(k):
-                t = C.c_void_p()
-                ctx.check(lib.sq_unpack_submit(ctx.h, hc, so + 64, hf, ne, hds[k % 2], ne * CHUNK, hress[k % 2], C.byref(t)))
-                utk[k % 2] = t
-
-            usubmit(0); usubmit(1)
-            t0 = None
-            for k in range(n_u):
-                ctx.check(lib.sq_unpack_wait(ctx.h, utk[k % 2]))
-                if k == n_uwarm - 1:
-                    t0 = time.perf_counter()
-                if k + 2 < n_u:
-                    usubmit(k + 2)
-            dt_u = time.perf_counter() - t0
-            ok_u = all(hress[j][k].status == 0 and hress[j][k].out_len == CHUNK for j in range(2) for k in range(ne))
-            back = np.frombuffer((C.c_uint8 * CHUNK).from_address(hds[1].value), dtype=np.uint8)
-            ok_u = ok_u and bool((torch.from_numpy(back.copy()).cuda() == corpus[int(sel[0]) * CHUNK:(int(sel[0]) + 1) * CHUNK]).all())
-            unpack["e2e"] = {"value": (n_u - n_uwarm) * ne * CHUNK / dt_u / 1e9, "unit": "GB/s", "frames": ne, "steps": n_u - n_uwarm, "h2d_bytes_per_step": so,
-                             "d2h_bytes_per_step": ne * CHUNK, "byte_identical": ok_u,
-                             "api": "sq_unpack_submit/sq_unpack_wait, rolling two-slot pipeline, pinned host buffers"}
-            # CPU baseline for unpack: the reference decodes serially on ONE thread (reader.rs:276-311)
-            if not args.no_cpu:
-                oracle_u = load_oracle()
-                nd = min(ne, 64)
-                t0 = time.perf_counter()
-                for pl in payloads[:nd]:
-                    assert oracle_u.decompress(pl.tobytes(), CHUNK) is not None
-                unpack["cpu_baseline"] = {"value": nd * CHUNK / (time.perf_counter() - t0) / 1e9, "unit": "GB/s", "cores": 1, "kind": "port",
-                                          "sample": f"{nd} GPU-written frames decoded by stock libzstd on one thread, as the reference's read_chunks does"}
-            lib.sq_host_free(ctx.h, hc); lib.sq_host_free(ctx.h, hds[0]); lib.sq_host_free(ctx.h, hds[1])
-        except Exception as e:
-            log("unpack e2e section failed:", repr(e))
         if cpu and cpu.get("ratio"):
-            m = sel[sel < cpu_n]
-            gpu_ratio = float(r["len"][m].sum()) / (len(m) * CHUNK) if len(m) else None
+            ctx.dedup_reset()
+            res = torch.empty(cpu_n * 32, dtype=torch.uint8, device="cuda")
+            used = C.c_uint64()
+            ctx.check(lib.sq_pack_device(ctx.h, corpus.data_ptr(), d_spans.data_ptr(), cpu_n, 0, res.data_ptr(), d_out.data_ptr(), out_cap - 64, C.byref(used), sp))
+            r = np.frombuffer(res.cpu().numpy().tobytes(), dtype=np.dtype([("d", "u1", 16), ("off", "<u8"), ("len", "<u4"), ("new", "u1"), ("pad", "u1", 3)]))
+            sel = np.nonzero(r["new"])[0]
+            gpu_ratio = float(r["len"][sel].sum()) / (len(sel) * CHUNK) if len(sel) else None
             cpu["gpu_ratio_same_sample"] = gpu_ratio
             cpu["ratio_delta_pct"] = (gpu_ratio / cpu["ratio"] - 1) * 100 if gpu_ratio else None
+        if oracle is not None:
+            cpu["ratio_delta_pct_real"] = real_data_ratio(ctx, oracle)
+    except Exception as e:
+        log("ratio section failed:", repr(e))
+
+    # ---- unpack (K4) on ORACLE-written level-12 frames: 2 MiB chunks of the corpus and small files (4-64 KiB) ----
+    unpack = None
+    try:
+        if oracle is None:
+            oracle = load_oracle()
+        unpack = unpack_section(ctx, lib, L, oracle, corpus, sp, stream, args)
     except Exception as e:
         log("unpack section failed:", repr(e))
 
@@ -682,7 +932,129 @@ def run_ours(args):
                        "streams": 1 if args.single_stream else 2,
                        "parallelism": f"dp{world} (chunks sharded by rank" + (", digest all-to-all over NCCL)" if world > 1 else ")")},
             "gpu_launches": int(launches1.value - launches0.value), "clocks": clk, "e2e": e2e, "roofline": roof, "cpu_baseline": cpu, "unpack": unpack,
-            "ratio": {"compressed_over_unique": out_bytes / (n_new * CHUNK) if n_new else None, "unique_fraction": n_new * CHUNK / in_bytes}}
+            "ratio": {"compressed_over_unique": out_bytes / (n_new * CHUNK) if n_new else None, "unique_fraction": n_new * CHUNK / in_bytes,
+                      "unique_fraction_planned": plan_new * CHUNK / in_bytes, "corpus_passes": (args.steps + n_batches - 1) // n_batches},
+            "scaling_diag": scaling_diag}
+    emit(line)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# --------------------------------------------------------------------------- our arm: unpack-only (configs[4])
+def run_unpack_ours(args):
+    """configs[4]: `--frames` small files (4-64 KiB) written by the oracle (libzstd level 12), decoded by K4.  The frames are
+    partitioned across ranks by index with no collective (strong scaling: the job is fixed).  A step = every rank decodes its
+    shard once from HBM; e2e = the same through sq_unpack_submit / sq_unpack_wait in batches over pinned host buffers."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import squishrs_b200 as sq
+    from squishrs_b200 import _lib as L
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lib = sq.load()
+    oracle = load_oracle()
+    total_frames = args.frames
+    n = total_frames // world
+    ctx = sq.Context(device=local, max_batch_chunks=max(n, 4096))
+    t0 = time.perf_counter()
+    buf, offs, sizes = small_files(oracle, total_frames)  # every rank derives the same job and takes its contiguous shard
+    lo = rank * n
+    offs_r, sizes_r = offs[lo: lo + n + 1] - offs[lo], sizes[lo: lo + n]
+    shard = (C.c_char * int(offs_r[-1] + 64)).from_buffer(buf, int(offs[lo]))
+    frames = oracle_frames(oracle, shard, offs_r, sizes_r)
+    log(f"[rank {rank}] {n} oracle-written frames ({int(sizes_r.sum()) / 1e9:.2f} GB restored, {sum(len(f) for f in frames) / 1e9:.2f} GB compressed) in {time.perf_counter() - t0:.1f}s")
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    sp = C.c_void_p(stream.cuda_stream)
+    raw = bytes(shard)
+    # device-resident: K warm-ups then K timed decodes of the whole shard
+    comp, fr, so, do = pack_frames(frames, sizes_r)
+    dst_off = fr["dst"].astype(np.int64)
+    d_comp = torch.from_numpy(comp).cuda()
+    d_fr = torch.frombuffer(bytearray(fr.tobytes()), dtype=torch.uint8).cuda()
+    dec = torch.empty(do + 64, dtype=torch.uint8, device="cuda")
+    d_res = torch.empty(n * 8, dtype=torch.uint8, device="cuda")
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    for _ in range(args.warmup):
+        ctx.check(lib.sq_decode_device(ctx.h, d_comp.data_ptr(), d_fr.data_ptr(), n, dec.data_ptr(), d_res.data_ptr(), sp))
+    barrier()
+    l0 = C.c_uint64(); lib.sq_kernel_launches(ctx.h, C.byref(l0))
+    clocks = Clocks(local)
+    clocks.start()
+    time.sleep(0.3)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        ctx.check(lib.sq_decode_device(ctx.h, d_comp.data_ptr(), d_fr.data_ptr(), n, dec.data_ptr(), d_res.data_ptr(), sp))
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clk = clocks.stop()
+    l1 = C.c_uint64(); lib.sq_kernel_launches(ctx.h, C.byref(l1))
+    st = np.frombuffer(d_res.cpu().numpy().tobytes(), dtype="<i4").reshape(-1, 2)
+    host = dec.cpu().numpy()
+    ok = int((st[:, 1] != 0).sum()) == 0 and all(host[dst_off[i]: dst_off[i] + int(sizes_r[i])].tobytes() == raw[int(offs_r[i]): int(offs_r[i]) + int(sizes_r[i])]
+                                                 for i in range(0, n, max(1, n // 256)))
+    restored = int(sizes_r.sum())
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    agg = torch.tensor([restored, so, 1.0 if ok else 0.0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(agg)
+    ms = float(t.item())
+    tot_restored, tot_comp, n_ok = (float(x) for x in agg.tolist())
+    value = args.steps * tot_restored / (ms * 1e-3) / 1e9
+    # e2e: the first <= 32768 frames of the shard per step through the host-buffer pipeline, scaled to the shard
+    ne = min(n, 32768)
+    comp_e, fr_e, so_e, do_e = pack_frames(frames[:ne], sizes_r[:ne])
+    e2e_v, ok_e, restored_e = unpack_e2e(ctx, lib, L, comp_e, fr_e, so_e, do_e, ne, steps=max(2, min(args.steps, 6)))
+    et = torch.tensor([restored / e2e_v], dtype=torch.float64, device="cuda")  # seconds per shard pass on this rank at the measured rate
+    if world > 1:
+        dist.all_reduce(et, op=dist.ReduceOp.MAX)
+    e2e_all = tot_restored / float(et.item())
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks = {}
+    try:
+        peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    alg = (so + restored) * args.steps  # A_unpack = C + U per step, this rank
+    cores = os.cpu_count() or 1
+    ns = min(n, 20000)
+    t1 = cpu_decode(oracle, frames[:ns], sizes_r[:ns], 1)
+    tp = cpu_decode(oracle, frames[:ns], sizes_r[:ns], cores)
+    rs = int(sizes_r[:ns].sum())
+    line = {"metric": "unpack_gb_per_s", "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": WORKLOADS["config5"], "frames_total": total_frames, "frames_per_gpu": n, "restored_bytes_total": tot_restored,
+                       "compressed_bytes_total": tot_comp, "l2_policy": "each step reads and writes the whole shard (compressed + restored bytes per GPU > L2)" if so + do > 126e6 else "shard smaller than L2",
+                       "parallelism": f"dp{world} (frames partitioned by index, no collective)", "libzstd": oracle.L.sqo_zstd_version()},
+            "gpu_launches": int(l1.value - l0.value), "clocks": clk, "byte_identical": bool(n_ok == world),
+            "e2e": {"value": e2e_all, "unit": "GB/s", "h2d_bytes_per_step": so_e, "d2h_bytes_per_step": do_e, "frames_per_step": ne, "byte_identical": bool(ok_e),
+                    "api": "sq_unpack_submit/sq_unpack_wait, rolling two-slot pipeline, pinned host buffers"},
+            "roofline": {"bound": "hbm", "kernel": "zstd_decode_kernel (K4)", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": alg / (ms * 1e-3) / 1e9 / peak, "traffic": None, "algorithmic_bytes_per_launch": so + restored,
+                         "what": "A_unpack = C + U of this rank's shard per launch"},
+            "cpu_baseline": {"value": rs / t1 / 1e9, "unit": "GB/s", "cores": 1, "kind": "port",
+                             "sample": f"first {ns} frames of rank 0's shard, stock libzstd on one thread (the reference's serial read_chunks, reader.rs:276-311)",
+                             "parallel_decode": {"value": rs / tp / 1e9, "cores": cores}}}
     emit(line)
     if world > 1:
         dist.destroy_process_group()
@@ -699,6 +1071,9 @@ def main():
     ap.add_argument("--corpus-gib", type=int, default=64)
     ap.add_argument("--e2e-chunks", type=int, default=2048)
     ap.add_argument("--ref-chunks", type=int, default=0)
+    ap.add_argument("--frames", type=int, default=200000, help="config5: small-file frames in the whole job")
+    ap.add_argument("--unpack-chunks", type=int, default=256, help="2 MiB oracle-written frames in the unpack section")
+    ap.add_argument("--unpack-small", type=int, default=16384, help="small-file frames in the unpack section")
     ap.add_argument("--single-stream", action="store_true", help="run every step on one stream (no overlap between consecutive steps)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -708,6 +1083,8 @@ def main():
         log("note: fewer than 3 warm-up steps requested; the timing rules ask for >= 3")
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "config5":
+        run_unpack_ours(args)
     else:
         run_ours(args)
 

@@ -74,10 +74,13 @@ typedef struct {
     uint32_t flags;             /* SQ_FLAG_* bits, 0 = defaults */
 } sq_config;
 
-/* The encoder's match search normally looks up every second position (the others inherit matches and are
- * reached through backward extension): about 1.3x faster, +0.3 % bytes on log/JSON/record data, about
- * +3 % on text and source code.  This flag makes it look up every position. */
+/* Round 1: "look up every position in the match search" (the default looked up every second one).  The search has looked
+ * up every position by default since round 2 (that is what keeps the frames within 3 % of zstd level 12 on real files);
+ * the flag is still accepted and changes nothing. */
 #define SQ_FLAG_DENSE_SEARCH 1u
+/* Record CUDA events between the encoder's kernels so sq_encode_stage_ms can report per-kernel durations (bench.py's
+ * roofline line).  Costs four event records per encode call. */
+#define SQ_FLAG_STAGE_TIMING 2u
 
 /* One chunk of a batch: bytes [off, off+len) of the batch buffer.
  * Chunk rule (reference src/archive/writer.rs:240-246): chunk i of a file is
@@ -179,6 +182,10 @@ int32_t sq_encode_device(sq_ctx *ctx, const void *d_data, const sq_span *d_spans
 /* Synchronizes and reports whether the most recent sq_encode_device on this context
  * overflowed d_out (SQ_ERR_CAPACITY) -- the Err arm of compress() (chunk.rs:90). */
 int32_t sq_encode_status(sq_ctx *ctx);
+/* Durations in ms of the last sq_encode_device call on `stream` (NULL = the context's stream): out[0] match search,
+ * out[1] parse (chase), out[2] entropy coding, out[3] frame sizing + placement + emission.  Needs SQ_FLAG_STAGE_TIMING;
+ * synchronizes on that call's last event. */
+int32_t sq_encode_stage_ms(sq_ctx *ctx, void *stream, float out[4]);
 
 /* ---- K4: decode  == zstd::bulk::decompress(bytes, orig_size) (src/archive/reader.rs:302-303) */
 /* Accepts everything stock ZSTD_decompress accepts whole: >=1 concatenated frames,

@@ -26,6 +26,7 @@ SQ_ERR_CUDA = -101
 SQ_ERR_INVALID_ARG = -102
 SQ_ERR_CAPACITY = -103
 SQ_FLAG_DENSE_SEARCH = 1
+SQ_FLAG_STAGE_TIMING = 2
 
 
 class SqConfig(C.Structure):
@@ -87,6 +88,7 @@ SYMBOLS = {
     "sq_encode_bound": (C.c_size_t, [C.c_size_t]),
     "sq_encode_device": (C.c_int32, [_P, _P, _P, _P, C.c_uint32, _P, C.c_uint64, _P, _P, _P, _P]),
     "sq_encode_status": (C.c_int32, [_P]),
+    "sq_encode_stage_ms": (C.c_int32, [_P, _P, C.POINTER(C.c_float)]),
     "sq_decode_device": (C.c_int32, [_P, _P, _P, C.c_uint32, _P, _P, _P]),
     "sq_pack_device": (C.c_int32, [_P, _P, _P, C.c_uint32, C.c_uint64, _P, _P, C.c_uint64, C.POINTER(C.c_uint64), _P]),
     "sq_pack_host": (C.c_int32, [_P, _P, C.c_size_t, _P, C.c_uint32, C.c_uint64, _P, _P, C.c_uint64, C.POINTER(C.c_uint64)]),

@@ -35,6 +35,8 @@ struct sq_enc_scratch {
     uint32_t ent_warps;
     uint32_t *tab2, *head2;  // round-2 search: one table (2 MB) + ring heads per resident CLUSTER
     uint32_t lz2_clusters; int lz2_cfg;
+    cudaEvent_t tev[5];      // SQ_FLAG_STAGE_TIMING: before search / after search / after chase / after entropy / after emit
+    int tev_valid;
     uint32_t cap_chunks;
     uint32_t *status;        // [0] != 0 => capacity overflow; [1],[2] work counters
 };
@@ -272,6 +274,7 @@ void sq_enc_destroy(sq_ctx *ctx) {
         sq_enc_scratch *e = ctx->enc_sets[set];
         if (!e) continue;
         cudaFree(e->blocks); cudaFree(e->frame_len); cudaFree(e->bodies); cudaFree(e->status); cudaFree(e->seqs); cudaFree(e->meta); cudaFree(e->rec);
+        for (int i = 0; i < 5; i++) if (e->tev[i]) cudaEventDestroy(e->tev[i]);
         cudaFree(e->tab2); cudaFree(e->head2); cudaFree(e->lits); cudaFree(e->sbits);
         delete e;
         ctx->enc_sets[set] = nullptr;
@@ -320,20 +323,27 @@ int32_t sq_encode_device_set(sq_ctx *ctx, int set, const void *d_data, const sq_
     SQ_CUDA(ctx, cudaMemsetAsync(e->status + 1, 0, 2 * sizeof(uint32_t), st));
     {
         static_assert(sizeof(lz::BlockOut) == sizeof(sq_block_info), "block info layout");
+        const bool timing = (ctx->flags & SQ_FLAG_STAGE_TIMING) != 0;
+        if (timing && !e->tev[0]) for (int i = 0; i < 5; i++) SQ_CUDA(ctx, cudaEventCreate(&e->tev[i]));
+        if (timing) SQ_CUDA(ctx, cudaEventRecord(e->tev[0], st));
         // search: one cluster per chunk in flight (tables L2-resident), then the parse (lazy choice + repeat offsets) per block
         const uint32_t clusters = n < e->lz2_clusters ? n : e->lz2_clusters;
         SQ_CUDA(ctx, lz2_dispatch(e->lz2_cfg, (int)clusters, nullptr, st, (const uint8_t *)d_data, d_spans, d_select, n, e->tab2, e->head2, e->rec, e->status + 1));
+        if (timing) SQ_CUDA(ctx, cudaEventRecord(e->tev[1], st));
         static const bool chase_thread = getenv("SQ_LZ2_DBG") && (atoi(getenv("SQ_LZ2_DBG")) & 4);  // debugging reference: the scalar parse, one thread per block
         if (chase_thread) lz2::chase_thread_kernel<<<(n * SQ_MAX_BLOCKS + 63) / 64, 64, 0, st>>>((const uint8_t *)d_data, d_spans, d_select, n, e->rec, e->seqs, e->meta);
         else lz2::chase_kernel<<<(n * SQ_MAX_BLOCKS + 3) / 4, 128, 0, st>>>((const uint8_t *)d_data, d_spans, d_select, n, e->rec, e->seqs, e->meta);
+        if (timing) SQ_CUDA(ctx, cudaEventRecord(e->tev[2], st));
         const uint32_t ent_ctas = e->ent_warps / 4;
         lz::entropy_kernel<<<ent_ctas, 128, 0, st>>>((const uint8_t *)d_data, d_spans, d_select, n, e->seqs, e->meta, e->lits, e->bodies,
                                                      reinterpret_cast<lz::BlockOut *>(e->blocks), e->sbits, e->status + 2);
     }
+    if (ctx->flags & SQ_FLAG_STAGE_TIMING) SQ_CUDA(ctx, cudaEventRecord(e->tev[3], st));
     enc_size_kernel<<<(n + 255) / 256, 256, 0, st>>>(d_spans, d_select, n, e->blocks, e->frame_len);
     enc_scan_kernel<<<1, 1024, 0, st>>>(e->frame_len, n, out_capacity, d_frame_off, d_frame_len, d_total, e->status);
     enc_emit_kernel<<<dim3(SQ_MAX_BLOCKS, n), 256, 0, st>>>((const uint8_t *)d_data, d_spans, n, e->blocks, e->bodies, d_frame_off, d_frame_len,
                                                             (uint8_t *)d_out, e->status);
+    if (ctx->flags & SQ_FLAG_STAGE_TIMING) { SQ_CUDA(ctx, cudaEventRecord(e->tev[4], st)); e->tev_valid = 1; }
     SQ_LAUNCHED(ctx, 7);
     SQ_CUDA(ctx, cudaGetLastError());
     SQ_CUDA(ctx, cudaEventRecord(ctx->enc_set_done[set], st));
@@ -354,4 +364,17 @@ extern "C" int32_t sq_encode_status(sq_ctx *ctx) {
         }
     }
     return SQ_OK;
+}
+
+extern "C" int32_t sq_encode_stage_ms(sq_ctx *ctx, void *stream, float out[4]) {
+    if (!ctx || !out) return SQ_ERR_INVALID_ARG;
+    cudaStream_t st = sq_stream(ctx, stream);
+    for (int set = 0; set < 2; set++) {
+        sq_enc_scratch *e = ctx->enc_sets[set];
+        if (!e || !e->tev_valid || !ctx->enc_set_bound[set] || ctx->enc_set_stream[set] != st) continue;
+        SQ_CUDA(ctx, cudaEventSynchronize(e->tev[4]));
+        for (int i = 0; i < 4; i++) SQ_CUDA(ctx, cudaEventElapsedTime(&out[i], e->tev[i], e->tev[i + 1]));
+        return SQ_OK;
+    }
+    return sq_set_error(ctx, SQ_ERR_INVALID_ARG, "sq_encode_stage_ms: no timed encode on this stream (SQ_FLAG_STAGE_TIMING set?)");
 }
