@@ -329,7 +329,7 @@ def run_reference(args):
     emit(line)
 
 
-def real_data_ratio(ctx, oracle, limit=4 * MiB):
+def real_data_ratio(ctx, oracle, limit=8 * MiB):
     """GPU frames against libzstd level 12 on real files of this image (the same files on the GPU box): per corpus, 2 MiB chunks,
     plus 24 KB pieces of all three.  Returns {corpus: delta in percent}."""
     import glob
@@ -761,6 +761,7 @@ def run_ours(args):
             t_n = torch.tensor([n_e2e], dtype=torch.int64, device="cuda")
             dist.all_reduce(t_n, op=dist.ReduceOp.MIN)
             n_e2e = int(t_n.item())
+        n_e2e = max(2, min(n_e2e, n_batches - n_warm))  # never wrap the corpus inside one dedup index
         total_steps = n_warm + n_e2e
         # Every step's input sits in its own pinned host buffer BEFORE the clock starts (staging it costs PCIe time that is not
         # part of the workload); outputs and results use a ring of two, like the two pipeline slots.

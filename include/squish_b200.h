@@ -69,7 +69,7 @@ typedef struct sq_ctx sq_ctx;
 typedef struct {
     int32_t device;             /* CUDA device ordinal */
     uint32_t chunk_size;        /* 0 = SQ_CHUNK_SIZE; must be <= SQ_CHUNK_SIZE */
-    uint64_t dedup_capacity;    /* max distinct digests the context will ever hold (0 = 1<<20) */
+    uint64_t dedup_capacity;    /* max distinct digests the context will ever hold (0 = 1<<20); must be < 2^30 */
     uint32_t max_batch_chunks;  /* largest n passed to any batch call (0 = 4096) */
     uint32_t flags;             /* SQ_FLAG_* bits, 0 = defaults */
 } sq_config;
@@ -155,7 +155,9 @@ int32_t sq_dedup_reset(sq_ctx *ctx);                /* ChunkStore::new (chunk.rs
  * blocks with an all-to-all over NCCL -> sq_dedup_insert_routed_device inserts what this rank
  * owns and writes one verdict byte per received record (same layout) -> reverse all-to-all ->
  * sq_unroute_verdicts_device scatters verdicts back to chunk order.  sq_dedup_len on each rank
- * counts the digests that rank owns; the store's len() is their sum. */
+ * counts the digests that rank owns; the store's len() is their sum.
+ * Constraint: count = world * cap_per_peer of a routed insert must not exceed the context's max_batch_chunks (the index
+ * keeps one slot reference per record of a batch): create the context with max_batch_chunks >= world * cap_per_peer. */
 int32_t sq_route_digests_device(sq_ctx *ctx, const void *d_digests, uint64_t gidx_base, uint32_t n,
                                 uint32_t world, uint32_t cap_per_peer, void *d_send,
                                 uint32_t *d_send_pos, void *stream);
@@ -163,6 +165,11 @@ int32_t sq_dedup_insert_routed_device(sq_ctx *ctx, const void *d_recv, uint32_t 
                                       uint8_t *d_verdict, void *stream);
 int32_t sq_unroute_verdicts_device(sq_ctx *ctx, const uint8_t *d_verdict_back, const uint32_t *d_send_pos,
                                    uint32_t n, uint8_t *d_is_new, void *stream);
+
+/* Buffer slack for the *_device entry points: the kernels read whole aligned words around the bytes they are given.  d_data
+ * (encode / digest) and d_comp (decode) must be readable for 16 bytes past the last span / payload and d_comp for 8 bytes
+ * before the first payload that does not start at offset 0; a buffer from cudaMalloc with 64 spare bytes at the end, payloads
+ * at 16-byte aligned offsets, always satisfies this (what the *_host entry points do). */
 
 /* ---- K3: encode  == zstd::bulk::compress(chunk, 12) (src/util/chunk.rs:89-90) */
 /* worst-case frame bytes for a chunk of `len` bytes (raw-block fallback) */

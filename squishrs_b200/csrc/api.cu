@@ -83,6 +83,8 @@ extern "C" int32_t sq_create(const sq_config *cfg, sq_ctx **out) {
     ctx->dedup_capacity = cfg && cfg->dedup_capacity ? cfg->dedup_capacity : (1ull << 20);
     int32_t rc = SQ_OK;
     auto fail = [&](int32_t code) { snprintf(g_create_err, sizeof g_create_err, "%s", ctx->err); sq_destroy(ctx); return code; };
+    if (ctx->dedup_capacity >= (1ull << 30)) {  // slot indices and key references are 32-bit (slots = 2 x capacity rounded up to a power of two)
+        sq_set_error(ctx, SQ_ERR_INVALID_ARG, "dedup_capacity %llu is not below 2^30", (unsigned long long)ctx->dedup_capacity); return fail(SQ_ERR_INVALID_ARG); }
     if (ctx->chunk_size > SQ_CHUNK_SIZE) { sq_set_error(ctx, SQ_ERR_INVALID_CHUNK_SIZE, "chunk_size %u > %u", ctx->chunk_size, SQ_CHUNK_SIZE); return fail(SQ_ERR_INVALID_CHUNK_SIZE); }
     if (cudaSetDevice(dev) != cudaSuccess) { sq_set_error(ctx, SQ_ERR_CUDA, "cudaSetDevice(%d) failed", dev); return fail(SQ_ERR_CUDA); }
     cudaDeviceProp prop;

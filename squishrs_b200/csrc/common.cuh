@@ -44,6 +44,7 @@ struct sq_ctx {
         cudaEvent_t h2d_done, compute_done;
         uint64_t *h_total;            // pinned
         uint32_t n; uint64_t out_capacity; void *h_out; int busy;
+        void *h_results; const void *d_results;  // results are downloaded in sq_pack_wait when the caller's array is not pinned
     } slots[2];
     cudaStream_t d2h_stream;
     // double-buffered unpack pipeline (sq_unpack_submit / sq_unpack_wait): uploads on copy_stream, decode on stream, downloads on d2h_stream
@@ -51,6 +52,7 @@ struct sq_ctx {
         void *d_in, *d_out, *d_meta; size_t in_cap, out_cap, meta_cap;
         cudaEvent_t h2d_done, compute_done, d2h_done;
         int busy;
+        void *h_results, *h_out; const void *d_results; size_t out_len; uint32_t n; int deferred;  // pageable host buffers: downloads happen in sq_unpack_wait
     } uslots[2];
     int next_uslot;
     cudaStream_t slot_stream[2];   // one compute stream per pipeline slot: the tail of one batch overlaps the head of the next

@@ -84,6 +84,14 @@ extern "C" int32_t sq_pack_device(sq_ctx *ctx, const void *d_data, const sq_span
 struct sq_ticket { int slot; };
 static sq_ticket g_tickets[2] = {{0}, {1}};
 
+// cudaMemcpyAsync device -> PAGEABLE host memory returns only when the copy has completed: issued inside a submit call it would
+// block the caller until the whole batch is done.  Downloads into memory that is not pinned are therefore left to the wait call.
+static bool host_pinned(const void *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
 extern "C" int32_t sq_pack_submit(sq_ctx *ctx, const void *h_data, size_t data_len, const sq_span *h_spans, uint32_t n,
                                   uint64_t gidx_base, sq_chunk_result *h_results, void *h_out, uint64_t out_capacity, sq_ticket **ticket) {
     if (!ctx || !ticket) return SQ_ERR_INVALID_ARG;
@@ -113,7 +121,9 @@ extern "C" int32_t sq_pack_submit(sq_ctx *ctx, const void *h_data, size_t data_l
     if (ctx->dedup_done_valid[si ^ 1]) SQ_CUDA(ctx, cudaStreamWaitEvent(cs, ctx->dedup_done[si ^ 1], 0));
     if ((rc = pack_device_impl(ctx, sl.d_in, m.spans, n, gidx_base, m, m.results, sl.d_out, bound, cs, si, ctx->dedup_done[si]))) return rc;
     ctx->dedup_done_valid[si] = 1;
-    SQ_CUDA(ctx, cudaMemcpyAsync(h_results, m.results, (size_t)n * sizeof(sq_chunk_result), cudaMemcpyDeviceToHost, cs));
+    sl.h_results = nullptr;
+    if (host_pinned(h_results)) SQ_CUDA(ctx, cudaMemcpyAsync(h_results, m.results, (size_t)n * sizeof(sq_chunk_result), cudaMemcpyDeviceToHost, cs));
+    else { sl.h_results = h_results; sl.d_results = m.results; }
     SQ_CUDA(ctx, cudaMemcpyAsync(sl.h_total, m.total, 8, cudaMemcpyDeviceToHost, cs));
     SQ_CUDA(ctx, cudaEventRecord(sl.compute_done, cs));
     sl.busy = 1; sl.n = n; sl.out_capacity = out_capacity; sl.h_out = h_out;
@@ -128,13 +138,12 @@ extern "C" int32_t sq_pack_wait(sq_ctx *ctx, sq_ticket *ticket, uint64_t *out_us
     if (!sl.busy) return sq_set_error(ctx, SQ_ERR_INVALID_ARG, "sq_pack_wait: ticket is not in flight");
     sl.busy = 0;
     SQ_CUDA(ctx, cudaEventSynchronize(sl.compute_done));
+    if (sl.h_results) SQ_CUDA(ctx, cudaMemcpyAsync(sl.h_results, sl.d_results, (size_t)sl.n * sizeof(sq_chunk_result), cudaMemcpyDeviceToHost, ctx->d2h_stream));
     const uint64_t used = *sl.h_total;
     if (used > sl.out_capacity)
         return sq_set_error(ctx, SQ_ERR_CAPACITY, "pack output needs %llu bytes, caller gave %llu", (unsigned long long)used, (unsigned long long)sl.out_capacity);
-    if (used) {
-        SQ_CUDA(ctx, cudaMemcpyAsync(sl.h_out, sl.d_out, used, cudaMemcpyDeviceToHost, ctx->d2h_stream));
-        SQ_CUDA(ctx, cudaStreamSynchronize(ctx->d2h_stream));
-    }
+    if (used) SQ_CUDA(ctx, cudaMemcpyAsync(sl.h_out, sl.d_out, used, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+    if (used || sl.h_results) SQ_CUDA(ctx, cudaStreamSynchronize(ctx->d2h_stream));
     if (out_used) *out_used = used;
     return SQ_OK;
 }
@@ -179,10 +188,14 @@ extern "C" int32_t sq_unpack_submit(sq_ctx *ctx, const void *h_comp, size_t comp
     SQ_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, sl.h2d_done, 0));
     if ((rc = sq_decode_device(ctx, sl.d_in, m.frames, n, sl.d_out, m.fres, ctx->stream))) return rc;
     SQ_CUDA(ctx, cudaEventRecord(sl.compute_done, ctx->stream));
-    SQ_CUDA(ctx, cudaStreamWaitEvent(ctx->d2h_stream, sl.compute_done, 0));
-    SQ_CUDA(ctx, cudaMemcpyAsync(h_results, m.fres, (size_t)n * sizeof(sq_frame_result), cudaMemcpyDeviceToHost, ctx->d2h_stream));
-    if (out_len) SQ_CUDA(ctx, cudaMemcpyAsync(h_out, sl.d_out, out_len, cudaMemcpyDeviceToHost, ctx->d2h_stream));
-    SQ_CUDA(ctx, cudaEventRecord(sl.d2h_done, ctx->d2h_stream));
+    sl.deferred = !(host_pinned(h_results) && (!out_len || host_pinned(h_out)));
+    sl.h_results = h_results; sl.h_out = h_out; sl.d_results = m.fres; sl.out_len = out_len; sl.n = n;
+    if (!sl.deferred) {
+        SQ_CUDA(ctx, cudaStreamWaitEvent(ctx->d2h_stream, sl.compute_done, 0));
+        SQ_CUDA(ctx, cudaMemcpyAsync(h_results, m.fres, (size_t)n * sizeof(sq_frame_result), cudaMemcpyDeviceToHost, ctx->d2h_stream));
+        if (out_len) SQ_CUDA(ctx, cudaMemcpyAsync(h_out, sl.d_out, out_len, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+        SQ_CUDA(ctx, cudaEventRecord(sl.d2h_done, ctx->d2h_stream));
+    }
     sl.busy = 1;
     ctx->next_uslot = si ^ 1;
     *ticket = &g_utickets[si];
@@ -194,6 +207,13 @@ extern "C" int32_t sq_unpack_wait(sq_ctx *ctx, sq_ticket *ticket) {
     sq_ctx::unpack_slot &sl = ctx->uslots[ticket->slot];
     if (!sl.busy) return sq_set_error(ctx, SQ_ERR_INVALID_ARG, "sq_unpack_wait: ticket is not in flight");
     sl.busy = 0;
+    if (sl.deferred) {  // pageable destination: the downloads block, so they happen here and not in the submit call
+        SQ_CUDA(ctx, cudaEventSynchronize(sl.compute_done));
+        SQ_CUDA(ctx, cudaMemcpyAsync(sl.h_results, sl.d_results, (size_t)sl.n * sizeof(sq_frame_result), cudaMemcpyDeviceToHost, ctx->d2h_stream));
+        if (sl.out_len) SQ_CUDA(ctx, cudaMemcpyAsync(sl.h_out, sl.d_out, sl.out_len, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+        SQ_CUDA(ctx, cudaStreamSynchronize(ctx->d2h_stream));
+        return SQ_OK;
+    }
     SQ_CUDA(ctx, cudaEventSynchronize(sl.d2h_done));
     return SQ_OK;
 }

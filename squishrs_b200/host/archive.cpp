@@ -212,7 +212,8 @@ int32_t read_manifest(sq_ctx *ctx, const Archive &a, std::vector<ManifestEntry> 
 
 // Upper bound of the decoded size of a record payload from its frame headers (all frames must carry
 // a Frame_Content_Size), else `fallback`.  Lets 200k small records avoid 2 MiB of capacity each.
-uint64_t payload_decoded_bound(const uint8_t *p, uint64_t n, uint64_t fallback) {
+uint64_t payload_decoded_bound(const uint8_t *p, uint64_t n, uint64_t fallback, bool *exact = nullptr) {
+    if (exact) *exact = false;
     // only the first frame is inspected: a single-frame payload with FCS is what every writer emits
     if (n < 6 || get32(p) != 0xFD2FB528u) return fallback;
     uint8_t fhd = p[4];
@@ -235,6 +236,7 @@ uint64_t payload_decoded_bound(const uint8_t *p, uint64_t n, uint64_t fallback) 
     }
     if (fhd & 4) q += 4;
     if (q != n) return fallback;  // trailing frames / garbage: let the decoder decide with the full capacity
+    if (exact) *exact = fcs <= fallback;
     return std::min<uint64_t>(fcs, fallback);
 }
 
@@ -325,16 +327,25 @@ extern "C" int32_t sq_archive_pack(sq_ctx *ctx, const char *input_dir, const cha
     const bool pin = total_bytes_all >= kPinThreshold;
     Batch bufs[2];
     Staging in_stage[2], out_stage[2];
+    auto bail = [&](int32_t code) {  // early exit: give the staging back and do not leave a truncated archive behind
+        for (int i = 0; i < 2; i++) { in_stage[i].release(ctx); out_stage[i].release(ctx); }
+        fclose(out);
+        remove(output_path);
+        return code;
+    };
     for (int i = 0; i < 2; i++) {
-        if ((rc = in_stage[i].alloc(ctx, slot_cap, pin))) { fclose(out); return rc; }
+        if ((rc = in_stage[i].alloc(ctx, slot_cap, pin))) return bail(rc);
         bufs[i].pinned = (uint8_t *)in_stage[i].p; bufs[i].cap = slot_cap;
     }
     uint64_t out_cap = sq_encode_bound(cs) * (uint64_t)(batch_bytes / cs + 1) + batch_bytes / 16;
-    struct Stage { std::vector<sq_chunk_result> res; void *h_out = nullptr; sq_ticket *ticket = nullptr; };
+    // the per-chunk results are small and always pinned: their download then never blocks sq_pack_submit
+    struct Stage { sq_chunk_result *res = nullptr; void *h_out = nullptr; sq_ticket *ticket = nullptr; bool live = false; };
     Stage stages[2];
+    Staging res_stage[2];
     for (int i = 0; i < 2; i++) {
-        stages[i].res.resize(ctx->max_batch);
-        if ((rc = out_stage[i].alloc(ctx, out_cap, pin))) { fclose(out); return rc; }
+        if ((rc = res_stage[i].alloc(ctx, (size_t)ctx->max_batch * sizeof(sq_chunk_result), true))) { res_stage[0].release(ctx); return bail(rc); }
+        stages[i].res = (sq_chunk_result *)res_stage[i].p;
+        if ((rc = out_stage[i].alloc(ctx, out_cap, pin))) { res_stage[0].release(ctx); res_stage[1].release(ctx); return bail(rc); }
         stages[i].h_out = out_stage[i].p;
     }
     std::vector<uint8_t> digests(total_chunks * 16);
@@ -377,10 +388,10 @@ extern "C" int32_t sq_archive_pack(sq_ctx *ctx, const char *input_dir, const cha
             fill(b, next, &next);
             if (b->err) { rc = sq_set_error(ctx, b->err, "Error reading from squish: input file changed or unreadable"); break; }
             double td = now_s();
-            rc = sq_pack_submit(ctx, b->pinned, b->used, b->spans.data(), (uint32_t)b->spans.size(), b->first_gidx, stages[head].res.data(),
+            rc = sq_pack_submit(ctx, b->pinned, b->used, b->spans.data(), (uint32_t)b->spans.size(), b->first_gidx, stages[head].res,
                                 stages[head].h_out, out_cap, &stages[head].ticket);
             t_dev += now_s() - td;
-            head ^= 1; inflight++;
+            if (!rc) { stages[head].live = true; head ^= 1; inflight++; }
             continue;
         }
         Batch *b = &bufs[tail];
@@ -388,6 +399,7 @@ extern "C" int32_t sq_archive_pack(sq_ctx *ctx, const char *input_dir, const cha
         uint64_t used = 0;
         double td = now_s();
         rc = sq_pack_wait(ctx, sg.ticket, &used);
+        sg.live = false;
         t_dev += now_s() - td;
         if (!rc) {
             const uint32_t n = (uint32_t)b->spans.size();
@@ -406,8 +418,8 @@ extern "C" int32_t sq_archive_pack(sq_ctx *ctx, const char *input_dir, const cha
         }
         tail ^= 1; inflight--;
     }
-    if (rc) {  // drain whatever is still in flight before the buffers go away
-        for (int i = 0; i < 2; i++) if (ctx->slots[i].busy) { uint64_t u; sq_pack_wait(ctx, stages[i].ticket, &u); }
+    if (rc) {  // drain whatever is still in flight (through the tickets that were issued) before the buffers go away
+        for (int i = 0; i < 2; i++) if (stages[i].live) { uint64_t u; sq_pack_wait(ctx, stages[i].ticket, &u); stages[i].live = false; }
     }
     SQ_T("all batches packed + records written");
     if (!rc) {
@@ -437,7 +449,7 @@ extern "C" int32_t sq_archive_pack(sq_ctx *ctx, const char *input_dir, const cha
     uint64_t asize = 0;
     if (!rc) { fseek(out, 0, SEEK_END); asize = (uint64_t)ftell(out); }
     fclose(out);
-    for (int i = 0; i < 2; i++) { in_stage[i].release(ctx); out_stage[i].release(ctx); }
+    for (int i = 0; i < 2; i++) { in_stage[i].release(ctx); out_stage[i].release(ctx); res_stage[i].release(ctx); }
     if (!rc && report) {
         memset(report, 0, sizeof *report);
         report->archive_size = asize; report->unique_chunks = unique; report->total_chunks = total_chunks;
@@ -446,6 +458,170 @@ extern "C" int32_t sq_archive_pack(sq_ctx *ctx, const char *input_dir, const cha
         report->seconds_total = now_s() - t0; report->seconds_device = t_dev;
     }
     return rc;
+}
+
+// ---- unpack, streaming: decoded batches go straight from the staging buffer into the files ------------------------------
+// read_chunks + rebuild_files (reader.rs:259-413) fused.  Every frame of the archive states its decoded size (every writer of the
+// format emits a Frame_Content_Size), so the byte offset of every chunk in every file is known before anything is decoded: a
+// batch that comes back from the GPU is written with pwrite by the host threads while the next batch decodes, and host memory
+// holds two staging pairs instead of all unique data (the reference keeps everything: reader.rs:268).
+int32_t unpack_streaming(sq_ctx *ctx, Archive &a, std::vector<ManifestEntry> &man, uint64_t total, const std::vector<uint64_t> &size,
+                         const char *output_dir, int32_t threads, sq_summary *summary, double t0) {
+    double t_dev = 0;
+    int32_t rc = SQ_OK;
+    const size_t nrec = a.records.size();
+    struct Key { uint64_t a, b; bool operator==(const Key &o) const { return a == o.a && b == o.b; } };
+    struct KeyHash { size_t operator()(const Key &k) const { return (size_t)(k.a ^ (k.b * 0x9E3779B97F4A7C15ULL)); } };
+    std::unordered_map<Key, size_t, KeyHash> map;  // digest -> record; later records overwrite earlier ones (reader.rs:305)
+    map.reserve(nrec * 2);
+    for (size_t k = 0; k < nrec; k++) map[{get64(a.records[k].digest), get64(a.records[k].digest + 8)}] = k;
+    // where every record's bytes go: (file, offset) references in CSR form
+    struct Ref { uint32_t file; uint64_t off; };
+    std::vector<uint32_t> ref_start(nrec + 1, 0);
+    std::vector<size_t> chunk_rec;
+    size_t total_refs = 0;
+    for (auto &e : man) total_refs += e.chunk_count;
+    chunk_rec.reserve(total_refs);
+    for (size_t fi = 0; fi < man.size(); fi++) {
+        const ManifestEntry &e = man[fi];
+        for (uint32_t c = 0; c < e.chunk_count; c++) {
+            auto it = map.find({get64(e.hashes + (size_t)c * 16), get64(e.hashes + (size_t)c * 16 + 8)});
+            if (it == map.end())  // reader.rs:397-401
+                return sq_set_error(ctx, SQ_ERR_MISSING_CHUNK, "%s `%.*s`", sq_strerror(SQ_ERR_MISSING_CHUNK), (int)e.path_len, (const char *)e.path);
+            chunk_rec.push_back(it->second);
+            ref_start[it->second + 1]++;
+        }
+    }
+    for (size_t k = 0; k < nrec; k++) ref_start[k + 1] += ref_start[k];
+    std::vector<Ref> refs(total_refs);
+    {
+        std::vector<uint32_t> fill(ref_start.begin(), ref_start.end() - 1);
+        size_t j = 0;
+        for (size_t fi = 0; fi < man.size(); fi++) {
+            uint64_t off = 0;
+            for (uint32_t c = 0; c < man[fi].chunk_count; c++, j++) {
+                refs[fill[chunk_rec[j]]++] = {(uint32_t)fi, off};
+                off += size[chunk_rec[j]];
+            }
+        }
+    }
+    // create_dir_all(parent) + File::create for every file (reader.rs:375-383); empty files are complete after this
+    std::string outdir(output_dir);
+    mkdir(outdir.c_str(), 0777);
+    std::vector<std::string> full(man.size());
+    std::atomic<int32_t> err{0};
+    std::atomic<size_t> err_idx{0};
+    parallel_for(man.size(), threads, [&](size_t fi) {
+        const ManifestEntry &e = man[fi];
+        full[fi] = outdir + "/" + std::string((const char *)e.path, e.path_len);
+        std::string &f = full[fi];
+        for (size_t p = outdir.size() + 1; p < f.size(); p++)
+            if (f[p] == '/') { f[p] = 0; mkdir(f.c_str(), 0777); f[p] = '/'; }
+        int fd = open(f.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0666);
+        if (fd < 0) { err = SQ_ERR_CREATE_FILE; err_idx = fi; return; }
+        close(fd);
+    });
+    if (err) {
+        const ManifestEntry &e = man[err_idx];
+        return sq_set_error(ctx, err, "%s `%.*s`", sq_strerror(err), (int)e.path_len, (const char *)e.path);
+    }
+    SQ_T("files created");
+    uint64_t total_out = 0, total_comp = 0;
+    for (size_t k = 0; k < nrec; k++) { total_out += (size[k] + 15) & ~15ull; total_comp += (a.records[k].comp + 15) & ~15ull; }
+    // batches: at most 1 GiB of output per slot, and at least four batches for jobs above 256 MiB so that upload, decode,
+    // download and file writes overlap
+    const uint64_t batch_out = std::min<uint64_t>(1024ull << 20, std::max<uint64_t>(total_out > (256ull << 20) ? total_out / 4 : total_out, 1u << 20)),
+                   batch_in = std::min<uint64_t>(1024ull << 20, std::max<uint64_t>(total_comp, 1u << 20));
+    struct UnpackBatch {
+        Staging comp, out, res;
+        std::vector<sq_frame> frames;
+        sq_frame_result *fres = nullptr;
+        size_t first = 0;
+        sq_ticket *ticket = nullptr; bool live = false;
+    } ub[2];
+    const bool pin = total_out >= kPinThreshold;
+    for (int k = 0; k < 2 && !rc; k++) {
+        if ((rc = ub[k].comp.alloc(ctx, batch_in + (4u << 20), pin))) break;
+        if ((rc = ub[k].out.alloc(ctx, batch_out + (4u << 20), pin))) break;
+        if ((rc = ub[k].res.alloc(ctx, (size_t)ctx->max_batch * sizeof(sq_frame_result), pin))) break;  // pinned with the data: downloads then never block a submit
+        ub[k].fres = (sq_frame_result *)ub[k].res.p;
+    }
+    auto release = [&]() { for (int k = 0; k < 2; k++) { ub[k].comp.release(ctx); ub[k].out.release(ctx); ub[k].res.release(ctx); } };
+    if (rc) { release(); return rc; }
+    auto finish = [&](UnpackBatch &b) -> int32_t {  // wait for the batch, check every payload, write its bytes where they belong
+        b.live = false;
+        double td = now_s();
+        int32_t r = sq_unpack_wait(ctx, b.ticket);
+        t_dev += now_s() - td;
+        if (r) return r;
+        for (size_t k = 0; k < b.frames.size(); k++)
+            if (b.fres[k].status != SQ_OK || b.fres[k].out_len != size[b.first + k])
+                return sq_set_error(ctx, SQ_ERR_READER, "Error reading from squish: chunk %zu failed to decode", b.first + k);
+        parallel_for(b.frames.size(), threads, [&](size_t k) {
+            const size_t ri = b.first + k;
+            const uint8_t *src = (const uint8_t *)b.out.p + b.frames[k].dst_off;
+            for (uint32_t j = ref_start[ri]; j < ref_start[ri + 1]; j++) {
+                int fd = open(full[refs[j].file].c_str(), O_WRONLY);
+                if (fd < 0) { err = SQ_ERR_CREATE_FILE; err_idx = refs[j].file; return; }
+                size_t w = 0;
+                while (w < size[ri]) {
+                    ssize_t n = pwrite(fd, src + w, size[ri] - w, (off_t)(refs[j].off + w));
+                    if (n <= 0) { err = SQ_ERR_IO; err_idx = refs[j].file; break; }
+                    w += (size_t)n;
+                }
+                close(fd);
+            }
+        });
+        return SQ_OK;
+    };
+    size_t i = 0;
+    int cur = 0;
+    while (i < nrec && !rc && !err) {
+        UnpackBatch &b = ub[cur];
+        if (b.live && (rc = finish(b))) break;  // the slot's previous batch must be on disk before its buffers are reused
+        b.frames.clear();
+        uint64_t so = 0, dof = 0;
+        b.first = i;
+        while (i < nrec && b.frames.size() < ctx->max_batch) {
+            const Record &r = a.records[i];
+            uint64_t sneed = (r.comp + 15) & ~15ull, dneed = (size[i] + 15) & ~15ull;
+            if (!b.frames.empty() && (so + sneed > batch_in || dof + dneed > batch_out)) break;
+            if (sneed > batch_in + (4u << 20) || dneed > batch_out + (4u << 20)) { rc = sq_set_error(ctx, SQ_ERR_INVALID_CHUNK_SIZE, "Invalid chunk size: %llu bytes", (unsigned long long)r.orig); break; }
+            b.frames.push_back({so, dof, (uint32_t)r.comp, (uint32_t)size[i]});
+            so += sneed; dof += dneed;
+            i++;
+        }
+        if (rc) break;
+        parallel_for(b.frames.size(), threads, [&](size_t k) { memcpy((uint8_t *)b.comp.p + b.frames[k].src_off, a.records[b.first + k].payload, b.frames[k].src_len); });
+        double td = now_s();
+        rc = sq_unpack_submit(ctx, b.comp.p, so, b.frames.data(), (uint32_t)b.frames.size(), b.out.p, dof, b.fres, &b.ticket);
+        t_dev += now_s() - td;
+        if (rc) break;
+        b.live = true;
+        cur ^= 1;
+    }
+    for (int k = 0; k < 2; k++) {  // drain, oldest first; on error still wait before the buffers go away
+        UnpackBatch &b = ub[cur ^ k];
+        if (!b.live) continue;
+        if (rc || err) { sq_unpack_wait(ctx, b.ticket); b.live = false; }
+        else rc = finish(b);
+    }
+    release();
+    SQ_T("all chunks decoded and written");
+    if (rc) return rc;
+    if (err) {
+        const ManifestEntry &e = man[err_idx];
+        return sq_set_error(ctx, err, "%s `%.*s`", sq_strerror(err), (int)e.path_len, (const char *)e.path);
+    }
+    if (summary) {
+        memset(summary, 0, sizeof *summary);
+        summary->unique_chunks = a.nchunks; summary->total_original_size = total; summary->archive_size = a.size;
+        summary->timestamp = a.timestamp; summary->file_count = a.file_count;
+        summary->compression_ratio = total ? (double)a.size / (double)total * 100.0 : 0.0;
+        snprintf(summary->version, sizeof summary->version, "%s", a.version);
+        summary->seconds_total = now_s() - t0; summary->seconds_device = t_dev;
+    }
+    return SQ_OK;
 }
 
 extern "C" int32_t sq_archive_unpack(sq_ctx *ctx, const char *archive_path, const char *output_dir, int32_t threads, sq_summary *summary) {
@@ -466,14 +642,21 @@ extern "C" int32_t sq_archive_unpack(sq_ctx *ctx, const char *archive_path, cons
     std::vector<Decoded> dec(a.records.size());
     std::vector<uint64_t> bound(a.records.size());
     uint64_t total_out = 0;
+    bool all_exact = true;
     for (size_t i = 0; i < a.records.size(); i++) {
         const Record &r = a.records[i];
         if (r.orig > (uint64_t)1 << 40) return sq_set_error(ctx, SQ_ERR_INVALID_CHUNK_SIZE, "Invalid chunk size: %llu bytes", (unsigned long long)r.orig);
         if (r.orig > 0xFFFFFFFFull || r.comp > 0xFFFFFFFFull) return sq_set_error(ctx, SQ_ERR_READER, "Error reading from squish: chunk record too large");
-        bound[i] = payload_decoded_bound(r.payload, r.comp, r.orig);
+        bool ex = false;
+        bound[i] = payload_decoded_bound(r.payload, r.comp, r.orig, &ex);
+        all_exact = all_exact && ex;
         total_out += (bound[i] + 15) & ~15ull;
     }
-    uint8_t *store = nullptr;  // all unique data resident in host RAM, like the reference (reader.rs:268)
+    if (all_exact && !getenv("SQ_UNPACK_STORE"))
+        return unpack_streaming(ctx, a, man, total, bound, output_dir, threads, summary, t0);
+    // Fallback for archives whose frames do not state their size (no writer of this format produces them): decode everything
+    // into host memory first, like the reference (reader.rs:268), then assemble the files.
+    uint8_t *store = nullptr;
     if (total_out) {
         store = (uint8_t *)malloc(total_out);
         if (!store) return sq_set_error(ctx, SQ_ERR_OTHER, "Unknown error: cannot allocate %llu bytes", (unsigned long long)total_out);

@@ -78,11 +78,23 @@ int main(int argc, char **argv) {
         int32_t rc = sq_archive_list(arg.c_str(), &s, &listing);
         if (rc) return fail(sq_last_error(nullptr)[0] ? sq_last_error(nullptr) : sq_strerror(rc));
         std::vector<std::pair<uint64_t, std::string>> files;
+        // "size path\n" records.  A stored path may itself contain '\n' (legal on Linux): a record ends at the first newline
+        // that is followed by the end of the listing or by the next record's "digits space".
         for (char *p = listing; p && *p;) {
-            char *nl = strchr(p, '\n');
             char *sp = strchr(p, ' ');
+            if (!sp) break;
+            char *nl = sp;
+            for (;;) {
+                nl = strchr(nl + 1, '\n');
+                if (!nl) { nl = sp + strlen(sp); break; }
+                const char *q = nl + 1;
+                if (!*q) break;
+                const char *d = q;
+                while (*d >= '0' && *d <= '9') d++;
+                if (d > q && *d == ' ') break;
+            }
             files.push_back({strtoull(p, nullptr, 10), std::string(sp + 1, nl)});
-            p = nl + 1;
+            p = *nl ? nl + 1 : nl;
         }
         sq_free(listing);
         if (simple) {
