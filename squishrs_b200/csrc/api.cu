@@ -1,4 +1,6 @@
 // Context, error plumbing, pinned staging and the fused batch entry points of the C ABI.
+#include <time.h>
+#include <stdlib.h>
 #include <stdarg.h>
 #include <stdlib.h>
 #include "common.cuh"
@@ -68,7 +70,12 @@ extern "C" int32_t sq_create(const sq_config *cfg, sq_ctx **out) {
     if (!out) return SQ_ERR_INVALID_ARG;
     *out = nullptr;
     int ndev = 0;
+    const bool tm = getenv("SQ_TIMING") != nullptr;  // start-up breakdown on stderr
+    auto now = [] { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + ts.tv_nsec * 1e-9; };
+    const double t0 = now();
+    auto mark = [&](const char *what) { if (tm) fprintf(stderr, "[sq_create %7.3f] %s\n", now() - t0, what); };
     cudaError_t e = cudaGetDeviceCount(&ndev);
+    mark("driver initialised (cudaGetDeviceCount)");
     if (e != cudaSuccess || ndev == 0)
         return sq_set_error(nullptr, SQ_ERR_NO_DEVICE, "no CUDA device available (%s); libsquish_b200 has no CPU fallback",
                             e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
@@ -91,6 +98,8 @@ extern "C" int32_t sq_create(const sq_config *cfg, sq_ctx **out) {
     if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) { sq_set_error(ctx, SQ_ERR_CUDA, "cudaGetDeviceProperties failed"); return fail(SQ_ERR_CUDA); }
     if (prop.major < 10) { sq_set_error(ctx, SQ_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", dev, prop.major, prop.minor); return fail(SQ_ERR_NO_DEVICE); }
     ctx->sm_count = prop.multiProcessorCount;
+    if (cudaFree(nullptr) != cudaSuccess) { sq_set_error(ctx, SQ_ERR_CUDA, "CUDA context creation failed"); return fail(SQ_ERR_CUDA); }
+    mark("CUDA context created");
     auto init = [&]() -> int32_t {
         SQ_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
         SQ_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
@@ -113,6 +122,7 @@ extern "C" int32_t sq_create(const sq_config *cfg, sq_ctx **out) {
     };
     rc = init();
     if (rc) return fail(rc);
+    mark("streams, events, digest constants ready (the dedup index and all scratch are allocated on first use)");
     *out = ctx;
     return SQ_OK;
 }

@@ -81,6 +81,7 @@ static inline cudaStream_t sq_stream(sq_ctx *ctx, void *s) { return s ? (cudaStr
 
 // entry points implemented per translation unit
 int32_t sq_dedup_create(sq_ctx *ctx);
+int32_t sq_dedup_ensure(sq_ctx *ctx, uint64_t capacity);  // (re)creates the index for `capacity` inserts if the current one is smaller
 void sq_dedup_destroy(sq_ctx *ctx);
 void sq_enc_destroy(sq_ctx *ctx);
 int32_t sq_encode_device_set(sq_ctx *ctx, int set, const void *d_data, const sq_span *d_spans, const uint8_t *d_select, uint32_t n, void *d_out,

@@ -127,13 +127,19 @@ __global__ void unroute_kernel(const uint8_t *__restrict__ verdict_back, const u
 
 }  // namespace
 
-int32_t sq_dedup_create(sq_ctx *ctx) {
+// The index is created on first use, sized for `capacity` inserts (a job that never dedups -- unpack, list -- never pays for it,
+// and the archive packer sizes it to the job's chunk count instead of the context's maximum).
+int32_t sq_dedup_ensure(sq_ctx *ctx, uint64_t capacity) {
+    if (capacity < 1024) capacity = 1024;
+    if (capacity >= (1ull << 30)) return sq_set_error(ctx, SQ_ERR_INVALID_ARG, "dedup index for %llu inserts: not below 2^30", (unsigned long long)capacity);
+    if (ctx->dedup && ctx->dedup->key_capacity >= capacity) return SQ_OK;
+    if (ctx->dedup) { SQ_CUDA(ctx, cudaDeviceSynchronize()); sq_dedup_destroy(ctx); }
     sq_dedup_table *t = new sq_dedup_table();
     memset(t, 0, sizeof *t);
     uint64_t slots = 1024;
-    while (slots < 2 * ctx->dedup_capacity) slots <<= 1;
+    while (slots < 2 * capacity) slots <<= 1;
     t->slots = slots;
-    t->key_capacity = ctx->dedup_capacity;
+    t->key_capacity = capacity;
     t->slot_of_cap = ctx->max_batch;
     ctx->dedup = t;
     SQ_CUDA(ctx, cudaMalloc(&t->key_ref, slots * sizeof(uint32_t)));
@@ -144,6 +150,8 @@ int32_t sq_dedup_create(sq_ctx *ctx) {
     return sq_dedup_reset(ctx);
 }
 
+int32_t sq_dedup_create(sq_ctx *ctx) { (void)ctx; return SQ_OK; }  // lazily: see sq_dedup_ensure
+
 void sq_dedup_destroy(sq_ctx *ctx) {
     sq_dedup_table *t = ctx->dedup;
     if (!t) return;
@@ -153,7 +161,8 @@ void sq_dedup_destroy(sq_ctx *ctx) {
 }
 
 extern "C" int32_t sq_dedup_reset(sq_ctx *ctx) {
-    if (!ctx || !ctx->dedup) return SQ_ERR_INVALID_ARG;
+    if (!ctx) return SQ_ERR_INVALID_ARG;
+    if (!ctx->dedup) return SQ_OK;  // nothing has been inserted yet: the index is created (empty) on first use
     sq_dedup_table *t = ctx->dedup;
     SQ_CUDA(ctx, cudaMemsetAsync(t->key_ref, 0, t->slots * sizeof(uint32_t), ctx->stream));
     SQ_CUDA(ctx, cudaMemsetAsync(t->min_gidx, 0xFF, t->slots * sizeof(unsigned long long), ctx->stream));
@@ -164,9 +173,10 @@ extern "C" int32_t sq_dedup_reset(sq_ctx *ctx) {
 
 extern "C" int32_t sq_dedup_insert_device(sq_ctx *ctx, const void *d_digests, const uint64_t *d_gidx, uint64_t gidx_base,
                                           uint32_t n, uint8_t *d_is_new, void *stream) {
-    if (!ctx || !ctx->dedup) return SQ_ERR_INVALID_ARG;
+    if (!ctx) return SQ_ERR_INVALID_ARG;
     if (n == 0) return SQ_OK;
     if (!d_digests || !d_is_new) return sq_set_error(ctx, SQ_ERR_INVALID_ARG, "sq_dedup_insert_device: null pointer");
+    if (!ctx->dedup) { int32_t r = sq_dedup_ensure(ctx, ctx->dedup_capacity); if (r) return r; }
     sq_dedup_table *t = ctx->dedup;
     if (n > t->slot_of_cap) return sq_set_error(ctx, SQ_ERR_INVALID_ARG, "batch of %u chunks exceeds max_batch_chunks %u", n, t->slot_of_cap);
     cudaStream_t st = sq_stream(ctx, stream);
@@ -180,7 +190,8 @@ extern "C" int32_t sq_dedup_insert_device(sq_ctx *ctx, const void *d_digests, co
 }
 
 extern "C" int32_t sq_dedup_len(sq_ctx *ctx, uint64_t *out) {
-    if (!ctx || !ctx->dedup || !out) return SQ_ERR_INVALID_ARG;
+    if (!ctx || !out) return SQ_ERR_INVALID_ARG;
+    if (!ctx->dedup) { *out = 0; return SQ_OK; }
     unsigned long long c[4];
     SQ_CUDA(ctx, cudaDeviceSynchronize());
     SQ_CUDA(ctx, cudaMemcpy(c, ctx->dedup->counters, sizeof c, cudaMemcpyDeviceToHost));
@@ -192,7 +203,8 @@ extern "C" int32_t sq_dedup_len(sq_ctx *ctx, uint64_t *out) {
 // ---- sharded index entry points ---------------------------------------------------------
 extern "C" int32_t sq_route_digests_device(sq_ctx *ctx, const void *d_digests, uint64_t gidx_base, uint32_t n, uint32_t world,
                                            uint32_t cap_per_peer, void *d_send, uint32_t *d_send_pos, void *stream) {
-    if (!ctx || !ctx->dedup) return SQ_ERR_INVALID_ARG;
+    if (!ctx) return SQ_ERR_INVALID_ARG;
+    if (!ctx->dedup) { int32_t r = sq_dedup_ensure(ctx, ctx->dedup_capacity); if (r) return r; }
     if (!d_digests || !d_send || !d_send_pos || world == 0 || cap_per_peer < n)
         return sq_set_error(ctx, SQ_ERR_INVALID_ARG, "sq_route_digests_device: bad arguments (cap_per_peer must be >= n)");
     if (world > 60) return sq_set_error(ctx, SQ_ERR_INVALID_ARG, "at most 60 ranks");
@@ -208,8 +220,9 @@ extern "C" int32_t sq_route_digests_device(sq_ctx *ctx, const void *d_digests, u
 }
 
 extern "C" int32_t sq_dedup_insert_routed_device(sq_ctx *ctx, const void *d_recv, uint32_t count, uint8_t *d_verdict, void *stream) {
-    if (!ctx || !ctx->dedup) return SQ_ERR_INVALID_ARG;
+    if (!ctx) return SQ_ERR_INVALID_ARG;
     if (count == 0) return SQ_OK;
+    if (!ctx->dedup) { int32_t r = sq_dedup_ensure(ctx, ctx->dedup_capacity); if (r) return r; }
     if (!d_recv || !d_verdict) return sq_set_error(ctx, SQ_ERR_INVALID_ARG, "sq_dedup_insert_routed_device: null pointer");
     cudaStream_t st = sq_stream(ctx, stream);
     int32_t rc = sq_ensure(ctx, &ctx->d_stage_meta, &ctx->stage_meta_cap, (size_t)count * 24 + 256);

@@ -180,7 +180,8 @@ __global__ void __launch_bounds__(256) enc_emit_kernel(const uint8_t *__restrict
 // ---- round-2 search kernel: launch configurations (cluster size, threads, positions per CTA and step, CTAs per SM) ----
 namespace {
 struct Lz2Cfg { int g, threads, sub, minb; };
-constexpr Lz2Cfg LZ2_CFGS[] = {{8, 256, 256, 2}, {8, 512, 512, 1}, {8, 256, 512, 2}, {4, 256, 256, 2}, {4, 512, 512, 1}, {1, 256, 256, 2}, {8, 256, 256, 1}, {8, 256, 256, 3}, {8, 256, 512, 3}, {8, 128, 256, 4}, {8, 128, 128, 4}, {2, 256, 1024, 2}, {4, 256, 1024, 2}, {4, 256, 512, 2}, {2, 256, 512, 2}, {1, 256, 1024, 2}, {8, 256, 1024, 2}};
+// cfg 0 ships; the others are the measured alternatives (SQ_LZ2_CFG): larger steps are ~10 % faster and cost ratio
+constexpr Lz2Cfg LZ2_CFGS[] = {{8, 256, 256, 2}, {8, 256, 512, 2}, {4, 256, 256, 2}, {1, 256, 256, 2}};
 constexpr int LZ2_NCFG = sizeof(LZ2_CFGS) / sizeof(LZ2_CFGS[0]);
 
 template <int G, int T, int SUB, int MINB>
@@ -215,7 +216,7 @@ cudaError_t lz2_dispatch(int c, int clusters, int *max_clusters, cudaStream_t st
     case i: return lz2_launch<LZ2_CFGS[i].g, LZ2_CFGS[i].threads, LZ2_CFGS[i].sub, LZ2_CFGS[i].minb>(clusters, max_clusters, st, data, spans, select, n, tab, \
                                                                                                    head, rec, counter);
     switch (c) {
-        LZ2_CASE(0) LZ2_CASE(1) LZ2_CASE(2) LZ2_CASE(3) LZ2_CASE(4) LZ2_CASE(5) LZ2_CASE(6) LZ2_CASE(7) LZ2_CASE(8) LZ2_CASE(9) LZ2_CASE(10) LZ2_CASE(11) LZ2_CASE(12) LZ2_CASE(13) LZ2_CASE(14) LZ2_CASE(15) LZ2_CASE(16)
+        LZ2_CASE(0) LZ2_CASE(1) LZ2_CASE(2) LZ2_CASE(3)
     }
 #undef LZ2_CASE
     return cudaErrorInvalidValue;

@@ -300,11 +300,10 @@ extern "C" int32_t sq_archive_pack(sq_ctx *ctx, const char *input_dir, const cha
         files[i].n_chunks = (uint32_t)(chunks.size() - files[i].first_chunk);
     }
     const uint64_t total_chunks = chunks.size();
-    if (total_chunks > ctx->dedup_capacity)
-        return sq_set_error(ctx, SQ_ERR_CAPACITY, "%llu chunks exceed the context's dedup_capacity %llu", (unsigned long long)total_chunks,
-                            (unsigned long long)ctx->dedup_capacity);
     SQ_T("stat + chunk plan done");
+    if ((rc = sq_dedup_ensure(ctx, total_chunks))) return rc;  // the index is sized to the job, not to the context's maximum
     if ((rc = sq_dedup_reset(ctx))) return rc;  // ChunkStore::new (writer.rs:88)
+    SQ_T("dedup index ready");
 
     FILE *out = fopen(output_path, "wb+");
     if (!out) return sq_set_error(ctx, SQ_ERR_IO, "I/O error: cannot create %s", output_path);

@@ -31,6 +31,12 @@ def run(cmd):
     return dt
 
 
+def phases(cmd):
+    """the same command once more with SQ_TIMING=1: the library's own phase marks (start-up breakdown)"""
+    r = subprocess.run(cmd, capture_output=True, text=True, env=dict(os.environ, SQ_TIMING="1"))
+    return [l for l in r.stderr.splitlines() if l.startswith("[sq")]
+
+
 def config1(total=1 << 30, nfiles=2000):
     rng = random.Random(0x51510001); src = BASE / "c1" / "tree"; sizes = [min(16 << 20, max(1024, rng.lognormvariate(math.log(256 << 10), 1.0))) for _ in range(nfiles)]
     k = total / sum(sizes); sizes = [max(1024, int(s * k)) for s in sizes]; originals = []; nbytes = 0
@@ -47,6 +53,9 @@ def config1(total=1 << 30, nfiles=2000):
     out["cross_gpu_archive_cpu_unpack_s"] = run([REF, "-j", threads, "unpack", str(BASE / "c1" / "gpu.squish"), "-o", str(BASE / "c1" / "x1")])
     out["cross_cpu_archive_gpu_unpack_s"] = run([CLI, "unpack", str(BASE / "c1" / "cpu.squish"), "-o", str(BASE / "c1" / "x2")])
     out["identical"] = all(same_tree(src, BASE / "c1" / d) for d in ("gpu_out", "cpu_out", "x1", "x2"))
+    out["gpu_pack_phases"] = phases([CLI, "pack", str(src), "-o", str(BASE / "c1" / "gpu2.squish")])
+    out["gpu_unpack_phases"] = phases([CLI, "unpack", str(BASE / "c1" / "gpu.squish"), "-o", str(BASE / "c1" / "gpu_out2")])
+    out["gpu_pack_second_run_s"] = run([CLI, "pack", str(src), "-o", str(BASE / "c1" / "gpu3.squish")])
     out["gpu_archive_bytes"] = (BASE / "c1" / "gpu.squish").stat().st_size; out["cpu_archive_bytes"] = (BASE / "c1" / "cpu.squish").stat().st_size
     out["ratio_delta_pct"] = (out["gpu_archive_bytes"] / out["cpu_archive_bytes"] - 1) * 100
     for k2 in ("gpu_pack", "gpu_unpack", "cpu_pack", "cpu_unpack"): out[k2 + "_gbs"] = nbytes / out[k2 + "_s"] / 1e9
@@ -63,6 +72,9 @@ def config5(nfiles=20000):
     out["gpu_unpack_s"] = run([CLI, "unpack", str(BASE / "c5" / "ref.squish"), "-o", str(BASE / "c5" / "gpu_out")])
     out["cpu_unpack_s"] = run([REF, "-j", threads, "unpack", str(BASE / "c5" / "ref.squish"), "-o", str(BASE / "c5" / "cpu_out")])
     out["identical"] = same_tree(src, BASE / "c5" / "gpu_out") and same_tree(src, BASE / "c5" / "cpu_out")
+    out["gpu_unpack_phases"] = phases([CLI, "unpack", str(BASE / "c5" / "ref.squish"), "-o", str(BASE / "c5" / "gpu_out2")])
+    out["gpu_unpack_second_run_s"] = run([CLI, "unpack", str(BASE / "c5" / "ref.squish"), "-o", str(BASE / "c5" / "gpu_out3")])
+    out["cpu_unpack_parallel_decode_s"] = run([REF, "-j", threads, "--parallel-decode", "unpack", str(BASE / "c5" / "ref.squish"), "-o", str(BASE / "c5" / "cpu_out2")]) if os.environ.get("SQ_REF_PD") else None
     out["gpu_unpack_gbs"] = nbytes / out["gpu_unpack_s"] / 1e9; out["cpu_unpack_gbs"] = nbytes / out["cpu_unpack_s"] / 1e9
     return out
 
