@@ -19,28 +19,32 @@
 
 struct sq_dec_scratch {
     uint8_t *lits;      // per resident warp: Z_BLOCK_MAX + 64
+    void *build;        // per resident warp: table-construction scratch (zd::Scratch, 2.3 KB; in HBM so that shared memory holds only
+                        // the decode tables and six CTAs fit an SM)
     uint32_t *counter;
     uint32_t warps;
 };
 
 namespace {
 constexpr uint32_t DEC_WARPS_PER_CTA = 4;
-struct WarpState { zd::Tables T; zd::Scratch S; };
+struct WarpState { zd::Tables T; };
 
-__global__ void __launch_bounds__(DEC_WARPS_PER_CTA * 32) zstd_decode_kernel(const uint8_t *__restrict__ comp, const sq_frame *__restrict__ frames,
+__global__ void __launch_bounds__(DEC_WARPS_PER_CTA * 32, 6) zstd_decode_kernel(const uint8_t *__restrict__ comp, const sq_frame *__restrict__ frames,
                                                                              uint32_t n, uint8_t *__restrict__ out, sq_frame_result *__restrict__ res,
-                                                                             uint8_t *__restrict__ lits_all, uint32_t *__restrict__ counter) {
+                                                                             uint8_t *__restrict__ lits_all, zd::Scratch *__restrict__ build_all,
+                                                                             uint32_t *__restrict__ counter) {
     extern __shared__ __align__(16) uint8_t smem[];
     const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     WarpState *ws = reinterpret_cast<WarpState *>(smem) + w;
     uint8_t *lits = lits_all + (size_t)(blockIdx.x * DEC_WARPS_PER_CTA + w) * (Z_BLOCK_MAX + 64);
+    zd::Scratch *S = build_all + (blockIdx.x * DEC_WARPS_PER_CTA + w);
     for (;;) {
         uint32_t i = 0;
         if (lane == 0) i = atomicAdd(counter, 1u);
         i = __shfl_sync(0xffffffffu, i, 0);
         if (i >= n) break;
         const sq_frame f = frames[i];
-        const int64_t r = zd::decode_payload(comp + f.src_off, f.src_len, out + f.dst_off, f.capacity, &ws->T, &ws->S, lits);
+        const int64_t r = zd::decode_payload(comp + f.src_off, f.src_len, out + f.dst_off, f.capacity, &ws->T, S, lits);
         __syncwarp();
         if (lane == 0) {
             sq_frame_result fr;
@@ -55,7 +59,7 @@ __global__ void __launch_bounds__(DEC_WARPS_PER_CTA * 32) zstd_decode_kernel(con
 void sq_dec_destroy(sq_ctx *ctx) {
     sq_dec_scratch *d = ctx->dec;
     if (!d) return;
-    cudaFree(d->lits); cudaFree(d->counter);
+    cudaFree(d->lits); cudaFree(d->build); cudaFree(d->counter);
     delete d;
     ctx->dec = nullptr;
 }
@@ -76,6 +80,7 @@ extern "C" int32_t sq_decode_device(sq_ctx *ctx, const void *d_comp, const sq_fr
         if (ctas_per_sm < 1) ctas_per_sm = 1;
         d->warps = (uint32_t)ctx->sm_count * (uint32_t)ctas_per_sm * DEC_WARPS_PER_CTA;
         SQ_CUDA(ctx, cudaMalloc(&d->lits, (size_t)d->warps * (Z_BLOCK_MAX + 64)));
+        SQ_CUDA(ctx, cudaMalloc(&d->build, (size_t)d->warps * sizeof(zd::Scratch)));
         SQ_CUDA(ctx, cudaMalloc(&d->counter, sizeof(uint32_t)));
     }
     sq_dec_scratch *d = ctx->dec;
@@ -85,7 +90,7 @@ extern "C" int32_t sq_decode_device(sq_ctx *ctx, const void *d_comp, const sq_fr
     const uint32_t need = (n + DEC_WARPS_PER_CTA - 1) / DEC_WARPS_PER_CTA;
     if (ctas > need) ctas = need;
     zstd_decode_kernel<<<ctas, DEC_WARPS_PER_CTA * 32, smem, st>>>((const uint8_t *)d_comp, d_frames, n, (uint8_t *)d_out, d_results, d->lits,
-                                                                   d->counter);
+                                                                   (zd::Scratch *)d->build, d->counter);
     SQ_LAUNCHED(ctx, 1);
     SQ_CUDA(ctx, cudaGetLastError());
     return SQ_OK;

@@ -464,10 +464,16 @@ extern "C" int32_t sq_archive_pack(sq_ctx *ctx, const char *input_dir, const cha
 // format emits a Frame_Content_Size), so the byte offset of every chunk in every file is known before anything is decoded: a
 // batch that comes back from the GPU is written with pwrite by the host threads while the next batch decodes, and host memory
 // holds two staging pairs instead of all unique data (the reference keeps everything: reader.rs:268).
-int32_t unpack_streaming(sq_ctx *ctx, Archive &a, std::vector<ManifestEntry> &man, uint64_t total, const std::vector<uint64_t> &size,
-                         const char *output_dir, int32_t threads, sq_summary *summary, double t0) {
-    double t_dev = 0;
-    int32_t rc = SQ_OK;
+struct UnpackJob {  // what every device of an unpack needs: where each record's bytes go, and the files, already created
+    struct Ref { uint32_t file; uint64_t off; };
+    std::vector<uint32_t> ref_start;
+    std::vector<Ref> refs;
+    std::vector<std::string> full;
+    uint64_t total_out = 0, total_comp = 0;
+};
+
+int32_t unpack_prepare(sq_ctx *ctx, Archive &a, std::vector<ManifestEntry> &man, const std::vector<uint64_t> &size, const char *output_dir,
+                       int32_t threads, UnpackJob *job) {
     const size_t nrec = a.records.size();
     struct Key { uint64_t a, b; bool operator==(const Key &o) const { return a == o.a && b == o.b; } };
     struct KeyHash { size_t operator()(const Key &k) const { return (size_t)(k.a ^ (k.b * 0x9E3779B97F4A7C15ULL)); } };
@@ -475,8 +481,7 @@ int32_t unpack_streaming(sq_ctx *ctx, Archive &a, std::vector<ManifestEntry> &ma
     map.reserve(nrec * 2);
     for (size_t k = 0; k < nrec; k++) map[{get64(a.records[k].digest), get64(a.records[k].digest + 8)}] = k;
     // where every record's bytes go: (file, offset) references in CSR form
-    struct Ref { uint32_t file; uint64_t off; };
-    std::vector<uint32_t> ref_start(nrec + 1, 0);
+    job->ref_start.assign(nrec + 1, 0);
     std::vector<size_t> chunk_rec;
     size_t total_refs = 0;
     for (auto &e : man) total_refs += e.chunk_count;
@@ -488,18 +493,18 @@ int32_t unpack_streaming(sq_ctx *ctx, Archive &a, std::vector<ManifestEntry> &ma
             if (it == map.end())  // reader.rs:397-401
                 return sq_set_error(ctx, SQ_ERR_MISSING_CHUNK, "%s `%.*s`", sq_strerror(SQ_ERR_MISSING_CHUNK), (int)e.path_len, (const char *)e.path);
             chunk_rec.push_back(it->second);
-            ref_start[it->second + 1]++;
+            job->ref_start[it->second + 1]++;
         }
     }
-    for (size_t k = 0; k < nrec; k++) ref_start[k + 1] += ref_start[k];
-    std::vector<Ref> refs(total_refs);
+    for (size_t k = 0; k < nrec; k++) job->ref_start[k + 1] += job->ref_start[k];
+    job->refs.resize(total_refs);
     {
-        std::vector<uint32_t> fill(ref_start.begin(), ref_start.end() - 1);
+        std::vector<uint32_t> fill(job->ref_start.begin(), job->ref_start.end() - 1);
         size_t j = 0;
         for (size_t fi = 0; fi < man.size(); fi++) {
             uint64_t off = 0;
             for (uint32_t c = 0; c < man[fi].chunk_count; c++, j++) {
-                refs[fill[chunk_rec[j]]++] = {(uint32_t)fi, off};
+                job->refs[fill[chunk_rec[j]]++] = {(uint32_t)fi, off};
                 off += size[chunk_rec[j]];
             }
         }
@@ -507,13 +512,13 @@ int32_t unpack_streaming(sq_ctx *ctx, Archive &a, std::vector<ManifestEntry> &ma
     // create_dir_all(parent) + File::create for every file (reader.rs:375-383); empty files are complete after this
     std::string outdir(output_dir);
     mkdir(outdir.c_str(), 0777);
-    std::vector<std::string> full(man.size());
+    job->full.resize(man.size());
     std::atomic<int32_t> err{0};
     std::atomic<size_t> err_idx{0};
     parallel_for(man.size(), threads, [&](size_t fi) {
         const ManifestEntry &e = man[fi];
-        full[fi] = outdir + "/" + std::string((const char *)e.path, e.path_len);
-        std::string &f = full[fi];
+        job->full[fi] = outdir + "/" + std::string((const char *)e.path, e.path_len);
+        std::string &f = job->full[fi];
         for (size_t p = outdir.size() + 1; p < f.size(); p++)
             if (f[p] == '/') { f[p] = 0; mkdir(f.c_str(), 0777); f[p] = '/'; }
         int fd = open(f.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0666);
@@ -524,9 +529,19 @@ int32_t unpack_streaming(sq_ctx *ctx, Archive &a, std::vector<ManifestEntry> &ma
         const ManifestEntry &e = man[err_idx];
         return sq_set_error(ctx, err, "%s `%.*s`", sq_strerror(err), (int)e.path_len, (const char *)e.path);
     }
-    SQ_T("files created");
+    for (size_t k = 0; k < nrec; k++) { job->total_out += (size[k] + 15) & ~15ull; job->total_comp += (a.records[k].comp + 15) & ~15ull; }
+    return SQ_OK;
+}
+
+// decodes records [lo, hi) on ctx's device and writes their bytes into the files (one call per device of a multi-GPU unpack)
+int32_t unpack_range(sq_ctx *ctx, Archive &a, std::vector<ManifestEntry> &man, const std::vector<uint64_t> &size, const UnpackJob &job,
+                     size_t lo, size_t hi, int32_t threads, double *t_dev_out) {
+    double t_dev = 0;
+    int32_t rc = SQ_OK;
     uint64_t total_out = 0, total_comp = 0;
-    for (size_t k = 0; k < nrec; k++) { total_out += (size[k] + 15) & ~15ull; total_comp += (a.records[k].comp + 15) & ~15ull; }
+    for (size_t k = lo; k < hi; k++) { total_out += (size[k] + 15) & ~15ull; total_comp += (a.records[k].comp + 15) & ~15ull; }
+    std::atomic<int32_t> err{0};
+    std::atomic<size_t> err_idx{0};
     // batches: at most 1 GiB of output per slot, and at least four batches for jobs above 256 MiB so that upload, decode,
     // download and file writes overlap
     const uint64_t batch_out = std::min<uint64_t>(1024ull << 20, std::max<uint64_t>(total_out > (256ull << 20) ? total_out / 4 : total_out, 1u << 20)),
@@ -559,13 +574,13 @@ int32_t unpack_streaming(sq_ctx *ctx, Archive &a, std::vector<ManifestEntry> &ma
         parallel_for(b.frames.size(), threads, [&](size_t k) {
             const size_t ri = b.first + k;
             const uint8_t *src = (const uint8_t *)b.out.p + b.frames[k].dst_off;
-            for (uint32_t j = ref_start[ri]; j < ref_start[ri + 1]; j++) {
-                int fd = open(full[refs[j].file].c_str(), O_WRONLY);
-                if (fd < 0) { err = SQ_ERR_CREATE_FILE; err_idx = refs[j].file; return; }
+            for (uint32_t j = job.ref_start[ri]; j < job.ref_start[ri + 1]; j++) {
+                int fd = open(job.full[job.refs[j].file].c_str(), O_WRONLY);
+                if (fd < 0) { err = SQ_ERR_CREATE_FILE; err_idx = job.refs[j].file; return; }
                 size_t w = 0;
                 while (w < size[ri]) {
-                    ssize_t n = pwrite(fd, src + w, size[ri] - w, (off_t)(refs[j].off + w));
-                    if (n <= 0) { err = SQ_ERR_IO; err_idx = refs[j].file; break; }
+                    ssize_t n = pwrite(fd, src + w, size[ri] - w, (off_t)(job.refs[j].off + w));
+                    if (n <= 0) { err = SQ_ERR_IO; err_idx = job.refs[j].file; break; }
                     w += (size_t)n;
                 }
                 close(fd);
@@ -573,15 +588,15 @@ int32_t unpack_streaming(sq_ctx *ctx, Archive &a, std::vector<ManifestEntry> &ma
         });
         return SQ_OK;
     };
-    size_t i = 0;
+    size_t i = lo;
     int cur = 0;
-    while (i < nrec && !rc && !err) {
+    while (i < hi && !rc && !err) {
         UnpackBatch &b = ub[cur];
         if (b.live && (rc = finish(b))) break;  // the slot's previous batch must be on disk before its buffers are reused
         b.frames.clear();
         uint64_t so = 0, dof = 0;
         b.first = i;
-        while (i < nrec && b.frames.size() < ctx->max_batch) {
+        while (i < hi && b.frames.size() < ctx->max_batch) {
             const Record &r = a.records[i];
             uint64_t sneed = (r.comp + 15) & ~15ull, dneed = (size[i] + 15) & ~15ull;
             if (!b.frames.empty() && (so + sneed > batch_in || dof + dneed > batch_out)) break;
@@ -606,20 +621,36 @@ int32_t unpack_streaming(sq_ctx *ctx, Archive &a, std::vector<ManifestEntry> &ma
         else rc = finish(b);
     }
     release();
-    SQ_T("all chunks decoded and written");
+    if (t_dev_out) *t_dev_out = t_dev;
     if (rc) return rc;
     if (err) {
         const ManifestEntry &e = man[err_idx];
         return sq_set_error(ctx, err, "%s `%.*s`", sq_strerror(err), (int)e.path_len, (const char *)e.path);
     }
-    if (summary) {
-        memset(summary, 0, sizeof *summary);
-        summary->unique_chunks = a.nchunks; summary->total_original_size = total; summary->archive_size = a.size;
-        summary->timestamp = a.timestamp; summary->file_count = a.file_count;
-        summary->compression_ratio = total ? (double)a.size / (double)total * 100.0 : 0.0;
-        snprintf(summary->version, sizeof summary->version, "%s", a.version);
-        summary->seconds_total = now_s() - t0; summary->seconds_device = t_dev;
-    }
+    return SQ_OK;
+}
+
+void fill_summary(sq_summary *summary, const Archive &a, uint64_t total, double t0, double t_dev) {
+    if (!summary) return;
+    memset(summary, 0, sizeof *summary);
+    summary->unique_chunks = a.nchunks; summary->total_original_size = total; summary->archive_size = a.size;
+    summary->timestamp = a.timestamp; summary->file_count = a.file_count;
+    summary->compression_ratio = total ? (double)a.size / (double)total * 100.0 : 0.0;
+    snprintf(summary->version, sizeof summary->version, "%s", a.version);
+    summary->seconds_total = now_s() - t0; summary->seconds_device = t_dev;
+}
+
+int32_t unpack_streaming(sq_ctx *ctx, Archive &a, std::vector<ManifestEntry> &man, uint64_t total, const std::vector<uint64_t> &size,
+                         const char *output_dir, int32_t threads, sq_summary *summary, double t0) {
+    UnpackJob job;
+    int32_t rc = unpack_prepare(ctx, a, man, size, output_dir, threads, &job);
+    if (rc) return rc;
+    SQ_T("files created");
+    double t_dev = 0;
+    rc = unpack_range(ctx, a, man, size, job, 0, a.records.size(), threads, &t_dev);
+    SQ_T("all chunks decoded and written");
+    if (rc) return rc;
+    fill_summary(summary, a, total, t0, t_dev);
     return SQ_OK;
 }
 
