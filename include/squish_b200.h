@@ -255,6 +255,22 @@ int32_t sq_archive_pack(sq_ctx *ctx, const char *input_dir, const char *output_p
                         sq_pack_report *report);
 int32_t sq_archive_unpack(sq_ctx *ctx, const char *archive_path, const char *output_dir, int32_t threads,
                           sq_summary *summary);
+/* The same over several GPUs of one box: one context per device (sq_create with cfg.device = ordinal), all owned by the
+ * calling process; ctxs[0] reports errors.  n_ctx == 1 is exactly the single-device call.
+ *  - unpack: chunk records are independent (reader.rs:276-305), so they are cut into contiguous ranges of equal bytes, one
+ *    range per device, no exchange between devices.
+ *  - pack: the chunk stream is dealt to the devices batch by batch in file order; digests of one round of batches meet in ONE
+ *    dedup index (on ctxs[0]'s device, digests travel device to device), so "first occurrence wins" (chunk.rs:83-99) holds
+ *    across devices and the archive has the records a single device would write, in the same order. */
+/* The building block of the multi-device pack: from now on `ctx` decides "new or duplicate" in `owner`'s index (the owner shares
+ * with itself).  K1 runs where the batch is; 16 digest bytes per chunk travel to the owner's device, K2 runs there on one stream
+ * in submission order, one verdict byte per chunk travels back; K3 runs where the batch is.  One host thread submits the batches
+ * of all sharing contexts in chunk order. */
+int32_t sq_share_dedup(sq_ctx *ctx, sq_ctx *owner);
+int32_t sq_archive_pack_multi(sq_ctx **ctxs, uint32_t n_ctx, const char *input_dir, const char *output_path,
+                              int32_t threads, sq_pack_report *report);
+int32_t sq_archive_unpack_multi(sq_ctx **ctxs, uint32_t n_ctx, const char *archive_path, const char *output_dir,
+                                int32_t threads, sq_summary *summary);
 /* list needs no device: ctx may be NULL.  *listing (optional) receives a malloc'd
  * "size path\n" text to release with sq_free. */
 int32_t sq_archive_list(const char *archive_path, sq_summary *summary, char **listing);

@@ -48,16 +48,22 @@ def walk_dir(root) -> List[Path]:
 
 
 class ArchiveWriter:
-    def __init__(self, input_dir, output_path, ctx: Optional[Context] = None, threads: int = 25):
+    def __init__(self, input_dir, output_path, ctx: Optional[Context] = None, threads: int = 25, ctxs: Optional[List[Context]] = None):
+        """`ctxs`: one Context per GPU of this box (sq_archive_pack_multi); the first one owns the dedup index."""
         self.input_dir, self.output_path, self.threads = str(input_dir), str(output_path), threads
-        self.ctx = ctx or Context()
+        self.ctxs = list(ctxs) if ctxs else [ctx or Context()]
+        self.ctx = self.ctxs[0]
         self.report = None
 
     def pack(self, files=None) -> int:
         """Packs the directory tree; returns the archive size like the reference.  `files` is accepted
         for signature parity; the native packer walks input_dir itself (same walk rule)."""
         rep = L.SqPackReport()
-        self.ctx.check(self.ctx.lib.sq_archive_pack(self.ctx.h, self.input_dir.encode(), self.output_path.encode(), self.threads, C.byref(rep)))
+        if len(self.ctxs) > 1:
+            hs = (C.c_void_p * len(self.ctxs))(*[c.h for c in self.ctxs])
+            self.ctx.check(self.ctx.lib.sq_archive_pack_multi(hs, len(self.ctxs), self.input_dir.encode(), self.output_path.encode(), self.threads, C.byref(rep)))
+        else:
+            self.ctx.check(self.ctx.lib.sq_archive_pack(self.ctx.h, self.input_dir.encode(), self.output_path.encode(), self.threads, C.byref(rep)))
         self.report = rep
         return rep.archive_size
 
@@ -86,8 +92,13 @@ class ArchiveReader:
     def get_summary(self) -> ArchiveSummary:
         return self._summary
 
-    def unpack(self, output_dir) -> None:
-        ctx = self.ctx or Context()
+    def unpack(self, output_dir, ctxs: Optional[List[Context]] = None) -> None:
+        """`ctxs`: one Context per GPU of this box (sq_archive_unpack_multi: records split into contiguous ranges)."""
+        ctx = ctxs[0] if ctxs else (self.ctx or Context())
         s = L.SqSummary()
-        ctx.check(ctx.lib.sq_archive_unpack(ctx.h, self.path.encode(), str(output_dir).encode(), self.threads, C.byref(s)))
+        if ctxs and len(ctxs) > 1:
+            hs = (C.c_void_p * len(ctxs))(*[c.h for c in ctxs])
+            ctx.check(ctx.lib.sq_archive_unpack_multi(hs, len(ctxs), self.path.encode(), str(output_dir).encode(), self.threads, C.byref(s)))
+        else:
+            ctx.check(ctx.lib.sq_archive_unpack(ctx.h, self.path.encode(), str(output_dir).encode(), self.threads, C.byref(s)))
         self.unpack_summary = s

@@ -154,6 +154,13 @@ extern "C" void sq_destroy(sq_ctx *ctx) {
         if (ctx->slot_stream[i]) cudaStreamDestroy(ctx->slot_stream[i]);
         if (ctx->dedup_done[i]) cudaEventDestroy(ctx->dedup_done[i]);
     }
+    for (int i = 0; i < 2; i++) {
+        if (ctx->digest_done[i]) cudaEventDestroy(ctx->digest_done[i]);
+        if (ctx->verdict_done[i]) cudaEventDestroy(ctx->verdict_done[i]);
+    }
+    if (ctx->dedup_stream) cudaStreamDestroy(ctx->dedup_stream);
+    if (ctx->d_peer_digests) cudaFree(ctx->d_peer_digests);
+    if (ctx->d_peer_verdict) cudaFree(ctx->d_peer_verdict);
     if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
@@ -168,7 +175,7 @@ extern "C" int32_t sq_synchronize(sq_ctx *ctx, void *stream) {
 
 extern "C" int32_t sq_host_alloc(sq_ctx *ctx, size_t bytes, void **out) {
     if (!ctx || !out) return SQ_ERR_INVALID_ARG;
-    SQ_CUDA(ctx, cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+    SQ_CUDA(ctx, cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable));
     return SQ_OK;
 }
 extern "C" int32_t sq_host_free(sq_ctx *ctx, void *p) {

@@ -63,6 +63,11 @@ struct sq_ctx {
     int enc_set_bound[2];
     cudaEvent_t enc_set_done[2];     // recorded after each encode on the set; a new stream taking the set over waits on it
     int enc_set_lru;
+    // one dedup index for several devices (sq_share_dedup): K2 of every batch runs on the owner's device, in submission order
+    sq_ctx *dedup_owner;           // nullptr or this: the context's own index
+    cudaStream_t dedup_stream;     // owner side: the one stream all shared inserts go through
+    void *d_peer_digests, *d_peer_verdict; size_t peer_digests_cap, peer_verdict_cap;  // owner side: one batch of digests / verdicts
+    cudaEvent_t digest_done[2], verdict_done[2];  // per pipeline slot; verdict_done lives on the owner's device
 };
 
 int32_t sq_set_error(sq_ctx *ctx, int32_t code, const char *fmt, ...);

@@ -49,7 +49,30 @@ static int32_t pack_device_impl(sq_ctx *ctx, const void *d_data, const sq_span *
                                 cudaEvent_t after_dedup = nullptr) {
     int32_t rc;
     if ((rc = sq_digest_device(ctx, d_data, d_spans, n, m.digests, st))) return rc;
-    if ((rc = sq_dedup_insert_device(ctx, m.digests, nullptr, gidx_base, n, m.is_new, st))) return rc;
+    sq_ctx *own = ctx->dedup_owner;
+    if (own && ctx->digest_done[set]) {
+        // Shared index (several devices, one process): the digests travel to the owner's device, the insert runs there on the one
+        // stream every shared insert goes through -- submission order is chunk order, so "lowest chunk index wins" is decided
+        // exactly as on one device -- and the verdict bytes travel back.  16 + 1 bytes per chunk over NVLink.
+        SQ_CUDA(ctx, cudaEventRecord(ctx->digest_done[set], st));
+        SQ_CUDA(ctx, cudaSetDevice(own->device));
+        cudaStream_t ds = own->dedup_stream;
+        rc = sq_ensure(own, &own->d_peer_digests, &own->peer_digests_cap, (size_t)n * 16);
+        if (!rc) rc = sq_ensure(own, &own->d_peer_verdict, &own->peer_verdict_cap, n);
+        cudaError_t ce = cudaSuccess;
+        if (!rc) {
+            if ((ce = cudaStreamWaitEvent(ds, ctx->digest_done[set], 0)) == cudaSuccess &&
+                (ce = cudaMemcpyPeerAsync(own->d_peer_digests, own->device, m.digests, ctx->device, (size_t)n * 16, ds)) == cudaSuccess) {
+                rc = sq_dedup_insert_device(own, own->d_peer_digests, nullptr, gidx_base, n, (uint8_t *)own->d_peer_verdict, ds);
+                if (!rc && (ce = cudaMemcpyPeerAsync(m.is_new, ctx->device, own->d_peer_verdict, own->device, n, ds)) == cudaSuccess)
+                    ce = cudaEventRecord(ctx->verdict_done[set], ds);
+            }
+        }
+        cudaSetDevice(ctx->device);
+        if (rc) { if (own != ctx) snprintf(ctx->err, sizeof ctx->err, "%s", own->err); return rc; }
+        if (ce != cudaSuccess) return sq_set_error(ctx, SQ_ERR_CUDA, "shared dedup insert failed: %s", cudaGetErrorString(ce));
+        SQ_CUDA(ctx, cudaStreamWaitEvent(st, ctx->verdict_done[set], 0));
+    } else if ((rc = sq_dedup_insert_device(ctx, m.digests, nullptr, gidx_base, n, m.is_new, st))) return rc;
     if (after_dedup) SQ_CUDA(ctx, cudaEventRecord(after_dedup, st));
     if ((rc = sq_encode_device_set(ctx, set, d_data, d_spans, m.is_new, n, d_out, out_capacity, m.frame_off, m.frame_len, m.total, st))) return rc;
     pack_results_kernel<<<(n + 127) / 128, 128, 0, st>>>((const uint4 *)m.digests, m.is_new, m.frame_off, m.frame_len, n, d_results);
@@ -73,6 +96,22 @@ extern "C" int32_t sq_pack_device(sq_ctx *ctx, const void *d_data, const sq_span
         SQ_CUDA(ctx, cudaStreamSynchronize(st));
         if ((rc = sq_encode_status(ctx))) return rc;
     }
+    return SQ_OK;
+}
+
+// Several devices, one index: after this call every pack of `ctx` (sq_pack_submit / sq_pack_device) decides "new or duplicate" in
+// `owner`'s index.  The owner shares with itself so that all contexts go through the same ordered stream.  One host thread must
+// submit the batches of all sharing contexts, in chunk order.
+extern "C" int32_t sq_share_dedup(sq_ctx *ctx, sq_ctx *owner) {
+    if (!ctx || !owner) return SQ_ERR_INVALID_ARG;
+    SQ_CUDA(owner, cudaSetDevice(owner->device));
+    if (!owner->dedup_stream) SQ_CUDA(owner, cudaStreamCreateWithFlags(&owner->dedup_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) if (!ctx->verdict_done[i]) SQ_CUDA(owner, cudaEventCreateWithFlags(&ctx->verdict_done[i], cudaEventDisableTiming));
+    if (owner != ctx) { cudaDeviceEnablePeerAccess(ctx->device, 0); cudaGetLastError(); }
+    SQ_CUDA(ctx, cudaSetDevice(ctx->device));
+    for (int i = 0; i < 2; i++) if (!ctx->digest_done[i]) SQ_CUDA(ctx, cudaEventCreateWithFlags(&ctx->digest_done[i], cudaEventDisableTiming));
+    if (owner != ctx) { cudaDeviceEnablePeerAccess(owner->device, 0); cudaGetLastError(); }
+    ctx->dedup_owner = owner;
     return SQ_OK;
 }
 

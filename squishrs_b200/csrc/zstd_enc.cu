@@ -33,8 +33,9 @@ struct sq_enc_scratch {
     uint8_t *lits;           // per entropy warp: gathered literals
     uint32_t *sbits;         // per entropy warp: FSE state-transition records + packed symbol codes, 4 x SEQ_PER_BLOCK
     uint32_t ent_warps;
-    uint32_t *tab2, *head2;  // round-2 search: one table (2 MB) + ring heads per resident CLUSTER
-    uint32_t lz2_clusters; int lz2_cfg;
+    uint32_t *list;          // [lz_sub * lz2::LIST_STRIDE] the chunks' sorted row lists (index_kernel -> search_kernel)
+    uint32_t *span_start;    // [lz_sub + 1] search spans of a sub-batch, exclusive prefix
+    uint32_t lz_sub, search_ctas;
     cudaEvent_t tev[5];      // SQ_FLAG_STAGE_TIMING: before search / after search / after chase / after entropy / after emit
     int tev_valid;
     uint32_t cap_chunks;
@@ -177,50 +178,11 @@ __global__ void __launch_bounds__(256) enc_emit_kernel(const uint8_t *__restrict
 }  // namespace
 
 
-// ---- round-2 search kernel: launch configurations (cluster size, threads, positions per CTA and step, CTAs per SM) ----
+// ---- search: sub-batches of at most LZ_SUB chunks go through span_plan -> index -> search; the list scratch (8 MB per chunk of a
+// sub-batch) is what bounds the sub-batch ----
 namespace {
-struct Lz2Cfg { int g, threads, sub, minb; };
-// cfg 0 ships; the others are the measured alternatives (SQ_LZ2_CFG): larger steps are ~10 % faster and cost ratio
-constexpr Lz2Cfg LZ2_CFGS[] = {{8, 256, 256, 2}, {8, 256, 512, 2}, {4, 256, 256, 2}, {1, 256, 256, 2}};
-constexpr int LZ2_NCFG = sizeof(LZ2_CFGS) / sizeof(LZ2_CFGS[0]);
-
-template <int G, int T, int SUB, int MINB>
-cudaError_t lz2_launch(int clusters_or_query, int *max_clusters, cudaStream_t st, const uint8_t *data, const sq_span *spans, const uint8_t *select,
-                       uint32_t n, uint32_t *tab, uint32_t *head, uint32_t *rec, uint32_t *counter) {
-    static const uint32_t dbg = getenv("SQ_LZ2_DBG") ? (uint32_t)atoi(getenv("SQ_LZ2_DBG")) : 0u;
-    auto kern = lz2::search_kernel<G, T, SUB, MINB>;
-    const size_t smem = lz2::SearchSmem<T, SUB>::BYTES;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof cfg);
-    cfg.blockDim = dim3(T, 1, 1);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = G; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    if (max_clusters) {  // query: how many clusters of this shape are resident at once
-        cfg.gridDim = dim3(G * 1024, 1, 1);
-        return cudaOccupancyMaxActiveClusters(max_clusters, kern, &cfg);
-    }
-    cfg.gridDim = dim3((unsigned)(clusters_or_query * G), 1, 1);
-    return cudaLaunchKernelEx(&cfg, kern, data, spans, select, n, tab, head, rec, counter, dbg);
-}
-
-cudaError_t lz2_dispatch(int c, int clusters, int *max_clusters, cudaStream_t st, const uint8_t *data, const sq_span *spans, const uint8_t *select,
-                         uint32_t n, uint32_t *tab, uint32_t *head, uint32_t *rec, uint32_t *counter) {
-#define LZ2_CASE(i)                                                                                                                     \
-    case i: return lz2_launch<LZ2_CFGS[i].g, LZ2_CFGS[i].threads, LZ2_CFGS[i].sub, LZ2_CFGS[i].minb>(clusters, max_clusters, st, data, spans, select, n, tab, \
-                                                                                                   head, rec, counter);
-    switch (c) {
-        LZ2_CASE(0) LZ2_CASE(1) LZ2_CASE(2) LZ2_CASE(3)
-    }
-#undef LZ2_CASE
-    return cudaErrorInvalidValue;
-}
+constexpr int LZ_SEARCH_THREADS = 256, LZ_SEARCH_MINB = 3, LZ_INDEX_THREADS = 1024;
+constexpr uint32_t LZ_SUB_MAX = 512;
 }  // namespace
 
 static int32_t enc_scratch(sq_ctx *ctx, uint32_t n, int set) {
@@ -229,25 +191,22 @@ static int32_t enc_scratch(sq_ctx *ctx, uint32_t n, int set) {
         memset(ctx->enc_sets[set], 0, sizeof(sq_enc_scratch));
     }
     sq_enc_scratch *e = ctx->enc_sets[set];
-    if (!e->tab2) {  // per-resident-worker state, sized once from the SM count
+    if (!e->lits) {  // per-resident-worker state, sized once from the SM count
         {   // entropy stage: one warp per block, 4 warps per CTA; shared memory (42.8 KB per CTA) allows 5 CTAs per SM
             const char *ov = getenv("SQ_ENT_WARPS_PER_SM");
             e->ent_warps = (uint32_t)ctx->sm_count * (ov && atoi(ov) > 0 ? (uint32_t)atoi(ov) : 20u);
             SQ_CUDA(ctx, cudaFuncSetAttribute(lz::entropy_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         }
-        {   // round-2 search: tables per resident cluster
-            static const int env_cfg = getenv("SQ_LZ2_CFG") ? atoi(getenv("SQ_LZ2_CFG")) : 0;
-            e->lz2_cfg = env_cfg >= 0 && env_cfg < LZ2_NCFG ? env_cfg : 0;
-            int maxc = 0;
-            SQ_CUDA(ctx, lz2_dispatch(e->lz2_cfg, 0, &maxc, 0, nullptr, nullptr, nullptr, 0, nullptr, nullptr, nullptr, nullptr));
-            if (maxc < 1) return sq_set_error(ctx, SQ_ERR_CUDA, "search kernel: no cluster of %d CTAs fits this device", LZ2_CFGS[e->lz2_cfg].g);
-            if (const char *cv = getenv("SQ_LZ2_CLUSTERS")) if (atoi(cv) > 0 && atoi(cv) < maxc) maxc = atoi(cv);
-            e->lz2_clusters = (uint32_t)maxc;
-            if (getenv("SQ_TIMING")) fprintf(stderr, "[sq] search kernel cfg %d: cluster %d x %d threads, %d positions per CTA and step, %d clusters resident\n", e->lz2_cfg,
-                                             LZ2_CFGS[e->lz2_cfg].g, LZ2_CFGS[e->lz2_cfg].threads, LZ2_CFGS[e->lz2_cfg].sub, maxc);
-            SQ_CUDA(ctx, cudaMalloc(&e->tab2, (size_t)maxc * lz2::ROWS * lz2::ROW_K * sizeof(uint32_t)));
-            SQ_CUDA(ctx, cudaMalloc(&e->head2, (size_t)maxc * lz2::ROWS * sizeof(uint32_t)));
-            SQ_CUDA(ctx, cudaMemset(e->head2, 0, (size_t)maxc * lz2::ROWS * sizeof(uint32_t)));
+        {   // search: all warps are interchangeable, the grid is what is resident
+            auto kern = lz2::search_kernel<LZ_SEARCH_THREADS, LZ_SEARCH_MINB>;
+            const int smem = (int)(lz2::SearchSmem::PER_WARP * (LZ_SEARCH_THREADS / 32));
+            SQ_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            SQ_CUDA(ctx, cudaFuncSetAttribute(lz2::index_kernel<LZ_INDEX_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(lz2::ROWS * sizeof(uint32_t))));
+            int per_sm = 0;
+            SQ_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, LZ_SEARCH_THREADS, smem));
+            if (per_sm < 1) return sq_set_error(ctx, SQ_ERR_CUDA, "search kernel does not fit this device");
+            e->search_ctas = (uint32_t)(per_sm * ctx->sm_count);
+            if (getenv("SQ_TIMING")) fprintf(stderr, "[sq] search kernel: %d threads, %d CTAs per SM, %d B of shared memory per CTA\n", LZ_SEARCH_THREADS, per_sm, smem);
         }
         SQ_CUDA(ctx, cudaMalloc(&e->lits, (size_t)e->ent_warps * (Z_BLOCK_MAX + 64)));
         SQ_CUDA(ctx, cudaMalloc(&e->sbits, (size_t)e->ent_warps * lz::SBITS_STRIDE * sizeof(uint32_t)));
@@ -257,6 +216,7 @@ static int32_t enc_scratch(sq_ctx *ctx, uint32_t n, int set) {
     if (e->cap_chunks < n) {
         SQ_CUDA(ctx, cudaDeviceSynchronize());
         cudaFree(e->blocks); cudaFree(e->frame_len); cudaFree(e->bodies); cudaFree(e->seqs); cudaFree(e->meta); cudaFree(e->rec);
+        cudaFree(e->list); cudaFree(e->span_start); e->list = nullptr; e->span_start = nullptr;
         e->rec = nullptr; e->blocks = nullptr; e->frame_len = nullptr; e->bodies = nullptr; e->seqs = nullptr; e->meta = nullptr; e->cap_chunks = 0;
         uint32_t cap = n;
         SQ_CUDA(ctx, cudaMalloc(&e->blocks, (size_t)cap * SQ_MAX_BLOCKS * sizeof(sq_block_info)));
@@ -265,6 +225,9 @@ static int32_t enc_scratch(sq_ctx *ctx, uint32_t n, int set) {
         SQ_CUDA(ctx, cudaMalloc(&e->seqs, (size_t)cap * lz::MAX_SEQ_PER_CHUNK * sizeof(zc::Seq)));
         SQ_CUDA(ctx, cudaMalloc(&e->meta, (size_t)cap * SQ_MAX_BLOCKS * sizeof(lz::BlockMeta)));
         SQ_CUDA(ctx, cudaMalloc(&e->rec, (size_t)cap * lz::REC_PER_CHUNK * sizeof(uint32_t)));
+        e->lz_sub = cap < LZ_SUB_MAX ? cap : LZ_SUB_MAX;
+        SQ_CUDA(ctx, cudaMalloc(&e->list, (size_t)e->lz_sub * lz2::LIST_STRIDE * sizeof(uint32_t)));
+        SQ_CUDA(ctx, cudaMalloc(&e->span_start, (size_t)(e->lz_sub + 1) * sizeof(uint32_t)));
         e->cap_chunks = cap;
     }
     return SQ_OK;
@@ -276,7 +239,7 @@ void sq_enc_destroy(sq_ctx *ctx) {
         if (!e) continue;
         cudaFree(e->blocks); cudaFree(e->frame_len); cudaFree(e->bodies); cudaFree(e->status); cudaFree(e->seqs); cudaFree(e->meta); cudaFree(e->rec);
         for (int i = 0; i < 5; i++) if (e->tev[i]) cudaEventDestroy(e->tev[i]);
-        cudaFree(e->tab2); cudaFree(e->head2); cudaFree(e->lits); cudaFree(e->sbits);
+        cudaFree(e->list); cudaFree(e->span_start); cudaFree(e->lits); cudaFree(e->sbits);
         delete e;
         ctx->enc_sets[set] = nullptr;
         if (ctx->enc_set_done[set]) cudaEventDestroy(ctx->enc_set_done[set]);
@@ -327,9 +290,19 @@ int32_t sq_encode_device_set(sq_ctx *ctx, int set, const void *d_data, const sq_
         const bool timing = (ctx->flags & SQ_FLAG_STAGE_TIMING) != 0;
         if (timing && !e->tev[0]) for (int i = 0; i < 5; i++) SQ_CUDA(ctx, cudaEventCreate(&e->tev[i]));
         if (timing) SQ_CUDA(ctx, cudaEventRecord(e->tev[0], st));
-        // search: one cluster per chunk in flight (tables L2-resident), then the parse (lazy choice + repeat offsets) per block
-        const uint32_t clusters = n < e->lz2_clusters ? n : e->lz2_clusters;
-        SQ_CUDA(ctx, lz2_dispatch(e->lz2_cfg, (int)clusters, nullptr, st, (const uint8_t *)d_data, d_spans, d_select, n, e->tab2, e->head2, e->rec, e->status + 1));
+        // search: per sub-batch, the chunks' sorted row lists (one CTA per chunk), then every warp of the grid on any 256 positions
+        static const uint32_t dbg = getenv("SQ_LZ2_DBG") ? (uint32_t)atoi(getenv("SQ_LZ2_DBG")) : 0u;
+        const int search_smem = (int)(lz2::SearchSmem::PER_WARP * (LZ_SEARCH_THREADS / 32));
+        for (uint32_t first = 0; first < n; first += e->lz_sub) {
+            const uint32_t count = n - first < e->lz_sub ? n - first : e->lz_sub;
+            lz2::span_plan_kernel<<<1, 1024, 0, st>>>(d_spans, d_select, first, count, e->span_start, e->status + 1);
+            const uint32_t ictas = count < (uint32_t)ctx->sm_count ? count : (uint32_t)ctx->sm_count;
+            lz2::index_kernel<LZ_INDEX_THREADS><<<ictas, LZ_INDEX_THREADS, lz2::ROWS * sizeof(uint32_t), st>>>((const uint8_t *)d_data, d_spans, d_select, first, count,
+                                                                                                             e->list, e->rec);
+            lz2::search_kernel<LZ_SEARCH_THREADS, LZ_SEARCH_MINB><<<e->search_ctas, LZ_SEARCH_THREADS, search_smem, st>>>((const uint8_t *)d_data, d_spans, first, count,
+                                                                                                                        e->span_start, e->list, e->rec, e->status + 1, dbg);
+            SQ_LAUNCHED(ctx, 3);
+        }
         if (timing) SQ_CUDA(ctx, cudaEventRecord(e->tev[1], st));
         static const bool chase_thread = getenv("SQ_LZ2_DBG") && (atoi(getenv("SQ_LZ2_DBG")) & 4);  // debugging reference: the scalar parse, one thread per block
         if (chase_thread) lz2::chase_thread_kernel<<<(n * SQ_MAX_BLOCKS + 63) / 64, 64, 0, st>>>((const uint8_t *)d_data, d_spans, d_select, n, e->rec, e->seqs, e->meta);
@@ -345,7 +318,7 @@ int32_t sq_encode_device_set(sq_ctx *ctx, int set, const void *d_data, const sq_
     enc_emit_kernel<<<dim3(SQ_MAX_BLOCKS, n), 256, 0, st>>>((const uint8_t *)d_data, d_spans, n, e->blocks, e->bodies, d_frame_off, d_frame_len,
                                                             (uint8_t *)d_out, e->status);
     if (ctx->flags & SQ_FLAG_STAGE_TIMING) { SQ_CUDA(ctx, cudaEventRecord(e->tev[4], st)); e->tev_valid = 1; }
-    SQ_LAUNCHED(ctx, 7);
+    SQ_LAUNCHED(ctx, 6);
     SQ_CUDA(ctx, cudaGetLastError());
     SQ_CUDA(ctx, cudaEventRecord(ctx->enc_set_done[set], st));
     return SQ_OK;

@@ -1,48 +1,55 @@
-// K3 stage "compress", round-2 design: match search by a thread-block CLUSTER per chunk (lz2::search_kernel) and a parse that
-// knows about repeat offsets (lz2::chase_kernel).  The entropy stage is lz::entropy_kernel, unchanged.
+// K3 stage "compress": match search (lz2::index_kernel + lz2::search_kernel) and a parse that knows about repeat offsets
+// (lz2::chase_kernel).  The entropy stage is lz::entropy_kernel.
 //
-// Why a cluster.  The round-1 search kept one 2 MB hash table per resident CTA (444 of them, 0.94 GB): every row read, ring
-// insert and candidate fetch was a random DRAM sector (142 B of DRAM traffic per input byte).  Here G CTAs (a cluster, one CTA
-// per SM) work on ONE chunk, so only <= 18 chunks are in flight and their tables (2 MB each), ring heads and input (2 MiB
-// each) stay resident in the 126 MB L2.  The CTAs of a cluster take interleaved sub-tiles of SUB positions; one hardware
-// cluster barrier per step orders "all inserts of step s" before "all searches of step s".
+// A GPU has the whole chunk before it starts, so the match finder does not have to be the incremental "insert, then search"
+// structure of a streaming encoder.  The search is split into two kernels with no synchronisation inside either:
 //
-// Table.  2^14 rows x 32 ring entries, keyed by a hash of 5 bytes.  entry = position | ptag << 21 | xtag << 26 where ptag = 5
-// more bits of the row hash and xtag = a 6-bit hash of bytes 5..7.  One xor with the searcher's own tag word classifies an
-// entry without touching the candidate's bytes:
+//   index_kernel   one CTA per chunk.  Every position is hashed (5 bytes; 4 in chunks <= 128 KiB) into one of 2^14 rows; a
+//                  counting sort in shared memory (histogram, prefix sum, scatter in position order) writes the chunk's
+//                  LIST: the entries of row 0 in position order, then row 1, ...  entry = position | ptag << 21 | xtag << 26
+//                  (ptag = 5 more bits of the row hash, xtag = a 6-bit hash of bytes 5..7).  Every position also gets the
+//                  end E of its window in the list: its row's fill level after the 1024-position tile the position lies in
+//                  (stored in the record array, which the search overwrites with its result).
+//   search_kernel  any warp can take any 256 positions of any chunk: the candidates of position p are the 32 list entries in
+//                  front of E(p), i.e. the 32 most recent positions of the same row up to the end of p's tile -- what a
+//                  32-entry ring per row would hold when a sequential encoder reaches p (plus at most a tile of lookahead),
+//                  without the ring, its atomics, its clearing, or any ordering between positions.
+//
+// History.  Round 1 kept one 2 MB table per resident CTA in HBM (142 B of DRAM traffic per input byte).  The first round-2
+// version put a thread-block cluster on each chunk with an L2-resident ring table and a cluster barrier every 2048 positions:
+// 14 B of DRAM per byte, but 43 % of all warp stalls sat on that barrier (each warp had ONE group of 32 positions per step, so
+// every step ran at the pace of the slowest of 64 warps), and positions inserted ahead of the searcher took ring slots.  The
+// list removes both: no barrier, and a window holds at most one tile (1024 positions) of later entries instead of 2048+.
+//
+// One xor with the searcher's own tag word classifies an entry without touching the candidate's bytes:
 //     long   all 11 tag bits agree  -> the candidate very likely shares >= 8 bytes           (x = e ^ T < p)
 //     short  only ptag agrees       -> it shares the 5-byte prefix but not 8 bytes           ((x & 0x03FFFFFF) < p, x != that)
 // Every long candidate is examined (after the continuation filter below); of the short ones only the nearest, because among
-// matches of 5..7 bytes only the offset matters.  This is what lets a 32-entry row cost fewer byte comparisons than the
-// round-1 16-entry row did (CPU model tests/harness/lz_model2.cc: 2.5-4 comparisons per position, ratio within 1.1 % of
-// libzstd level 12 on source code, binaries and small files).
+// matches of 5..7 bytes only the offset matters (CPU model tests/harness/lz_model2.cc).
 //
 // Per group of 32 positions (one warp):
-//   rows      four lanes share a 128-byte row (two 16-byte loads each), 8 positions per pass, 4 passes; all 8 loads of a lane are
-//             in flight together
+//   rows      four lanes share a 128-byte window of the list (two 16-byte loads each, the window start rounded up to 16 bytes:
+//             the 29..32 entries in front of E), 8 positions per pass, 4 passes; all 8 loads of a lane are in flight together
 //   filter    long candidates -> (position, offset) pairs in the warp's queue; nearest short per position kept aside
 //   continue  a long pair (p, o) whose left neighbour (p-1, o) is also a pair continues a match that is (or will be) found one
 //             position earlier: dropped, its result arrives by inheritance.  Done in pair space through a direct-mapped table
-//             of 16-bit keys; columns 0 and 16 keep everything so inheritance never runs dry.
+//             of 16-bit keys; column 0 keeps everything so inheritance never runs dry.
 //   verify    one pair per lane per trip: 40 candidate bytes (five aligned 8-byte loads, all requested up front) against the
 //             position's bytes in shared memory, up to CAP = 32 matching bytes; best per position by atomicMax on
 //             (2 len - log2 offset, nearer offset first)
 //   inherit   one max-scan over the warp hands a match at position j to j + d as (offset, len - d)
 //   emit      <= 3 bytes of backward extension, clamp to the block end, one 4-byte record per position (streaming store)
-// The lazy decision and everything that depends on the parser's state moved to the chase kernel.
 //
 // chase_kernel: one warp per 128 KiB block walks the records.  At the cursor it resolves the lazy choice (depth 2, zstd's
-// gains) from the 64 records it holds in registers, extends capped matches warp-wide, and -- new -- looks for repeat-offset
+// gains) from the 64 records it holds in registers, extends capped matches warp-wide, and looks for repeat-offset
 // matches the way a sequential encoder does: every literal position in front of the chosen match is tested against the three
 // repeat offsets (>= 3 bytes is enough, they cost almost nothing to code), and at the match start a repeat offset wins when
-// zstd's rule of thumb says so.  This is where the round-1 parse lost 3-7 % on binaries and records.
+// zstd's rule of thumb says so.
 #pragma once
-#include <cooperative_groups.h>
 #include "zstd_enc_lz.cuh"
 #include "zstd_enc_parse.h"
 
 namespace lz2 {
-namespace cg = cooperative_groups;
 
 constexpr uint32_t ROW_LOG = 14, ROWS = 1u << ROW_LOG, ROW_K = 32;
 constexpr uint32_t POS_BITS = 21, POS_MASK = (1u << POS_BITS) - 1, PTAG_BITS = 5, PFX_MASK = (1u << (POS_BITS + PTAG_BITS)) - 1;
@@ -51,9 +58,13 @@ constexpr uint32_t LEN_BASE = zparse::LEN_BASE, CAP = zparse::CAP, MAX_SHIFT = z
 constexpr uint32_t SMALL_CHUNK = 128u * 1024u;  // up to here matches of 4 bytes are searched (hash of 4 bytes), above 5: libzstd's level-12 parameters make the same switch
 constexpr int32_t ACCEPT_THR = zparse::ACCEPT_THR;
 constexpr uint32_t LOOKAHEAD = CAP + 16;
-constexpr uint32_t QUEUE_WORDS = 32 * ROW_K + 32;  // per warp: every entry of every row could be a long candidate, plus one short per position
+constexpr uint32_t QUEUE_WORDS = 32 * ROW_K + 32;  // per warp: every entry of every window could be a long candidate, plus one short per position
 constexpr uint32_t SEQ_PER_BLOCK = lz::SEQ_PER_BLOCK, MAX_SEQ_PER_CHUNK = lz::MAX_SEQ_PER_CHUNK, BLOCKS_PER_CHUNK = lz::BLOCKS_PER_CHUNK;
 constexpr uint32_t REC_PER_CHUNK = lz::REC_PER_CHUNK;
+// the list of one chunk: LIST_PAD empty entries (a window may start up to 32 entries in front of the first row), then at most
+// one entry per position; slots are 16-byte aligned
+constexpr uint32_t LIST_PAD = 64, LIST_STRIDE = REC_PER_CHUNK + LIST_PAD + 64;
+constexpr uint32_t SPAN = 256;  // positions a search warp takes at a time
 
 // row index (14 bits) and ptag (5 bits) from a hash of the first five bytes (hshift = 24) or four (hshift = 32); xtag from bytes 5..7
 __device__ __forceinline__ uint32_t hash_row_ptag(uint64_t v, uint32_t hshift) { return (uint32_t)(((v << hshift) * 889523592379ULL) >> (64 - (ROW_LOG + PTAG_BITS))); }
@@ -68,13 +79,6 @@ __device__ __forceinline__ uint32_t pack_rec(uint32_t off, uint32_t len, uint32_
     return off | (len - LEN_BASE) << 21 | capped << 26 | back << 27;
 }
 
-template <int G> __device__ __forceinline__ void group_sync() {
-    if (G > 1) cg::this_cluster().sync(); else __syncthreads();
-}
-// split-phase cluster barrier: arrive (release) early, wait (acquire) late
-template <int G> __device__ __forceinline__ void cl_arrive() { if (G > 1) asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
-template <int G> __device__ __forceinline__ void cl_wait() { if (G > 1) asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
-
 // 8 bytes at position p of the chunk, straight from global memory (any alignment)
 __device__ __forceinline__ uint64_t gld8(const uint8_t *__restrict__ in, uint32_t p, uint32_t n) {
     if (p + 12 <= n) return lz::ld8(in, p);
@@ -83,292 +87,373 @@ __device__ __forceinline__ uint64_t gld8(const uint8_t *__restrict__ in, uint32_
     return v;
 }
 
-// ---- search -----------------------------------------------------------------------------------------------------------
-// Step pipeline of one CTA (rank r of a cluster of G); step s covers positions [(s G + r) SUB, + SUB) of the chunk:
-//     reserve   ring slots (atomicAdd on the row heads) for my positions of step s+1: the round trips hide behind the search
-//     stage     bytes of my sub-tile of step s+1 -> the free half of the stage buffer
-//     search    step s (every CTA's entries of steps <= s are in the table)
-//     publish   my entries of step s+1 into the reserved slots
-//     barrier   cluster-wide (release / acquire): all entries of step s+1 are visible
-// A measured alternative -- publish two steps ahead, arrive at the top of the iteration and wait at the bottom, so that a CTA
-// only ever waits for one that has not even started the same step -- was 14 % faster but cost 1.2 % of ratio on real files
-// (entries of later positions are never candidates, but they take ring slots early); the tolerance decides.
-template <int THREADS, int SUB> struct SearchSmem {
-    static constexpr uint32_t WARPS = THREADS / 32, SIN = SUB + LOOKAHEAD + 32;
-    static constexpr uint32_t OFF_IN = 0, OFF_QUEUE = OFF_IN + 2 * SIN, OFF_CONT = OFF_QUEUE + WARPS * QUEUE_WORDS * 4,
-                              OFF_BEST = OFF_CONT + WARPS * 1024 * 4, BYTES = OFF_BEST + SUB * 4;
-    static_assert(SIN % 16 == 0, "stage buffer shape");
-};
-
-template <int G, int THREADS, int SUB, int MINB>
-__global__ void __launch_bounds__(THREADS, MINB) search_kernel(const uint8_t *__restrict__ data, const sq_span *__restrict__ spans,
-                                                               const uint8_t *__restrict__ select, uint32_t n_chunks,
-                                                               uint32_t *__restrict__ tab_all, uint32_t *__restrict__ head_all,
-                                                               uint32_t *__restrict__ rec_all, uint32_t *__restrict__ counter, uint32_t dbg) {
-    constexpr uint32_t WARPS = THREADS / 32, PER_THREAD = SUB / THREADS, GROUPS = SUB / 32;
-    using L = SearchSmem<THREADS, SUB>;
-    constexpr uint32_t SIN = L::SIN, SIN_WORDS = SIN / 4;
-    static_assert(SUB % THREADS == 0 && SUB <= 1024, "tile shape");
-    extern __shared__ __align__(16) uint8_t s_dyn[];
-    uint8_t (*s_in2)[SIN] = reinterpret_cast<uint8_t (*)[SIN]>(s_dyn + L::OFF_IN);
-    uint32_t *s_queue = reinterpret_cast<uint32_t *>(s_dyn + L::OFF_QUEUE);
-    uint32_t *s_cont = reinterpret_cast<uint32_t *>(s_dyn + L::OFF_CONT);
-    uint32_t *s_best = reinterpret_cast<uint32_t *>(s_dyn + L::OFF_BEST);
-    __shared__ uint32_t s_chunk, s_gctr[2];  // group counters alternate by step parity
-
-    const uint32_t tid = threadIdx.x, wq = tid >> 5, lane = tid & 31;
-    uint32_t rank = 0;
-    if (G > 1) rank = cg::this_cluster().block_rank();
-    const uint32_t cid = blockIdx.x / G;
-    uint32_t *tab = tab_all + (size_t)cid * ROWS * ROW_K;
-    uint32_t *head = head_all + (size_t)cid * ROWS;
-    uint32_t *queue = s_queue + wq * QUEUE_WORDS;
-    uint32_t *T = s_cont + wq * 1024;  // continuation keys: (pair | epoch << 26), never cleared (the epoch changes with every group)
-    const uint32_t sub = lane >> 2, part = lane & 3u;
-    uint32_t epoch = 0;
-
-    for (;;) {
-        // ---- the cluster takes the next selected chunk ----
-        if (rank == 0 && tid == 0) {
-            uint32_t c;
-            do { c = atomicAdd(counter, 1u); } while (c < n_chunks && select && !select[c]);
-            if (G > 1) { for (uint32_t r = 0; r < (uint32_t)G; r++) *cg::this_cluster().map_shared_rank(&s_chunk, r) = c; }
-            else s_chunk = c;
+// ---- plan: 256-position spans of the selected chunks of one sub-batch, as an exclusive prefix (one CTA) ------------------
+__global__ void __launch_bounds__(1024) span_plan_kernel(const sq_span *__restrict__ spans, const uint8_t *__restrict__ select, uint32_t first,
+                                                          uint32_t count, uint32_t *__restrict__ span_start, uint32_t *__restrict__ counter) {
+    __shared__ uint32_t warp_sums[32];
+    __shared__ uint32_t carry;
+    const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < count; base += 1024) {
+        const uint32_t i = base + threadIdx.x;
+        uint32_t v = 0;
+        if (i < count && (!select || select[first + i])) v = (spans[first + i].len + SPAN - 1) / SPAN;
+        uint32_t x = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, d); if ((int)lane >= d) x += y; }
+        if (lane == 31) warp_sums[w] = x;
+        __syncthreads();
+        if (w == 0) {
+            const uint32_t s = warp_sums[lane];
+            uint32_t z = s;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, z, d); if ((int)lane >= d) z += y; }
+            warp_sums[lane] = z - s;
         }
-        if (tid == 0) { s_gctr[0] = WARPS; s_gctr[1] = WARPS; }
-        group_sync<G>();  // also: every CTA is done with the previous chunk's table
-        const uint32_t chunk = s_chunk;
-        if (chunk >= n_chunks) break;
+        __syncthreads();
+        const uint32_t excl = carry + warp_sums[w] + x - v;
+        if (i < count) span_start[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { span_start[count] = carry; *counter = 0; }  // the search kernel's ticket counter
+}
+
+// ---- index: the chunk's list (rows in position order) and every position's window end ---------------------------------
+// Inside a run of one byte (the five bytes here are the five bytes one position earlier) nothing is inserted: the run's first
+// position stands for it, and a hot row is not flooded with interchangeable entries.
+//
+// One CTA per chunk, two passes.  Pass 1 hashes every position once -- eight consecutive positions per thread from three aligned
+// 8-byte loads -- counts the rows in shared memory and leaves a 26-bit word per position in the record array (row + tags +
+// "insert" flag).  After a prefix sum over the rows, pass 2 reads those words back (coalesced) and scatters the entries, one tile
+// of THREADS positions at a time.  Inside a tile the order of two entries of one row is the order of their shared-memory
+// atomics, so a position does not take "its own index" as the end of its window but the row's fill level E at the END of its
+// tile: the window [E - 32, E) then holds every earlier position of the tile regardless of the race (and the tile's later ones,
+// which the search discards by position).
+// (Measured and dropped: PARTS CTAs per chunk, each scattering a quarter of the rows, to keep the open 32-byte sectors of the
+// 16384 append streams in L2 -- the kernel was bound by instruction issue and load latency, not by partial sector writes, and
+// hashing every position PARTS times doubled its time.)
+constexpr uint32_t IDX_INS = 1u << 25;
+__device__ __forceinline__ uint32_t index_word(uint64_t v, uint32_t prev, uint32_t hshift, bool first) {
+    const uint32_t hv = hash_row_ptag(v, hshift), xt = ((uint32_t)(v >> 40) * 0x9E3779B1u) >> 26;
+    const bool run = !first && (uint32_t)v == prev * 0x01010101u && ((uint32_t)(v >> 32) & 0xFFu) == prev;
+    return hv | xt << (ROW_LOG + PTAG_BITS) | (run ? 0u : IDX_INS);
+}
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, 1) index_kernel(const uint8_t *__restrict__ data, const sq_span *__restrict__ spans,
+                                                            const uint8_t *__restrict__ select, uint32_t first, uint32_t count,
+                                                            uint32_t *__restrict__ list_all, uint32_t *__restrict__ rec_all) {
+    extern __shared__ __align__(16) uint32_t s_cnt[];  // ROWS counters, then running list indices
+    __shared__ uint32_t s_warp[THREADS / 32];
+    constexpr uint32_t PER = ROWS / THREADS;
+    static_assert(ROWS % THREADS == 0, "row counters per thread");
+    const uint32_t tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    for (uint32_t ci = blockIdx.x; ci < count; ci += gridDim.x) {
+        const uint32_t chunk = first + ci;
+        if (select && !select[chunk]) continue;
         const uint8_t *in = data + spans[chunk].off;
         const uint32_t n = spans[chunk].len;
         uint32_t *rec = rec_all + (size_t)chunk * REC_PER_CHUNK;
-        const bool aligned = (reinterpret_cast<uintptr_t>(in) & 7) == 0;
-        const uint32_t MIN_MATCH = n <= SMALL_CHUNK ? 4u : 5u, hshift = n <= SMALL_CHUNK ? 32u : 24u;
-        // every CTA clears its slice of the table (entries only: a ring head may start anywhere)
-        {
-            constexpr uint32_t SLICE4 = ROWS * ROW_K / 4 / G;
-            uint4 *t4 = reinterpret_cast<uint4 *>(tab) + (size_t)rank * SLICE4;
-            for (uint32_t i = tid; i < SLICE4; i += THREADS) __stcg(t4 + i, make_uint4(EMPTY, EMPTY, EMPTY, EMPTY));
+        uint32_t *list = list_all + (size_t)ci * LIST_STRIDE + LIST_PAD;
+        const uint32_t hshift = n <= SMALL_CHUNK ? 32u : 24u;
+        const uint32_t np = n >= 8 ? n - 7 : 0;  // positions that have 8 bytes
+        __syncthreads();
+        for (uint32_t i = tid; i < ROWS; i += THREADS) s_cnt[i] = 0;
+        __syncthreads();
+        // pass 1: one word per position, row histogram
+        uint32_t done = 0;  // positions covered by the vector path
+        if ((reinterpret_cast<uintptr_t>(in) & 7) == 0 && n >= 16) {
+            const uint32_t n8 = (n - 16) / 8 + 1;  // groups of eight positions whose 16 bytes lie inside the chunk
+            done = n8 * 8;
+            for (uint32_t i = tid; i < n8; i += THREADS) {
+                const uint32_t p0 = i * 8;
+                const uint2 B = __ldg(reinterpret_cast<const uint2 *>(in + p0)), Cw = __ldg(reinterpret_cast<const uint2 *>(in + p0 + 8));
+                uint32_t prev = p0 ? __ldg(reinterpret_cast<const uint32_t *>(in + p0 - 4)) >> 24 : 0u;
+                const uint32_t wd[4] = {B.x, B.y, Cw.x, Cw.y};
+                uint32_t out[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const uint32_t sh = (k & 3) * 8, a = k >> 2;
+                    const uint32_t lo = __funnelshift_r(wd[a], wd[a + 1], sh), hi = __funnelshift_r(wd[a + 1], wd[a + 2], sh);
+                    const uint32_t wv = index_word((uint64_t)hi << 32 | lo, prev, hshift, p0 + k == 0);
+                    if (wv & IDX_INS) atomicAdd(&s_cnt[(wv >> PTAG_BITS) & (ROWS - 1)], 1u);
+                    out[k] = wv;
+                    prev = lo & 0xFFu;
+                }
+                uint4 *dst = reinterpret_cast<uint4 *>(rec + p0);
+                dst[0] = make_uint4(out[0], out[1], out[2], out[3]);
+                dst[1] = make_uint4(out[4], out[5], out[6], out[7]);
+            }
         }
-        const uint32_t n_steps = (n + G * SUB - 1) / (G * SUB);
-        for (uint32_t i = tid; i < SIN_WORDS; i += THREADS)
-            reinterpret_cast<uint32_t *>(s_in2[0])[i] = lz::stage_word(in, rank * SUB + i * 4, n, aligned);
-        group_sync<G>();  // the clear is visible everywhere
-        // ring-slot reservation and entry store for my positions of one step
-        uint32_t r_ent[PER_THREAD], r_idx[PER_THREAD], r_slot[PER_THREAD];
-        auto reserve = [&](uint32_t step) {
+        for (uint32_t p = done + tid; p < np; p += THREADS) {  // the chunk's last positions, or all of an unaligned chunk
+            const uint32_t wv = index_word(gld8(in, p, n), p ? in[p - 1] : 0u, hshift, p == 0);
+            if (wv & IDX_INS) atomicAdd(&s_cnt[(wv >> PTAG_BITS) & (ROWS - 1)], 1u);
+            rec[p] = wv;
+        }
+        __syncthreads();
+        // exclusive prefix over the rows: thread t owns rows [t PER, +PER)
+        {
+            uint32_t c[PER], sum = 0;
 #pragma unroll
-            for (uint32_t k = 0; k < PER_THREAD; k++) {
-                const uint32_t p = (step * G + rank) * SUB + tid + k * THREADS;
-                r_ent[k] = EMPTY; r_idx[k] = 0; r_slot[k] = 0;
-                if (p + 8 <= n) {
-                    const uint64_t v = gld8(in, p, n);
-                    // inside a run of one byte (the five bytes here are the five bytes one position earlier) nothing is inserted: the run's
-                    // first position stands for it, and a hot row is not flooded with interchangeable entries
-                    if (p > 0 && (v & 0xFFFFFFFFFFull) == (uint64_t)in[p - 1] * 0x0101010101ull) continue;
-                    const uint32_t hv = hash_row_ptag(v, hshift);
-                    r_ent[k] = p | tag_word(hv, v);
-                    r_idx[k] = (hv >> PTAG_BITS) * ROW_K;
-                    r_slot[k] = atomicAdd(&head[hv >> PTAG_BITS], 1u);
-                }
+            for (uint32_t k = 0; k < PER; k++) { c[k] = s_cnt[tid * PER + k]; sum += c[k]; }
+            uint32_t x = sum;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, d); if ((int)lane >= d) x += y; }
+            if (lane == 31) s_warp[w] = x;
+            __syncthreads();
+            if (w == 0) {
+                const uint32_t sv = lane < THREADS / 32 ? s_warp[lane] : 0u;
+                uint32_t z = sv;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, z, d); if ((int)lane >= d) z += y; }
+                if (lane < THREADS / 32) s_warp[lane] = z - sv;
             }
-        };
-        auto publish = [&]() {
+            __syncthreads();
+            uint32_t run = s_warp[w] + x - sum;
 #pragma unroll
-            for (uint32_t k = 0; k < PER_THREAD; k++)
-                if (r_ent[k] != EMPTY) __stcg(&tab[r_idx[k] + (r_slot[k] & (ROW_K - 1))], r_ent[k]);
-        };
-        reserve(0); publish();
-        group_sync<G>();  // step 0 is in the table
-
-        for (uint32_t s = 0; s < n_steps; s++) {
-            reserve(s + 1);  // ring slots for my positions of the next step: the atomics' round trips hide behind this step's search
-            const uint32_t t0 = (s * G + rank) * SUB, t1 = min(n, t0 + SUB);
-            const uint8_t *s_in = s_in2[s & 1];
-            {   // stage my sub-tile of the next step
-                const uint32_t g1 = ((s + 1) * G + rank) * SUB;
-                uint32_t *dst = reinterpret_cast<uint32_t *>(s_in2[(s + 1) & 1]);
-                if (g1 < n) for (uint32_t i = tid; i < SIN_WORDS; i += THREADS) dst[i] = lz::stage_word(in, g1 + i * 4, n, aligned);
-            }
-            // ---- search: warps take groups of 32 positions ----
-            uint32_t g = wq;
-#pragma unroll 1
-            while (g < GROUPS && t0 + g * 32 < n) {
-                const uint32_t gl = g * 32, li = gl + lane, p = t0 + li, pg = t0 + gl;
-                const bool searchable = p + 8 <= n;
-                const bool gfast = pg + 32 + CAP + 16 <= n;
-                const uint64_t v_own = lz::smem_u64(s_in, li);
-                const uint32_t hv_own = hash_row_ptag(v_own, hshift);
-                const uint32_t T_own = tag_word(hv_own, v_own);
-                epoch = (epoch + 1u) & 63u;
-                // rows: pass k serves position 8 k + sub; this lane reads entries [4 part, +4) and [16 + 4 part, +4) of that row
-                uint4 ea[4], eb[4];
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const uint32_t hk = __shfl_sync(0xffffffffu, hv_own, 8 * k + sub);
-                    const uint4 *rp = reinterpret_cast<const uint4 *>(tab + (hk >> PTAG_BITS) * ROW_K) + part;
-                    ea[k] = __ldcg(rp); eb[k] = __ldcg(rp + 4);
-                }
-                s_best[li] = 0u;
-                // filter: long candidates (all tag bits agree, before the position) and the nearest short one (ptag only)
-                uint32_t lmask = 0, smax[4];
-                uint32_t xs[32];
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const uint32_t src = 8 * k + sub;
-                    const uint32_t Tk = __shfl_sync(0xffffffffu, T_own, src);
-                    const uint32_t pk = pg + src;
-                    const uint32_t plim = pk + 8 <= n ? pk : 0u;
-                    const uint32_t e[8] = {ea[k].x, ea[k].y, ea[k].z, ea[k].w, eb[k].x, eb[k].y, eb[k].z, eb[k].w};
-                    uint32_t sm = 0;
-#pragma unroll
-                    for (int m = 0; m < 8; m++) {
-                        const uint32_t x = e[m] ^ Tk, z = x & PFX_MASK;
-                        xs[8 * k + m] = x;
-                        if (x < plim) lmask |= 1u << (8 * k + m);
-                        sm = max(sm, (z < plim && x != z) ? z : 0u);  // candidate position 0 is not worth a special case
-                    }
-                    sm = max(sm, __shfl_xor_sync(0xffffffffu, sm, 1));
-                    sm = max(sm, __shfl_xor_sync(0xffffffffu, sm, 2));
-                    smax[k] = sm;
-                }
-                // long pairs -> queue as (candidate position | group column << 21)
-                uint32_t nlong;
-                uint32_t wpos = ent::warp_excl_scan(__popc(lmask), lane, &nlong);
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const uint32_t colsh = (8 * k + sub) << POS_BITS;
-#pragma unroll
-                    for (int m = 0; m < 8; m++)
-                        if (lmask >> (8 * k + m) & 1) queue[wpos++] = xs[8 * k + m] | colsh;
-                }
-                __syncwarp();
-                // ---- continuation filter in pair space: (col, c) is dropped when (col - 1, c - 1) is a pair too ----
-                const uint32_t ep = epoch << 26;
-                for (uint32_t i = lane; i < nlong; i += 32) {
-                    const uint32_t pr = queue[i], col = pr >> POS_BITS, o = pg + col - (pr & POS_MASK);
-                    T[(o * 37u + col) & 1023u] = pr | ep;
-                }
-                __syncwarp();
-                uint32_t total = 0;
-                for (uint32_t base = 0; base < nlong; base += 32) {
-                    const uint32_t i = base + lane;
-                    const bool valid = i < nlong;
-                    const uint32_t pr = valid ? queue[i] : 0u, col = pr >> POS_BITS, o = pg + col - (pr & POS_MASK);
-                    const bool hit = T[(o * 37u + col - 1u) & 1023u] == ((pr - (1u << POS_BITS) - 1u) | ep);  // col 0 keeps everything: its key would wrap
-                    const bool keep = valid && !(hit && col != 0 && !((dbg & 1u) && col == 16));
-                    const uint32_t b = __ballot_sync(0xffffffffu, keep);
-                    __syncwarp();
-                    if (keep) queue[total + __popc(b & ((1u << lane) - 1u))] = pr;
-                    total += __popc(b);
-                }
-                // nearest short candidate of each position (lane = column)
-                {
-                    uint32_t sm = 0;
-#pragma unroll
-                    for (int k = 0; k < 4; k++) {
-                        const uint32_t vk = __shfl_sync(0xffffffffu, smax[k], (lane & 7u) * 4u);
-                        if ((int)(lane >> 3) == k) sm = vk;
-                    }
-                    const bool has = sm != 0;
-                    const uint32_t b = __ballot_sync(0xffffffffu, has);
-                    if (has) queue[total + __popc(b & ((1u << lane) - 1u))] = sm | lane << POS_BITS;
-                    total += __popc(b);
-                }
-                __syncwarp();
-                // ---- verify ----
-                if (gfast) {
-#pragma unroll 1
-                    for (uint32_t i = lane; i < total; i += 32) {
-                        const uint32_t pr = queue[i], l0 = gl + (pr >> POS_BITS), c0 = pr & POS_MASK, o = t0 + l0 - c0;
-                        const uint32_t *wp = reinterpret_cast<const uint32_t *>(s_in) + (l0 >> 2);
-                        const uintptr_t ga = reinterpret_cast<uintptr_t>(in + c0);
-                        const uint2 *wc = reinterpret_cast<const uint2 *>(ga & ~(uintptr_t)7);
-                        const uint32_t sp = (l0 & 3u) * 8, sc = (uint32_t)(ga & 3u) * 8;
-                        const bool up = (ga & 4u) != 0;
-                        const uint2 A0 = __ldg(wc), A1 = __ldg(wc + 1), A2 = __ldg(wc + 2), A3 = __ldg(wc + 3), A4 = __ldg(wc + 4);
-                        uint32_t pw[9];
-#pragma unroll
-                        for (int j = 0; j < 9; j++) pw[j] = wp[j];
-                        uint32_t cw[9];
-                        cw[0] = up ? A0.y : A0.x; cw[1] = up ? A1.x : A0.y; cw[2] = up ? A1.y : A1.x; cw[3] = up ? A2.x : A1.y; cw[4] = up ? A2.y : A2.x;
-                        cw[5] = up ? A3.x : A2.y; cw[6] = up ? A3.y : A3.x; cw[7] = up ? A4.x : A3.y; cw[8] = up ? A4.y : A4.x;
-                        uint64_t d[4];
-#pragma unroll
-                        for (int j = 0; j < 4; j++)
-                            d[j] = (uint64_t)(__funnelshift_r(pw[2 * j + 1], pw[2 * j + 2], sp) ^ __funnelshift_r(cw[2 * j + 1], cw[2 * j + 2], sc)) << 32 |
-                                   (__funnelshift_r(pw[2 * j], pw[2 * j + 1], sp) ^ __funnelshift_r(cw[2 * j], cw[2 * j + 1], sc));
-                        uint64_t x = d[0]; uint32_t mb = 0;
-                        if (!x) { x = d[1]; mb = 8; if (!x) { x = d[2]; mb = 16; if (!x) { x = d[3]; mb = 24; } } }
-                        const uint32_t m = x ? mb + ((uint32_t)(__ffsll((long long)x) - 1) >> 3) : CAP;
-                        if (m >= MIN_MATCH)
-                            atomicMax(&s_best[l0], (uint32_t)((int32_t)(2 * m) - (int32_t)zc::highbit(o + 3) + 12) << POS_BITS | (POS_MASK - o));
-                    }
-                } else {  // the last bytes of the chunk: careful scalar comparison
-#pragma unroll 1
-                    for (uint32_t i = lane; i < total; i += 32) {
-                        const uint32_t pr = queue[i], l0 = gl + (pr >> POS_BITS), pp = t0 + l0, o = pp - (pr & POS_MASK);
-                        const uint32_t m = lz::match_length(in, pp, pp - o, min(n - pp, CAP), n);
-                        if (m >= MIN_MATCH)
-                            atomicMax(&s_best[l0], (uint32_t)((int32_t)(2 * m) - (int32_t)zc::highbit(o + 3) + 12) << POS_BITS | (POS_MASK - o));
-                    }
-                }
-                __syncwarp();
-                // ---- inherit + emit ----
-                uint32_t blen = 0, boff = 0;
-                if (searchable) {
-                    const uint32_t best = s_best[li];
-                    if (best) {
-                        boff = POS_MASK - (best & POS_MASK);
-                        blen = ((best >> POS_BITS) - 12u + zc::highbit(boff + 3)) >> 1;
-                    }
-                }
-                uint32_t capped = blen >= CAP ? 1u : 0u;
-                {
-                    const uint32_t own = blen ? (lane + blen) << 22 | capped << 21 | boff : 0u;
-                    uint32_t v = own;
-                    int32_t e = blen ? (int32_t)(2 * (lane + blen)) - (int32_t)zc::highbit(boff + 3) : -1000;
-#pragma unroll
-                    for (uint32_t d = 1; d < 32; d <<= 1) {
-                        const uint32_t u = __shfl_up_sync(0xffffffffu, v, d);
-                        const int32_t eu = __shfl_up_sync(0xffffffffu, e, d);
-                        if (lane >= d && eu > e) { v = u; e = eu; }
-                    }
-                    const uint32_t end = v >> 22;
-                    if (v != own && end >= lane + MIN_MATCH && searchable) { blen = end - lane; boff = v & POS_MASK; capped = v >> 21 & 1u; }
-                }
-                if (p < t1) {
-                    uint32_t r = 0;
-                    if (blen) {
-                        const uint32_t be = min(n, (p / Z_BLOCK_MAX + 1) * Z_BLOCK_MAX);
-                        if (p + blen > be) { blen = be - p; capped = 0; }
-                        if (blen >= MIN_MATCH) {
-                            const uint32_t c = p - boff;
-                            uint32_t bback = 0;
-                            if (c >= 4 && p + 8 <= n) {  // one unaligned load each side: bytes [x-4, x)
-                                const uint32_t diff = (uint32_t)lz::ld8(in, p - 4) ^ (uint32_t)lz::ld8(in, c - 4);
-                                bback = diff == 0 ? 3u : (uint32_t)__clz((int)diff) >> 3;
-                                if (bback > 3) bback = 3;
-                            } else {
-                                while (bback < 3 && p > bback && c > bback && in[p - bback - 1] == in[c - bback - 1]) bback++;
-                            }
-                            r = pack_rec(boff, blen, capped, bback);
-                        }
-                    }
-                    __stcs(&rec[p], r);
-                }
-                if (lane == 0) g = atomicAdd(&s_gctr[s & 1], 1u);
-                g = __shfl_sync(0xffffffffu, g, 0);
-            }
-            // ---- publish the next step's entries into the slots reserved above; every CTA's entries of step s+1 are visible after the barrier ----
-#pragma unroll
-            for (uint32_t k = 0; k < PER_THREAD; k++) asm volatile("" : "+r"(r_slot[k]) :: "memory");
-            publish();
-            cl_arrive<G>();
-            cl_wait<G>();
-            if (tid == 0) s_gctr[(s + 1) & 1] = WARPS;  // nobody touches the other parity's counter during this iteration
+            for (uint32_t k = 0; k < PER; k++) { s_cnt[tid * PER + k] = run; run += c[k]; }
+        }
+        __syncthreads();
+        // pass 2: scatter, tile by tile
+        uint32_t w_next = tid < np ? __ldcg(rec + tid) : 0u;
+        for (uint32_t t0 = 0; t0 < np; t0 += THREADS) {
+            const uint32_t p = t0 + tid, wv = w_next;
+            if (p + THREADS < np) w_next = __ldcg(rec + p + THREADS);
+            const uint32_t row = (wv >> PTAG_BITS) & (ROWS - 1);
+            if (p < np && (wv & IDX_INS))
+                list[atomicAdd(&s_cnt[row], 1u)] = p | (wv & ((1u << PTAG_BITS) - 1)) << POS_BITS | (wv >> (ROW_LOG + PTAG_BITS) & 63u) << (POS_BITS + PTAG_BITS);
+            __syncthreads();
+            if (p < np) rec[p] = s_cnt[row];
             __syncthreads();
         }
+    }
+}
+
+// ---- search ------------------------------------------------------------------------------------------------------------
+struct SearchSmem {
+    static constexpr uint32_t WIN = SPAN + LOOKAHEAD + 32;  // staged bytes of a span
+    static constexpr uint32_t PER_WARP = QUEUE_WORDS * 4 + 1024 * 4 + WIN + 32 * 4;
+    static_assert(WIN % 16 == 0 && PER_WARP % 16 == 0, "per-warp shared memory shape");
+};
+
+template <int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) search_kernel(const uint8_t *__restrict__ data, const sq_span *__restrict__ spans, uint32_t first,
+                                                               uint32_t count, const uint32_t *__restrict__ span_start,
+                                                               const uint32_t *__restrict__ list_all, uint32_t *__restrict__ rec_all, uint32_t *__restrict__ counter, uint32_t dbg) {
+    constexpr uint32_t WARPS = THREADS / 32, WIN = SearchSmem::WIN, WIN_WORDS = WIN / 4, GROUPS = SPAN / 32;
+    extern __shared__ __align__(16) uint8_t s_dyn[];
+    const uint32_t tid = threadIdx.x, wq = tid >> 5, lane = tid & 31;
+    uint8_t *s_warp = s_dyn + wq * SearchSmem::PER_WARP;
+    uint32_t *queue = reinterpret_cast<uint32_t *>(s_warp);
+    uint32_t *T = queue + QUEUE_WORDS;  // continuation keys: (pair | epoch << 26), never cleared (the epoch changes with every group)
+    uint8_t *s_in = reinterpret_cast<uint8_t *>(T + 1024);
+    uint32_t *s_best = reinterpret_cast<uint32_t *>(s_in + WIN);
+    const uint32_t sub = lane >> 2, part = lane & 3u;
+    uint32_t epoch = 0;
+    const uint32_t total_spans = span_start[count];
+
+    // Spans are handed out through one counter, in order: all warps of the grid then work within a few hundred KB of each other,
+    // so the chunk they read -- input, list, records -- stays in L2.  (A fixed warp -> span assignment let fast warps run tens of
+    // chunks ahead of slow ones: 473 MB of DRAM reads per 2 MiB chunk, L2 hit rate 43 %.)  The next ticket is requested at the
+    // top of a span and first looked at when the span is done.
+    uint32_t sp = 0;
+    if (lane == 0) sp = atomicAdd(counter, 1u);
+    sp = __shfl_sync(0xffffffffu, sp, 0);
+    while (sp < total_spans) {
+        uint32_t sp_next = 0;
+        if (lane == 0) sp_next = atomicAdd(counter, 1u);
+        // which chunk: the last ci with span_start[ci] <= sp
+        uint32_t lo = 0, hi = count;
+        while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (span_start[mid] <= sp) lo = mid; else hi = mid; }
+        const uint32_t chunk = first + lo, t0 = (sp - span_start[lo]) * SPAN;
+        const uint8_t *in = data + spans[chunk].off;
+        const uint32_t n = spans[chunk].len;
+        uint32_t *rec = rec_all + (size_t)chunk * REC_PER_CHUNK;
+        const uint32_t *list = list_all + (size_t)lo * LIST_STRIDE + LIST_PAD;
+        const bool aligned = (reinterpret_cast<uintptr_t>(in) & 7) == 0;
+        const uint32_t MIN_MATCH = n <= SMALL_CHUNK ? 4u : 5u, hshift = n <= SMALL_CHUNK ? 32u : 24u;
+        const uint32_t t1 = min(n, t0 + SPAN);
+        __syncwarp();
+        for (uint32_t i = lane; i < WIN_WORDS; i += 32) reinterpret_cast<uint32_t *>(s_in)[i] = lz::stage_word(in, t0 + i * 4, n, aligned);
+        // every position's window end, for the whole span (the index kernel left it in the record array)
+        uint32_t jv[GROUPS];
+#pragma unroll
+        for (uint32_t g = 0; g < GROUPS; g++) { const uint32_t p = t0 + g * 32 + lane; jv[g] = p + 8 <= n ? __ldcs(rec + p) : 0u; }
+        __syncwarp();
+#pragma unroll 1
+        for (uint32_t g = 0; g < GROUPS && t0 + g * 32 < n; g++) {
+            const uint32_t gl = g * 32, li = gl + lane, p = t0 + li, pg = t0 + gl;
+            const bool searchable = p + 8 <= n;
+            const bool gfast = pg + 32 + CAP + 16 <= n;
+            uint32_t j_own = jv[0];
+#pragma unroll
+            for (uint32_t k = 1; k < GROUPS; k++) if (g == k) j_own = jv[k];
+            // windows: pass k serves position 8 k + sub; this lane reads entries [4 part, +4) and [16 + 4 part, +4) of that window
+            uint4 ea[4], eb[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int32_t jk = (int32_t)__shfl_sync(0xffffffffu, j_own, 8 * k + sub);
+                const uint4 *rp = reinterpret_cast<const uint4 *>(list + ((jk + 3 - (int32_t)ROW_K) & ~3)) + part;
+                ea[k] = __ldcg(rp); eb[k] = __ldcg(rp + 4);
+            }
+            const uint64_t v_own = lz::smem_u64(s_in, li);
+            const uint32_t hv_own = hash_row_ptag(v_own, hshift);
+            const uint32_t T_own = tag_word(hv_own, v_own);
+            epoch = (epoch + 1u) & 63u;
+            s_best[lane] = 0u;
+            // filter: long candidates (all tag bits agree, before the position) and the nearest short one (ptag only)
+            uint32_t lmask = 0, smax[4];
+            uint32_t xs[32];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const uint32_t src = 8 * k + sub;
+                const uint32_t Tk = __shfl_sync(0xffffffffu, T_own, src);
+                const uint32_t pk = pg + src;
+                const uint32_t plim = pk + 8 <= n ? pk : 0u;
+                const uint32_t e[8] = {ea[k].x, ea[k].y, ea[k].z, ea[k].w, eb[k].x, eb[k].y, eb[k].z, eb[k].w};
+                uint32_t sm = 0;
+#pragma unroll
+                for (int m = 0; m < 8; m++) {
+                    const uint32_t x = e[m] ^ Tk, z = x & PFX_MASK;
+                    xs[8 * k + m] = x;
+                    if (x < plim) lmask |= 1u << (8 * k + m);
+                    sm = max(sm, (z < plim && x != z) ? z : 0u);  // candidate position 0 is not worth a special case
+                }
+                sm = max(sm, __shfl_xor_sync(0xffffffffu, sm, 1));
+                sm = max(sm, __shfl_xor_sync(0xffffffffu, sm, 2));
+                smax[k] = sm;
+            }
+            // long pairs -> queue as (candidate position | group column << 21)
+            uint32_t nlong;
+            uint32_t wpos = ent::warp_excl_scan(__popc(lmask), lane, &nlong);
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const uint32_t colsh = (8 * k + sub) << POS_BITS;
+#pragma unroll
+                for (int m = 0; m < 8; m++)
+                    if (lmask >> (8 * k + m) & 1) queue[wpos++] = xs[8 * k + m] | colsh;
+            }
+            __syncwarp();
+            // ---- continuation filter in pair space: (col, c) is dropped when (col - 1, c - 1) is a pair too ----
+            const uint32_t ep = epoch << 26;
+            for (uint32_t i = lane; i < nlong; i += 32) {
+                const uint32_t pr = queue[i], col = pr >> POS_BITS, o = pg + col - (pr & POS_MASK);
+                T[(o * 37u + col) & 1023u] = pr | ep;
+            }
+            __syncwarp();
+            uint32_t total = 0;
+            for (uint32_t base = 0; base < nlong; base += 32) {
+                const uint32_t i = base + lane;
+                const bool valid = i < nlong;
+                const uint32_t pr = valid ? queue[i] : 0u, col = pr >> POS_BITS, o = pg + col - (pr & POS_MASK);
+                const bool hit = T[(o * 37u + col - 1u) & 1023u] == ((pr - (1u << POS_BITS) - 1u) | ep);  // col 0 keeps everything: its key would wrap
+                const bool keep = valid && !(hit && col != 0 && !((dbg & 1u) && col == 16));
+                const uint32_t b = __ballot_sync(0xffffffffu, keep);
+                __syncwarp();
+                if (keep) queue[total + __popc(b & ((1u << lane) - 1u))] = pr;
+                total += __popc(b);
+            }
+            // nearest short candidate of each position (lane = column)
+            {
+                uint32_t sm = 0;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const uint32_t vk = __shfl_sync(0xffffffffu, smax[k], (lane & 7u) * 4u);
+                    if ((int)(lane >> 3) == k) sm = vk;
+                }
+                const bool has = sm != 0;
+                const uint32_t b = __ballot_sync(0xffffffffu, has);
+                if (has) queue[total + __popc(b & ((1u << lane) - 1u))] = sm | lane << POS_BITS;
+                total += __popc(b);
+            }
+            __syncwarp();
+            // ---- verify ----
+            if (gfast) {
+#pragma unroll 1
+                for (uint32_t i = lane; i < total; i += 32) {
+                    const uint32_t pr = queue[i], l0 = gl + (pr >> POS_BITS), c0 = pr & POS_MASK, o = t0 + l0 - c0;
+                    const uint32_t *wp = reinterpret_cast<const uint32_t *>(s_in) + (l0 >> 2);
+                    const uintptr_t ga = reinterpret_cast<uintptr_t>(in + c0);
+                    const uint2 *wc = reinterpret_cast<const uint2 *>(ga & ~(uintptr_t)7);
+                    const uint32_t sp8 = (l0 & 3u) * 8, sc = (uint32_t)(ga & 3u) * 8;
+                    const bool up = (ga & 4u) != 0;
+                    const uint2 A0 = __ldg(wc), A1 = __ldg(wc + 1), A2 = __ldg(wc + 2), A3 = __ldg(wc + 3), A4 = __ldg(wc + 4);
+                    uint32_t pw[9];
+#pragma unroll
+                    for (int j = 0; j < 9; j++) pw[j] = wp[j];
+                    uint32_t cw[9];
+                    cw[0] = up ? A0.y : A0.x; cw[1] = up ? A1.x : A0.y; cw[2] = up ? A1.y : A1.x; cw[3] = up ? A2.x : A1.y; cw[4] = up ? A2.y : A2.x;
+                    cw[5] = up ? A3.x : A2.y; cw[6] = up ? A3.y : A3.x; cw[7] = up ? A4.x : A3.y; cw[8] = up ? A4.y : A4.x;
+                    uint64_t d[4];
+#pragma unroll
+                    for (int j = 0; j < 4; j++)
+                        d[j] = (uint64_t)(__funnelshift_r(pw[2 * j + 1], pw[2 * j + 2], sp8) ^ __funnelshift_r(cw[2 * j + 1], cw[2 * j + 2], sc)) << 32 |
+                               (__funnelshift_r(pw[2 * j], pw[2 * j + 1], sp8) ^ __funnelshift_r(cw[2 * j], cw[2 * j + 1], sc));
+                    uint64_t x = d[0]; uint32_t mb = 0;
+                    if (!x) { x = d[1]; mb = 8; if (!x) { x = d[2]; mb = 16; if (!x) { x = d[3]; mb = 24; } } }
+                    const uint32_t m = x ? mb + ((uint32_t)(__ffsll((long long)x) - 1) >> 3) : CAP;
+                    if (m >= MIN_MATCH)
+                        atomicMax(&s_best[pr >> POS_BITS], (uint32_t)((int32_t)(2 * m) - (int32_t)zc::highbit(o + 3) + 12) << POS_BITS | (POS_MASK - o));
+                }
+            } else {  // the last bytes of the chunk: careful scalar comparison
+#pragma unroll 1
+                for (uint32_t i = lane; i < total; i += 32) {
+                    const uint32_t pr = queue[i], l0 = gl + (pr >> POS_BITS), pp = t0 + l0, o = pp - (pr & POS_MASK);
+                    const uint32_t m = lz::match_length(in, pp, pp - o, min(n - pp, CAP), n);
+                    if (m >= MIN_MATCH)
+                        atomicMax(&s_best[pr >> POS_BITS], (uint32_t)((int32_t)(2 * m) - (int32_t)zc::highbit(o + 3) + 12) << POS_BITS | (POS_MASK - o));
+                }
+            }
+            __syncwarp();
+            // ---- inherit + emit ----
+            uint32_t blen = 0, boff = 0;
+            if (searchable) {
+                const uint32_t best = s_best[lane];
+                if (best) {
+                    boff = POS_MASK - (best & POS_MASK);
+                    blen = ((best >> POS_BITS) - 12u + zc::highbit(boff + 3)) >> 1;
+                }
+            }
+            uint32_t capped = blen >= CAP ? 1u : 0u;
+            {
+                const uint32_t own = blen ? (lane + blen) << 22 | capped << 21 | boff : 0u;
+                uint32_t v = own;
+                int32_t e = blen ? (int32_t)(2 * (lane + blen)) - (int32_t)zc::highbit(boff + 3) : -1000;
+#pragma unroll
+                for (uint32_t d = 1; d < 32; d <<= 1) {
+                    const uint32_t u = __shfl_up_sync(0xffffffffu, v, d);
+                    const int32_t eu = __shfl_up_sync(0xffffffffu, e, d);
+                    if (lane >= d && eu > e) { v = u; e = eu; }
+                }
+                const uint32_t end = v >> 22;
+                if (v != own && end >= lane + MIN_MATCH && searchable) { blen = end - lane; boff = v & POS_MASK; capped = v >> 21 & 1u; }
+            }
+            if (p < t1) {
+                uint32_t r = 0;
+                if (blen) {
+                    const uint32_t be = min(n, (p / Z_BLOCK_MAX + 1) * Z_BLOCK_MAX);
+                    if (p + blen > be) { blen = be - p; capped = 0; }
+                    if (blen >= MIN_MATCH) {
+                        const uint32_t c = p - boff;
+                        uint32_t bback = 0;
+                        if (c >= 4 && p + 8 <= n) {  // one unaligned load each side: bytes [x-4, x)
+                            const uint32_t diff = (uint32_t)lz::ld8(in, p - 4) ^ (uint32_t)lz::ld8(in, c - 4);
+                            bback = diff == 0 ? 3u : (uint32_t)__clz((int)diff) >> 3;
+                            if (bback > 3) bback = 3;
+                        } else {
+                            while (bback < 3 && p > bback && c > bback && in[p - bback - 1] == in[c - bback - 1]) bback++;
+                        }
+                        r = pack_rec(boff, blen, capped, bback);
+                    }
+                }
+                __stcs(&rec[p], r);
+            }
+            __syncwarp();
+        }
+        sp = __shfl_sync(0xffffffffu, sp_next, 0);
     }
 }
 

@@ -29,6 +29,8 @@
 
 #include "../csrc/common.cuh"
 
+extern "C" int32_t sq_share_dedup(sq_ctx *ctx, sq_ctx *owner);
+
 namespace {
 
 const char kPrefix[] = "squish";           // header.rs:10
@@ -270,8 +272,12 @@ extern "C" int32_t sq_archive_list(const char *archive_path, sq_summary *summary
     return SQ_OK;
 }
 
-extern "C" int32_t sq_archive_pack(sq_ctx *ctx, const char *input_dir, const char *output_path, int32_t threads, sq_pack_report *report) {
-    if (!ctx || !input_dir || !output_path) return SQ_ERR_INVALID_ARG;
+// One host thread drives every device: batch k of the chunk stream goes to device k % D, pipeline slot (k / D) % 2, and batches
+// are waited for in the order they were submitted, so records reach the archive in chunk order.  With D > 1 the contexts share
+// ctxs[0]'s dedup index (sq_share_dedup): digests meet there in submission order.
+static int32_t pack_impl(sq_ctx **ctxs, uint32_t D, const char *input_dir, const char *output_path, int32_t threads, sq_pack_report *report) {
+    sq_ctx *ctx = ctxs[0];
+    auto on = [&](uint32_t d) -> sq_ctx * { if (D > 1) cudaSetDevice(ctxs[d]->device); return ctxs[d]; };
     const double t0 = now_s();
     double t_dev = 0;
     if (threads < 1) threads = 1;
@@ -301,6 +307,8 @@ extern "C" int32_t sq_archive_pack(sq_ctx *ctx, const char *input_dir, const cha
     }
     const uint64_t total_chunks = chunks.size();
     SQ_T("stat + chunk plan done");
+    for (uint32_t d = 0; d < D && D > 1; d++) if ((rc = sq_share_dedup(ctxs[d], ctx))) { if (d) snprintf(ctx->err, sizeof ctx->err, "%s", ctxs[d]->err); return rc; }
+    on(0);
     if ((rc = sq_dedup_ensure(ctx, total_chunks))) return rc;  // the index is sized to the job, not to the context's maximum
     if ((rc = sq_dedup_reset(ctx))) return rc;  // ChunkStore::new (writer.rs:88)
     SQ_T("dedup index ready");
@@ -321,30 +329,32 @@ extern "C" int32_t sq_archive_pack(sq_ctx *ctx, const char *input_dir, const cha
     // offer a few hundred chunks; pinned staging is sized to the job, because pinning memory costs ~0.4 s per GiB.
     uint64_t total_bytes_all = 0;
     for (auto &f : files) total_bytes_all += f.size + 16;
-    const size_t batch_bytes = (size_t)std::min<uint64_t>(512ull << 20, std::max<uint64_t>(total_bytes_all, 1u << 20));
+    size_t batch_bytes = (size_t)std::min<uint64_t>(512ull << 20, std::max<uint64_t>(total_bytes_all / D, 1u << 20));
+    if (const char *bb = getenv("SQ_PACK_BATCH_BYTES")) if (atoll(bb) > 0) batch_bytes = (size_t)atoll(bb);  // tests: many small batches
     const size_t slot_cap = batch_bytes + (size_t)cs;
     const bool pin = total_bytes_all >= kPinThreshold;
-    Batch bufs[2];
-    Staging in_stage[2], out_stage[2];
+    const uint32_t S = 2 * D;  // pipeline slots: two per device
+    std::vector<Batch> bufs(S);
+    std::vector<Staging> in_stage(S), out_stage(S), res_stage(S);
     auto bail = [&](int32_t code) {  // early exit: give the staging back and do not leave a truncated archive behind
-        for (int i = 0; i < 2; i++) { in_stage[i].release(ctx); out_stage[i].release(ctx); }
+        for (uint32_t i = 0; i < S; i++) { sq_ctx *c = on(i % D); in_stage[i].release(c); out_stage[i].release(c); res_stage[i].release(c); }
+        on(0);
         fclose(out);
         remove(output_path);
         return code;
     };
-    for (int i = 0; i < 2; i++) {
-        if ((rc = in_stage[i].alloc(ctx, slot_cap, pin))) return bail(rc);
+    for (uint32_t i = 0; i < S; i++) {
+        if ((rc = in_stage[i].alloc(on(i % D), slot_cap, pin))) return bail(rc);
         bufs[i].pinned = (uint8_t *)in_stage[i].p; bufs[i].cap = slot_cap;
     }
     uint64_t out_cap = sq_encode_bound(cs) * (uint64_t)(batch_bytes / cs + 1) + batch_bytes / 16;
     // the per-chunk results are small and always pinned: their download then never blocks sq_pack_submit
     struct Stage { sq_chunk_result *res = nullptr; void *h_out = nullptr; sq_ticket *ticket = nullptr; bool live = false; };
-    Stage stages[2];
-    Staging res_stage[2];
-    for (int i = 0; i < 2; i++) {
-        if ((rc = res_stage[i].alloc(ctx, (size_t)ctx->max_batch * sizeof(sq_chunk_result), true))) { res_stage[0].release(ctx); return bail(rc); }
+    std::vector<Stage> stages(S);
+    for (uint32_t i = 0; i < S; i++) {
+        if ((rc = res_stage[i].alloc(on(i % D), (size_t)ctx->max_batch * sizeof(sq_chunk_result), true))) return bail(rc);
         stages[i].res = (sq_chunk_result *)res_stage[i].p;
-        if ((rc = out_stage[i].alloc(ctx, out_cap, pin))) { res_stage[0].release(ctx); res_stage[1].release(ctx); return bail(rc); }
+        if ((rc = out_stage[i].alloc(on(i % D), out_cap, pin))) return bail(rc);
         stages[i].h_out = out_stage[i].p;
     }
     std::vector<uint8_t> digests(total_chunks * 16);
@@ -380,24 +390,26 @@ extern "C" int32_t sq_archive_pack(sq_ctx *ctx, const char *input_dir, const cha
     // Software pipeline over two slots: while batch k is on the GPU (sq_pack_submit), the host threads read batch k+1
     // into the other pinned buffer; sq_pack_wait(k) then overlaps its frame download with the kernels of batch k+1.
     uint64_t next = 0, unique = 0, payload = 0;
-    int head = 0, tail = 0, inflight = 0;
+    uint32_t head = 0, tail = 0, inflight = 0;
     while ((next < total_chunks || inflight) && !rc) {
-        if (next < total_chunks && inflight < 2) {
+        if (next < total_chunks && inflight < S) {
             Batch *b = &bufs[head];
             fill(b, next, &next);
             if (b->err) { rc = sq_set_error(ctx, b->err, "Error reading from squish: input file changed or unreadable"); break; }
             double td = now_s();
-            rc = sq_pack_submit(ctx, b->pinned, b->used, b->spans.data(), (uint32_t)b->spans.size(), b->first_gidx, stages[head].res,
+            rc = sq_pack_submit(on(head % D), b->pinned, b->used, b->spans.data(), (uint32_t)b->spans.size(), b->first_gidx, stages[head].res,
                                 stages[head].h_out, out_cap, &stages[head].ticket);
             t_dev += now_s() - td;
-            if (!rc) { stages[head].live = true; head ^= 1; inflight++; }
+            if (rc && head % D) snprintf(ctx->err, sizeof ctx->err, "%s", ctxs[head % D]->err);
+            if (!rc) { stages[head].live = true; head = (head + 1) % S; inflight++; }
             continue;
         }
         Batch *b = &bufs[tail];
         Stage &sg = stages[tail];
         uint64_t used = 0;
         double td = now_s();
-        rc = sq_pack_wait(ctx, sg.ticket, &used);
+        rc = sq_pack_wait(on(tail % D), sg.ticket, &used);
+        if (rc && tail % D) snprintf(ctx->err, sizeof ctx->err, "%s", ctxs[tail % D]->err);
         sg.live = false;
         t_dev += now_s() - td;
         if (!rc) {
@@ -415,15 +427,15 @@ extern "C" int32_t sq_archive_pack(sq_ctx *ctx, const char *input_dir, const cha
                 payload += sg.res[i].frame_len;
             }
         }
-        tail ^= 1; inflight--;
+        tail = (tail + 1) % S; inflight--;
     }
     if (rc) {  // drain whatever is still in flight (through the tickets that were issued) before the buffers go away
-        for (int i = 0; i < 2; i++) if (stages[i].live) { uint64_t u; sq_pack_wait(ctx, stages[i].ticket, &u); stages[i].live = false; }
+        for (uint32_t i = 0; i < S; i++) if (stages[i].live) { uint64_t u; sq_pack_wait(on(i % D), stages[i].ticket, &u); stages[i].live = false; }
     }
     SQ_T("all batches packed + records written");
     if (!rc) {
         uint64_t dl = 0;
-        rc = sq_dedup_len(ctx, &dl);  // chunk_store.len() (writer.rs:177-184)
+        rc = sq_dedup_len(on(0), &dl);  // chunk_store.len() (writer.rs:177-184)
         if (!rc && dl != unique) rc = sq_set_error(ctx, SQ_ERR_OTHER, "Unknown error: dedup index holds %llu digests, %llu records written", (unsigned long long)dl, (unsigned long long)unique);
     }
     if (!rc) {
@@ -448,7 +460,8 @@ extern "C" int32_t sq_archive_pack(sq_ctx *ctx, const char *input_dir, const cha
     uint64_t asize = 0;
     if (!rc) { fseek(out, 0, SEEK_END); asize = (uint64_t)ftell(out); }
     fclose(out);
-    for (int i = 0; i < 2; i++) { in_stage[i].release(ctx); out_stage[i].release(ctx); res_stage[i].release(ctx); }
+    for (uint32_t i = 0; i < S; i++) { sq_ctx *c = on(i % D); in_stage[i].release(c); out_stage[i].release(c); res_stage[i].release(c); }
+    on(0);
     if (!rc && report) {
         memset(report, 0, sizeof *report);
         report->archive_size = asize; report->unique_chunks = unique; report->total_chunks = total_chunks;
@@ -457,6 +470,18 @@ extern "C" int32_t sq_archive_pack(sq_ctx *ctx, const char *input_dir, const cha
         report->seconds_total = now_s() - t0; report->seconds_device = t_dev;
     }
     return rc;
+}
+
+extern "C" int32_t sq_archive_pack(sq_ctx *ctx, const char *input_dir, const char *output_path, int32_t threads, sq_pack_report *report) {
+    if (!ctx || !input_dir || !output_path) return SQ_ERR_INVALID_ARG;
+    return pack_impl(&ctx, 1, input_dir, output_path, threads, report);
+}
+
+extern "C" int32_t sq_archive_pack_multi(sq_ctx **ctxs, uint32_t n_ctx, const char *input_dir, const char *output_path, int32_t threads,
+                                         sq_pack_report *report) {
+    if (!ctxs || n_ctx == 0 || !input_dir || !output_path) return SQ_ERR_INVALID_ARG;
+    for (uint32_t i = 0; i < n_ctx; i++) if (!ctxs[i]) return SQ_ERR_INVALID_ARG;
+    return pack_impl(ctxs, n_ctx, input_dir, output_path, threads, report);
 }
 
 // ---- unpack, streaming: decoded batches go straight from the staging buffer into the files ------------------------------
@@ -649,6 +674,71 @@ int32_t unpack_streaming(sq_ctx *ctx, Archive &a, std::vector<ManifestEntry> &ma
     double t_dev = 0;
     rc = unpack_range(ctx, a, man, size, job, 0, a.records.size(), threads, &t_dev);
     SQ_T("all chunks decoded and written");
+    if (rc) return rc;
+    fill_summary(summary, a, total, t0, t_dev);
+    return SQ_OK;
+}
+
+// Unpack on several GPUs of one box (records are independent, so the path shards with no collective): the records
+// are cut into contiguous ranges of equal compressed + restored bytes, one range per context; every context runs the same
+// two-slot pipeline on its own device from its own host thread, and all of them write into the files created up front.
+extern "C" int32_t sq_archive_unpack_multi(sq_ctx **ctxs, uint32_t n_ctx, const char *archive_path, const char *output_dir, int32_t threads,
+                                           sq_summary *summary) {
+    if (!ctxs || n_ctx == 0 || !ctxs[0]) return SQ_ERR_INVALID_ARG;
+    for (uint32_t i = 0; i < n_ctx; i++) if (!ctxs[i]) return SQ_ERR_INVALID_ARG;
+    if (n_ctx == 1) return sq_archive_unpack(ctxs[0], archive_path, output_dir, threads, summary);
+    if (!archive_path || !output_dir) return SQ_ERR_INVALID_ARG;
+    sq_ctx *ctx = ctxs[0];
+    const double t0 = now_s();
+    if (threads < 1) threads = 1;
+    Archive a;
+    int32_t rc = open_archive(ctx, archive_path, &a, true);
+    if (rc) return rc;
+    std::vector<ManifestEntry> man;
+    uint64_t total = 0;
+    if ((rc = read_manifest(ctx, a, &man, &total))) return rc;
+    const size_t nrec = a.records.size();
+    std::vector<uint64_t> bound(nrec);
+    bool all_exact = true;
+    for (size_t i = 0; i < nrec; i++) {
+        const Record &r = a.records[i];
+        if (r.orig > (uint64_t)1 << 40) return sq_set_error(ctx, SQ_ERR_INVALID_CHUNK_SIZE, "Invalid chunk size: %llu bytes", (unsigned long long)r.orig);
+        if (r.orig > 0xFFFFFFFFull || r.comp > 0xFFFFFFFFull) return sq_set_error(ctx, SQ_ERR_READER, "Error reading from squish: chunk record too large");
+        bool ex = false;
+        bound[i] = payload_decoded_bound(r.payload, r.comp, r.orig, &ex);
+        all_exact = all_exact && ex;
+    }
+    if (!all_exact) return sq_archive_unpack(ctx, archive_path, output_dir, threads, summary);  // frames without a stated size: the one-device store path
+    UnpackJob job;
+    if ((rc = unpack_prepare(ctx, a, man, bound, output_dir, threads, &job))) return rc;
+    std::vector<size_t> cut(n_ctx + 1, nrec);
+    {
+        const uint64_t all = job.total_out + job.total_comp;
+        uint64_t acc = 0;
+        uint32_t k = 1;
+        cut[0] = 0;
+        for (size_t i = 0; i < nrec && k < n_ctx; i++) {
+            acc += ((bound[i] + 15) & ~15ull) + ((a.records[i].comp + 15) & ~15ull);
+            while (k < n_ctx && acc * n_ctx >= all * k) cut[k++] = i + 1;
+        }
+    }
+    std::vector<int32_t> rcs(n_ctx, SQ_OK);
+    std::vector<double> tdev(n_ctx, 0.0);
+    std::vector<std::thread> workers;
+    const int32_t per = std::max<int32_t>(1, threads / (int32_t)n_ctx);
+    for (uint32_t k = 0; k < n_ctx; k++)
+        workers.emplace_back([&, k] {
+            if (cut[k] >= cut[k + 1]) return;
+            if (cudaSetDevice(ctxs[k]->device) != cudaSuccess) { rcs[k] = sq_set_error(ctxs[k], SQ_ERR_CUDA, "cudaSetDevice(%d) failed", ctxs[k]->device); return; }
+            rcs[k] = unpack_range(ctxs[k], a, man, bound, job, cut[k], cut[k + 1], per, &tdev[k]);
+        });
+    for (auto &w : workers) w.join();
+    cudaSetDevice(ctx->device);
+    double t_dev = 0;
+    for (uint32_t k = 0; k < n_ctx; k++) {
+        t_dev = std::max(t_dev, tdev[k]);
+        if (rcs[k] && !rc) { rc = rcs[k]; if (k) snprintf(ctx->err, sizeof ctx->err, "%s", ctxs[k]->err); }
+    }
     if (rc) return rc;
     fill_summary(summary, a, total, t0, t_dev);
     return SQ_OK;

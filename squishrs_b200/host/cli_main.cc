@@ -48,7 +48,8 @@ static void usage() {
             "Compact, compress, and deduplicate files into a single archive\n\n"
             "Usage: squishrs [OPTIONS] <COMMAND>\n\nCommands:\n  pack    Pack a directory\n  list    List files in an archive\n"
             "  unpack  Extract archive contents\n\nOptions:\n  -j, --max-threads <MAX_THREADS>  [default: 25]\n"
-            "      --device <N>                 CUDA device ordinal [default: 0]\n");
+            "      --device <N>                 CUDA device ordinal [default: 0]\n"
+            "      --devices <K>                use K GPUs of this box, ordinals device .. device+K-1 [default: 1]\n");
 }
 static int fail(const char *what) {
     fprintf(stderr, "\033[31mError: %s\033[0m\n", what);  // main.rs:6-8
@@ -56,7 +57,7 @@ static int fail(const char *what) {
 }
 
 int main(int argc, char **argv) {
-    int threads = 25, device = 0;  // cmd/mod.rs:16
+    int threads = 25, device = 0, devices = 1;  // cmd/mod.rs:16
     bool simple = false;
     std::string cmd, arg, output;
     bool have_out = false;
@@ -64,6 +65,7 @@ int main(int argc, char **argv) {
         std::string a = argv[i];
         if ((a == "-j" || a == "--max-threads") && i + 1 < argc) threads = atoi(argv[++i]);
         else if (a == "--device" && i + 1 < argc) device = atoi(argv[++i]);
+        else if (a == "--devices" && i + 1 < argc) devices = atoi(argv[++i]);
         else if ((a == "-o" || a == "--output") && i + 1 < argc) { output = argv[++i]; have_out = true; }
         else if (a == "--simple") simple = true;
         else if (a == "-h" || a == "--help") { usage(); return 0; }
@@ -136,10 +138,18 @@ int main(int argc, char **argv) {
     int32_t rc = sq_create(&cfg, &ctx);
     tmark("sq_create done", t_start);
     if (rc) return fail(sq_last_error(nullptr));
+    std::vector<sq_ctx *> ctxs{ctx};
+    for (int k = 1; k < devices; k++) {  // one context per GPU, all owned by this process
+        sq_config ck = cfg;
+        ck.device = device + k;
+        sq_ctx *c = nullptr;
+        if ((rc = sq_create(&ck, &c))) return fail(sq_last_error(nullptr));
+        ctxs.push_back(c);
+    }
     if (cmd == "pack") {  // lib.rs:26-56
         if (!have_out) output = arg + ".squish";  // default uses the UNtrimmed input (lib.rs:31)
         sq_pack_report rep;
-        rc = sq_archive_pack(ctx, arg.c_str(), output.c_str(), threads, &rep);
+        rc = sq_archive_pack_multi(ctxs.data(), (uint32_t)ctxs.size(), arg.c_str(), output.c_str(), threads, &rep);
         if (rc) { std::string m = sq_last_error(ctx); sq_destroy(ctx); return fail(m.c_str()); }
         const char *shown = output.rfind("./", 0) == 0 ? output.c_str() + 2 : output.c_str();
         printf("\033[32mPacking complete!\033[0m\nCompressed to %s\n\033[34mFinal archive size\033[0m: %s\n", shown, format_bytes(rep.archive_size).c_str());
@@ -150,7 +160,7 @@ int main(int argc, char **argv) {
             if (output.size() >= suf.size() && output.compare(output.size() - suf.size(), suf.size(), suf) == 0) output.resize(output.size() - suf.size());
         }
         sq_summary s;
-        rc = sq_archive_unpack(ctx, arg.c_str(), output.c_str(), threads, &s);
+        rc = sq_archive_unpack_multi(ctxs.data(), (uint32_t)ctxs.size(), arg.c_str(), output.c_str(), threads, &s);
         if (rc) { std::string m = sq_last_error(ctx); sq_destroy(ctx); return fail(m.c_str()); }
         printf("\033[32mUnpacking complete!\033[0m\n%s was unsquished into /%s\n", arg.c_str(), output.c_str());
     }

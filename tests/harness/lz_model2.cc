@@ -22,11 +22,14 @@ struct P2 {
     int chain;        // 1: candidates come from a full per-position hash chain (upper bound study), depth = K
     int short_keep;   // > 0: candidates whose first 8 bytes do not all match ("short") are verified only for the short_keep nearest; 0 = all
     int tag_bits;     // > 0 (with short_keep): long/short classes come from ptag (5 bits of the row hash) and xtag (tag_bits bits of a hash of bytes 5..7) instead of the bytes
-    int long_cap;     // > 0: at most this many long candidates per position enter the pair queue (slot order)
+    int long_cap;     // > 0: at most this many long candidates per position enter the pair queue (the nearest ones)
     int skip_capped;  // > 0: positions p with p % skip_capped != 0 are not searched when their anchor (p rounded down) found a match still >= CAP long at p
     int ins_stride;   // > 1: only positions p % ins_stride == 0 enter the table (every position is still searched; continuation = same pair ins_stride positions earlier)
     int skip_runs;    // 1: a position whose 5-byte prefix equals the previous position's (inside a run of one byte) is not inserted
     int cont;         // continuation filter: 0 off, 1 exact (pair (p-1,c-1) was a candidate pair), 2 previous byte equal; refresh every 16 positions
+    int group_skip;   // 1: a group of 32 positions that lies inside a match already known to be long (the record in front of the group is capped and the
+                      // match goes on for 64 more bytes) is not searched: every position inherits (offset, CAP, may-be-longer)
+    int cont_period;  // > 0: the filter keeps everything at positions p % cont_period == 0 (the first column of a search group) and is independent of the tile
 };
 
 static inline uint64_t rd64(const uint8_t *p) { uint64_t v; memcpy(&v, p, 8); return v; }
@@ -77,6 +80,11 @@ extern "C" long lz_model2_frame(const uint8_t *s, uint32_t n, uint8_t *dst, uint
             for (int phase = 0; phase < (P.skip_capped ? 2 : 1); phase++)
             for (uint32_t p = t0; p < t1 && p + 8 <= n; p++) {
                 if (p % (uint32_t)P.stride) continue;
+                if (P.group_skip && (p & 31u) == 0 && p >= 32 && (p & 255u) != 0 && p + 32 + CAP + 16 <= n) {
+                    uint32_t q = p - 1, go = 0;
+                    for (uint32_t d = 0; d < 32 && !go; d++) if (blen[p - 1 - d] >= CAP && blen[p - 1 - d] > d) { go = boff[p - 1 - d]; q = p - 1 - d; }
+                    if (go && match_len(s, p, p - go, n, 64) >= 64) { for (uint32_t k = 0; k < 32; k++) { blen[p + k] = CAP; boff[p + k] = go; } nskipped += 32; p += 31; continue; }
+                }
                 if (P.skip_capped) {
                     const uint32_t a = p - p % (uint32_t)P.skip_capped;
                     if ((phase == 0) != (a == p)) continue;
@@ -84,14 +92,14 @@ extern "C" long lz_model2_frame(const uint8_t *s, uint32_t n, uint8_t *dst, uint
                 }
                 uint32_t bl = 0, bo = 0; int32_t bs = -1000;
                 if (P.ins_stride > 1) { hist[p & 3] = curc; prevc = hist[(p + 4 - P.ins_stride) & 3]; if (p < t0 + (uint32_t)P.ins_stride) prevc.clear(); curc.clear(); }
-                else { prevc.swap(curc); curc.clear(); if (p == t0) prevc.clear(); }
+                else { prevc.swap(curc); curc.clear(); if (p == t0 && !P.cont_period) prevc.clear(); }
                 auto consider = [&](uint32_t c) {
                     if (c >= p) return;
                     if (rd32(s + c) != rd32(s + p)) return;
                     if (P.cont) {
                         if (std::find(curc.begin(), curc.end(), c) != curc.end()) return;  // same candidate from the second table
                         curc.push_back(c);
-                        if ((p & 15u) != 0 && p > t0 && c > 0) {
+                        if ((P.cont_period ? p % (uint32_t)P.cont_period != 0 : ((p & 15u) != 0 && p > t0)) && c > 0) {
                             const uint32_t st = P.ins_stride > 1 ? (uint32_t)P.ins_stride : 1u;
                             if (P.cont == 1 && c >= st && std::find(prevc.begin(), prevc.end(), c - st) != prevc.end()) return;
                             if (P.cont == 2 && s[p - 1] == s[c - 1]) return;
@@ -113,7 +121,8 @@ extern "C" long lz_model2_frame(const uint8_t *s, uint32_t n, uint8_t *dst, uint
                     const uint32_t h = hashN(rd64(s + p), P.mm, P.rows_log);
                     if (P.short_keep) {
                         uint32_t shorts[64]; int ns = 0, nl = 0;
-                        auto consider_long = [&](uint32_t c) { nlong++; if (P.long_cap && nl >= P.long_cap) return; nl++; consider(c); };
+                        uint32_t longs[64]; int nlq = 0;
+                        auto consider_long = [&](uint32_t c) { nlong++; if (P.long_cap) { longs[nlq++] = c; return; } nl++; consider(c); };
                         for (uint32_t k = 0; k < K; k++) {
                             const uint32_t e = tab[(size_t)h * K + k];
                             if (!e || e - 1 >= p) continue;
@@ -128,6 +137,7 @@ extern "C" long lz_model2_frame(const uint8_t *s, uint32_t n, uint8_t *dst, uint
                             if (rd64(s + e - 1) == rd64(s + p)) consider(e - 1);
                             else if (rd32(s + e - 1) == rd32(s + p) && s[e - 1 + 4] == s[p + 4]) shorts[ns++] = e - 1;
                         }
+                        if (P.long_cap) { std::sort(longs, longs + nlq); for (int i = 0; i < P.long_cap && i < nlq; i++) consider(longs[nlq - 1 - i]); }  // the nearest long_cap long candidates
                         std::sort(shorts, shorts + ns);
                         for (int i = 0; i < P.short_keep && i < ns; i++) consider(shorts[ns - 1 - i]);
                     } else
@@ -207,13 +217,14 @@ extern "C" long lz_model2_frame(const uint8_t *s, uint32_t n, uint8_t *dst, uint
     return o - dst;
 }
 
-// The parameters the GPU ships (zstd_enc_lz2.cuh): 2^14 rows x 32 entries, 5 + 6 tag bits, nearest short candidate only, exact
-// continuation filter, one step of 2048 positions inserted before it is searched, 5-byte matches (4 in chunks <= 128 KiB), no
-// inserts inside runs of one byte.
+// The parameters the GPU ships (zstd_enc_lz2.cuh): 2^14 rows, the 32 most recent earlier positions of the row as candidates
+// (tile = 1024: the window of a position ends at its row's fill level after the 1024-position tile it lies in), 5 + 6 tag bits, nearest
+// short candidate only, exact continuation filter refreshed at the first column of every group of 32, 5-byte matches (4 in
+// chunks <= 128 KiB), no inserts inside runs of one byte.
 extern "C" long lz_model2_shipped(const uint8_t *s, uint32_t n, uint8_t *dst, uint32_t cap_dst) {
     P2 P;
     memset(&P, 0, sizeof P);
-    P.rows_log = 14; P.K = 32; P.mm = n <= 128u * 1024u ? 4 : 5; P.cap = 32; P.stride = 1; P.tile = 2048; P.sel_mul = 2;
+    P.rows_log = 14; P.K = 32; P.mm = n <= 128u * 1024u ? 4 : 5; P.cap = 32; P.stride = 1; P.tile = 1024; P.sel_mul = 2; P.cont_period = 32;
     P.short_keep = 1; P.tag_bits = 6; P.cont = 1; P.skip_runs = 1;
     return lz_model2_frame(s, n, dst, cap_dst, &P, nullptr);
 }

@@ -282,6 +282,47 @@ def test_archive_roundtrip_both_directions(sq, oracle, tmp_path):
     assert read_tree(tmp_path / "out_from_gpu") == read_tree(src)
 
 
+def record_digests(path):
+    a = Path(path).read_bytes()
+    n = struct.unpack_from("<Q", a, 19)[0]
+    p, out = 27, []
+    for _ in range(n):
+        out.append(a[p:p + 16])
+        p += 32 + struct.unpack_from("<Q", a, p + 24)[0]
+    return out
+
+
+def test_archive_several_contexts_share_one_index(sq, oracle, tmp_path, monkeypatch):
+    """sq_archive_pack_multi / sq_archive_unpack_multi: batches dealt to several contexts (two GPUs when the box has them, else
+    two contexts on one GPU -- the same code path, the digests then travel device-to-device on one device).  The archive must
+    hold exactly the records a single context writes, in the same order (first occurrence wins across devices), the reference
+    reader must restore the tree from it, and the multi-context unpack must restore it too."""
+    import torch
+    from squishrs_b200.archive import ArchiveReader, ArchiveWriter
+    src = tmp_path / "in"
+    spec = tree_spec()
+    rng = random.Random(9)
+    for i in range(6):  # more chunks, with duplicates that sit in different batches
+        spec[f"more/f{i}.bin"] = rng.randbytes(2 * MiB + 999 * i) + spec["big.bin"][:2 * MiB]
+    make_tree(src, spec)
+    monkeypatch.setenv("SQ_PACK_BATCH_BYTES", str(5 * MiB))
+    ArchiveWriter(src, tmp_path / "one.squish", ctx=sq.Context(), threads=8).pack()
+    devs = [0, 1] if torch.cuda.device_count() >= 2 else [0, 0]
+    ctxs = [sq.Context(device=d) for d in devs]
+    w = ArchiveWriter(src, tmp_path / "multi.squish", ctxs=ctxs, threads=8)
+    w.pack()
+    assert record_digests(tmp_path / "multi.squish") == record_digests(tmp_path / "one.squish")
+    assert parse_manifest(tmp_path / "multi.squish") == parse_manifest(tmp_path / "one.squish")
+    rc, _ = oracle.unpack(tmp_path / "multi.squish", tmp_path / "out_ref")
+    assert rc == 0 and read_tree(tmp_path / "out_ref") == read_tree(src)
+    ArchiveReader(tmp_path / "multi.squish", threads=8).unpack(tmp_path / "out_multi", ctxs=ctxs)
+    assert read_tree(tmp_path / "out_multi") == read_tree(src)
+    rc, _ = oracle.pack_dir(src, tmp_path / "cpu.squish", threads=8)
+    assert rc == 0
+    ArchiveReader(tmp_path / "cpu.squish", threads=8).unpack(tmp_path / "out_multi2", ctxs=ctxs)
+    assert read_tree(tmp_path / "out_multi2") == read_tree(src)
+
+
 def test_unpack_reference_fixture(sq, tmp_path):
     # reference src/archive/tests.rs:141-166
     from squishrs_b200.archive import ArchiveReader
