@@ -34,8 +34,9 @@ struct sq_enc_scratch {
     uint32_t *sbits;         // per entropy warp: FSE state-transition records + packed symbol codes, 4 x SEQ_PER_BLOCK
     uint32_t ent_warps;
     uint32_t *list;          // [lz_sub * lz2::LIST_STRIDE] the chunks' sorted row lists (index_kernel -> search_kernel)
+    uint32_t *words;         // [lz_sub * lz::REC_PER_CHUNK] index_kernel pass 1 -> pass 2: row + tags of every position
     uint32_t *span_start;    // [lz_sub + 1] search spans of a sub-batch, exclusive prefix
-    uint32_t lz_sub, search_ctas;
+    uint32_t lz_sub, search_ctas; int lz_variant;
     cudaEvent_t tev[5];      // SQ_FLAG_STAGE_TIMING: before search / after search / after chase / after entropy / after emit
     int tev_valid;
     uint32_t cap_chunks;
@@ -181,8 +182,10 @@ __global__ void __launch_bounds__(256) enc_emit_kernel(const uint8_t *__restrict
 // ---- search: sub-batches of at most LZ_SUB chunks go through span_plan -> index -> search; the list scratch (8 MB per chunk of a
 // sub-batch) is what bounds the sub-batch ----
 namespace {
-constexpr int LZ_SEARCH_THREADS = 256, LZ_SEARCH_MINB = 3, LZ_INDEX_THREADS = 1024;
+constexpr int LZ_SEARCH_THREADS = 256, LZ_INDEX_THREADS = 512, LZ_INDEX_PARTS = 4;
 constexpr uint32_t LZ_SUB_MAX = 512;
+// variant 0 ships: three CTAs per SM (80 registers), 1024-entry continuation table; variant 1 (SQ_LZ_VARIANT=1): four CTAs per SM (64 registers), 512 entries
+static int search_smem(int variant) { return (int)((variant == 1 ? lz2::SearchSmem<9>::PER_WARP : lz2::SearchSmem<10>::PER_WARP) * (LZ_SEARCH_THREADS / 32)); }
 }  // namespace
 
 static int32_t enc_scratch(sq_ctx *ctx, uint32_t n, int set) {
@@ -198,15 +201,21 @@ static int32_t enc_scratch(sq_ctx *ctx, uint32_t n, int set) {
             SQ_CUDA(ctx, cudaFuncSetAttribute(lz::entropy_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         }
         {   // search: all warps are interchangeable, the grid is what is resident
-            auto kern = lz2::search_kernel<LZ_SEARCH_THREADS, LZ_SEARCH_MINB>;
-            const int smem = (int)(lz2::SearchSmem::PER_WARP * (LZ_SEARCH_THREADS / 32));
-            SQ_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            SQ_CUDA(ctx, cudaFuncSetAttribute(lz2::index_kernel<LZ_INDEX_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(lz2::ROWS * sizeof(uint32_t))));
+            static const int var = getenv("SQ_LZ_VARIANT") ? atoi(getenv("SQ_LZ_VARIANT")) : 0;
+            e->lz_variant = var == 1 ? 1 : 0;
+            SQ_CUDA(ctx, cudaFuncSetAttribute(lz2::index_kernel<LZ_INDEX_THREADS, LZ_INDEX_PARTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(lz2::ROWS * sizeof(uint32_t))));
             int per_sm = 0;
-            SQ_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, LZ_SEARCH_THREADS, smem));
+            const int smem = search_smem(e->lz_variant);
+            if (e->lz_variant == 1) {
+                SQ_CUDA(ctx, cudaFuncSetAttribute(lz2::search_kernel<LZ_SEARCH_THREADS, 4, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+                SQ_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lz2::search_kernel<LZ_SEARCH_THREADS, 4, 9>, LZ_SEARCH_THREADS, smem));
+            } else {
+                SQ_CUDA(ctx, cudaFuncSetAttribute(lz2::search_kernel<LZ_SEARCH_THREADS, 3, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+                SQ_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lz2::search_kernel<LZ_SEARCH_THREADS, 3, 10>, LZ_SEARCH_THREADS, smem));
+            }
             if (per_sm < 1) return sq_set_error(ctx, SQ_ERR_CUDA, "search kernel does not fit this device");
             e->search_ctas = (uint32_t)(per_sm * ctx->sm_count);
-            if (getenv("SQ_TIMING")) fprintf(stderr, "[sq] search kernel: %d threads, %d CTAs per SM, %d B of shared memory per CTA\n", LZ_SEARCH_THREADS, per_sm, smem);
+            if (getenv("SQ_TIMING")) fprintf(stderr, "[sq] search kernel variant %d: %d threads, %d CTAs per SM, %d B of shared memory per CTA\n", e->lz_variant, LZ_SEARCH_THREADS, per_sm, smem);
         }
         SQ_CUDA(ctx, cudaMalloc(&e->lits, (size_t)e->ent_warps * (Z_BLOCK_MAX + 64)));
         SQ_CUDA(ctx, cudaMalloc(&e->sbits, (size_t)e->ent_warps * lz::SBITS_STRIDE * sizeof(uint32_t)));
@@ -216,7 +225,7 @@ static int32_t enc_scratch(sq_ctx *ctx, uint32_t n, int set) {
     if (e->cap_chunks < n) {
         SQ_CUDA(ctx, cudaDeviceSynchronize());
         cudaFree(e->blocks); cudaFree(e->frame_len); cudaFree(e->bodies); cudaFree(e->seqs); cudaFree(e->meta); cudaFree(e->rec);
-        cudaFree(e->list); cudaFree(e->span_start); e->list = nullptr; e->span_start = nullptr;
+        cudaFree(e->list); cudaFree(e->words); cudaFree(e->span_start); e->list = nullptr; e->words = nullptr; e->span_start = nullptr;
         e->rec = nullptr; e->blocks = nullptr; e->frame_len = nullptr; e->bodies = nullptr; e->seqs = nullptr; e->meta = nullptr; e->cap_chunks = 0;
         uint32_t cap = n;
         SQ_CUDA(ctx, cudaMalloc(&e->blocks, (size_t)cap * SQ_MAX_BLOCKS * sizeof(sq_block_info)));
@@ -227,6 +236,7 @@ static int32_t enc_scratch(sq_ctx *ctx, uint32_t n, int set) {
         SQ_CUDA(ctx, cudaMalloc(&e->rec, (size_t)cap * lz::REC_PER_CHUNK * sizeof(uint32_t)));
         e->lz_sub = cap < LZ_SUB_MAX ? cap : LZ_SUB_MAX;
         SQ_CUDA(ctx, cudaMalloc(&e->list, (size_t)e->lz_sub * lz2::LIST_STRIDE * sizeof(uint32_t)));
+        SQ_CUDA(ctx, cudaMalloc(&e->words, (size_t)e->lz_sub * lz::REC_PER_CHUNK * sizeof(uint32_t)));
         SQ_CUDA(ctx, cudaMalloc(&e->span_start, (size_t)(e->lz_sub + 1) * sizeof(uint32_t)));
         e->cap_chunks = cap;
     }
@@ -239,7 +249,7 @@ void sq_enc_destroy(sq_ctx *ctx) {
         if (!e) continue;
         cudaFree(e->blocks); cudaFree(e->frame_len); cudaFree(e->bodies); cudaFree(e->status); cudaFree(e->seqs); cudaFree(e->meta); cudaFree(e->rec);
         for (int i = 0; i < 5; i++) if (e->tev[i]) cudaEventDestroy(e->tev[i]);
-        cudaFree(e->list); cudaFree(e->span_start); cudaFree(e->lits); cudaFree(e->sbits);
+        cudaFree(e->list); cudaFree(e->words); cudaFree(e->span_start); cudaFree(e->lits); cudaFree(e->sbits);
         delete e;
         ctx->enc_sets[set] = nullptr;
         if (ctx->enc_set_done[set]) cudaEventDestroy(ctx->enc_set_done[set]);
@@ -292,15 +302,31 @@ int32_t sq_encode_device_set(sq_ctx *ctx, int set, const void *d_data, const sq_
         if (timing) SQ_CUDA(ctx, cudaEventRecord(e->tev[0], st));
         // search: per sub-batch, the chunks' sorted row lists (one CTA per chunk), then every warp of the grid on any 256 positions
         static const uint32_t dbg = getenv("SQ_LZ2_DBG") ? (uint32_t)atoi(getenv("SQ_LZ2_DBG")) : 0u;
-        const int search_smem = (int)(lz2::SearchSmem::PER_WARP * (LZ_SEARCH_THREADS / 32));
         for (uint32_t first = 0; first < n; first += e->lz_sub) {
             const uint32_t count = n - first < e->lz_sub ? n - first : e->lz_sub;
             lz2::span_plan_kernel<<<1, 1024, 0, st>>>(d_spans, d_select, first, count, e->span_start, e->status + 1);
-            const uint32_t ictas = count < (uint32_t)ctx->sm_count ? count : (uint32_t)ctx->sm_count;
-            lz2::index_kernel<LZ_INDEX_THREADS><<<ictas, LZ_INDEX_THREADS, lz2::ROWS * sizeof(uint32_t), st>>>((const uint8_t *)d_data, d_spans, d_select, first, count,
-                                                                                                             e->list, e->rec);
-            lz2::search_kernel<LZ_SEARCH_THREADS, LZ_SEARCH_MINB><<<e->search_ctas, LZ_SEARCH_THREADS, search_smem, st>>>((const uint8_t *)d_data, d_spans, first, count,
-                                                                                                                        e->span_start, e->list, e->rec, e->status + 1, dbg);
+            {   // one cluster of LZ_INDEX_PARTS CTAs per chunk in flight, two CTAs per SM
+                const uint32_t resident = 2u * (uint32_t)ctx->sm_count / LZ_INDEX_PARTS;
+                cudaLaunchConfig_t cfg;
+                memset(&cfg, 0, sizeof cfg);
+                cfg.gridDim = dim3((count < resident ? count : resident) * LZ_INDEX_PARTS, 1, 1);
+                cfg.blockDim = dim3(LZ_INDEX_THREADS, 1, 1);
+                cfg.dynamicSmemBytes = lz2::ROWS * sizeof(uint32_t);
+                cfg.stream = st;
+                cudaLaunchAttribute attr[1];
+                attr[0].id = cudaLaunchAttributeClusterDimension;
+                attr[0].val.clusterDim.x = LZ_INDEX_PARTS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+                cfg.attrs = attr;
+                cfg.numAttrs = 1;
+                SQ_CUDA(ctx, cudaLaunchKernelEx(&cfg, lz2::index_kernel<LZ_INDEX_THREADS, LZ_INDEX_PARTS>, (const uint8_t *)d_data, d_spans, d_select, first, count,
+                                                e->list, e->words, e->rec));
+            }
+            if (e->lz_variant == 1)
+                lz2::search_kernel<LZ_SEARCH_THREADS, 4, 9><<<e->search_ctas, LZ_SEARCH_THREADS, search_smem(1), st>>>((const uint8_t *)d_data, d_spans, first, count, e->span_start,
+                                                                                                                   e->list, e->rec, e->status + 1, dbg);
+            else
+                lz2::search_kernel<LZ_SEARCH_THREADS, 3, 10><<<e->search_ctas, LZ_SEARCH_THREADS, search_smem(0), st>>>((const uint8_t *)d_data, d_spans, first, count, e->span_start,
+                                                                                                                    e->list, e->rec, e->status + 1, dbg);
             SQ_LAUNCHED(ctx, 3);
         }
         if (timing) SQ_CUDA(ctx, cudaEventRecord(e->tev[1], st));

@@ -56,6 +56,7 @@ extern "C" long lz_model2_frame(const uint8_t *s, uint32_t n, uint8_t *dst, uint
     const P2 P = *Pp;
     const uint32_t MM = (uint32_t)P.mm, CAP = (uint32_t)P.cap;
     std::vector<uint32_t> blen(n + 64, 0), boff(n + 64, 0);
+    std::vector<uint8_t> noback(n + 64, 0);
     uint64_t nverify = 0, nrows = 0, nlong = 0, nskipped = 0;
     // ---- stage S: search ----
     {
@@ -83,7 +84,7 @@ extern "C" long lz_model2_frame(const uint8_t *s, uint32_t n, uint8_t *dst, uint
                 if (P.group_skip && (p & 31u) == 0 && p >= 32 && (p & 255u) != 0 && p + 32 + CAP + 16 <= n) {
                     uint32_t q = p - 1, go = 0;
                     for (uint32_t d = 0; d < 32 && !go; d++) if (blen[p - 1 - d] >= CAP && blen[p - 1 - d] > d) { go = boff[p - 1 - d]; q = p - 1 - d; }
-                    if (go && match_len(s, p, p - go, n, 64) >= 64) { for (uint32_t k = 0; k < 32; k++) { blen[p + k] = CAP; boff[p + k] = go; } nskipped += 32; p += 31; continue; }
+                    if (go && match_len(s, p, p - go, n, 64) >= 64) { for (uint32_t k = 0; k < 32; k++) { blen[p + k] = CAP; boff[p + k] = go; noback[p + k] = 1; } nskipped += 32; p += 31; continue; }
                 }
                 if (P.skip_capped) {
                     const uint32_t a = p - p % (uint32_t)P.skip_capped;
@@ -176,7 +177,7 @@ extern "C" long lz_model2_frame(const uint8_t *s, uint32_t n, uint8_t *dst, uint
         if (l < MM) continue;
         uint32_t k = 0;
         const uint32_t c = p - boff[p];
-        while (k < 3 && p > k && c > k && s[p - k - 1] == s[c - k - 1]) k++;
+        while (!noback[p] && k < 3 && p > k && c > k && s[p - k - 1] == s[c - k - 1]) k++;
         rec[p] = boff[p] | (l - zparse::LEN_BASE) << 21 | capped << 26 | k << 27;
     }
     uint8_t *o = dst;
@@ -218,13 +219,13 @@ extern "C" long lz_model2_frame(const uint8_t *s, uint32_t n, uint8_t *dst, uint
 }
 
 // The parameters the GPU ships (zstd_enc_lz2.cuh): 2^14 rows, the 32 most recent earlier positions of the row as candidates
-// (tile = 1024: the window of a position ends at its row's fill level after the 1024-position tile it lies in), 5 + 6 tag bits, nearest
+// (tile = 512: the window of a position ends at its row's fill level after the 512-position tile it lies in), 5 + 6 tag bits, nearest
 // short candidate only, exact continuation filter refreshed at the first column of every group of 32, 5-byte matches (4 in
 // chunks <= 128 KiB), no inserts inside runs of one byte.
 extern "C" long lz_model2_shipped(const uint8_t *s, uint32_t n, uint8_t *dst, uint32_t cap_dst) {
     P2 P;
     memset(&P, 0, sizeof P);
-    P.rows_log = 14; P.K = 32; P.mm = n <= 128u * 1024u ? 4 : 5; P.cap = 32; P.stride = 1; P.tile = 1024; P.sel_mul = 2; P.cont_period = 32;
+    P.rows_log = 14; P.K = 32; P.mm = n <= 128u * 1024u ? 4 : 5; P.cap = 32; P.stride = 1; P.tile = 512; P.sel_mul = 2; P.cont_period = 32; P.group_skip = 1;
     P.short_keep = 1; P.tag_bits = 6; P.cont = 1; P.skip_runs = 1;
     return lz_model2_frame(s, n, dst, cap_dst, &P, nullptr);
 }
