@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(256) enc_emit_kernel(const uint8_t *__restrict
 // sub-batch) is what bounds the sub-batch ----
 namespace {
 constexpr int LZ_SEARCH_THREADS = 256, LZ_INDEX_THREADS = 512, LZ_INDEX_PARTS = 4;
-constexpr uint32_t LZ_SUB_MAX = 512;
+constexpr uint32_t LZ_SUB_MAX = 256;
 // variant 0 ships: three CTAs per SM (80 registers), 1024-entry continuation table; variant 1 (SQ_LZ_VARIANT=1): four CTAs per SM (64 registers), 512 entries
 static int search_smem(int variant) { return (int)((variant == 1 ? lz2::SearchSmem<9>::PER_WARP : lz2::SearchSmem<10>::PER_WARP) * (LZ_SEARCH_THREADS / 32)); }
 }  // namespace
