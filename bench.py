@@ -1073,7 +1073,7 @@ def main():
     ap.add_argument("--e2e-chunks", type=int, default=2048)
     ap.add_argument("--ref-chunks", type=int, default=0)
     ap.add_argument("--frames", type=int, default=200000, help="config5: small-file frames in the whole job")
-    ap.add_argument("--unpack-chunks", type=int, default=256, help="2 MiB oracle-written frames in the unpack section")
+    ap.add_argument("--unpack-chunks", type=int, default=1536, help="2 MiB oracle-written frames in the unpack section")
     ap.add_argument("--unpack-small", type=int, default=16384, help="small-file frames in the unpack section")
     ap.add_argument("--single-stream", action="store_true", help="run every step on one stream (no overlap between consecutive steps)")
     ap.add_argument("--no-e2e", action="store_true")

@@ -343,20 +343,24 @@ static int32_t pack_impl(sq_ctx **ctxs, uint32_t D, const char *input_dir, const
         remove(output_path);
         return code;
     };
-    for (uint32_t i = 0; i < S; i++) {
-        if ((rc = in_stage[i].alloc(on(i % D), slot_cap, pin))) return bail(rc);
-        bufs[i].pinned = (uint8_t *)in_stage[i].p; bufs[i].cap = slot_cap;
-    }
     uint64_t out_cap = sq_encode_bound(cs) * (uint64_t)(batch_bytes / cs + 1) + batch_bytes / 16;
     // the per-chunk results are small and always pinned: their download then never blocks sq_pack_submit
     struct Stage { sq_chunk_result *res = nullptr; void *h_out = nullptr; sq_ticket *ticket = nullptr; bool live = false; };
     std::vector<Stage> stages(S);
-    for (uint32_t i = 0; i < S; i++) {
-        if ((rc = res_stage[i].alloc(on(i % D), (size_t)ctx->max_batch * sizeof(sq_chunk_result), true))) return bail(rc);
+    // A slot's staging is allocated when the slot is first used: pinning costs ~0.4 s per GiB, and this way the first batch is on
+    // its GPU while the memory of the later slots is still being pinned (a job of one batch never pays for the others).
+    auto ensure_slot = [&](uint32_t i) -> int32_t {
+        if (in_stage[i].p) return SQ_OK;
+        sq_ctx *c = on(i % D);
+        int32_t r;
+        if ((r = in_stage[i].alloc(c, slot_cap, pin))) return r;
+        bufs[i].pinned = (uint8_t *)in_stage[i].p; bufs[i].cap = slot_cap;
+        if ((r = res_stage[i].alloc(c, (size_t)ctx->max_batch * sizeof(sq_chunk_result), true))) return r;
         stages[i].res = (sq_chunk_result *)res_stage[i].p;
-        if ((rc = out_stage[i].alloc(on(i % D), out_cap, pin))) return bail(rc);
+        if ((r = out_stage[i].alloc(c, out_cap, pin))) return r;
         stages[i].h_out = out_stage[i].p;
-    }
+        return SQ_OK;
+    };
     std::vector<uint8_t> digests(total_chunks * 16);
 
     auto fill = [&](Batch *b, uint64_t first, uint64_t *next) {  // host reader pool -> pinned buffer
@@ -386,13 +390,13 @@ static int32_t pack_impl(sq_ctx **ctxs, uint32_t D, const char *input_dir, const
         b->err = err;
     };
 
-    SQ_T("pinned buffers allocated");
     // Software pipeline over two slots: while batch k is on the GPU (sq_pack_submit), the host threads read batch k+1
     // into the other pinned buffer; sq_pack_wait(k) then overlaps its frame download with the kernels of batch k+1.
     uint64_t next = 0, unique = 0, payload = 0;
     uint32_t head = 0, tail = 0, inflight = 0;
     while ((next < total_chunks || inflight) && !rc) {
         if (next < total_chunks && inflight < S) {
+            if ((rc = ensure_slot(head))) { if (head % D) snprintf(ctx->err, sizeof ctx->err, "%s", ctxs[head % D]->err); break; }
             Batch *b = &bufs[head];
             fill(b, next, &next);
             if (b->err) { rc = sq_set_error(ctx, b->err, "Error reading from squish: input file changed or unreadable"); break; }

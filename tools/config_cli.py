@@ -9,6 +9,7 @@ sys.path.insert(0, str(ROOT))
 import squishrs_b200 as sq
 lib = sq.load()
 CLI, REF = str(ROOT / "bin" / "squishrs"), str(ROOT / "oracle" / "refcpu")
+DEV = ["--devices", os.environ["SQ_DEVICES"]] if os.environ.get("SQ_DEVICES") else []  # several GPUs of the box through one process
 BASE = Path(os.environ.get("SQ_TMP", "/dev/shm")) / f"sq_cfg_{os.getpid()}"
 
 
@@ -46,16 +47,19 @@ def config1(total=1 << 30, nfiles=2000):
         p = src / f"d{i % 20}" / f"s{i % 7}" / f"f{i}.txt"; p.parent.mkdir(parents=True, exist_ok=True); p.write_bytes(data); nbytes += len(data)
     out = {"bytes": nbytes, "files": nfiles}
     threads = str(os.cpu_count())
-    out["gpu_pack_s"] = run([CLI, "pack", str(src), "-o", str(BASE / "c1" / "gpu.squish")])
-    out["gpu_unpack_s"] = run([CLI, "unpack", str(BASE / "c1" / "gpu.squish"), "-o", str(BASE / "c1" / "gpu_out")])
+    out["gpu_pack_s"] = run([CLI, *DEV, "pack", str(src), "-o", str(BASE / "c1" / "gpu.squish")])
+    out["gpu_unpack_s"] = run([CLI, *DEV, "unpack", str(BASE / "c1" / "gpu.squish"), "-o", str(BASE / "c1" / "gpu_out")])
     out["cpu_pack_s"] = run([REF, "-j", threads, "pack", str(src), "-o", str(BASE / "c1" / "cpu.squish")])
     out["cpu_unpack_s"] = run([REF, "-j", threads, "unpack", str(BASE / "c1" / "cpu.squish"), "-o", str(BASE / "c1" / "cpu_out")])
     out["cross_gpu_archive_cpu_unpack_s"] = run([REF, "-j", threads, "unpack", str(BASE / "c1" / "gpu.squish"), "-o", str(BASE / "c1" / "x1")])
-    out["cross_cpu_archive_gpu_unpack_s"] = run([CLI, "unpack", str(BASE / "c1" / "cpu.squish"), "-o", str(BASE / "c1" / "x2")])
+    out["cross_cpu_archive_gpu_unpack_s"] = run([CLI, *DEV, "unpack", str(BASE / "c1" / "cpu.squish"), "-o", str(BASE / "c1" / "x2")])
     out["identical"] = all(same_tree(src, BASE / "c1" / d) for d in ("gpu_out", "cpu_out", "x1", "x2"))
-    out["gpu_pack_phases"] = phases([CLI, "pack", str(src), "-o", str(BASE / "c1" / "gpu2.squish")])
-    out["gpu_unpack_phases"] = phases([CLI, "unpack", str(BASE / "c1" / "gpu.squish"), "-o", str(BASE / "c1" / "gpu_out2")])
-    out["gpu_pack_second_run_s"] = run([CLI, "pack", str(src), "-o", str(BASE / "c1" / "gpu3.squish")])
+    for d in ("gpu_out", "cpu_out", "x1", "x2"): shutil.rmtree(BASE / "c1" / d, ignore_errors=True)  # bounded /dev/shm use
+    out["gpu_pack_phases"] = phases([CLI, *DEV, "pack", str(src), "-o", str(BASE / "c1" / "gpu2.squish")])
+    out["gpu_unpack_phases"] = phases([CLI, *DEV, "unpack", str(BASE / "c1" / "gpu.squish"), "-o", str(BASE / "c1" / "gpu_out2")])
+    shutil.rmtree(BASE / "c1" / "gpu_out2", ignore_errors=True)
+    out["gpu_pack_second_run_s"] = run([CLI, *DEV, "pack", str(src), "-o", str(BASE / "c1" / "gpu3.squish")])
+    out["devices"] = int(os.environ.get("SQ_DEVICES", "1"))
     out["gpu_archive_bytes"] = (BASE / "c1" / "gpu.squish").stat().st_size; out["cpu_archive_bytes"] = (BASE / "c1" / "cpu.squish").stat().st_size
     out["ratio_delta_pct"] = (out["gpu_archive_bytes"] / out["cpu_archive_bytes"] - 1) * 100
     for k2 in ("gpu_pack", "gpu_unpack", "cpu_pack", "cpu_unpack"): out[k2 + "_gbs"] = nbytes / out[k2 + "_s"] / 1e9
@@ -69,7 +73,7 @@ def config5(nfiles=20000):
         p.write_bytes(gen(n, i, 0 if i % 2 else 2)); nbytes += n
     threads = str(os.cpu_count()); out = {"bytes": nbytes, "files": nfiles}
     out["ref_pack_s"] = run([REF, "-j", threads, "pack", str(src), "-o", str(BASE / "c5" / "ref.squish")])
-    out["gpu_unpack_s"] = run([CLI, "unpack", str(BASE / "c5" / "ref.squish"), "-o", str(BASE / "c5" / "gpu_out")])
+    out["gpu_unpack_s"] = run([CLI, *DEV, "unpack", str(BASE / "c5" / "ref.squish"), "-o", str(BASE / "c5" / "gpu_out")])
     out["cpu_unpack_s"] = run([REF, "-j", threads, "unpack", str(BASE / "c5" / "ref.squish"), "-o", str(BASE / "c5" / "cpu_out")])
     out["identical"] = same_tree(src, BASE / "c5" / "gpu_out") and same_tree(src, BASE / "c5" / "cpu_out")
     out["gpu_unpack_phases"] = phases([CLI, "unpack", str(BASE / "c5" / "ref.squish"), "-o", str(BASE / "c5" / "gpu_out2")])
@@ -81,7 +85,7 @@ def config5(nfiles=20000):
 
 if __name__ == "__main__":
     try:
-        res = {"host_cores": os.cpu_count(), "config1": config1(int(float(os.environ.get("SQ_C1_GIB", "1")) * (1 << 30))), "config5": config5(int(os.environ.get("SQ_C5_FILES", "20000")))}
+        res = {"host_cores": os.cpu_count(), "config1": None if os.environ.get("SQ_SKIP_C1") else config1(int(float(os.environ.get("SQ_C1_GIB", "1")) * (1 << 30))), "config5": None if os.environ.get("SQ_SKIP_C5") else config5(int(os.environ.get("SQ_C5_FILES", "20000")))}
         print(json.dumps(res))
     finally:
         shutil.rmtree(BASE, ignore_errors=True)
