@@ -294,7 +294,7 @@ int32_t sq_encode_device_set(sq_ctx *ctx, int set, const void *d_data, const sq_
     ctx->enc_set_stream[set] = st;
     const uint32_t nb = n * SQ_MAX_BLOCKS;
     enc_plan_kernel<<<(nb + 255) / 256, 256, 0, st>>>(d_spans, d_select, n, e->blocks);
-    SQ_CUDA(ctx, cudaMemsetAsync(e->status + 1, 0, 2 * sizeof(uint32_t), st));
+    SQ_CUDA(ctx, cudaMemsetAsync(e->status + 1, 0, 3 * sizeof(uint32_t), st));
     {
         static_assert(sizeof(lz::BlockOut) == sizeof(sq_block_info), "block info layout");
         const bool timing = (ctx->flags & SQ_FLAG_STAGE_TIMING) != 0;
@@ -332,7 +332,10 @@ int32_t sq_encode_device_set(sq_ctx *ctx, int set, const void *d_data, const sq_
         if (timing) SQ_CUDA(ctx, cudaEventRecord(e->tev[1], st));
         static const bool chase_thread = getenv("SQ_LZ2_DBG") && (atoi(getenv("SQ_LZ2_DBG")) & 4);  // debugging reference: the scalar parse, one thread per block
         if (chase_thread) lz2::chase_thread_kernel<<<(n * SQ_MAX_BLOCKS + 63) / 64, 64, 0, st>>>((const uint8_t *)d_data, d_spans, d_select, n, e->rec, e->seqs, e->meta);
-        else lz2::chase_kernel<<<(n * SQ_MAX_BLOCKS + 3) / 4, 128, 0, st>>>((const uint8_t *)d_data, d_spans, d_select, n, e->rec, e->seqs, e->meta);
+        else {
+            const uint32_t want = (n * SQ_MAX_BLOCKS + 3) / 4, resident = (uint32_t)ctx->sm_count * 10u;  // 10 CTAs of 4 warps per SM at 48 registers
+            lz2::chase_kernel<<<want < resident ? want : resident, 128, 0, st>>>((const uint8_t *)d_data, d_spans, d_select, n, e->rec, e->seqs, e->meta, e->status + 3);
+        }
         if (timing) SQ_CUDA(ctx, cudaEventRecord(e->tev[2], st));
         const uint32_t ent_ctas = e->ent_warps / 4;
         lz::entropy_kernel<<<ent_ctas, 128, 0, st>>>((const uint8_t *)d_data, d_spans, d_select, n, e->seqs, e->meta, e->lits, e->bodies,

@@ -33,7 +33,8 @@
 //   filter    long candidates -> (position, offset) pairs in the warp's queue; nearest short per position kept aside
 //   continue  a long pair (p, o) whose left neighbour (p-1, o) is also a pair continues a match that is (or will be) found one
 //             position earlier: dropped, its result arrives by inheritance.  Done in pair space through a direct-mapped table
-//             of 16-bit keys; column 0 keeps everything so inheritance never runs dry.
+//             of 16-bit keys (hash of the offset, slot shifted by the column); column 0 keeps everything so inheritance never
+//             runs dry.
 //   verify    one pair per lane per trip: 40 candidate bytes (five aligned 8-byte loads, all requested up front) against the
 //             position's bytes in shared memory, up to CAP = 32 matching bytes; best per position by atomicMax on
 //             (2 len - log2 offset, nearer offset first)
@@ -277,13 +278,16 @@ template <int THREADS, int MINB, int TLOG>
 __global__ void __launch_bounds__(THREADS, MINB) search_kernel(const uint8_t *__restrict__ data, const sq_span *__restrict__ spans, uint32_t first,
                                                                uint32_t count, const uint32_t *__restrict__ span_start,
                                                                const uint32_t *__restrict__ list_all, uint32_t *__restrict__ rec_all, uint32_t *__restrict__ counter, uint32_t dbg) {
-    constexpr uint32_t WARPS = THREADS / 32, WIN = SearchSmem<TLOG>::WIN, WIN_WORDS = WIN / 4, GROUPS = SPAN / 32, TMASK = (1u << TLOG) - 1;
+    constexpr uint32_t WARPS = THREADS / 32, WIN = SearchSmem<TLOG>::WIN, WIN_WORDS = WIN / 4, GROUPS = SPAN / 32, TMASK = (2u << TLOG) - 1;
     extern __shared__ __align__(16) uint8_t s_dyn[];
     const uint32_t tid = threadIdx.x, wq = tid >> 5, lane = tid & 31;
     uint8_t *s_warp = s_dyn + wq * SearchSmem<TLOG>::PER_WARP;
     uint32_t *queue = reinterpret_cast<uint32_t *>(s_warp);
-    uint32_t *T = queue + QUEUE_WORDS;  // continuation keys: (pair | epoch << 26), never cleared (the epoch changes with every group)
-    uint8_t *s_in = reinterpret_cast<uint8_t *>(T + (1u << TLOG));
+    // continuation keys, 16 bits each (twice the slots of a 32-bit table in the same memory: fewer keys overwritten before they are
+    // looked up, so fewer pairs survive the filter for nothing): 10 bits of the offset's hash | epoch << 10; never cleared, the
+    // epoch changes with every group
+    uint16_t *T = reinterpret_cast<uint16_t *>(queue + QUEUE_WORDS);
+    uint8_t *s_in = reinterpret_cast<uint8_t *>(queue + QUEUE_WORDS + (1u << TLOG));
     uint32_t *s_best = reinterpret_cast<uint32_t *>(s_in + WIN);
     const uint32_t sub = lane >> 2, part = lane & 3u;
     uint32_t epoch = 0;
@@ -390,18 +394,18 @@ __global__ void __launch_bounds__(THREADS, MINB) search_kernel(const uint8_t *__
             }
             __syncwarp();
             // ---- continuation filter in pair space: (col, c) is dropped when (col - 1, c - 1) is a pair too ----
-            const uint32_t ep = epoch << 26;
+            const uint32_t ep = epoch << 10;
             for (uint32_t i = lane; i < nlong; i += 32) {
-                const uint32_t pr = queue[i], col = pr >> POS_BITS, o = pg + col - (pr & POS_MASK);
-                T[(o * 37u + col) & TMASK] = pr | ep;
+                const uint32_t pr = queue[i], col = pr >> POS_BITS, ho = (pg + col - (pr & POS_MASK)) * 0x9E3779B1u;
+                T[((ho >> 11) + col) & TMASK] = (uint16_t)((ho >> 1 & 0x3FFu) | ep);
             }
             __syncwarp();
             uint32_t total = 0;
             for (uint32_t base = 0; base < nlong; base += 32) {
                 const uint32_t i = base + lane;
                 const bool valid = i < nlong;
-                const uint32_t pr = valid ? queue[i] : 0u, col = pr >> POS_BITS, o = pg + col - (pr & POS_MASK);
-                const bool hit = T[(o * 37u + col - 1u) & TMASK] == ((pr - (1u << POS_BITS) - 1u) | ep);  // col 0 keeps everything: its key would wrap
+                const uint32_t pr = valid ? queue[i] : 0u, col = pr >> POS_BITS, ho = (pg + col - (pr & POS_MASK)) * 0x9E3779B1u;
+                const bool hit = T[((ho >> 11) + col - 1u) & TMASK] == (uint16_t)((ho >> 1 & 0x3FFu) | ep);  // the pair one column to the left has the same offset
                 const bool keep = valid && !(hit && col != 0 && !((dbg & 1u) && col == 16));
                 const uint32_t b = __ballot_sync(0xffffffffu, keep);
                 __syncwarp();
@@ -526,15 +530,20 @@ __device__ __forceinline__ uint32_t load4(const uint8_t *__restrict__ in, uint32
 __global__ void __launch_bounds__(128) chase_kernel(const uint8_t *__restrict__ data, const sq_span *__restrict__ spans,
                                                      const uint8_t *__restrict__ select, uint32_t n_chunks,
                                                      const uint32_t *__restrict__ rec_all, zc::Seq *__restrict__ seqs_all,
-                                                     lz::BlockMeta *__restrict__ meta_all) {
+                                                     lz::BlockMeta *__restrict__ meta_all, uint32_t *__restrict__ counter) {
     const uint32_t lane = threadIdx.x & 31;
-    const uint32_t item = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    // blocks are handed out through a counter: a warp that drew a short block (or one of an unselected chunk) takes the next one
+    // instead of idling until the slowest warp of its CTA is done (a fixed block -> warp assignment reached 39 % occupancy of 62 %)
+    for (;;) {
+    uint32_t item = 0;
+    if (lane == 0) item = atomicAdd(counter, 1u);
+    item = __shfl_sync(0xffffffffu, item, 0);
     if (item >= n_chunks * BLOCKS_PER_CHUNK) return;
     const uint32_t chunk = item / BLOCKS_PER_CHUNK, b = item % BLOCKS_PER_CHUNK;
-    if (select && !select[chunk]) return;
+    if (select && !select[chunk]) continue;
     const uint32_t n = spans[chunk].len;
     const uint32_t bs = b * Z_BLOCK_MAX;
-    if (bs >= n) return;
+    if (bs >= n) continue;
     const uint32_t be = min(n, bs + Z_BLOCK_MAX);
     const uint8_t *in = data + spans[chunk].off;
     const uint32_t *rec = rec_all + (size_t)chunk * REC_PER_CHUNK;
@@ -655,6 +664,7 @@ __global__ void __launch_bounds__(128) chase_kernel(const uint8_t *__restrict__ 
         lz::BlockMeta m;
         m.seq_start = b * SEQ_PER_BLOCK; m.nseq = nseq; m.last_lits = be - anchor; m.reserved = 0;
         meta_all[(size_t)chunk * BLOCKS_PER_CHUNK + b] = m;
+    }
     }
 }
 
