@@ -142,6 +142,8 @@ ZHDN uint32_t chase_block(const uint8_t *in, uint32_t n, const uint32_t *rec, ui
         const uint32_t off = r & POS_MASK;
         uint32_t len = ((r >> 21) & 31u) + LEN_BASE, back = (r >> 27) & 3u;
         if ((r >> 26 & 1u) && start + len < be) len += common_len(in, n, start + len, start + len - off, be - start - len);
+        if (start + len > be) len = be - start;  // the range may end inside a block (sub-block parsing): a match never crosses it
+        if (len < REP_MIN) { P.p = q + 1; continue; }
         if (back > start - P.anchor) back = start - P.anchor;
         start -= back; len += back;
         // literal positions in front of the match: the first one where a repeat offset matches takes over

@@ -29,6 +29,7 @@ struct P2 {
     int cont;         // continuation filter: 0 off, 1 exact (pair (p-1,c-1) was a candidate pair), 2 previous byte equal; refresh every 16 positions
     int group_skip;   // 1: a group of 32 positions that lies inside a match already known to be long (the record in front of the group is capped and the
                       // match goes on for 64 more bytes) is not searched: every position inherits (offset, CAP, may-be-longer)
+    int sub_len;      // > 0: every block is parsed in independent pieces of this many bytes (repeat offsets unknown at each start), sequences merged afterwards
     int cont_period;  // > 0: the filter keeps everything at positions p % cont_period == 0 (the first column of a search group) and is independent of the tile
 };
 
@@ -192,6 +193,18 @@ extern "C" long lz_model2_frame(const uint8_t *s, uint32_t n, uint8_t *dst, uint
     for (uint32_t b = 0; b < nblocks; b++) {
         const uint32_t bs = b * Z_BLOCK_MAX, be = std::min(n, bs + Z_BLOCK_MAX);
         uint32_t last_lits = be - bs, ns = 0;
+        if (be > bs && P.sub_len > 0) {
+            uint32_t carry = 0;
+            std::vector<Seq> tmp(P.sub_len / 6 + 8);
+            for (uint32_t sb = bs; sb < be; sb += (uint32_t)P.sub_len) {
+                const uint32_t se = std::min(be, sb + (uint32_t)P.sub_len);
+                uint32_t ll_last = 0;
+                const uint32_t k = zparse::chase_block(s, n, rec.data(), sb, se, sb == 0, tmp.data(), (uint32_t)P.sub_len / 6, &ll_last);
+                for (uint32_t i = 0; i < k; i++) { Seq q = tmp[i]; if (i == 0) q.ll += carry; seqs[ns++] = q; }
+                carry = k ? ll_last : carry + ll_last;
+            }
+            last_lits = carry;
+        } else
         if (be > bs) ns = zparse::chase_block(s, n, rec.data(), bs, be, b == 0, seqs.data(), Z_BLOCK_MAX / 6 + 8, &last_lits);
         lits.clear();
         uint32_t pos = bs;
