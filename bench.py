@@ -466,6 +466,20 @@ def unpack_section(ctx, lib, L, oracle, corpus, sp, stream, args):
                 "cpu_baseline": {"value": min(n_big, 96) * CHUNK / t1 / 1e9, "unit": "GB/s", "cores": 1, "kind": "port",
                                  "sample": "the same frames, stock libzstd on one thread (the reference's serial read_chunks)",
                                  "parallel_decode": {"value": restored / tp / 1e9, "cores": cores}}})
+    # (a2) frames written by K3 itself, at a count where one warp per frame cannot fill the GPU: the block-parallel decode path
+    try:
+        n_own = min(512, n_big)
+        own = [host[i * CHUNK:(i + 1) * CHUNK].tobytes() for i in range(n_own)]
+        ctx.dedup_reset()
+        pairs = [(c, f) for c, (_, f) in zip(own, ctx.pack_batch(own)) if f is not None]
+        ms_o, ok_o, _, do_o, _ = decode_frames_device(ctx, lib, L, [f for _, f in pairs], np.full(len(pairs), CHUNK, dtype=np.int64), sp, stream,
+                                                      check=lambda i: pairs[i][0])
+        out["own_frames"] = {"value": len(pairs) * CHUNK / (ms_o * 1e-3) / 1e9, "unit": "GB/s", "frames": len(pairs), "byte_identical": bool(ok_o),
+                             "what": "K4 decode of frames written by K3 (2 MiB chunks), device-resident; <= 512 frames per call take the block-parallel "
+                                     "path: entropy decoding per block on its own warp, execution per frame in order"}
+        ctx.check(lib.sq_release_scratch(ctx.h))
+    except Exception as e:
+        log("own-frames unpack failed:", repr(e))
     # (b) small files
     n_small = args.unpack_small
     sbuf, soffs, ssizes = small_files(oracle, n_small)
@@ -920,6 +934,8 @@ def run_ours(args):
     try:
         if oracle is None:
             oracle = load_oracle()
+        ctx.check(lib.sq_release_scratch(ctx.h))  # the pack's scratch (two encoder sets, pipeline staging) makes room for the unpack buffers
+        torch.cuda.empty_cache()
         unpack = unpack_section(ctx, lib, L, oracle, corpus, sp, stream, args)
     except Exception as e:
         log("unpack section failed:", repr(e))

@@ -122,6 +122,9 @@ const char *sq_last_error(const sq_ctx *ctx);   /* ctx may be NULL: last create 
 const char *sq_strerror(int32_t status);        /* AppError display text (errors.rs:7-65) */
 int32_t sq_abi_version(void);
 int32_t sq_synchronize(sq_ctx *ctx, void *stream);
+/* Returns the device memory the context caches (encoder / decoder scratch, pipeline staging) to the driver; it is allocated
+ * again on demand.  Synchronizes the device; fails while a pipeline ticket is in flight. */
+int32_t sq_release_scratch(sq_ctx *ctx);
 /* number of CUDA kernels this context has launched so far (bench.py's gpu_launches) */
 int32_t sq_kernel_launches(sq_ctx *ctx, uint64_t *out);
 

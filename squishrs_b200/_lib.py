@@ -102,6 +102,7 @@ SYMBOLS = {
     "sq_archive_pack_multi": (C.c_int32, [C.POINTER(_P), C.c_uint32, C.c_char_p, C.c_char_p, C.c_int32, C.POINTER(SqPackReport)]),
     "sq_archive_unpack_multi": (C.c_int32, [C.POINTER(_P), C.c_uint32, C.c_char_p, C.c_char_p, C.c_int32, C.POINTER(SqSummary)]),
     "sq_share_dedup": (C.c_int32, [_P, _P]),
+    "sq_release_scratch": (C.c_int32, [_P]),
     "sq_archive_list": (C.c_int32, [C.c_char_p, C.POINTER(SqSummary), C.POINTER(C.c_char_p)]),
     "sq_free": (None, [_P]),
     "sq_corpus_fill_device": (C.c_int32, [_P, _P, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, _P]),

@@ -167,6 +167,31 @@ extern "C" void sq_destroy(sq_ctx *ctx) {
     free(ctx);
 }
 
+// Gives the device memory the context has cached back to the driver: encoder scratch sets, pipeline staging, decoder scratch.
+// Everything is allocated again on demand.  Synchronizes the device first.
+extern "C" int32_t sq_release_scratch(sq_ctx *ctx) {
+    if (!ctx) return SQ_ERR_INVALID_ARG;
+    SQ_CUDA(ctx, cudaSetDevice(ctx->device));
+    SQ_CUDA(ctx, cudaDeviceSynchronize());
+    for (int i = 0; i < 2; i++) if (ctx->slots[i].busy || ctx->uslots[i].busy) return sq_set_error(ctx, SQ_ERR_OTHER, "sq_release_scratch: a pipeline slot is in flight");
+    sq_enc_destroy(ctx);
+    sq_dec_destroy(ctx);
+    for (int i = 0; i < 2; i++) {
+        ctx->enc_set_bound[i] = 0; ctx->enc_set_stream[i] = nullptr;
+        cudaFree(ctx->slots[i].d_in); cudaFree(ctx->slots[i].d_out); cudaFree(ctx->slots[i].d_meta);
+        ctx->slots[i].d_in = ctx->slots[i].d_out = ctx->slots[i].d_meta = nullptr;
+        ctx->slots[i].in_cap = ctx->slots[i].out_cap = ctx->slots[i].meta_cap = 0;
+        cudaFree(ctx->uslots[i].d_in); cudaFree(ctx->uslots[i].d_out); cudaFree(ctx->uslots[i].d_meta);
+        ctx->uslots[i].d_in = ctx->uslots[i].d_out = ctx->uslots[i].d_meta = nullptr;
+        ctx->uslots[i].in_cap = ctx->uslots[i].out_cap = ctx->uslots[i].meta_cap = 0;
+    }
+    cudaFree(ctx->d_stage_in); cudaFree(ctx->d_stage_out); cudaFree(ctx->d_stage_meta);
+    ctx->d_stage_in = ctx->d_stage_out = ctx->d_stage_meta = nullptr;
+    ctx->stage_in_cap = ctx->stage_out_cap = ctx->stage_meta_cap = 0;
+    ctx->enc_set_lru = 0;
+    return SQ_OK;
+}
+
 extern "C" int32_t sq_synchronize(sq_ctx *ctx, void *stream) {
     if (!ctx) return SQ_ERR_INVALID_ARG;
     SQ_CUDA(ctx, cudaStreamSynchronize(sq_stream(ctx, stream)));

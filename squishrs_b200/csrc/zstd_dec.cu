@@ -14,6 +14,14 @@
 // Per-warp tables (Huffman 4 KB, LL/ML/OF cells 5 KB) live in shared memory; decoded Huffman literals go
 // to a 128 KiB per-warp slot in HBM (L2 resident).  Algorithmic traffic = payload bytes read + decoded
 // bytes written.
+//
+// Block-parallel path (batches of at most BP_MAX_FRAMES payloads, i.e. exactly when frames alone cannot fill the GPU).  A payload
+// that is one frame whose compressed blocks bring all their own tables -- everything the K3 encoder writes, and the libzstd frames
+// that happen not to use Treeless literals or Repeat_Mode -- is decoded in two passes: bp_entropy_kernel gives every BLOCK its own
+// warp for the entropy decoding (Huffman literals into the block's literal buffer, the FSE chain into an array of {ll, ml, offset
+// value}), which is where a frame spends most of its time; bp_execute_kernel then gives every FRAME a warp that resolves repeat
+// offsets and copies literals and matches block by block, in order (matches reach back across blocks, so execution stays
+// serial).  bp_scan_kernel decides eligibility from the headers; everything else goes through the one-pass kernel as before.
 #include "common.cuh"
 #include "zstd_dec_core.h"
 
@@ -21,18 +29,31 @@ struct sq_dec_scratch {
     uint8_t *lits;      // per resident warp: Z_BLOCK_MAX + 64
     void *build;        // per resident warp: table-construction scratch (zd::Scratch, 2.3 KB; in HBM so that shared memory holds only
                         // the decode tables and six CTAs fit an SM)
-    uint32_t *counter;
+    uint32_t *counter;      // [0] one-pass work counter, [1] bp_entropy, [2] bp_execute
     uint32_t warps;
+    // block-parallel path, sized for bp_cap frames
+    uint32_t bp_cap;
+    uint8_t *bp_elig;         // [bp_cap] 1 = decoded by the two-pass path
+    zd::FrameInfo *bp_info;   // [bp_cap]
+    zd::BlockTask *bp_tasks;  // [bp_cap * BP_MAX_BLOCKS]
+    zd::BlockState *bp_states;
+    uint8_t *bp_lits;         // [bp_cap * BP_MAX_BLOCKS * (Z_BLOCK_MAX + 64)]
+    zd::StoredSeq *bp_seqs;   // [bp_cap * BP_MAX_BLOCKS * BP_SEQ_CAP]
+    void *bp_build;           // per resident warp of bp_entropy_kernel: its own table-construction scratch (it runs beside the one-pass kernel)
+    cudaStream_t aux;         // the one-pass kernel for the frames that are not eligible runs here, beside the two passes
+    cudaEvent_t ev_fork, ev_join;
 };
 
 namespace {
+constexpr uint32_t BP_MAX_FRAMES = 512, BP_MAX_BLOCKS = 16, BP_SEQ_CAP = Z_BLOCK_MAX / 3 + 1;
+constexpr size_t BP_LIT_STRIDE = Z_BLOCK_MAX + 64;
 constexpr uint32_t DEC_WARPS_PER_CTA = 4;
 struct WarpState { zd::Tables T; };
 
 __global__ void __launch_bounds__(DEC_WARPS_PER_CTA * 32, 6) zstd_decode_kernel(const uint8_t *__restrict__ comp, const sq_frame *__restrict__ frames,
                                                                              uint32_t n, uint8_t *__restrict__ out, sq_frame_result *__restrict__ res,
                                                                              uint8_t *__restrict__ lits_all, zd::Scratch *__restrict__ build_all,
-                                                                             uint32_t *__restrict__ counter) {
+                                                                             uint32_t *__restrict__ counter, const uint8_t *__restrict__ skip) {
     extern __shared__ __align__(16) uint8_t smem[];
     const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     WarpState *ws = reinterpret_cast<WarpState *>(smem) + w;
@@ -43,6 +64,7 @@ __global__ void __launch_bounds__(DEC_WARPS_PER_CTA * 32, 6) zstd_decode_kernel(
         if (lane == 0) i = atomicAdd(counter, 1u);
         i = __shfl_sync(0xffffffffu, i, 0);
         if (i >= n) break;
+        if (skip && skip[i]) continue;  // the block-parallel path has it
         const sq_frame f = frames[i];
         const int64_t r = zd::decode_payload(comp + f.src_off, f.src_len, out + f.dst_off, f.capacity, &ws->T, S, lits);
         __syncwarp();
@@ -54,12 +76,81 @@ __global__ void __launch_bounds__(DEC_WARPS_PER_CTA * 32, 6) zstd_decode_kernel(
         }
     }
 }
+
+// ---- block-parallel path ------------------------------------------------------------------------------------------------
+__global__ void bp_scan_kernel(const uint8_t *__restrict__ comp, const sq_frame *__restrict__ frames, uint32_t n, uint8_t *__restrict__ elig,
+                               zd::FrameInfo *__restrict__ info, zd::BlockTask *__restrict__ tasks) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const sq_frame f = frames[i];
+    zd::FrameInfo fi;
+    fi.nblocks = 0; fi.has_fcs = 0; fi.fcs = 0;
+    const uint32_t nb = zd::scan_frame(comp + f.src_off, f.src_len, BP_MAX_BLOCKS, tasks + (size_t)i * BP_MAX_BLOCKS, &fi);
+    bool any = false;  // a frame of raw / RLE blocks only gains nothing
+    for (uint32_t b = 0; b < nb; b++) any = any || tasks[(size_t)i * BP_MAX_BLOCKS + b].type == 2;
+    elig[i] = nb && any ? 1 : 0;
+    info[i] = fi;
+}
+
+__global__ void __launch_bounds__(DEC_WARPS_PER_CTA * 32, 6) bp_entropy_kernel(const uint8_t *__restrict__ comp, const sq_frame *__restrict__ frames, uint32_t n,
+                                                                               const uint8_t *__restrict__ elig, const zd::FrameInfo *__restrict__ info,
+                                                                               const zd::BlockTask *__restrict__ tasks, zd::BlockState *__restrict__ states,
+                                                                               uint8_t *__restrict__ lits, zd::StoredSeq *__restrict__ seqs,
+                                                                               zd::Scratch *__restrict__ build_all, uint32_t *__restrict__ counter) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    WarpState *ws = reinterpret_cast<WarpState *>(smem) + w;
+    zd::Scratch *S = build_all + (blockIdx.x * DEC_WARPS_PER_CTA + w);
+    for (;;) {
+        uint32_t item = 0;
+        if (lane == 0) item = atomicAdd(counter, 1u);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= n * BP_MAX_BLOCKS) break;
+        const uint32_t i = item / BP_MAX_BLOCKS, b = item % BP_MAX_BLOCKS;
+        if (!elig[i] || b >= info[i].nblocks) continue;
+        const zd::BlockTask t = tasks[item];
+        if (t.type != 2) continue;
+        zd::decode_block_entropy(comp + frames[i].src_off + t.src_off, t.size, &ws->T, S, lits + (size_t)item * BP_LIT_STRIDE, seqs + (size_t)item * BP_SEQ_CAP,
+                                 BP_SEQ_CAP, states + item);
+        __syncwarp();
+    }
+}
+
+__global__ void __launch_bounds__(128) bp_execute_kernel(const uint8_t *__restrict__ comp, const sq_frame *__restrict__ frames, uint32_t n,
+                                                          const uint8_t *__restrict__ elig, const zd::FrameInfo *__restrict__ info,
+                                                          const zd::BlockTask *__restrict__ tasks, const zd::BlockState *__restrict__ states,
+                                                          const uint8_t *__restrict__ lits, const zd::StoredSeq *__restrict__ seqs, uint8_t *__restrict__ out,
+                                                          sq_frame_result *__restrict__ res, uint32_t *__restrict__ counter) {
+    const uint32_t lane = threadIdx.x & 31;
+    for (;;) {
+        uint32_t i = 0;
+        if (lane == 0) i = atomicAdd(counter, 1u);
+        i = __shfl_sync(0xffffffffu, i, 0);
+        if (i >= n) break;
+        if (!elig[i]) continue;
+        const sq_frame f = frames[i];
+        const size_t first = (size_t)i * BP_MAX_BLOCKS;
+        const int64_t r = zd::execute_frame(comp + f.src_off, tasks + first, info + i, states + first, lits + first * BP_LIT_STRIDE, BP_LIT_STRIDE,
+                                            seqs + first * BP_SEQ_CAP, BP_SEQ_CAP, out + f.dst_off, f.capacity);
+        __syncwarp();
+        if (lane == 0) {
+            sq_frame_result fr;
+            fr.out_len = r >= 0 ? (uint32_t)r : 0u;
+            fr.status = r >= 0 ? SQ_OK : SQ_ERR_READER;
+            res[i] = fr;
+        }
+    }
+}
 }  // namespace
 
 void sq_dec_destroy(sq_ctx *ctx) {
     sq_dec_scratch *d = ctx->dec;
     if (!d) return;
     cudaFree(d->lits); cudaFree(d->build); cudaFree(d->counter);
+    cudaFree(d->bp_elig); cudaFree(d->bp_info); cudaFree(d->bp_tasks); cudaFree(d->bp_states); cudaFree(d->bp_lits); cudaFree(d->bp_seqs); cudaFree(d->bp_build);
+    if (d->aux) cudaStreamDestroy(d->aux);
+    if (d->ev_fork) cudaEventDestroy(d->ev_fork);
+    if (d->ev_join) cudaEventDestroy(d->ev_join);
     delete d;
     ctx->dec = nullptr;
 }
@@ -81,16 +172,54 @@ extern "C" int32_t sq_decode_device(sq_ctx *ctx, const void *d_comp, const sq_fr
         d->warps = (uint32_t)ctx->sm_count * (uint32_t)ctas_per_sm * DEC_WARPS_PER_CTA;
         SQ_CUDA(ctx, cudaMalloc(&d->lits, (size_t)d->warps * (Z_BLOCK_MAX + 64)));
         SQ_CUDA(ctx, cudaMalloc(&d->build, (size_t)d->warps * sizeof(zd::Scratch)));
-        SQ_CUDA(ctx, cudaMalloc(&d->counter, sizeof(uint32_t)));
+        SQ_CUDA(ctx, cudaMalloc(&d->counter, 4 * sizeof(uint32_t)));
+        SQ_CUDA(ctx, cudaFuncSetAttribute(bp_entropy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SQ_CUDA(ctx, cudaMalloc(&d->bp_build, (size_t)d->warps * sizeof(zd::Scratch)));
+        SQ_CUDA(ctx, cudaStreamCreateWithFlags(&d->aux, cudaStreamNonBlocking));
+        SQ_CUDA(ctx, cudaEventCreateWithFlags(&d->ev_fork, cudaEventDisableTiming));
+        SQ_CUDA(ctx, cudaEventCreateWithFlags(&d->ev_join, cudaEventDisableTiming));
     }
     sq_dec_scratch *d = ctx->dec;
     cudaStream_t st = sq_stream(ctx, stream);
-    SQ_CUDA(ctx, cudaMemsetAsync(d->counter, 0, sizeof(uint32_t), st));
+    SQ_CUDA(ctx, cudaMemsetAsync(d->counter, 0, 4 * sizeof(uint32_t), st));
     uint32_t ctas = d->warps / DEC_WARPS_PER_CTA;
+    static const bool bp_off = getenv("SQ_NO_BLOCK_PARALLEL") != nullptr;
+    if (n <= BP_MAX_FRAMES && !bp_off) {  // too few frames to fill the GPU with one warp each: give the blocks of eligible frames their own warps
+        if (d->bp_cap < n) {
+            SQ_CUDA(ctx, cudaStreamSynchronize(st));
+            cudaFree(d->bp_elig); cudaFree(d->bp_info); cudaFree(d->bp_tasks); cudaFree(d->bp_states); cudaFree(d->bp_lits); cudaFree(d->bp_seqs);
+            d->bp_elig = nullptr; d->bp_info = nullptr; d->bp_tasks = nullptr; d->bp_states = nullptr; d->bp_lits = nullptr; d->bp_seqs = nullptr; d->bp_cap = 0;
+            const size_t items = (size_t)n * BP_MAX_BLOCKS;
+            SQ_CUDA(ctx, cudaMalloc(&d->bp_elig, n));
+            SQ_CUDA(ctx, cudaMalloc(&d->bp_info, (size_t)n * sizeof(zd::FrameInfo)));
+            SQ_CUDA(ctx, cudaMalloc(&d->bp_tasks, items * sizeof(zd::BlockTask)));
+            SQ_CUDA(ctx, cudaMalloc(&d->bp_states, items * sizeof(zd::BlockState)));
+            SQ_CUDA(ctx, cudaMalloc(&d->bp_lits, items * BP_LIT_STRIDE));
+            SQ_CUDA(ctx, cudaMalloc(&d->bp_seqs, items * BP_SEQ_CAP * sizeof(zd::StoredSeq)));
+            d->bp_cap = n;
+        }
+        bp_scan_kernel<<<(n + 127) / 128, 128, 0, st>>>((const uint8_t *)d_comp, d_frames, n, d->bp_elig, d->bp_info, d->bp_tasks);
+        // fork: the one-pass kernel takes the frames the scan left to it, beside the two passes
+        SQ_CUDA(ctx, cudaEventRecord(d->ev_fork, st));
+        SQ_CUDA(ctx, cudaStreamWaitEvent(d->aux, d->ev_fork, 0));
+        const uint32_t need1 = (n + DEC_WARPS_PER_CTA - 1) / DEC_WARPS_PER_CTA;
+        zstd_decode_kernel<<<ctas < need1 ? ctas : need1, DEC_WARPS_PER_CTA * 32, smem, d->aux>>>((const uint8_t *)d_comp, d_frames, n, (uint8_t *)d_out, d_results, d->lits,
+                                                                                                    (zd::Scratch *)d->build, d->counter, d->bp_elig);
+        SQ_CUDA(ctx, cudaEventRecord(d->ev_join, d->aux));
+        const uint32_t want = (n * BP_MAX_BLOCKS + DEC_WARPS_PER_CTA - 1) / DEC_WARPS_PER_CTA;
+        bp_entropy_kernel<<<want < ctas ? want : ctas, DEC_WARPS_PER_CTA * 32, smem, st>>>((const uint8_t *)d_comp, d_frames, n, d->bp_elig, d->bp_info, d->bp_tasks,
+                                                                                             d->bp_states, d->bp_lits, d->bp_seqs, (zd::Scratch *)d->bp_build, d->counter + 1);
+        bp_execute_kernel<<<(n + 3) / 4, 128, 0, st>>>((const uint8_t *)d_comp, d_frames, n, d->bp_elig, d->bp_info, d->bp_tasks, d->bp_states, d->bp_lits,
+                                                       d->bp_seqs, (uint8_t *)d_out, d_results, d->counter + 2);
+        SQ_CUDA(ctx, cudaStreamWaitEvent(st, d->ev_join, 0));
+        SQ_LAUNCHED(ctx, 4);
+        SQ_CUDA(ctx, cudaGetLastError());
+        return SQ_OK;
+    }
     const uint32_t need = (n + DEC_WARPS_PER_CTA - 1) / DEC_WARPS_PER_CTA;
     if (ctas > need) ctas = need;
     zstd_decode_kernel<<<ctas, DEC_WARPS_PER_CTA * 32, smem, st>>>((const uint8_t *)d_comp, d_frames, n, (uint8_t *)d_out, d_results, d->lits,
-                                                                   (zd::Scratch *)d->build, d->counter);
+                                                                   (zd::Scratch *)d->build, d->counter, nullptr);
     SQ_LAUNCHED(ctx, 1);
     SQ_CUDA(ctx, cudaGetLastError());
     return SQ_OK;

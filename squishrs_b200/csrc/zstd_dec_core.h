@@ -376,21 +376,17 @@ struct Scratch {  // per warp, not persistent across blocks
     zc::FseDCell cells[512];
 };
 
-// One compressed block: literals + sequences executed into out[pos..].  Returns new pos or < 0.
-ZD_DEV int64_t decode_compressed_block(const uint8_t *src, uint32_t size, uint8_t *out, uint32_t pos, uint32_t cap, uint32_t frame_start,
-                                       Tables *T, Scratch *S, uint8_t *litbuf, uint32_t rep[3], uint32_t *synced) {
-    Literals L;
-    const int lused = decode_literals(src, size, T, litbuf, &L, S->weights, S->cells);
-    if (lused < 0) return lused;
-    const uint8_t *p = src + lused;
-    uint32_t left = size - (uint32_t)lused;
+// ---- pieces of a compressed block, shared by the one-pass decoder and the two-pass (block-parallel) one ----------------
+// Sequences section header: number of sequences, then the three tables.  On return *pp / *pleft are the FSE bitstream.
+ZD_DEV int read_sequences_header(const uint8_t **pp, uint32_t *pleft, uint32_t *pnseq, Tables *T, Scratch *S) {
+    const uint8_t *p = *pp;
+    uint32_t left = *pleft;
     if (left < 1) return ERR_CORRUPT;
     uint32_t nseq = p[0];
     if (nseq == 0) { p += 1; left -= 1; }
     else if (nseq < 128) { p += 1; left -= 1; }
     else if (nseq < 255) { if (left < 2) return ERR_CORRUPT; nseq = ((nseq - 128) << 8) + p[1]; p += 2; left -= 2; }
     else { if (left < 3) return ERR_CORRUPT; nseq = p[1] + (p[2] << 8) + 0x7F00; p += 3; left -= 3; }
-    uint32_t lit_pos = 0;
     if (nseq) {
         if (left < 1) return ERR_CORRUPT;
         const uint32_t modes = p[0];
@@ -406,112 +402,282 @@ ZD_DEV int64_t decode_compressed_block(const uint8_t *src, uint32_t size, uint8_
         if (u < 0) return u;
         p += u; left -= (uint32_t)u;
         ZD_SYNC();
+    }
+    *pp = p; *pleft = left; *pnseq = nseq;
+    return 0;
+}
+
+// One step of the serial FSE chain: the sequence's literal length, match length and offset VALUE (1..3 = repeat-offset codes),
+// then the state transitions unless it is the block's last sequence.  Identical on every lane.
+struct FseStates { uint32_t ll, of, ml; };
+ZD_DEV void fse_step(BitReader *b, const Tables *T, FseStates *st, bool last, uint32_t *ll_out, uint32_t *ml_out, uint32_t *ofv_out) {
+    const SeqCell cl = T->ll[st->ll], co = T->of[st->of], cm = T->ml[st->ml];
+    // One refill per sequence covers its extra bits and state transitions in the common case (the window then holds more than 56
+    // bits); the two further refills only happen for very long offsets / lengths.  All branches are warp-uniform.
+    const uint32_t ofb = co.sym /* <= 31, checked when the table was built */, mlb = zc::ZTAB(ML_bits)[cm.sym], llb = zc::ZTAB(LL_bits)[cl.sym];
+    br_refill(b);
+    *ofv_out = (1u << ofb) + br_take(b, ofb);
+    if (ofb + mlb + llb > 56) br_refill(b);
+    *ml_out = zc::ZTAB(ML_base)[cm.sym] + br_take(b, mlb);
+    *ll_out = zc::ZTAB(LL_base)[cl.sym] + br_take(b, llb);
+    if (!last) {  // state updates: LL, ML, OF (at most 9 + 9 + 8 bits)
+        if (ofb + mlb + llb > 56 - 26) br_refill(b);
+        st->ll = cl.next_base + br_take(b, cl.nb_bits);
+        st->ml = cm.next_base + br_take(b, cm.nb_bits);
+        st->of = co.next_base + br_take(b, co.nb_bits);
+    }
+}
+
+// Offset value -> offset, with the repeat-offset history update (RFC 8878 3.1.1.5).  Returns 0 for a corrupt code.
+ZD_DEV uint32_t resolve_offset(uint32_t ofv, uint32_t ll, uint32_t *r0, uint32_t *r1, uint32_t *r2) {
+    if (ofv > 3) { const uint32_t off = ofv - 3; *r2 = *r1; *r1 = *r0; *r0 = off; return off; }
+    const uint32_t idx = ofv - 1 + (ll == 0 ? 1 : 0);
+    if (idx == 0) return *r0;
+    const uint32_t off = idx == 1 ? *r1 : idx == 2 ? *r2 : *r0 - 1;
+    if (off == 0) return 0;
+    if (idx >= 2) *r2 = *r1;
+    *r1 = *r0; *r0 = off;
+    return off;
+}
+
+// Executes one batch of sequences (lane j holds sequence j of the batch): a warp scan turns lengths into positions, all literal
+// runs are copied at once (their sources are never the output), matches that only read output older than the batch are copied
+// lane-parallel, the rest in order with the whole warp on each.  Returns the new output position or < 0.
+ZD_DEV int64_t execute_batch(uint8_t *out, uint32_t pos, uint32_t cap, uint32_t frame_start, const Literals *L, uint32_t *lit_pos_io,
+                             uint32_t my_ll, uint32_t my_ml, uint32_t my_off, uint32_t nbatch, uint32_t *synced) {
+    const uint32_t lit_pos = *lit_pos_io;
+    uint32_t lit_excl, out_excl, lit_tot, out_tot;
+#if defined(__CUDA_ARCH__)
+    {
+        uint32_t xl = my_ll, xo = my_ll + my_ml;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t yl = __shfl_up_sync(0xffffffffu, xl, d), yo = __shfl_up_sync(0xffffffffu, xo, d);
+            if ((int)ZD_LANE() >= d) { xl += yl; xo += yo; }
+        }
+        lit_excl = xl - my_ll; out_excl = xo - (my_ll + my_ml);
+        lit_tot = __shfl_sync(0xffffffffu, xl, 31); out_tot = __shfl_sync(0xffffffffu, xo, 31);
+    }
+#else
+    lit_excl = 0; out_excl = 0; lit_tot = my_ll; out_tot = my_ll + my_ml;
+#endif
+    if (lit_pos + lit_tot > L->size) return ERR_CORRUPT;
+    if ((uint64_t)pos + out_tot > cap) return ERR_CAPACITY;
+    const uint32_t my_lit_out = pos + out_excl, my_match = my_lit_out + my_ll;
+    const bool mine = ZD_LANE() < nbatch;
+    int bad = mine && my_off > my_match - frame_start;
+#if defined(__CUDA_ARCH__)
+    bad = __any_sync(0xffffffffu, bad);
+#endif
+    if (bad) return ERR_CORRUPT;
+    // literal runs (sources are the literal buffer / the input, never the output): each lane its own run
+    if (mine) {
+        const uint8_t *ls = L->ptr + lit_pos + lit_excl;
+        if (L->rle) for (uint32_t t = 0; t < my_ll; t++) out[my_lit_out + t] = L->rle_byte;
+        else lane_copy(out + my_lit_out, ls, my_ll);
+    }
+    // matches.  A match is independent if everything it reads was synced before this batch started.
+    const uint32_t batch_synced = *synced;
+    const uint32_t src_end = my_match - my_off + (my_off < my_ml ? my_off : my_ml);
+    const bool indep = mine && src_end <= batch_synced;
+    if (indep) {
+        const uint8_t *from = out + my_match - my_off;  // non-overlapping with anything written in this batch
+        if (my_off >= my_ml) lane_copy(out + my_match, from, my_ml);
+        else for (uint32_t t = 0; t < my_ml; t++) out[my_match + t] = from[t % my_off];
+    }
+#if defined(__CUDA_ARCH__)
+    // The rest read output of this very batch.  They go in waves: everything below the destination of the first unfinished
+    // match is final (literals are all placed, earlier matches are done), so every short match whose source ends there or earlier
+    // is copied by its own lane, all of them at once; a long or self-overlapping (periodic) match at the front takes the whole
+    // warp.  In repetitive data offsets are a few hundred bytes, i.e. a dozen sequences back: three or four waves per batch
+    // instead of up to 32 warp-wide copies one after the other.
+    uint32_t pending = __ballot_sync(0xffffffffu, mine && !indep);
+    __syncwarp();  // literals and independent matches of the batch are visible
+    while (pending) {
+        const int first = __ffs((int)pending) - 1;
+        const uint32_t first_dst = __shfl_sync(0xffffffffu, my_match, first);
+        const bool ready = (pending >> ZD_LANE() & 1u) && src_end <= first_dst && my_ml <= 64u && my_off >= my_ml;
+        const uint32_t rmask = __ballot_sync(0xffffffffu, ready);
+        if (rmask >> first & 1u) {
+            if (ready) lane_copy(out + my_match, out + my_match - my_off, my_ml);
+            pending &= ~rmask;
+        } else {
+            const uint32_t moff = __shfl_sync(0xffffffffu, my_off, first), mlen = __shfl_sync(0xffffffffu, my_ml, first);
+            copy_match(out, first_dst, moff, mlen);
+            pending &= pending - 1;
+        }
+        __syncwarp();
+    }
+#else
+    if (mine && !indep) copy_match(out, my_match, my_off, my_ml);
+#endif
+    *lit_pos_io = lit_pos + lit_tot;
+    *synced = pos + out_tot;
+    return (int64_t)pos + out_tot;
+}
+
+// One compressed block: literals + sequences executed into out[pos..].  Returns new pos or < 0.
+ZD_DEV int64_t decode_compressed_block(const uint8_t *src, uint32_t size, uint8_t *out, uint32_t pos, uint32_t cap, uint32_t frame_start,
+                                       Tables *T, Scratch *S, uint8_t *litbuf, uint32_t rep[3], uint32_t *synced) {
+    Literals L;
+    const int lused = decode_literals(src, size, T, litbuf, &L, S->weights, S->cells);
+    if (lused < 0) return lused;
+    const uint8_t *p = src + lused;
+    uint32_t left = size - (uint32_t)lused, nseq = 0;
+    const int hu = read_sequences_header(&p, &left, &nseq, T, S);
+    if (hu < 0) return hu;
+    uint32_t lit_pos = 0;
+    if (nseq) {
         BitReader b;
         if (br_init(&b, p, left) < 0) return ERR_CORRUPT;
-        uint32_t s_ll = br_read(&b, T->ll_log), s_of = br_read(&b, T->of_log), s_ml = br_read(&b, T->ml_log);
+        FseStates st;
+        st.ll = br_read(&b, T->ll_log); st.of = br_read(&b, T->of_log); st.ml = br_read(&b, T->ml_log);
         uint32_t r0 = rep[0], r1 = rep[1], r2 = rep[2];
-        // Sequences are handled in batches of one per lane.  Phase A walks the serial FSE chain (identical on every lane)
-        // and lane j keeps sequence j; phase B turns lengths into positions with a warp scan; phase C copies all literal runs
-        // at once; phase D copies matches -- those that only read output older than the batch go lane-parallel, the rest
-        // in order with the whole warp on each.
+        // Sequences are handled in batches of one per lane: the serial FSE chain is walked identically by every lane and lane j
+        // keeps sequence j; execute_batch then places and copies the batch.
         for (uint32_t i0 = 0; i0 < nseq; i0 += ZD_WARP) {
             const uint32_t nbatch = nseq - i0 < ZD_WARP ? nseq - i0 : ZD_WARP;
             uint32_t my_ll = 0, my_ml = 0, my_off = 1;
             int err = 0;
             for (uint32_t k = 0; k < nbatch; k++) {
-                const SeqCell cl = T->ll[s_ll], co = T->of[s_of], cm = T->ml[s_ml];
-                // One refill per sequence covers its extra bits and state transitions in the common case (the window then holds
-                // more than 56 bits); the two further refills only happen for very long offsets / lengths.  All branches are
-                // warp-uniform: every lane walks the same chain.
-                const uint32_t ofb = co.sym /* <= 31, checked when the table was built */, mlb = zc::ZTAB(ML_bits)[cm.sym], llb = zc::ZTAB(LL_bits)[cl.sym];
-                br_refill(&b);
-                // extra bits: offset, match length, literal length
-                const uint32_t ofv = (1u << ofb) + br_take(&b, ofb);
-                if (ofb + mlb + llb > 56) br_refill(&b);
-                const uint32_t ml = zc::ZTAB(ML_base)[cm.sym] + br_take(&b, mlb);
-                const uint32_t ll = zc::ZTAB(LL_base)[cl.sym] + br_take(&b, llb);
-                uint32_t off;
-                if (ofv > 3) { off = ofv - 3; r2 = r1; r1 = r0; r0 = off; }
-                else {
-                    const uint32_t idx = ofv - 1 + (ll == 0 ? 1 : 0);
-                    if (idx == 0) off = r0;
-                    else {
-                        off = idx == 1 ? r1 : idx == 2 ? r2 : r0 - 1;
-                        if (off == 0) { err = 1; off = 1; }
-                        if (idx >= 2) r2 = r1;
-                        r1 = r0; r0 = off;
-                    }
-                }
-                if (i0 + k + 1 < nseq) {  // state updates: LL, ML, OF (at most 9 + 9 + 8 bits)
-                    if (ofb + mlb + llb > 56 - 26) br_refill(&b);
-                    s_ll = cl.next_base + br_take(&b, cl.nb_bits);
-                    s_ml = cm.next_base + br_take(&b, cm.nb_bits);
-                    s_of = co.next_base + br_take(&b, co.nb_bits);
-                }
+                uint32_t ll, ml, ofv;
+                fse_step(&b, T, &st, i0 + k + 1 >= nseq, &ll, &ml, &ofv);
+                uint32_t off = resolve_offset(ofv, ll, &r0, &r1, &r2);
+                if (off == 0) { err = 1; off = 1; }
                 if (k == ZD_LANE()) { my_ll = ll; my_ml = ml; my_off = off; }
             }
             if (err || b.pos < 0) return ERR_CORRUPT;
-            // phase B: positions
-            uint32_t lit_excl, out_excl, lit_tot, out_tot;
-#if defined(__CUDA_ARCH__)
-            {
-                uint32_t xl = my_ll, xo = my_ll + my_ml;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const uint32_t yl = __shfl_up_sync(0xffffffffu, xl, d), yo = __shfl_up_sync(0xffffffffu, xo, d);
-                    if ((int)ZD_LANE() >= d) { xl += yl; xo += yo; }
-                }
-                lit_excl = xl - my_ll; out_excl = xo - (my_ll + my_ml);
-                lit_tot = __shfl_sync(0xffffffffu, xl, 31); out_tot = __shfl_sync(0xffffffffu, xo, 31);
-            }
-#else
-            lit_excl = 0; out_excl = 0; lit_tot = my_ll; out_tot = my_ll + my_ml;
-#endif
-            if (lit_pos + lit_tot > L.size) return ERR_CORRUPT;
-            if ((uint64_t)pos + out_tot > cap) return ERR_CAPACITY;
-            const uint32_t my_lit_out = pos + out_excl, my_match = my_lit_out + my_ll;
-            const bool mine = ZD_LANE() < nbatch;
-            int bad = mine && my_off > my_match - frame_start;
-#if defined(__CUDA_ARCH__)
-            bad = __any_sync(0xffffffffu, bad);
-#endif
-            if (bad) return ERR_CORRUPT;
-            // phase C: literal runs (sources are the literal buffer / the input, never the output): each lane its own run
-            if (mine) {
-                const uint8_t *ls = L.ptr + lit_pos + lit_excl;
-                if (L.rle) for (uint32_t t = 0; t < my_ll; t++) out[my_lit_out + t] = L.rle_byte;
-                else lane_copy(out + my_lit_out, ls, my_ll);
-            }
-            // phase D: matches.  A match is independent if everything it reads was synced before this batch started.
-            const uint32_t batch_synced = *synced;
-            const uint32_t src_end = my_match - my_off + (my_off < my_ml ? my_off : my_ml);
-            const bool indep = mine && src_end <= batch_synced;
-            if (indep) {
-                const uint8_t *from = out + my_match - my_off;  // non-overlapping with anything written in this batch
-                if (my_off >= my_ml) lane_copy(out + my_match, from, my_ml);
-                else for (uint32_t t = 0; t < my_ml; t++) out[my_match + t] = from[t % my_off];
-            }
-#if defined(__CUDA_ARCH__)
-            uint32_t dep_mask = __ballot_sync(0xffffffffu, mine && !indep);
-            __syncwarp();  // literals and independent matches of the batch are visible
-            while (dep_mask) {
-                const int k = __ffs((int)dep_mask) - 1;
-                dep_mask &= dep_mask - 1;
-                const uint32_t mpos = __shfl_sync(0xffffffffu, my_match, k), moff = __shfl_sync(0xffffffffu, my_off, k),
-                               mlen = __shfl_sync(0xffffffffu, my_ml, k);
-                copy_match(out, mpos, moff, mlen);
-                __syncwarp();
-            }
-#else
-            if (mine && !indep) copy_match(out, my_match, my_off, my_ml);
-#endif
-            lit_pos += lit_tot;
-            pos += out_tot;
-            *synced = pos;
+            const int64_t np = execute_batch(out, pos, cap, frame_start, &L, &lit_pos, my_ll, my_ml, my_off, nbatch, synced);
+            if (np < 0) return np;
+            pos = (uint32_t)np;
         }
         if (b.pos != 0) return ERR_CORRUPT;
         rep[0] = r0; rep[1] = r1; rep[2] = r2;
     } else if (left != 0) return ERR_CORRUPT;
+    const uint32_t rest = L.size - lit_pos;
+    if ((uint64_t)pos + rest > cap) return ERR_CAPACITY;
+    if (L.rle) fill_bytes(out + pos, L.rle_byte, rest); else copy_bytes(out + pos, L.ptr + lit_pos, rest);
+    ZD_SYNC();
+    return (int64_t)pos + rest;
+}
+
+// ---- two passes over a frame whose blocks do not chain through repeated tables (everything the K3 encoder writes) -------------
+// Pass 1 (one warp per BLOCK, all blocks of all frames at once): entropy decoding only -- Huffman literals into the block's own
+// literal buffer, the FSE chain into an array of {ll, ml, offset value} -- which is where a frame spends ~80 % of its time and
+// what makes it serial.  Pass 2 (one warp per FRAME): resolves repeat offsets and executes the stored sequences block by block
+// with execute_batch.  A block is independent for pass 1 when its literals are not Treeless and none of its three sequence
+// tables is in Repeat_Mode; block_is_independent answers that from the headers alone.
+struct StoredSeq { uint32_t ll, ml, ofv; };
+struct BlockState {          // pass 1 -> pass 2
+    int32_t status;          // 0 or an ERR_ code
+    uint32_t nseq;
+    uint32_t lit_size, lit_rle;       // Literals: size, RLE flag | byte << 8
+    uint32_t lit_src_off, lit_in_buf; // where they are: offset into the block's compressed bytes, or the block's literal buffer
+};
+
+ZD_DEV bool block_is_independent(const uint8_t *src, uint32_t size) {
+    if (size < 1) return false;
+    const uint32_t type = src[0] & 3, sf = (src[0] >> 2) & 3;
+    uint32_t used;
+    if (type == 3) return false;  // Treeless
+    if (type < 2) {
+        uint32_t hl, n;
+        if (sf == 0 || sf == 2) { hl = 1; n = src[0] >> 3; }
+        else if (sf == 1) { if (size < 2) return false; hl = 2; n = (src[0] | src[1] << 8) >> 4; }
+        else { if (size < 3) return false; hl = 3; n = (src[0] | src[1] << 8 | (uint32_t)src[2] << 16) >> 4; }
+        used = type == 0 ? hl + n : hl + 1;
+    } else {
+        uint32_t hl, comp;
+        if (sf <= 1) { if (size < 3) return false; hl = 3; comp = (src[0] | src[1] << 8 | (uint32_t)src[2] << 16) >> 14; }
+        else if (sf == 2) { if (size < 4) return false; hl = 4; comp = (src[0] | src[1] << 8 | (uint32_t)src[2] << 16 | (uint32_t)src[3] << 24) >> 18; }
+        else { if (size < 5) return false; hl = 5; comp = (uint32_t)((src[0] | src[1] << 8 | (uint32_t)src[2] << 16 | (uint64_t)src[3] << 24 | (uint64_t)src[4] << 32) >> 22); }
+        used = hl + comp;
+    }
+    if (used >= size) return false;  // malformed: let the one-pass decoder report it
+    const uint8_t *p = src + used;
+    uint32_t left = size - used, nseq = p[0];
+    if (nseq == 0) return true;
+    const uint32_t nh = nseq < 128 ? 1 : nseq < 255 ? 2 : 3;
+    if (left < nh + 1) return false;
+    const uint32_t modes = p[nh];
+    return (modes >> 6) != 3 && ((modes >> 4) & 3) != 3 && ((modes >> 2) & 3) != 3;
+}
+
+// pass 1 of one compressed block
+ZD_DEV void decode_block_entropy(const uint8_t *src, uint32_t size, Tables *T, Scratch *S, uint8_t *litbuf, StoredSeq *seqs, uint32_t seq_cap,
+                                 BlockState *bs_out) {
+    BlockState bs;
+    bs.status = 0; bs.nseq = 0; bs.lit_size = 0; bs.lit_rle = 0; bs.lit_src_off = 0; bs.lit_in_buf = 0;
+    T->have_huf = T->have_ll = T->have_ml = T->have_of = 0;  // an independent block brings all its tables
+    Literals L;
+    const int lused = decode_literals(src, size, T, litbuf, &L, S->weights, S->cells);
+    int rc = lused < 0 ? lused : 0;
+    if (!rc) {
+        bs.lit_size = L.size; bs.lit_rle = L.rle ? (1u | (uint32_t)L.rle_byte << 8) : 0u;
+        bs.lit_in_buf = L.ptr == litbuf ? 1u : 0u;
+        bs.lit_src_off = bs.lit_in_buf ? 0u : (uint32_t)(L.ptr - src);
+        const uint8_t *p = src + lused;
+        uint32_t left = size - (uint32_t)lused, nseq = 0;
+        rc = read_sequences_header(&p, &left, &nseq, T, S);
+        if (!rc && nseq > seq_cap) rc = ERR_CORRUPT;
+        if (!rc && nseq) {
+            BitReader b;
+            if (br_init(&b, p, left) < 0) rc = ERR_CORRUPT;
+            else {
+                FseStates st;
+                st.ll = br_read(&b, T->ll_log); st.of = br_read(&b, T->of_log); st.ml = br_read(&b, T->ml_log);
+                for (uint32_t i0 = 0; i0 < nseq; i0 += ZD_WARP) {
+                    const uint32_t nbatch = nseq - i0 < ZD_WARP ? nseq - i0 : ZD_WARP;
+                    StoredSeq mine;
+                    mine.ll = 0; mine.ml = 0; mine.ofv = 4;
+                    for (uint32_t k = 0; k < nbatch; k++) {
+                        uint32_t ll, ml, ofv;
+                        fse_step(&b, T, &st, i0 + k + 1 >= nseq, &ll, &ml, &ofv);
+                        if (k == ZD_LANE()) { mine.ll = ll; mine.ml = ml; mine.ofv = ofv; }
+                    }
+                    if (ZD_LANE() < nbatch) seqs[i0 + ZD_LANE()] = mine;
+                }
+                if (b.pos != 0) rc = ERR_CORRUPT;
+            }
+        } else if (!rc && left != 0) rc = ERR_CORRUPT;
+        bs.nseq = nseq;
+    }
+    bs.status = rc;
+    ZD_SYNC();
+    if (ZD_LANE() == 0) *bs_out = bs;
+}
+
+// pass 2 of one compressed block: returns new pos or < 0
+ZD_DEV int64_t execute_stored_block(const uint8_t *src, const BlockState *bsp, const uint8_t *litbuf, const StoredSeq *seqs, uint8_t *out, uint32_t pos,
+                                    uint32_t cap, uint32_t frame_start, uint32_t rep[3], uint32_t *synced) {
+    const BlockState bs = *bsp;
+    if (bs.status < 0) return bs.status;
+    Literals L;
+    L.ptr = bs.lit_in_buf ? litbuf : src + bs.lit_src_off; L.size = bs.lit_size; L.rle = bs.lit_rle & 1u; L.rle_byte = (uint8_t)(bs.lit_rle >> 8);
+    uint32_t lit_pos = 0, r0 = rep[0], r1 = rep[1], r2 = rep[2];
+    for (uint32_t i0 = 0; i0 < bs.nseq; i0 += ZD_WARP) {
+        const uint32_t nbatch = bs.nseq - i0 < ZD_WARP ? bs.nseq - i0 : ZD_WARP;
+        StoredSeq mine;
+        mine.ll = 0; mine.ml = 0; mine.ofv = 4;
+        if (ZD_LANE() < nbatch) mine = seqs[i0 + ZD_LANE()];
+        uint32_t my_off = 1;
+        int err = 0;
+        for (uint32_t k = 0; k < nbatch; k++) {  // the history is a chain over the batch; every lane walks it
+#if defined(__CUDA_ARCH__)
+            const uint32_t ofv = __shfl_sync(0xffffffffu, mine.ofv, k), ll = __shfl_sync(0xffffffffu, mine.ll, k);
+#else
+            const uint32_t ofv = mine.ofv, ll = mine.ll;
+#endif
+            uint32_t off = resolve_offset(ofv, ll, &r0, &r1, &r2);
+            if (off == 0) { err = 1; off = 1; }
+            if (k == ZD_LANE()) my_off = off;
+        }
+        if (err) return ERR_CORRUPT;
+        const int64_t np = execute_batch(out, pos, cap, frame_start, &L, &lit_pos, mine.ll, mine.ml, my_off, nbatch, synced);
+        if (np < 0) return np;
+        pos = (uint32_t)np;
+    }
+    rep[0] = r0; rep[1] = r1; rep[2] = r2;
     const uint32_t rest = L.size - lit_pos;
     if ((uint64_t)pos + rest > cap) return ERR_CAPACITY;
     if (L.rle) fill_bytes(out + pos, L.rle_byte, rest); else copy_bytes(out + pos, L.ptr + lit_pos, rest);
@@ -592,6 +758,77 @@ ZD_DEV int64_t decode_payload(const uint8_t *src, uint32_t size, uint8_t *out, u
         if (fcs_bytes && (uint64_t)(pos - frame_start) != fcs) return ERR_CORRUPT;
         if (has_checksum) { if (size - ip < 4) return ERR_CORRUPT; ip += 4; }  // content checksum is not verified (the reference never writes one)
     }
+    return pos;
+}
+
+// Two-pass eligibility of a payload: exactly one zstd frame, at most max_blocks blocks, every compressed block independent
+// (block_is_independent).  Anything else -- several frames, skippable frames, malformed headers -- is left to decode_payload,
+// which also produces the error.  Fills tasks[] and returns the number of blocks, or 0 if not eligible.
+struct BlockTask { uint32_t src_off, size, type; };
+struct FrameInfo { uint32_t nblocks, has_fcs; uint64_t fcs; };
+ZD_DEV uint32_t scan_frame(const uint8_t *src, uint32_t size, uint32_t max_blocks, BlockTask *tasks, FrameInfo *fi) {
+    if (size < 6) return 0;
+    const uint32_t magic = src[0] | src[1] << 8 | (uint32_t)src[2] << 16 | (uint32_t)src[3] << 24;
+    if (magic != Z_MAGIC) return 0;
+    const uint32_t fhd = src[4];
+    const uint32_t fcs_flag = fhd >> 6, single = (fhd >> 5) & 1, has_checksum = (fhd >> 2) & 1, did = fhd & 3;
+    if ((fhd & 0x08) || did) return 0;
+    uint32_t h = 5;
+    if (!single) { if (size < h + 1 || 10 + (src[h] >> 3) > 31) return 0; h += 1; }
+    const uint32_t fcs_bytes = fcs_flag == 0 ? single : fcs_flag == 1 ? 2 : fcs_flag == 2 ? 4 : 8;
+    if (size < h + fcs_bytes) return 0;
+    uint64_t fcs = 0;
+    for (uint32_t i = 0; i < fcs_bytes; i++) fcs |= (uint64_t)src[h + i] << (8 * i);
+    if (fcs_flag == 1) fcs += 256;
+    uint32_t ip = h + fcs_bytes, nb = 0;
+    for (;;) {
+        if (size - ip < 3 || nb >= max_blocks) return 0;
+        const uint32_t bh = src[ip] | src[ip + 1] << 8 | (uint32_t)src[ip + 2] << 16;
+        const uint32_t last = bh & 1, type = (bh >> 1) & 3, bsz = bh >> 3;
+        ip += 3;
+        if (type == 3 || bsz > Z_BLOCK_MAX) return 0;
+        const uint32_t body = type == 1 ? 1u : bsz;
+        if (body > size - ip) return 0;
+        if (type == 2 && !block_is_independent(src + ip, bsz)) return 0;
+        tasks[nb].src_off = ip; tasks[nb].size = bsz; tasks[nb].type = type;
+        nb++;
+        ip += body;
+        if (last) break;
+    }
+    if (has_checksum) { if (size - ip < 4) return 0; ip += 4; }
+    if (ip != size) return 0;
+    fi->nblocks = nb; fi->has_fcs = fcs_bytes != 0; fi->fcs = fcs;
+    return nb;
+}
+
+// pass 2 of a whole frame scanned by scan_frame: returns the decoded size or < 0
+ZD_DEV int64_t execute_frame(const uint8_t *src, const BlockTask *tasks, const FrameInfo *fi, const BlockState *states, const uint8_t *litbufs,
+                             size_t litbuf_stride, const StoredSeq *seqs, size_t seq_stride, uint8_t *out, uint32_t cap) {
+    if (fi->has_fcs && fi->fcs > cap) return ERR_CAPACITY;
+    uint32_t pos = 0, synced = 0;
+    uint32_t rep[3] = {1, 4, 8};
+    for (uint32_t b = 0; b < fi->nblocks; b++) {
+        const BlockTask t = tasks[b];
+        if (t.type == 0) {
+            if (t.size > cap - pos) return ERR_CAPACITY;
+            copy_bytes(out + pos, src + t.src_off, t.size);
+            ZD_SYNC();
+            pos += t.size; synced = pos;
+        } else if (t.type == 1) {
+            if (t.size > cap - pos) return ERR_CAPACITY;
+            fill_bytes(out + pos, src[t.src_off], t.size);
+            ZD_SYNC();
+            pos += t.size; synced = pos;
+        } else {
+            const int64_t np = execute_stored_block(src + t.src_off, states + b, litbufs + (size_t)b * litbuf_stride, seqs + (size_t)b * seq_stride, out, pos, cap,
+                                                    0, rep, &synced);
+            if (np < 0) return np;
+            if ((uint64_t)np - pos > Z_BLOCK_MAX) return ERR_CORRUPT;
+            synced = (uint32_t)np;
+            pos = (uint32_t)np;
+        }
+    }
+    if (fi->has_fcs && (uint64_t)pos != fi->fcs) return ERR_CORRUPT;
     return pos;
 }
 

@@ -15,3 +15,28 @@ extern "C" long dec_model_payload(const uint8_t *src, uint32_t n, uint8_t *dst, 
     delete T; delete S;
     return r;
 }
+
+// The two-pass (block-parallel) decoder on the host: scan, pass 1 block by block into per-block buffers, pass 2 in order.
+// Returns the decoded size, < 0 for an error, or -100 if the payload is not eligible (the product then uses the one-pass path).
+extern "C" long dec_model_payload_two_pass(const uint8_t *src, uint32_t n, uint8_t *dst, uint32_t cap) {
+    std::vector<uint8_t> padded(n + 64, 0);
+    memcpy(padded.data() + 16, src, n);
+    const uint8_t *p = padded.data() + 16;
+    const uint32_t MAXB = 16, SEQ_CAP = Z_BLOCK_MAX / 3 + 1;
+    std::vector<zd::BlockTask> tasks(MAXB);
+    zd::FrameInfo fi;
+    const uint32_t nb = zd::scan_frame(p, n, MAXB, tasks.data(), &fi);
+    if (!nb) return -100;
+    zd::Tables *T = new zd::Tables();
+    zd::Scratch *S = new zd::Scratch();
+    memset(T, 0, sizeof *T);
+    const size_t lstride = Z_BLOCK_MAX + 64;
+    std::vector<uint8_t> lits(nb * lstride);
+    std::vector<zd::StoredSeq> seqs((size_t)nb * SEQ_CAP);
+    std::vector<zd::BlockState> states(nb);
+    for (uint32_t b = 0; b < nb; b++)
+        if (tasks[b].type == 2) zd::decode_block_entropy(p + tasks[b].src_off, tasks[b].size, T, S, lits.data() + b * lstride, seqs.data() + (size_t)b * SEQ_CAP, SEQ_CAP, &states[b]);
+    long r = (long)zd::execute_frame(p, tasks.data(), &fi, states.data(), lits.data(), lstride, seqs.data(), SEQ_CAP, dst, cap);
+    delete T; delete S;
+    return r;
+}

@@ -28,10 +28,21 @@ def dec():
     lib.dec_model_payload.restype = C.c_long
     lib.dec_model_payload.argtypes = [C.c_char_p, C.c_uint32, C.c_char_p, C.c_uint32]
 
+    lib.dec_model_payload_two_pass.restype = C.c_long
+    lib.dec_model_payload_two_pass.argtypes = [C.c_char_p, C.c_uint32, C.c_char_p, C.c_uint32]
+
     def run(payload: bytes, cap: int):
         out = C.create_string_buffer(max(cap, 1))
         n = lib.dec_model_payload(payload, len(payload), out, cap)
         return None if n < 0 else out.raw[:n]
+
+    def two_pass(payload: bytes, cap: int):
+        """the block-parallel decoder's two passes run in order on the host: bytes, None for an error, "n/a" when the payload is
+        not eligible (several frames, chained tables ...) and the product uses the one-pass decoder"""
+        out = C.create_string_buffer(max(cap, 1))
+        n = lib.dec_model_payload_two_pass(payload, len(payload), out, cap)
+        return "n/a" if n == -100 else None if n < 0 else out.raw[:n]
+    run.two_pass = two_pass
     return run
 
 
@@ -110,3 +121,32 @@ def test_encoder_core_frames_decode_with_stock_libzstd_and_ratio(sq, oracle, enc
             tot_gpu += len(frame)
             tot_ref += len(oracle.compress(data, 12))
     assert tot_gpu <= 1.03 * tot_ref, (tot_gpu, tot_ref)  # the north_star tolerance on the parse model
+
+
+def test_two_pass_decoder_core(sq, oracle, enc, dec):
+    """zstd_dec_core.h's two-pass path (entropy decoding per block, then in-order execution): every frame the encoder core writes
+    is eligible and decodes to the same bytes; stock libzstd frames either decode identically or are declared not eligible
+    (Treeless literals / Repeat_Mode tables chain their blocks); truncation and bit flips never crash it."""
+    rng = random.Random(6)
+    eligible_ref = 0
+    for data in samples(sq, (1, 100, 4096, 70000, 131072, 131073, 300000, 2 << 20)):
+        frame = enc(data)
+        assert dec.two_pass(frame, len(data)) == data, len(data)
+        assert dec.two_pass(frame, len(data) - 1) is None                      # capacity
+        for lvl in (1, 12):
+            ref = oracle.compress(data, lvl)
+            got = dec.two_pass(ref, len(data))
+            assert got == "n/a" or got == data, (len(data), lvl)
+            eligible_ref += got != "n/a"
+    assert eligible_ref > 0
+    assert dec.two_pass(oracle.compress(b"hello ") + oracle.compress(b"squish"), 64) == "n/a"  # two frames: one-pass decoder
+    data = samples(sq, (200000,))[2]
+    f = bytearray(enc(data))
+    for _ in range(600):
+        g = bytearray(f)
+        for _ in range(rng.randrange(1, 4)):
+            g[rng.randrange(4, len(g))] ^= 1 << rng.randrange(8)
+        got = dec.two_pass(bytes(g), len(data))
+        ref = oracle.decompress(bytes(g), len(data))
+        if got not in (None, "n/a"):
+            assert ref == got
