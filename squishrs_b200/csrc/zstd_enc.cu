@@ -36,7 +36,7 @@ struct sq_enc_scratch {
     uint32_t *list;          // [lz_sub * lz2::LIST_STRIDE] the chunks' sorted row lists (index_kernel -> search_kernel)
     uint32_t *words;         // [lz_sub * lz::REC_PER_CHUNK] index_kernel pass 1 -> pass 2: row + tags of every position
     uint32_t *span_start;    // [lz_sub + 1] search spans of a sub-batch, exclusive prefix
-    uint32_t lz_sub, search_ctas; int lz_variant;
+    uint32_t lz_sub, search_ctas;
     cudaEvent_t tev[5];      // SQ_FLAG_STAGE_TIMING: before search / after search / after chase / after entropy / after emit
     int tev_valid;
     uint32_t cap_chunks;
@@ -182,10 +182,11 @@ __global__ void __launch_bounds__(256) enc_emit_kernel(const uint8_t *__restrict
 // ---- search: sub-batches of at most LZ_SUB chunks go through span_plan -> index -> search; the list scratch (8 MB per chunk of a
 // sub-batch) is what bounds the sub-batch ----
 namespace {
-constexpr int LZ_SEARCH_THREADS = 256, LZ_INDEX_THREADS = 512, LZ_INDEX_PARTS = 4;
+// search: three CTAs of eight warps per SM (80 registers, 2048 x 16-bit continuation table per warp); four CTAs at 64
+// registers spill and were 9 % slower
+constexpr int LZ_SEARCH_THREADS = 256, LZ_SEARCH_MINB = 3, LZ_SEARCH_TLOG = 10, LZ_INDEX_THREADS = 512, LZ_INDEX_PARTS = 4;
 constexpr uint32_t LZ_SUB_MAX = 256;
-// variant 0 ships: three CTAs per SM (80 registers), 1024-entry continuation table; variant 1 (SQ_LZ_VARIANT=1): four CTAs per SM (64 registers), 512 entries
-static int search_smem(int variant) { return (int)((variant == 1 ? lz2::SearchSmem<9>::PER_WARP : lz2::SearchSmem<10>::PER_WARP) * (LZ_SEARCH_THREADS / 32)); }
+constexpr int SEARCH_SMEM = (int)(lz2::SearchSmem<LZ_SEARCH_TLOG>::PER_WARP * (LZ_SEARCH_THREADS / 32));
 }  // namespace
 
 static int32_t enc_scratch(sq_ctx *ctx, uint32_t n, int set) {
@@ -201,21 +202,13 @@ static int32_t enc_scratch(sq_ctx *ctx, uint32_t n, int set) {
             SQ_CUDA(ctx, cudaFuncSetAttribute(lz::entropy_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         }
         {   // search: all warps are interchangeable, the grid is what is resident
-            static const int var = getenv("SQ_LZ_VARIANT") ? atoi(getenv("SQ_LZ_VARIANT")) : 0;
-            e->lz_variant = var == 1 ? 1 : 0;
             SQ_CUDA(ctx, cudaFuncSetAttribute(lz2::index_kernel<LZ_INDEX_THREADS, LZ_INDEX_PARTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(lz2::ROWS * sizeof(uint32_t))));
             int per_sm = 0;
-            const int smem = search_smem(e->lz_variant);
-            if (e->lz_variant == 1) {
-                SQ_CUDA(ctx, cudaFuncSetAttribute(lz2::search_kernel<LZ_SEARCH_THREADS, 4, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-                SQ_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lz2::search_kernel<LZ_SEARCH_THREADS, 4, 9>, LZ_SEARCH_THREADS, smem));
-            } else {
-                SQ_CUDA(ctx, cudaFuncSetAttribute(lz2::search_kernel<LZ_SEARCH_THREADS, 3, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-                SQ_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lz2::search_kernel<LZ_SEARCH_THREADS, 3, 10>, LZ_SEARCH_THREADS, smem));
-            }
+            SQ_CUDA(ctx, cudaFuncSetAttribute(lz2::search_kernel<LZ_SEARCH_THREADS, LZ_SEARCH_MINB, LZ_SEARCH_TLOG>, cudaFuncAttributeMaxDynamicSharedMemorySize, SEARCH_SMEM));
+            SQ_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lz2::search_kernel<LZ_SEARCH_THREADS, LZ_SEARCH_MINB, LZ_SEARCH_TLOG>, LZ_SEARCH_THREADS, SEARCH_SMEM));
             if (per_sm < 1) return sq_set_error(ctx, SQ_ERR_CUDA, "search kernel does not fit this device");
             e->search_ctas = (uint32_t)(per_sm * ctx->sm_count);
-            if (getenv("SQ_TIMING")) fprintf(stderr, "[sq] search kernel variant %d: %d threads, %d CTAs per SM, %d B of shared memory per CTA\n", e->lz_variant, LZ_SEARCH_THREADS, per_sm, smem);
+            if (getenv("SQ_TIMING")) fprintf(stderr, "[sq] search kernel: %d threads, %d CTAs per SM, %d B of shared memory per CTA\n", LZ_SEARCH_THREADS, per_sm, SEARCH_SMEM);
         }
         SQ_CUDA(ctx, cudaMalloc(&e->lits, (size_t)e->ent_warps * (Z_BLOCK_MAX + 64)));
         SQ_CUDA(ctx, cudaMalloc(&e->sbits, (size_t)e->ent_warps * lz::SBITS_STRIDE * sizeof(uint32_t)));
@@ -321,12 +314,8 @@ int32_t sq_encode_device_set(sq_ctx *ctx, int set, const void *d_data, const sq_
                 SQ_CUDA(ctx, cudaLaunchKernelEx(&cfg, lz2::index_kernel<LZ_INDEX_THREADS, LZ_INDEX_PARTS>, (const uint8_t *)d_data, d_spans, d_select, first, count,
                                                 e->list, e->words, e->rec));
             }
-            if (e->lz_variant == 1)
-                lz2::search_kernel<LZ_SEARCH_THREADS, 4, 9><<<e->search_ctas, LZ_SEARCH_THREADS, search_smem(1), st>>>((const uint8_t *)d_data, d_spans, first, count, e->span_start,
-                                                                                                                   e->list, e->rec, e->status + 1, dbg);
-            else
-                lz2::search_kernel<LZ_SEARCH_THREADS, 3, 10><<<e->search_ctas, LZ_SEARCH_THREADS, search_smem(0), st>>>((const uint8_t *)d_data, d_spans, first, count, e->span_start,
-                                                                                                                    e->list, e->rec, e->status + 1, dbg);
+            lz2::search_kernel<LZ_SEARCH_THREADS, LZ_SEARCH_MINB, LZ_SEARCH_TLOG><<<e->search_ctas, LZ_SEARCH_THREADS, SEARCH_SMEM, st>>>((const uint8_t *)d_data, d_spans, first, count,
+                                                                                                                                    e->span_start, e->list, e->rec, e->status + 1, dbg);
             SQ_LAUNCHED(ctx, 3);
         }
         if (timing) SQ_CUDA(ctx, cudaEventRecord(e->tev[1], st));

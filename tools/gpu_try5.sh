@@ -4,7 +4,7 @@ mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest.log
 tail -8 gpurun_out/pytest.log
 timeout 300 python tools/real_data_ratio.py --gpu-only > gpurun_out/ratio.log 2>&1; tail -3 gpurun_out/ratio.log
-for v in 0 1; do SQ_LZ_VARIANT=$v SQ_TIMING=1 timeout 200 python tools/enc_probe.py ${NCH:-2048} variant$v 2>&1 | grep -E "variant|rror" | tail -3; done | tee gpurun_out/cfgs.log
+SQ_TIMING=1 timeout 200 python tools/enc_probe.py ${NCH:-2048} probe 2>&1 | grep -E "probe|rror" | tail -3 | tee gpurun_out/cfgs.log
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file gpurun_out/launches.csv python tools/enc_probe.py ${NCH:-2048} > gpurun_out/ncu1.log 2>&1
 python - <<'PY'
 import csv, collections
