@@ -15,13 +15,13 @@
 // to a 128 KiB per-warp slot in HBM (L2 resident).  Algorithmic traffic = payload bytes read + decoded
 // bytes written.
 //
-// Block-parallel path (batches of at most BP_MAX_FRAMES payloads, i.e. exactly when frames alone cannot fill the GPU).  A payload
-// that is one frame whose compressed blocks bring all their own tables -- everything the K3 encoder writes, and the libzstd frames
-// that happen not to use Treeless literals or Repeat_Mode -- is decoded in two passes: bp_entropy_kernel gives every BLOCK its own
-// warp for the entropy decoding (Huffman literals into the block's literal buffer, the FSE chain into an array of {ll, ml, offset
-// value}), which is where a frame spends most of its time; bp_execute_kernel then gives every FRAME a warp that resolves repeat
-// offsets and copies literals and matches block by block, in order (matches reach back across blocks, so execution stays
-// serial).  bp_scan_kernel decides eligibility from the headers; everything else goes through the one-pass kernel as before.
+// Block-parallel path (calls of at most BP_MAX_FRAMES payloads, i.e. exactly when frames alone cannot fill the GPU).  A payload that
+// is one frame of self-contained blocks (zstd_dec_core.h: own tables, no repeat offset from before the block, regular block
+// starts) -- everything the K3 encoder writes -- is decoded in two passes: bp_first_pass_kernel gives every BLOCK a warp for all
+// work that does not read the output (Huffman literals, FSE chain, repeat offsets, positions, and placing the literals);
+// bp_matches_kernel then gives every FRAME a warp that copies the matches block by block, in order (matches reach back across
+// blocks).  bp_scan_kernel decides from the headers which payloads try this; the others run through the one-pass kernel on a
+// second stream beside the two passes, and so does, afterwards, any frame whose blocks turned out not to be self-contained.
 #include "common.cuh"
 #include "zstd_dec_core.h"
 
@@ -29,17 +29,17 @@ struct sq_dec_scratch {
     uint8_t *lits;      // per resident warp: Z_BLOCK_MAX + 64
     void *build;        // per resident warp: table-construction scratch (zd::Scratch, 2.3 KB; in HBM so that shared memory holds only
                         // the decode tables and six CTAs fit an SM)
-    uint32_t *counter;      // [0] one-pass work counter, [1] bp_entropy, [2] bp_execute
+    uint32_t *counter;      // [0] one-pass work counter, [1] bp_first_pass, [2] bp_matches, [3] one-pass for frames the two passes gave back
     uint32_t warps;
     // block-parallel path, sized for bp_cap frames
     uint32_t bp_cap;
-    uint8_t *bp_elig;         // [bp_cap] 1 = decoded by the two-pass path
+    uint8_t *bp_elig;         // [bp_cap] 0 = one-pass kernel, 1 = two passes, 2 = two passes gave up: one-pass kernel afterwards
     zd::FrameInfo *bp_info;   // [bp_cap]
     zd::BlockTask *bp_tasks;  // [bp_cap * BP_MAX_BLOCKS]
     zd::BlockState *bp_states;
-    uint8_t *bp_lits;         // [bp_cap * BP_MAX_BLOCKS * (Z_BLOCK_MAX + 64)]
+    uint8_t *bp_lits;         // per resident warp of bp_first_pass_kernel: Z_BLOCK_MAX + 64 (it runs beside the one-pass kernel, which has its own)
     zd::StoredSeq *bp_seqs;   // [bp_cap * BP_MAX_BLOCKS * BP_SEQ_CAP]
-    void *bp_build;           // per resident warp of bp_entropy_kernel: its own table-construction scratch (it runs beside the one-pass kernel)
+    void *bp_build;           // per resident warp of bp_first_pass_kernel: its own table-construction scratch
     cudaStream_t aux;         // the one-pass kernel for the frames that are not eligible runs here, beside the two passes
     cudaEvent_t ev_fork, ev_join;
 };
@@ -53,7 +53,7 @@ struct WarpState { zd::Tables T; };
 __global__ void __launch_bounds__(DEC_WARPS_PER_CTA * 32, 6) zstd_decode_kernel(const uint8_t *__restrict__ comp, const sq_frame *__restrict__ frames,
                                                                              uint32_t n, uint8_t *__restrict__ out, sq_frame_result *__restrict__ res,
                                                                              uint8_t *__restrict__ lits_all, zd::Scratch *__restrict__ build_all,
-                                                                             uint32_t *__restrict__ counter, const uint8_t *__restrict__ skip) {
+                                                                             uint32_t *__restrict__ counter, const uint8_t *__restrict__ sel, uint32_t want) {
     extern __shared__ __align__(16) uint8_t smem[];
     const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     WarpState *ws = reinterpret_cast<WarpState *>(smem) + w;
@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(DEC_WARPS_PER_CTA * 32, 6) zstd_decode_kernel(
         if (lane == 0) i = atomicAdd(counter, 1u);
         i = __shfl_sync(0xffffffffu, i, 0);
         if (i >= n) break;
-        if (skip && skip[i]) continue;  // the block-parallel path has it
+        if (sel && sel[i] != want) continue;  // the block-parallel path has it (or had it and gave it back: want == 2)
         const sq_frame f = frames[i];
         const int64_t r = zd::decode_payload(comp + f.src_off, f.src_len, out + f.dst_off, f.capacity, &ws->T, S, lits);
         __syncwarp();
@@ -92,34 +92,35 @@ __global__ void bp_scan_kernel(const uint8_t *__restrict__ comp, const sq_frame 
     info[i] = fi;
 }
 
-__global__ void __launch_bounds__(DEC_WARPS_PER_CTA * 32, 6) bp_entropy_kernel(const uint8_t *__restrict__ comp, const sq_frame *__restrict__ frames, uint32_t n,
-                                                                               const uint8_t *__restrict__ elig, const zd::FrameInfo *__restrict__ info,
-                                                                               const zd::BlockTask *__restrict__ tasks, zd::BlockState *__restrict__ states,
-                                                                               uint8_t *__restrict__ lits, zd::StoredSeq *__restrict__ seqs,
-                                                                               zd::Scratch *__restrict__ build_all, uint32_t *__restrict__ counter) {
+__global__ void __launch_bounds__(DEC_WARPS_PER_CTA * 32, 6) bp_first_pass_kernel(const uint8_t *__restrict__ comp, const sq_frame *__restrict__ frames, uint32_t n,
+                                                                                  const uint8_t *__restrict__ elig, const zd::FrameInfo *__restrict__ info,
+                                                                                  const zd::BlockTask *__restrict__ tasks, zd::BlockState *__restrict__ states,
+                                                                                  uint8_t *__restrict__ lits_all, zd::StoredSeq *__restrict__ seqs, uint8_t *__restrict__ out,
+                                                                                  zd::Scratch *__restrict__ build_all, uint32_t *__restrict__ counter) {
     extern __shared__ __align__(16) uint8_t smem[];
     const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     WarpState *ws = reinterpret_cast<WarpState *>(smem) + w;
     zd::Scratch *S = build_all + (blockIdx.x * DEC_WARPS_PER_CTA + w);
+    uint8_t *lits = lits_all + (size_t)(blockIdx.x * DEC_WARPS_PER_CTA + w) * BP_LIT_STRIDE;
     for (;;) {
         uint32_t item = 0;
         if (lane == 0) item = atomicAdd(counter, 1u);
         item = __shfl_sync(0xffffffffu, item, 0);
         if (item >= n * BP_MAX_BLOCKS) break;
         const uint32_t i = item / BP_MAX_BLOCKS, b = item % BP_MAX_BLOCKS;
-        if (!elig[i] || b >= info[i].nblocks) continue;
+        if (elig[i] != 1 || b >= info[i].nblocks) continue;
         const zd::BlockTask t = tasks[item];
         if (t.type != 2) continue;
-        zd::decode_block_entropy(comp + frames[i].src_off + t.src_off, t.size, &ws->T, S, lits + (size_t)item * BP_LIT_STRIDE, seqs + (size_t)item * BP_SEQ_CAP,
-                                 BP_SEQ_CAP, states + item);
+        const sq_frame f = frames[i];
+        zd::decode_block_first_pass(comp + f.src_off + t.src_off, t.size, &ws->T, S, lits, out + f.dst_off, t.out_start, f.capacity, b == 0,
+                                    seqs + (size_t)item * BP_SEQ_CAP, BP_SEQ_CAP, states + item);
         __syncwarp();
     }
 }
 
-__global__ void __launch_bounds__(128) bp_execute_kernel(const uint8_t *__restrict__ comp, const sq_frame *__restrict__ frames, uint32_t n,
-                                                          const uint8_t *__restrict__ elig, const zd::FrameInfo *__restrict__ info,
-                                                          const zd::BlockTask *__restrict__ tasks, const zd::BlockState *__restrict__ states,
-                                                          const uint8_t *__restrict__ lits, const zd::StoredSeq *__restrict__ seqs, uint8_t *__restrict__ out,
+__global__ void __launch_bounds__(128) bp_matches_kernel(const uint8_t *__restrict__ comp, const sq_frame *__restrict__ frames, uint32_t n, uint8_t *__restrict__ elig,
+                                                          const zd::FrameInfo *__restrict__ info, const zd::BlockTask *__restrict__ tasks,
+                                                          const zd::BlockState *__restrict__ states, const zd::StoredSeq *__restrict__ seqs, uint8_t *__restrict__ out,
                                                           sq_frame_result *__restrict__ res, uint32_t *__restrict__ counter) {
     const uint32_t lane = threadIdx.x & 31;
     for (;;) {
@@ -127,17 +128,20 @@ __global__ void __launch_bounds__(128) bp_execute_kernel(const uint8_t *__restri
         if (lane == 0) i = atomicAdd(counter, 1u);
         i = __shfl_sync(0xffffffffu, i, 0);
         if (i >= n) break;
-        if (!elig[i]) continue;
+        if (elig[i] != 1) continue;
         const sq_frame f = frames[i];
         const size_t first = (size_t)i * BP_MAX_BLOCKS;
-        const int64_t r = zd::execute_frame(comp + f.src_off, tasks + first, info + i, states + first, lits + first * BP_LIT_STRIDE, BP_LIT_STRIDE,
-                                            seqs + first * BP_SEQ_CAP, BP_SEQ_CAP, out + f.dst_off, f.capacity);
+        const int64_t r = zd::execute_frame_matches(comp + f.src_off, tasks + first, info + i, states + first, seqs + first * BP_SEQ_CAP, BP_SEQ_CAP, out + f.dst_off,
+                                                    f.capacity);
         __syncwarp();
         if (lane == 0) {
-            sq_frame_result fr;
-            fr.out_len = r >= 0 ? (uint32_t)r : 0u;
-            fr.status = r >= 0 ? SQ_OK : SQ_ERR_READER;
-            res[i] = fr;
+            if (r < 0) elig[i] = 2;  // not self-contained after all, or malformed: the one-pass kernel decodes it (and reports the error)
+            else {
+                sq_frame_result fr;
+                fr.out_len = (uint32_t)r;
+                fr.status = SQ_OK;
+                res[i] = fr;
+            }
         }
     }
 }
@@ -173,8 +177,9 @@ extern "C" int32_t sq_decode_device(sq_ctx *ctx, const void *d_comp, const sq_fr
         SQ_CUDA(ctx, cudaMalloc(&d->lits, (size_t)d->warps * (Z_BLOCK_MAX + 64)));
         SQ_CUDA(ctx, cudaMalloc(&d->build, (size_t)d->warps * sizeof(zd::Scratch)));
         SQ_CUDA(ctx, cudaMalloc(&d->counter, 4 * sizeof(uint32_t)));
-        SQ_CUDA(ctx, cudaFuncSetAttribute(bp_entropy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SQ_CUDA(ctx, cudaFuncSetAttribute(bp_first_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         SQ_CUDA(ctx, cudaMalloc(&d->bp_build, (size_t)d->warps * sizeof(zd::Scratch)));
+        SQ_CUDA(ctx, cudaMalloc(&d->bp_lits, (size_t)d->warps * BP_LIT_STRIDE));
         SQ_CUDA(ctx, cudaStreamCreateWithFlags(&d->aux, cudaStreamNonBlocking));
         SQ_CUDA(ctx, cudaEventCreateWithFlags(&d->ev_fork, cudaEventDisableTiming));
         SQ_CUDA(ctx, cudaEventCreateWithFlags(&d->ev_join, cudaEventDisableTiming));
@@ -187,14 +192,13 @@ extern "C" int32_t sq_decode_device(sq_ctx *ctx, const void *d_comp, const sq_fr
     if (n <= BP_MAX_FRAMES && !bp_off) {  // too few frames to fill the GPU with one warp each: give the blocks of eligible frames their own warps
         if (d->bp_cap < n) {
             SQ_CUDA(ctx, cudaStreamSynchronize(st));
-            cudaFree(d->bp_elig); cudaFree(d->bp_info); cudaFree(d->bp_tasks); cudaFree(d->bp_states); cudaFree(d->bp_lits); cudaFree(d->bp_seqs);
-            d->bp_elig = nullptr; d->bp_info = nullptr; d->bp_tasks = nullptr; d->bp_states = nullptr; d->bp_lits = nullptr; d->bp_seqs = nullptr; d->bp_cap = 0;
+            cudaFree(d->bp_elig); cudaFree(d->bp_info); cudaFree(d->bp_tasks); cudaFree(d->bp_states); cudaFree(d->bp_seqs);
+            d->bp_elig = nullptr; d->bp_info = nullptr; d->bp_tasks = nullptr; d->bp_states = nullptr; d->bp_seqs = nullptr; d->bp_cap = 0;
             const size_t items = (size_t)n * BP_MAX_BLOCKS;
             SQ_CUDA(ctx, cudaMalloc(&d->bp_elig, n));
             SQ_CUDA(ctx, cudaMalloc(&d->bp_info, (size_t)n * sizeof(zd::FrameInfo)));
             SQ_CUDA(ctx, cudaMalloc(&d->bp_tasks, items * sizeof(zd::BlockTask)));
             SQ_CUDA(ctx, cudaMalloc(&d->bp_states, items * sizeof(zd::BlockState)));
-            SQ_CUDA(ctx, cudaMalloc(&d->bp_lits, items * BP_LIT_STRIDE));
             SQ_CUDA(ctx, cudaMalloc(&d->bp_seqs, items * BP_SEQ_CAP * sizeof(zd::StoredSeq)));
             d->bp_cap = n;
         }
@@ -204,22 +208,26 @@ extern "C" int32_t sq_decode_device(sq_ctx *ctx, const void *d_comp, const sq_fr
         SQ_CUDA(ctx, cudaStreamWaitEvent(d->aux, d->ev_fork, 0));
         const uint32_t need1 = (n + DEC_WARPS_PER_CTA - 1) / DEC_WARPS_PER_CTA;
         zstd_decode_kernel<<<ctas < need1 ? ctas : need1, DEC_WARPS_PER_CTA * 32, smem, d->aux>>>((const uint8_t *)d_comp, d_frames, n, (uint8_t *)d_out, d_results, d->lits,
-                                                                                                    (zd::Scratch *)d->build, d->counter, d->bp_elig);
+                                                                                                    (zd::Scratch *)d->build, d->counter, d->bp_elig, 0u);
         SQ_CUDA(ctx, cudaEventRecord(d->ev_join, d->aux));
         const uint32_t want = (n * BP_MAX_BLOCKS + DEC_WARPS_PER_CTA - 1) / DEC_WARPS_PER_CTA;
-        bp_entropy_kernel<<<want < ctas ? want : ctas, DEC_WARPS_PER_CTA * 32, smem, st>>>((const uint8_t *)d_comp, d_frames, n, d->bp_elig, d->bp_info, d->bp_tasks,
-                                                                                             d->bp_states, d->bp_lits, d->bp_seqs, (zd::Scratch *)d->bp_build, d->counter + 1);
-        bp_execute_kernel<<<(n + 3) / 4, 128, 0, st>>>((const uint8_t *)d_comp, d_frames, n, d->bp_elig, d->bp_info, d->bp_tasks, d->bp_states, d->bp_lits,
-                                                       d->bp_seqs, (uint8_t *)d_out, d_results, d->counter + 2);
+        bp_first_pass_kernel<<<want < ctas ? want : ctas, DEC_WARPS_PER_CTA * 32, smem, st>>>((const uint8_t *)d_comp, d_frames, n, d->bp_elig, d->bp_info, d->bp_tasks,
+                                                                                                d->bp_states, d->bp_lits, d->bp_seqs, (uint8_t *)d_out,
+                                                                                                (zd::Scratch *)d->bp_build, d->counter + 1);
+        bp_matches_kernel<<<(n + 3) / 4, 128, 0, st>>>((const uint8_t *)d_comp, d_frames, n, d->bp_elig, d->bp_info, d->bp_tasks, d->bp_states, d->bp_seqs,
+                                                       (uint8_t *)d_out, d_results, d->counter + 2);
         SQ_CUDA(ctx, cudaStreamWaitEvent(st, d->ev_join, 0));
-        SQ_LAUNCHED(ctx, 4);
+        // frames the two passes gave back (none for K3-written archives): one-pass, after everything else (it shares the one-pass scratch)
+        zstd_decode_kernel<<<ctas < need1 ? ctas : need1, DEC_WARPS_PER_CTA * 32, smem, st>>>((const uint8_t *)d_comp, d_frames, n, (uint8_t *)d_out, d_results, d->lits,
+                                                                                                (zd::Scratch *)d->build, d->counter + 3, d->bp_elig, 2u);
+        SQ_LAUNCHED(ctx, 5);
         SQ_CUDA(ctx, cudaGetLastError());
         return SQ_OK;
     }
     const uint32_t need = (n + DEC_WARPS_PER_CTA - 1) / DEC_WARPS_PER_CTA;
     if (ctas > need) ctas = need;
     zstd_decode_kernel<<<ctas, DEC_WARPS_PER_CTA * 32, smem, st>>>((const uint8_t *)d_comp, d_frames, n, (uint8_t *)d_out, d_results, d->lits,
-                                                                   (zd::Scratch *)d->build, d->counter, nullptr);
+                                                                   (zd::Scratch *)d->build, d->counter, nullptr, 0u);
     SQ_LAUNCHED(ctx, 1);
     SQ_CUDA(ctx, cudaGetLastError());
     return SQ_OK;

@@ -440,6 +440,32 @@ ZD_DEV uint32_t resolve_offset(uint32_t ofv, uint32_t ll, uint32_t *r0, uint32_t
     return off;
 }
 
+// Matches that read output of their own batch go in waves: everything below the destination of the first unfinished match is
+// final (literals are all placed, earlier matches are done), so every short match whose source ends there or earlier is copied by
+// its own lane, all of them at once; a long or self-overlapping (periodic) match at the front takes the whole warp.  In repetitive
+// data offsets are a few hundred bytes, i.e. a dozen sequences back: three or four waves per batch instead of up to 32 warp-wide
+// copies one after the other.
+#if defined(__CUDA_ARCH__)
+ZD_DEV void run_match_waves(uint8_t *out, uint32_t my_match, uint32_t my_ml, uint32_t my_off, uint32_t src_end, uint32_t pending) {
+    __syncwarp();  // what was written before (literals, independent matches) is visible
+    while (pending) {
+        const int first = __ffs((int)pending) - 1;
+        const uint32_t first_dst = __shfl_sync(0xffffffffu, my_match, first);
+        const bool ready = (pending >> ZD_LANE() & 1u) && src_end <= first_dst && my_ml <= 64u && my_off >= my_ml;
+        const uint32_t rmask = __ballot_sync(0xffffffffu, ready);
+        if (rmask >> first & 1u) {
+            if (ready) lane_copy(out + my_match, out + my_match - my_off, my_ml);
+            pending &= ~rmask;
+        } else {
+            const uint32_t moff = __shfl_sync(0xffffffffu, my_off, first), mlen = __shfl_sync(0xffffffffu, my_ml, first);
+            copy_match(out, first_dst, moff, mlen);
+            pending &= pending - 1;
+        }
+        __syncwarp();
+    }
+}
+#endif
+
 // Executes one batch of sequences (lane j holds sequence j of the batch): a warp scan turns lengths into positions, all literal
 // runs are copied at once (their sources are never the output), matches that only read output older than the batch are copied
 // lane-parallel, the rest in order with the whole warp on each.  Returns the new output position or < 0.
@@ -486,28 +512,7 @@ ZD_DEV int64_t execute_batch(uint8_t *out, uint32_t pos, uint32_t cap, uint32_t 
         else for (uint32_t t = 0; t < my_ml; t++) out[my_match + t] = from[t % my_off];
     }
 #if defined(__CUDA_ARCH__)
-    // The rest read output of this very batch.  They go in waves: everything below the destination of the first unfinished
-    // match is final (literals are all placed, earlier matches are done), so every short match whose source ends there or earlier
-    // is copied by its own lane, all of them at once; a long or self-overlapping (periodic) match at the front takes the whole
-    // warp.  In repetitive data offsets are a few hundred bytes, i.e. a dozen sequences back: three or four waves per batch
-    // instead of up to 32 warp-wide copies one after the other.
-    uint32_t pending = __ballot_sync(0xffffffffu, mine && !indep);
-    __syncwarp();  // literals and independent matches of the batch are visible
-    while (pending) {
-        const int first = __ffs((int)pending) - 1;
-        const uint32_t first_dst = __shfl_sync(0xffffffffu, my_match, first);
-        const bool ready = (pending >> ZD_LANE() & 1u) && src_end <= first_dst && my_ml <= 64u && my_off >= my_ml;
-        const uint32_t rmask = __ballot_sync(0xffffffffu, ready);
-        if (rmask >> first & 1u) {
-            if (ready) lane_copy(out + my_match, out + my_match - my_off, my_ml);
-            pending &= ~rmask;
-        } else {
-            const uint32_t moff = __shfl_sync(0xffffffffu, my_off, first), mlen = __shfl_sync(0xffffffffu, my_ml, first);
-            copy_match(out, first_dst, moff, mlen);
-            pending &= pending - 1;
-        }
-        __syncwarp();
-    }
+    run_match_waves(out, my_match, my_ml, my_off, src_end, __ballot_sync(0xffffffffu, mine && !indep));
 #else
     if (mine && !indep) copy_match(out, my_match, my_off, my_ml);
 #endif
@@ -561,19 +566,18 @@ ZD_DEV int64_t decode_compressed_block(const uint8_t *src, uint32_t size, uint8_
     return (int64_t)pos + rest;
 }
 
-// ---- two passes over a frame whose blocks do not chain through repeated tables (everything the K3 encoder writes) -------------
-// Pass 1 (one warp per BLOCK, all blocks of all frames at once): entropy decoding only -- Huffman literals into the block's own
-// literal buffer, the FSE chain into an array of {ll, ml, offset value} -- which is where a frame spends ~80 % of its time and
-// what makes it serial.  Pass 2 (one warp per FRAME): resolves repeat offsets and executes the stored sequences block by block
-// with execute_batch.  A block is independent for pass 1 when its literals are not Treeless and none of its three sequence
-// tables is in Repeat_Mode; block_is_independent answers that from the headers alone.
-struct StoredSeq { uint32_t ll, ml, ofv; };
-struct BlockState {          // pass 1 -> pass 2
-    int32_t status;          // 0 or an ERR_ code
-    uint32_t nseq;
-    uint32_t lit_size, lit_rle;       // Literals: size, RLE flag | byte << 8
-    uint32_t lit_src_off, lit_in_buf; // where they are: offset into the block's compressed bytes, or the block's literal buffer
-};
+// ---- two passes over a frame whose blocks are self-contained (everything the K3 encoder writes) ------------------------------
+// A block is self-contained when (a) its literals are not Treeless and none of its three sequence tables is in Repeat_Mode
+// (block_is_independent answers that from the headers), (b) no sequence reads a repeat offset it has not set itself (found out
+// while decoding: the history is tracked with "known" flags), and (c) it starts where a frame of 128 KiB blocks puts it (every
+// block but the last regenerates exactly 128 KiB in all frames K3 and libzstd level <= 15 write; checked afterwards).
+// Pass 1 (one warp per BLOCK, all blocks of all frames at once) does everything that does not read the output: Huffman literals,
+// the FSE chain, repeat-offset resolution, positions, and it PLACES THE LITERALS in the output.  What is left for pass 2 (one warp
+// per FRAME, in order, because matches reach back across blocks) is one {destination, length, offset} triple per match.
+// Anything that breaks an assumption sends the frame through the one-pass decoder afterwards.
+struct StoredSeq { uint32_t mpos, ml, off; };  // match destination (frame-relative), length, offset
+struct BlockState { int32_t status; uint32_t nseq, regen, self_contained; };
+enum { NEED_ONE_PASS = -100 };
 
 ZD_DEV bool block_is_independent(const uint8_t *src, uint32_t size) {
     if (size < 1) return false;
@@ -603,86 +607,103 @@ ZD_DEV bool block_is_independent(const uint8_t *src, uint32_t size) {
     return (modes >> 6) != 3 && ((modes >> 4) & 3) != 3 && ((modes >> 2) & 3) != 3;
 }
 
-// pass 1 of one compressed block
-ZD_DEV void decode_block_entropy(const uint8_t *src, uint32_t size, Tables *T, Scratch *S, uint8_t *litbuf, StoredSeq *seqs, uint32_t seq_cap,
-                                 BlockState *bs_out) {
+// pass 1 of one compressed block whose output starts at out[out_start] (frame-relative; out is the frame's output, cap its size)
+ZD_DEV void decode_block_first_pass(const uint8_t *src, uint32_t size, Tables *T, Scratch *S, uint8_t *litbuf, uint8_t *out, uint32_t out_start, uint32_t cap,
+                                    bool first_block, StoredSeq *seqs, uint32_t seq_cap, BlockState *bs_out) {
     BlockState bs;
-    bs.status = 0; bs.nseq = 0; bs.lit_size = 0; bs.lit_rle = 0; bs.lit_src_off = 0; bs.lit_in_buf = 0;
+    bs.status = 0; bs.nseq = 0; bs.regen = 0; bs.self_contained = 1;
     T->have_huf = T->have_ll = T->have_ml = T->have_of = 0;  // an independent block brings all its tables
     Literals L;
     const int lused = decode_literals(src, size, T, litbuf, &L, S->weights, S->cells);
     int rc = lused < 0 ? lused : 0;
+    uint32_t pos = out_start, lit_pos = 0, nseq = 0;
     if (!rc) {
-        bs.lit_size = L.size; bs.lit_rle = L.rle ? (1u | (uint32_t)L.rle_byte << 8) : 0u;
-        bs.lit_in_buf = L.ptr == litbuf ? 1u : 0u;
-        bs.lit_src_off = bs.lit_in_buf ? 0u : (uint32_t)(L.ptr - src);
         const uint8_t *p = src + lused;
-        uint32_t left = size - (uint32_t)lused, nseq = 0;
+        uint32_t left = size - (uint32_t)lused;
         rc = read_sequences_header(&p, &left, &nseq, T, S);
         if (!rc && nseq > seq_cap) rc = ERR_CORRUPT;
         if (!rc && nseq) {
             BitReader b;
             if (br_init(&b, p, left) < 0) rc = ERR_CORRUPT;
-            else {
-                FseStates st;
-                st.ll = br_read(&b, T->ll_log); st.of = br_read(&b, T->of_log); st.ml = br_read(&b, T->ml_log);
-                for (uint32_t i0 = 0; i0 < nseq; i0 += ZD_WARP) {
-                    const uint32_t nbatch = nseq - i0 < ZD_WARP ? nseq - i0 : ZD_WARP;
-                    StoredSeq mine;
-                    mine.ll = 0; mine.ml = 0; mine.ofv = 4;
-                    for (uint32_t k = 0; k < nbatch; k++) {
-                        uint32_t ll, ml, ofv;
-                        fse_step(&b, T, &st, i0 + k + 1 >= nseq, &ll, &ml, &ofv);
-                        if (k == ZD_LANE()) { mine.ll = ll; mine.ml = ml; mine.ofv = ofv; }
+            FseStates st;
+            if (!rc) { st.ll = br_read(&b, T->ll_log); st.of = br_read(&b, T->of_log); st.ml = br_read(&b, T->ml_log); }
+            // repeat offsets with "known" flags: only the frame's first block knows 1, 4, 8
+            uint32_t r0 = first_block ? 1u : 0u, r1 = first_block ? 4u : 0u, r2 = first_block ? 8u : 0u;
+            bool k0 = first_block, k1 = first_block, k2 = first_block, foreign = false;
+            for (uint32_t i0 = 0; i0 < nseq && !rc && !foreign; i0 += ZD_WARP) {
+                const uint32_t nbatch = nseq - i0 < ZD_WARP ? nseq - i0 : ZD_WARP;
+                uint32_t my_ll = 0, my_ml = 0, my_off = 1;
+                int err = 0;
+                for (uint32_t k = 0; k < nbatch; k++) {
+                    uint32_t ll, ml, ofv, off;
+                    fse_step(&b, T, &st, i0 + k + 1 >= nseq, &ll, &ml, &ofv);
+                    if (ofv > 3) { off = ofv - 3; r2 = r1; k2 = k1; r1 = r0; k1 = k0; r0 = off; k0 = true; }
+                    else {
+                        const uint32_t idx = ofv - 1 + (ll == 0 ? 1 : 0);
+                        if (idx == 0) { off = r0; foreign = foreign || !k0; }
+                        else {
+                            const bool ks = idx == 1 ? k1 : idx == 2 ? k2 : k0;
+                            off = idx == 1 ? r1 : idx == 2 ? r2 : r0 - 1;
+                            foreign = foreign || !ks;
+                            if (ks && off == 0) err = 1;
+                            if (idx >= 2) { r2 = r1; k2 = k1; }
+                            r1 = r0; k1 = k0; r0 = off; k0 = ks;
+                        }
                     }
-                    if (ZD_LANE() < nbatch) seqs[i0 + ZD_LANE()] = mine;
+                    if (k == ZD_LANE()) { my_ll = ll; my_ml = ml; my_off = off; }
                 }
-                if (b.pos != 0) rc = ERR_CORRUPT;
+                if (foreign) break;  // a sequence reads history from before the block: the one-pass decoder takes the frame
+                if (err || b.pos < 0) { rc = ERR_CORRUPT; break; }
+                // positions
+                uint32_t lit_excl, out_excl, lit_tot, out_tot;
+#if defined(__CUDA_ARCH__)
+                {
+                    uint32_t xl = my_ll, xo = my_ll + my_ml;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const uint32_t yl = __shfl_up_sync(0xffffffffu, xl, d), yo = __shfl_up_sync(0xffffffffu, xo, d);
+                        if ((int)ZD_LANE() >= d) { xl += yl; xo += yo; }
+                    }
+                    lit_excl = xl - my_ll; out_excl = xo - (my_ll + my_ml);
+                    lit_tot = __shfl_sync(0xffffffffu, xl, 31); out_tot = __shfl_sync(0xffffffffu, xo, 31);
+                }
+#else
+                lit_excl = 0; out_excl = 0; lit_tot = my_ll; out_tot = my_ll + my_ml;
+#endif
+                if (lit_pos + lit_tot > L.size) { rc = ERR_CORRUPT; break; }
+                if ((uint64_t)pos + out_tot > cap) { rc = ERR_CAPACITY; break; }
+                const uint32_t my_lit_out = pos + out_excl, my_match = my_lit_out + my_ll;
+                const bool mine = ZD_LANE() < nbatch;
+                int bad = mine && my_off > my_match;
+#if defined(__CUDA_ARCH__)
+                bad = __any_sync(0xffffffffu, bad);
+#endif
+                if (bad) { rc = ERR_CORRUPT; break; }
+                if (mine) {
+                    if (L.rle) for (uint32_t t = 0; t < my_ll; t++) out[my_lit_out + t] = L.rle_byte;
+                    else lane_copy(out + my_lit_out, L.ptr + lit_pos + lit_excl, my_ll);
+                    StoredSeq sq;
+                    sq.mpos = my_match; sq.ml = my_ml; sq.off = my_off;
+                    seqs[i0 + ZD_LANE()] = sq;
+                }
+                lit_pos += lit_tot;
+                pos += out_tot;
             }
+            if (!rc && !foreign && b.pos != 0) rc = ERR_CORRUPT;
+            if (foreign) bs.self_contained = 0;
         } else if (!rc && left != 0) rc = ERR_CORRUPT;
-        bs.nseq = nseq;
+        if (!rc && bs.self_contained) {
+            const uint32_t rest = L.size - lit_pos;
+            if ((uint64_t)pos + rest > cap) rc = ERR_CAPACITY;
+            else {
+                if (L.rle) fill_bytes(out + pos, L.rle_byte, rest); else copy_bytes(out + pos, L.ptr + lit_pos, rest);
+                pos += rest;
+            }
+        }
     }
-    bs.status = rc;
+    bs.status = rc; bs.nseq = nseq; bs.regen = pos - out_start;
     ZD_SYNC();
     if (ZD_LANE() == 0) *bs_out = bs;
-}
-
-// pass 2 of one compressed block: returns new pos or < 0
-ZD_DEV int64_t execute_stored_block(const uint8_t *src, const BlockState *bsp, const uint8_t *litbuf, const StoredSeq *seqs, uint8_t *out, uint32_t pos,
-                                    uint32_t cap, uint32_t frame_start, uint32_t rep[3], uint32_t *synced) {
-    const BlockState bs = *bsp;
-    if (bs.status < 0) return bs.status;
-    Literals L;
-    L.ptr = bs.lit_in_buf ? litbuf : src + bs.lit_src_off; L.size = bs.lit_size; L.rle = bs.lit_rle & 1u; L.rle_byte = (uint8_t)(bs.lit_rle >> 8);
-    uint32_t lit_pos = 0, r0 = rep[0], r1 = rep[1], r2 = rep[2];
-    for (uint32_t i0 = 0; i0 < bs.nseq; i0 += ZD_WARP) {
-        const uint32_t nbatch = bs.nseq - i0 < ZD_WARP ? bs.nseq - i0 : ZD_WARP;
-        StoredSeq mine;
-        mine.ll = 0; mine.ml = 0; mine.ofv = 4;
-        if (ZD_LANE() < nbatch) mine = seqs[i0 + ZD_LANE()];
-        uint32_t my_off = 1;
-        int err = 0;
-        for (uint32_t k = 0; k < nbatch; k++) {  // the history is a chain over the batch; every lane walks it
-#if defined(__CUDA_ARCH__)
-            const uint32_t ofv = __shfl_sync(0xffffffffu, mine.ofv, k), ll = __shfl_sync(0xffffffffu, mine.ll, k);
-#else
-            const uint32_t ofv = mine.ofv, ll = mine.ll;
-#endif
-            uint32_t off = resolve_offset(ofv, ll, &r0, &r1, &r2);
-            if (off == 0) { err = 1; off = 1; }
-            if (k == ZD_LANE()) my_off = off;
-        }
-        if (err) return ERR_CORRUPT;
-        const int64_t np = execute_batch(out, pos, cap, frame_start, &L, &lit_pos, mine.ll, mine.ml, my_off, nbatch, synced);
-        if (np < 0) return np;
-        pos = (uint32_t)np;
-    }
-    rep[0] = r0; rep[1] = r1; rep[2] = r2;
-    const uint32_t rest = L.size - lit_pos;
-    if ((uint64_t)pos + rest > cap) return ERR_CAPACITY;
-    if (L.rle) fill_bytes(out + pos, L.rle_byte, rest); else copy_bytes(out + pos, L.ptr + lit_pos, rest);
-    ZD_SYNC();
-    return (int64_t)pos + rest;
 }
 
 // A whole chunk-record payload: >= 1 zstd frames and skippable frames, nothing else (what stock
@@ -763,8 +784,9 @@ ZD_DEV int64_t decode_payload(const uint8_t *src, uint32_t size, uint8_t *out, u
 
 // Two-pass eligibility of a payload: exactly one zstd frame, at most max_blocks blocks, every compressed block independent
 // (block_is_independent).  Anything else -- several frames, skippable frames, malformed headers -- is left to decode_payload,
-// which also produces the error.  Fills tasks[] and returns the number of blocks, or 0 if not eligible.
-struct BlockTask { uint32_t src_off, size, type; };
+// which also produces the error.  Fills tasks[] (with the output start of every block under the 128 KiB assumption) and returns
+// the number of blocks, or 0 if not eligible.
+struct BlockTask { uint32_t src_off, size, type, out_start; };
 struct FrameInfo { uint32_t nblocks, has_fcs; uint64_t fcs; };
 ZD_DEV uint32_t scan_frame(const uint8_t *src, uint32_t size, uint32_t max_blocks, BlockTask *tasks, FrameInfo *fi) {
     if (size < 6) return 0;
@@ -780,7 +802,7 @@ ZD_DEV uint32_t scan_frame(const uint8_t *src, uint32_t size, uint32_t max_block
     uint64_t fcs = 0;
     for (uint32_t i = 0; i < fcs_bytes; i++) fcs |= (uint64_t)src[h + i] << (8 * i);
     if (fcs_flag == 1) fcs += 256;
-    uint32_t ip = h + fcs_bytes, nb = 0;
+    uint32_t ip = h + fcs_bytes, nb = 0, start = 0;
     for (;;) {
         if (size - ip < 3 || nb >= max_blocks) return 0;
         const uint32_t bh = src[ip] | src[ip + 1] << 8 | (uint32_t)src[ip + 2] << 16;
@@ -790,7 +812,8 @@ ZD_DEV uint32_t scan_frame(const uint8_t *src, uint32_t size, uint32_t max_block
         const uint32_t body = type == 1 ? 1u : bsz;
         if (body > size - ip) return 0;
         if (type == 2 && !block_is_independent(src + ip, bsz)) return 0;
-        tasks[nb].src_off = ip; tasks[nb].size = bsz; tasks[nb].type = type;
+        tasks[nb].src_off = ip; tasks[nb].size = bsz; tasks[nb].type = type; tasks[nb].out_start = start;
+        start += type == 2 ? Z_BLOCK_MAX : bsz;
         nb++;
         ip += body;
         if (last) break;
@@ -801,34 +824,44 @@ ZD_DEV uint32_t scan_frame(const uint8_t *src, uint32_t size, uint32_t max_block
     return nb;
 }
 
-// pass 2 of a whole frame scanned by scan_frame: returns the decoded size or < 0
-ZD_DEV int64_t execute_frame(const uint8_t *src, const BlockTask *tasks, const FrameInfo *fi, const BlockState *states, const uint8_t *litbufs,
-                             size_t litbuf_stride, const StoredSeq *seqs, size_t seq_stride, uint8_t *out, uint32_t cap) {
-    if (fi->has_fcs && fi->fcs > cap) return ERR_CAPACITY;
-    uint32_t pos = 0, synced = 0;
-    uint32_t rep[3] = {1, 4, 8};
+// pass 2 of a whole frame: raw / RLE blocks and the matches of the compressed ones, in order.  Returns the decoded size, or
+// NEED_ONE_PASS when pass 1 found a block that is not self-contained, failed, or does not start where it was assumed to.
+ZD_DEV int64_t execute_frame_matches(const uint8_t *src, const BlockTask *tasks, const FrameInfo *fi, const BlockState *states, const StoredSeq *seqs,
+                                     size_t seq_stride, uint8_t *out, uint32_t cap) {
+    uint32_t pos = 0;
     for (uint32_t b = 0; b < fi->nblocks; b++) {
         const BlockTask t = tasks[b];
+        if (pos != t.out_start) return NEED_ONE_PASS;
         if (t.type == 0) {
-            if (t.size > cap - pos) return ERR_CAPACITY;
+            if (t.size > cap - pos) return NEED_ONE_PASS;
             copy_bytes(out + pos, src + t.src_off, t.size);
             ZD_SYNC();
-            pos += t.size; synced = pos;
+            pos += t.size;
         } else if (t.type == 1) {
-            if (t.size > cap - pos) return ERR_CAPACITY;
+            if (t.size > cap - pos) return NEED_ONE_PASS;
             fill_bytes(out + pos, src[t.src_off], t.size);
             ZD_SYNC();
-            pos += t.size; synced = pos;
+            pos += t.size;
         } else {
-            const int64_t np = execute_stored_block(src + t.src_off, states + b, litbufs + (size_t)b * litbuf_stride, seqs + (size_t)b * seq_stride, out, pos, cap,
-                                                    0, rep, &synced);
-            if (np < 0) return np;
-            if ((uint64_t)np - pos > Z_BLOCK_MAX) return ERR_CORRUPT;
-            synced = (uint32_t)np;
-            pos = (uint32_t)np;
+            const BlockState bs = states[b];
+            if (bs.status < 0 || !bs.self_contained || bs.regen > Z_BLOCK_MAX) return NEED_ONE_PASS;
+            const StoredSeq *sq = seqs + (size_t)b * seq_stride;
+            for (uint32_t i0 = 0; i0 < bs.nseq; i0 += ZD_WARP) {
+                const uint32_t nbatch = bs.nseq - i0 < ZD_WARP ? bs.nseq - i0 : ZD_WARP;
+                StoredSeq mine;
+                mine.mpos = 0; mine.ml = 0; mine.off = 1;
+                if (ZD_LANE() < nbatch) mine = sq[i0 + ZD_LANE()];
+#if defined(__CUDA_ARCH__)
+                const uint32_t src_end = mine.mpos - mine.off + (mine.off < mine.ml ? mine.off : mine.ml);
+                run_match_waves(out, mine.mpos, mine.ml, mine.off, src_end, nbatch >= 32 ? 0xffffffffu : (1u << nbatch) - 1u);
+#else
+                copy_match(out, mine.mpos, mine.off, mine.ml);
+#endif
+            }
+            pos += bs.regen;
         }
     }
-    if (fi->has_fcs && (uint64_t)pos != fi->fcs) return ERR_CORRUPT;
+    if (fi->has_fcs && (uint64_t)pos != fi->fcs) return NEED_ONE_PASS;
     return pos;
 }
 

@@ -16,8 +16,9 @@ extern "C" long dec_model_payload(const uint8_t *src, uint32_t n, uint8_t *dst, 
     return r;
 }
 
-// The two-pass (block-parallel) decoder on the host: scan, pass 1 block by block into per-block buffers, pass 2 in order.
-// Returns the decoded size, < 0 for an error, or -100 if the payload is not eligible (the product then uses the one-pass path).
+// The two-pass (block-parallel) decoder on the host: scan, pass 1 block by block (literals placed, matches stored), pass 2 in order.
+// Returns the decoded size, -100 if the payload is not eligible or pass 2 hands it to the one-pass decoder (the product then runs
+// decode_payload, which also produces any error).
 extern "C" long dec_model_payload_two_pass(const uint8_t *src, uint32_t n, uint8_t *dst, uint32_t cap) {
     std::vector<uint8_t> padded(n + 64, 0);
     memcpy(padded.data() + 16, src, n);
@@ -30,13 +31,14 @@ extern "C" long dec_model_payload_two_pass(const uint8_t *src, uint32_t n, uint8
     zd::Tables *T = new zd::Tables();
     zd::Scratch *S = new zd::Scratch();
     memset(T, 0, sizeof *T);
-    const size_t lstride = Z_BLOCK_MAX + 64;
-    std::vector<uint8_t> lits(nb * lstride);
+    std::vector<uint8_t> lits(Z_BLOCK_MAX + 64);
     std::vector<zd::StoredSeq> seqs((size_t)nb * SEQ_CAP);
     std::vector<zd::BlockState> states(nb);
     for (uint32_t b = 0; b < nb; b++)
-        if (tasks[b].type == 2) zd::decode_block_entropy(p + tasks[b].src_off, tasks[b].size, T, S, lits.data() + b * lstride, seqs.data() + (size_t)b * SEQ_CAP, SEQ_CAP, &states[b]);
-    long r = (long)zd::execute_frame(p, tasks.data(), &fi, states.data(), lits.data(), lstride, seqs.data(), SEQ_CAP, dst, cap);
+        if (tasks[b].type == 2)
+            zd::decode_block_first_pass(p + tasks[b].src_off, tasks[b].size, T, S, lits.data(), dst, tasks[b].out_start, cap, b == 0, seqs.data() + (size_t)b * SEQ_CAP,
+                                        SEQ_CAP, &states[b]);
+    long r = (long)zd::execute_frame_matches(p, tasks.data(), &fi, states.data(), seqs.data(), SEQ_CAP, dst, cap);
     delete T; delete S;
     return r;
 }

@@ -141,7 +141,7 @@ extern "C" long lz_model2_frame(const uint8_t *s, uint32_t n, uint8_t *dst, uint
                         }
                         if (P.long_cap) { std::sort(longs, longs + nlq); for (int i = 0; i < P.long_cap && i < nlq; i++) consider(longs[nlq - 1 - i]); }  // the nearest long_cap long candidates
                         std::sort(shorts, shorts + ns);
-                        for (int i = 0; i < P.short_keep && i < ns; i++) consider(shorts[ns - 1 - i]);
+                        for (int i = 0; i < P.short_keep && i < ns && P.short_keep < 100; i++) consider(shorts[ns - 1 - i]);  // short_keep >= 100: short candidates are dropped
                     } else
                     for (uint32_t k = 0; k < K; k++) { const uint32_t e = tab[(size_t)h * K + k]; if (e) consider(e - 1); }
                     if (rows2) {
