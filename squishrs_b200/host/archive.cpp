@@ -498,6 +498,7 @@ struct UnpackJob {  // what every device of an unpack needs: where each record's
     std::vector<uint32_t> ref_start;
     std::vector<Ref> refs;
     std::vector<std::string> full;
+    bool lazy_create = false;  // the output directory is new: a file is created by whoever writes one of its chunks first
     uint64_t total_out = 0, total_comp = 0;
 };
 
@@ -538,19 +539,33 @@ int32_t unpack_prepare(sq_ctx *ctx, Archive &a, std::vector<ManifestEntry> &man,
             }
         }
     }
-    // create_dir_all(parent) + File::create for every file (reader.rs:375-383); empty files are complete after this
+    // create_dir_all(parent) + File::create for every file (reader.rs:375-383).  Directories are made once each, not once per
+    // file.  When the output directory did not exist before, nothing stale can be in it: only the empty files are created here and
+    // every other file is created by whoever writes one of its chunks first (O_CREAT) -- two system calls fewer per file, which is
+    // most of the host time of an archive of 200 000 small files.  Into an existing directory every file is created and truncated
+    // up front, as the reference does.
     std::string outdir(output_dir);
-    mkdir(outdir.c_str(), 0777);
+    job->lazy_create = mkdir(outdir.c_str(), 0777) == 0 && !getenv("SQ_UNPACK_EAGER_CREATE");
     job->full.resize(man.size());
     std::atomic<int32_t> err{0};
     std::atomic<size_t> err_idx{0};
+    {
+        std::unordered_map<std::string, char> seen;
+        std::vector<std::string> dirs;  // parents before children
+        for (size_t fi = 0; fi < man.size(); fi++) {
+            const ManifestEntry &e = man[fi];
+            job->full[fi] = outdir + "/" + std::string((const char *)e.path, e.path_len);
+            const std::string &f = job->full[fi];
+            const size_t last = f.rfind('/');
+            if (last == std::string::npos || last <= outdir.size() || seen.count(f.substr(0, last))) continue;
+            for (size_t p = outdir.size() + 1; p <= last; p++)
+                if (f[p] == '/' && seen.emplace(f.substr(0, p), 1).second) dirs.push_back(f.substr(0, p));
+        }
+        for (auto &d : dirs) mkdir(d.c_str(), 0777);
+    }
     parallel_for(man.size(), threads, [&](size_t fi) {
-        const ManifestEntry &e = man[fi];
-        job->full[fi] = outdir + "/" + std::string((const char *)e.path, e.path_len);
-        std::string &f = job->full[fi];
-        for (size_t p = outdir.size() + 1; p < f.size(); p++)
-            if (f[p] == '/') { f[p] = 0; mkdir(f.c_str(), 0777); f[p] = '/'; }
-        int fd = open(f.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0666);
+        if (job->lazy_create && man[fi].chunk_count) return;
+        int fd = open(job->full[fi].c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0666);
         if (fd < 0) { err = SQ_ERR_CREATE_FILE; err_idx = fi; return; }
         close(fd);
     });
@@ -604,7 +619,7 @@ int32_t unpack_range(sq_ctx *ctx, Archive &a, std::vector<ManifestEntry> &man, c
             const size_t ri = b.first + k;
             const uint8_t *src = (const uint8_t *)b.out.p + b.frames[k].dst_off;
             for (uint32_t j = job.ref_start[ri]; j < job.ref_start[ri + 1]; j++) {
-                int fd = open(job.full[job.refs[j].file].c_str(), O_WRONLY);
+                int fd = open(job.full[job.refs[j].file].c_str(), job.lazy_create ? O_WRONLY | O_CREAT : O_WRONLY, 0666);
                 if (fd < 0) { err = SQ_ERR_CREATE_FILE; err_idx = job.refs[j].file; return; }
                 size_t w = 0;
                 while (w < size[ri]) {

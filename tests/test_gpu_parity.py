@@ -280,6 +280,12 @@ def test_archive_roundtrip_both_directions(sq, oracle, tmp_path):
     ArchiveWriter(src, tmp_path / "gpu.squish", ctx=c, threads=8).pack()
     ArchiveReader(tmp_path / "gpu.squish", ctx=c, threads=8).unpack(tmp_path / "out_from_gpu")
     assert read_tree(tmp_path / "out_from_gpu") == read_tree(src)
+    # into a directory that already exists (files are then created and truncated up front), over stale, longer files
+    for f in (tmp_path / "out_from_gpu").rglob("*"):
+        if f.is_file():
+            f.write_bytes(f.read_bytes() + b"stale tail")
+    ArchiveReader(tmp_path / "cpu.squish", ctx=c, threads=8).unpack(tmp_path / "out_from_gpu")
+    assert read_tree(tmp_path / "out_from_gpu") == read_tree(src)
 
 
 def record_digests(path):
