@@ -30,6 +30,7 @@ struct P2 {
     int group_skip;   // 1: a group of 32 positions that lies inside a match already known to be long (the record in front of the group is capped and the
                       // match goes on for 64 more bytes) is not searched: every position inherits (offset, CAP, may-be-longer)
     int sub_len;      // > 0: every block is parsed in independent pieces of this many bytes (repeat offsets unknown at each start), sequences merged afterwards
+    int xtag_more;    // > 0: the 6-bit tag covers this many more bytes (from byte 8 on), so "long" means 8 + xtag_more common bytes
     int cont_period;  // > 0: the filter keeps everything at positions p % cont_period == 0 (the first column of a search group) and is independent of the tile
 };
 
@@ -131,7 +132,12 @@ extern "C" long lz_model2_frame(const uint8_t *s, uint32_t n, uint8_t *dst, uint
                             if (P.tag_bits) {
                                 const uint64_t vc = rd64(s + e - 1), vp = rd64(s + p);
                                 const uint32_t pc = hashN(vc, P.mm, 19) & 31u, pp = hashN(vp, P.mm, 19) & 31u;
-                                const uint32_t xc = (uint32_t)(((vc >> 40) * 0x9E3779B1u) & 0xFFFFFFFFu) >> (32 - P.tag_bits), xp = (uint32_t)(((vp >> 40) * 0x9E3779B1u) & 0xFFFFFFFFu) >> (32 - P.tag_bits);
+                                uint32_t xc = (uint32_t)(((vc >> 40) * 0x9E3779B1u) & 0xFFFFFFFFu) >> (32 - P.tag_bits), xp = (uint32_t)(((vp >> 40) * 0x9E3779B1u) & 0xFFFFFFFFu) >> (32 - P.tag_bits);
+                                if (P.xtag_more > 0 && p + 16 <= n) {  // the tag also covers xtag_more bytes from byte 8 on
+                                    const uint64_t mk = P.xtag_more >= 8 ? ~0ull : (1ull << (8 * P.xtag_more)) - 1;
+                                    const uint64_t wc = (vc >> 40) | (rd64(s + e - 1 + 8) & mk) << 24, wp = (vp >> 40) | (rd64(s + p + 8) & mk) << 24;
+                                    xc = (uint32_t)((wc * 0x9E3779B97F4A7C15ull) >> (64 - P.tag_bits)); xp = (uint32_t)((wp * 0x9E3779B97F4A7C15ull) >> (64 - P.tag_bits));
+                                }
                                 if (pc != pp) continue;
                                 if (xc == xp) consider_long(e - 1); else shorts[ns++] = e - 1;
                                 continue;
