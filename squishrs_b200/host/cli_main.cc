@@ -133,6 +133,13 @@ int main(int argc, char **argv) {
     }
 
     const double t_start = now_s();
+    // Driver initialisation touches every visible GPU (seconds on an 8-GPU box): show it only the devices this command uses.
+    if (!getenv("CUDA_VISIBLE_DEVICES") && device >= 0 && devices >= 1) {
+        std::string vis;
+        for (int k = 0; k < devices; k++) vis += (k ? "," : "") + std::to_string(device + k);
+        setenv("CUDA_VISIBLE_DEVICES", vis.c_str(), 1);
+        device = 0;
+    }
     sq_config cfg = {device, 0, 1ull << 22, 4096, 0};
     sq_ctx *ctx = nullptr;
     int32_t rc = sq_create(&cfg, &ctx);

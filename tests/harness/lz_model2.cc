@@ -31,6 +31,7 @@ struct P2 {
                       // match goes on for 64 more bytes) is not searched: every position inherits (offset, CAP, may-be-longer)
     int sub_len;      // > 0: every block is parsed in independent pieces of this many bytes (repeat offsets unknown at each start), sequences merged afterwards
     int xtag_more;    // > 0: the 6-bit tag covers this many more bytes (from byte 8 on), so "long" means 8 + xtag_more common bytes
+    int part_skip;    // > 0: positions at the start of a group covered by the match that crosses into it are not searched, in units of part_skip positions
     int cont_period;  // > 0: the filter keeps everything at positions p % cont_period == 0 (the first column of a search group) and is independent of the tile
 };
 
@@ -80,9 +81,24 @@ extern "C" long lz_model2_frame(const uint8_t *s, uint32_t n, uint8_t *dst, uint
                 if (P.chain) { const uint32_t hc = hashN(rd64(s + p), P.mm, 20); chain_prev[p] = chain_head[hc]; chain_head[hc] = p + 1; }
             }
             std::vector<uint32_t> prevc, curc, hist[4];
+            uint32_t part_until = 0;
             for (int phase = 0; phase < (P.skip_capped ? 2 : 1); phase++)
             for (uint32_t p = t0; p < t1 && p + 8 <= n; p++) {
                 if (p % (uint32_t)P.stride) continue;
+                if (P.part_skip && (p & 31u) == 0 && p >= 32 && (p & 255u) != 0 && p + 32 + CAP + 16 <= n) {
+                    // positions at the start of a group that lie inside the match reaching furthest across the group boundary inherit it
+                    uint32_t best_end = 0, bo2 = 0;
+                    for (uint32_t d = 0; d < 32; d++) { const uint32_t q = p - 1 - d; if (blen[q] && q + std::min(blen[q], CAP) > best_end) { best_end = q + std::min(blen[q], CAP); bo2 = boff[q]; } }
+                    part_until = 0;
+                    if (best_end > p + MM) {
+                        uint32_t cov = best_end - p - MM + 1;            // positions p .. p+cov-1 still have >= MM bytes of that match
+                        cov = (cov / (uint32_t)P.part_skip) * (uint32_t)P.part_skip;  // whole passes only
+                        if (cov > 32) cov = 32;
+                        for (uint32_t k = 0; k < cov; k++) { blen[p + k] = best_end - (p + k); boff[p + k] = bo2; noback[p + k] = 1; }
+                        part_until = p + cov; nskipped += cov;
+                    }
+                }
+                if (P.part_skip && p < part_until) continue;
                 if (P.group_skip && (p & 31u) == 0 && p >= 32 && (p & 255u) != 0 && p + 32 + CAP + 16 <= n) {
                     uint32_t q = p - 1, go = 0;
                     for (uint32_t d = 0; d < 32 && !go; d++) if (blen[p - 1 - d] >= CAP && blen[p - 1 - d] > d) { go = boff[p - 1 - d]; q = p - 1 - d; }
