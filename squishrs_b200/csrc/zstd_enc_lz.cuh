@@ -1,7 +1,7 @@
 // K3 stage "compress", shared pieces: byte-access helpers, per-block metadata, warp-wide match extension, and the entropy
 // stage (entropy_kernel: one warp per 128 KiB block gathers literals and writes the block body warp-parallel, see
-// zstd_enc_entropy.cuh).  The match search and the parse live in zstd_enc_lz2.cuh (round 2: cluster per chunk, L2-resident
-// tables); the round-1 search kernel (one CTA per chunk, tables in HBM, 142 B of DRAM traffic per input byte) is gone.
+// zstd_enc_entropy.cuh).  The match search (index_kernel + search_kernel: the chunk's positions sorted by hash row, then a search
+// without any synchronisation) and the parse (chase_kernel) live in zstd_enc_lz2.cuh.
 #pragma once
 #include "common.cuh"
 #include "zstd_enc_block.h"
