@@ -475,8 +475,8 @@ def unpack_section(ctx, lib, L, oracle, corpus, sp, stream, args):
         ms_o, ok_o, _, do_o, _ = decode_frames_device(ctx, lib, L, [f for _, f in pairs], np.full(len(pairs), CHUNK, dtype=np.int64), sp, stream,
                                                       check=lambda i: pairs[i][0])
         out["own_frames"] = {"value": len(pairs) * CHUNK / (ms_o * 1e-3) / 1e9, "unit": "GB/s", "frames": len(pairs), "byte_identical": bool(ok_o),
-                             "what": "K4 decode of frames written by K3 (2 MiB chunks), device-resident; <= 512 frames per call take the block-parallel "
-                                     "path: entropy decoding per block on its own warp, execution per frame in order"}
+                             "what": "K4 decode of frames written by K3 (2 MiB chunks), device-resident, block-parallel path (<= 2048 multi-block frames per call): "
+                                     "entropy decoding + literal placement per block on its own warp, matches per frame in order"}
         ctx.check(lib.sq_release_scratch(ctx.h))
     except Exception as e:
         log("own-frames unpack failed:", repr(e))

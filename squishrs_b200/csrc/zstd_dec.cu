@@ -15,13 +15,15 @@
 // to a 128 KiB per-warp slot in HBM (L2 resident).  Algorithmic traffic = payload bytes read + decoded
 // bytes written.
 //
-// Block-parallel path (calls of at most BP_MAX_FRAMES payloads, i.e. exactly when frames alone cannot fill the GPU).  A payload that
-// is one frame of self-contained blocks (zstd_dec_core.h: own tables, no repeat offset from before the block, regular block
-// starts) -- everything the K3 encoder writes -- is decoded in two passes: bp_first_pass_kernel gives every BLOCK a warp for all
-// work that does not read the output (Huffman literals, FSE chain, repeat offsets, positions, and placing the literals);
-// bp_matches_kernel then gives every FRAME a warp that copies the matches block by block, in order (matches reach back across
-// blocks).  bp_scan_kernel decides from the headers which payloads try this; the others run through the one-pass kernel on a
-// second stream beside the two passes, and so does, afterwards, any frame whose blocks turned out not to be self-contained.
+// Block-parallel path (calls of at most BP_MAX_FRAMES payloads, i.e. when frames alone cannot fill the GPU; zstd_dec_core.h has the
+// reasoning).  A payload that is one frame of several blocks is decoded in two passes, whoever wrote it: bp_snapshot_kernel walks
+// the table descriptions of a frame's blocks (serial, cheap) so that every block knows the tables it decodes with;
+// bp_first_pass_kernel gives every BLOCK a warp for all work that does not read the output (Huffman literals, FSE chain, repeat
+// offsets kept symbolic, positions, and placing the literals); bp_matches_kernel then gives every FRAME a warp that resolves the
+// offsets and copies the matches block by block, in order (matches reach back across blocks).  bp_scan_kernel decides from the
+// headers which payloads try this; the others run through the one-pass kernel on a second stream beside the passes, and so does,
+// afterwards, any frame that broke an assumption (a block that does not regenerate 128 KiB, more sequences than a slot holds,
+// anything malformed).
 #include "common.cuh"
 #include "zstd_dec_core.h"
 
@@ -29,7 +31,7 @@ struct sq_dec_scratch {
     uint8_t *lits;      // per resident warp: Z_BLOCK_MAX + 64
     void *build;        // per resident warp: table-construction scratch (zd::Scratch, 2.3 KB; in HBM so that shared memory holds only
                         // the decode tables and six CTAs fit an SM)
-    uint32_t *counter;      // [0] one-pass work counter, [1] bp_first_pass, [2] bp_matches, [3] one-pass for frames the two passes gave back
+    uint32_t *counter;      // [0] one-pass work counter, [1] bp_first_pass, [2] bp_matches, [3] one-pass for frames the two passes gave back, [4] bp_snapshot
     uint32_t warps;
     // block-parallel path, sized for bp_cap frames
     uint32_t bp_cap;
@@ -37,6 +39,7 @@ struct sq_dec_scratch {
     zd::FrameInfo *bp_info;   // [bp_cap]
     zd::BlockTask *bp_tasks;  // [bp_cap * BP_MAX_BLOCKS]
     zd::BlockState *bp_states;
+    zd::Tables *bp_snaps;     // [bp_cap * BP_MAX_BLOCKS] the tables every compressed block decodes with
     uint8_t *bp_lits;         // per resident warp of bp_first_pass_kernel: Z_BLOCK_MAX + 64 (it runs beside the one-pass kernel, which has its own)
     zd::StoredSeq *bp_seqs;   // [bp_cap * BP_MAX_BLOCKS * BP_SEQ_CAP]
     void *bp_build;           // per resident warp of bp_first_pass_kernel: its own table-construction scratch
@@ -45,7 +48,7 @@ struct sq_dec_scratch {
 };
 
 namespace {
-constexpr uint32_t BP_MAX_FRAMES = 512, BP_MAX_BLOCKS = 16, BP_SEQ_CAP = Z_BLOCK_MAX / 3 + 1;
+constexpr uint32_t BP_MAX_FRAMES = 2048, BP_MAX_BLOCKS = 16, BP_SEQ_CAP = Z_BLOCK_MAX / 6 + 8;  // a block with more than one sequence per 6 bytes falls back
 constexpr size_t BP_LIT_STRIDE = Z_BLOCK_MAX + 64;
 constexpr uint32_t DEC_WARPS_PER_CTA = 4;
 struct WarpState { zd::Tables T; };
@@ -84,18 +87,37 @@ __global__ void bp_scan_kernel(const uint8_t *__restrict__ comp, const sq_frame 
     if (i >= n) return;
     const sq_frame f = frames[i];
     zd::FrameInfo fi;
-    fi.nblocks = 0; fi.has_fcs = 0; fi.fcs = 0;
+    fi.nblocks = 0; fi.has_fcs = 0; fi.fcs = 0; fi.chained = 0; fi.reserved = 0;
     const uint32_t nb = zd::scan_frame(comp + f.src_off, f.src_len, BP_MAX_BLOCKS, tasks + (size_t)i * BP_MAX_BLOCKS, &fi);
-    bool any = false;  // a frame of raw / RLE blocks only gains nothing
-    for (uint32_t b = 0; b < nb; b++) any = any || tasks[(size_t)i * BP_MAX_BLOCKS + b].type == 2;
-    elig[i] = nb && any ? 1 : 0;
+    elig[i] = nb ? 1 : 0;
     info[i] = fi;
+}
+
+__global__ void __launch_bounds__(DEC_WARPS_PER_CTA * 32, 6) bp_snapshot_kernel(const uint8_t *__restrict__ comp, const sq_frame *__restrict__ frames, uint32_t n,
+                                                                                uint8_t *__restrict__ elig, const zd::FrameInfo *__restrict__ info,
+                                                                                const zd::BlockTask *__restrict__ tasks, zd::Tables *__restrict__ snaps,
+                                                                                zd::Scratch *__restrict__ build_all, uint32_t *__restrict__ counter) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    WarpState *ws = reinterpret_cast<WarpState *>(smem) + w;
+    zd::Scratch *S = build_all + (blockIdx.x * DEC_WARPS_PER_CTA + w);
+    for (;;) {
+        uint32_t i = 0;
+        if (lane == 0) i = atomicAdd(counter, 1u);
+        i = __shfl_sync(0xffffffffu, i, 0);
+        if (i >= n) break;
+        if (elig[i] != 1 || !info[i].chained) continue;  // frames whose blocks bring all their own tables need no snapshots
+        const size_t first = (size_t)i * BP_MAX_BLOCKS;
+        const bool ok = zd::snapshot_frame_tables(comp + frames[i].src_off, tasks + first, info[i].nblocks, &ws->T, S, snaps + first);
+        __syncwarp();
+        if (!ok && lane == 0) elig[i] = 2;  // malformed table descriptions: the one-pass kernel reports it
+    }
 }
 
 __global__ void __launch_bounds__(DEC_WARPS_PER_CTA * 32, 6) bp_first_pass_kernel(const uint8_t *__restrict__ comp, const sq_frame *__restrict__ frames, uint32_t n,
                                                                                   const uint8_t *__restrict__ elig, const zd::FrameInfo *__restrict__ info,
-                                                                                  const zd::BlockTask *__restrict__ tasks, zd::BlockState *__restrict__ states,
-                                                                                  uint8_t *__restrict__ lits_all, zd::StoredSeq *__restrict__ seqs, uint8_t *__restrict__ out,
+                                                                                  const zd::BlockTask *__restrict__ tasks, const zd::Tables *__restrict__ snaps,
+                                                                                  zd::BlockState *__restrict__ states, uint8_t *__restrict__ lits_all, zd::StoredSeq *__restrict__ seqs, uint8_t *__restrict__ out,
                                                                                   zd::Scratch *__restrict__ build_all, uint32_t *__restrict__ counter) {
     extern __shared__ __align__(16) uint8_t smem[];
     const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -112,7 +134,14 @@ __global__ void __launch_bounds__(DEC_WARPS_PER_CTA * 32, 6) bp_first_pass_kerne
         const zd::BlockTask t = tasks[item];
         if (t.type != 2) continue;
         const sq_frame f = frames[i];
-        zd::decode_block_first_pass(comp + f.src_off + t.src_off, t.size, &ws->T, S, lits, out + f.dst_off, t.out_start, f.capacity, b == 0,
+        const bool chained = info[i].chained != 0;
+        if (chained) {  // the tables this block decodes with
+            const uint32_t *from = reinterpret_cast<const uint32_t *>(snaps + item);
+            uint32_t *to = reinterpret_cast<uint32_t *>(&ws->T);
+            for (uint32_t k = lane; k < sizeof(zd::Tables) / 4; k += 32) to[k] = from[k];
+            __syncwarp();
+        }
+        zd::decode_block_first_pass(comp + f.src_off + t.src_off, t.size, chained, &ws->T, S, lits, out + f.dst_off, t.out_start, f.capacity, b == 0,
                                     seqs + (size_t)item * BP_SEQ_CAP, BP_SEQ_CAP, states + item);
         __syncwarp();
     }
@@ -151,7 +180,7 @@ void sq_dec_destroy(sq_ctx *ctx) {
     sq_dec_scratch *d = ctx->dec;
     if (!d) return;
     cudaFree(d->lits); cudaFree(d->build); cudaFree(d->counter);
-    cudaFree(d->bp_elig); cudaFree(d->bp_info); cudaFree(d->bp_tasks); cudaFree(d->bp_states); cudaFree(d->bp_lits); cudaFree(d->bp_seqs); cudaFree(d->bp_build);
+    cudaFree(d->bp_elig); cudaFree(d->bp_info); cudaFree(d->bp_tasks); cudaFree(d->bp_states); cudaFree(d->bp_snaps); cudaFree(d->bp_lits); cudaFree(d->bp_seqs); cudaFree(d->bp_build);
     if (d->aux) cudaStreamDestroy(d->aux);
     if (d->ev_fork) cudaEventDestroy(d->ev_fork);
     if (d->ev_join) cudaEventDestroy(d->ev_join);
@@ -176,8 +205,9 @@ extern "C" int32_t sq_decode_device(sq_ctx *ctx, const void *d_comp, const sq_fr
         d->warps = (uint32_t)ctx->sm_count * (uint32_t)ctas_per_sm * DEC_WARPS_PER_CTA;
         SQ_CUDA(ctx, cudaMalloc(&d->lits, (size_t)d->warps * (Z_BLOCK_MAX + 64)));
         SQ_CUDA(ctx, cudaMalloc(&d->build, (size_t)d->warps * sizeof(zd::Scratch)));
-        SQ_CUDA(ctx, cudaMalloc(&d->counter, 4 * sizeof(uint32_t)));
+        SQ_CUDA(ctx, cudaMalloc(&d->counter, 8 * sizeof(uint32_t)));
         SQ_CUDA(ctx, cudaFuncSetAttribute(bp_first_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SQ_CUDA(ctx, cudaFuncSetAttribute(bp_snapshot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         SQ_CUDA(ctx, cudaMalloc(&d->bp_build, (size_t)d->warps * sizeof(zd::Scratch)));
         SQ_CUDA(ctx, cudaMalloc(&d->bp_lits, (size_t)d->warps * BP_LIT_STRIDE));
         SQ_CUDA(ctx, cudaStreamCreateWithFlags(&d->aux, cudaStreamNonBlocking));
@@ -186,19 +216,20 @@ extern "C" int32_t sq_decode_device(sq_ctx *ctx, const void *d_comp, const sq_fr
     }
     sq_dec_scratch *d = ctx->dec;
     cudaStream_t st = sq_stream(ctx, stream);
-    SQ_CUDA(ctx, cudaMemsetAsync(d->counter, 0, 4 * sizeof(uint32_t), st));
+    SQ_CUDA(ctx, cudaMemsetAsync(d->counter, 0, 8 * sizeof(uint32_t), st));
     uint32_t ctas = d->warps / DEC_WARPS_PER_CTA;
     static const bool bp_off = getenv("SQ_NO_BLOCK_PARALLEL") != nullptr;
     if (n <= BP_MAX_FRAMES && !bp_off) {  // too few frames to fill the GPU with one warp each: give the blocks of eligible frames their own warps
         if (d->bp_cap < n) {
             SQ_CUDA(ctx, cudaStreamSynchronize(st));
-            cudaFree(d->bp_elig); cudaFree(d->bp_info); cudaFree(d->bp_tasks); cudaFree(d->bp_states); cudaFree(d->bp_seqs);
-            d->bp_elig = nullptr; d->bp_info = nullptr; d->bp_tasks = nullptr; d->bp_states = nullptr; d->bp_seqs = nullptr; d->bp_cap = 0;
+            cudaFree(d->bp_elig); cudaFree(d->bp_info); cudaFree(d->bp_tasks); cudaFree(d->bp_states); cudaFree(d->bp_snaps); cudaFree(d->bp_seqs);
+            d->bp_elig = nullptr; d->bp_info = nullptr; d->bp_tasks = nullptr; d->bp_states = nullptr; d->bp_snaps = nullptr; d->bp_seqs = nullptr; d->bp_cap = 0;
             const size_t items = (size_t)n * BP_MAX_BLOCKS;
             SQ_CUDA(ctx, cudaMalloc(&d->bp_elig, n));
             SQ_CUDA(ctx, cudaMalloc(&d->bp_info, (size_t)n * sizeof(zd::FrameInfo)));
             SQ_CUDA(ctx, cudaMalloc(&d->bp_tasks, items * sizeof(zd::BlockTask)));
             SQ_CUDA(ctx, cudaMalloc(&d->bp_states, items * sizeof(zd::BlockState)));
+            SQ_CUDA(ctx, cudaMalloc(&d->bp_snaps, items * sizeof(zd::Tables)));
             SQ_CUDA(ctx, cudaMalloc(&d->bp_seqs, items * BP_SEQ_CAP * sizeof(zd::StoredSeq)));
             d->bp_cap = n;
         }
@@ -210,9 +241,11 @@ extern "C" int32_t sq_decode_device(sq_ctx *ctx, const void *d_comp, const sq_fr
         zstd_decode_kernel<<<ctas < need1 ? ctas : need1, DEC_WARPS_PER_CTA * 32, smem, d->aux>>>((const uint8_t *)d_comp, d_frames, n, (uint8_t *)d_out, d_results, d->lits,
                                                                                                     (zd::Scratch *)d->build, d->counter, d->bp_elig, 0u);
         SQ_CUDA(ctx, cudaEventRecord(d->ev_join, d->aux));
+        bp_snapshot_kernel<<<ctas < need1 ? ctas : need1, DEC_WARPS_PER_CTA * 32, smem, st>>>((const uint8_t *)d_comp, d_frames, n, d->bp_elig, d->bp_info, d->bp_tasks,
+                                                                                                d->bp_snaps, (zd::Scratch *)d->bp_build, d->counter + 4);
         const uint32_t want = (n * BP_MAX_BLOCKS + DEC_WARPS_PER_CTA - 1) / DEC_WARPS_PER_CTA;
         bp_first_pass_kernel<<<want < ctas ? want : ctas, DEC_WARPS_PER_CTA * 32, smem, st>>>((const uint8_t *)d_comp, d_frames, n, d->bp_elig, d->bp_info, d->bp_tasks,
-                                                                                                d->bp_states, d->bp_lits, d->bp_seqs, (uint8_t *)d_out,
+                                                                                                d->bp_snaps, d->bp_states, d->bp_lits, d->bp_seqs, (uint8_t *)d_out,
                                                                                                 (zd::Scratch *)d->bp_build, d->counter + 1);
         bp_matches_kernel<<<(n + 3) / 4, 128, 0, st>>>((const uint8_t *)d_comp, d_frames, n, d->bp_elig, d->bp_info, d->bp_tasks, d->bp_states, d->bp_seqs,
                                                        (uint8_t *)d_out, d_results, d->counter + 2);
@@ -220,7 +253,7 @@ extern "C" int32_t sq_decode_device(sq_ctx *ctx, const void *d_comp, const sq_fr
         // frames the two passes gave back (none for K3-written archives): one-pass, after everything else (it shares the one-pass scratch)
         zstd_decode_kernel<<<ctas < need1 ? ctas : need1, DEC_WARPS_PER_CTA * 32, smem, st>>>((const uint8_t *)d_comp, d_frames, n, (uint8_t *)d_out, d_results, d->lits,
                                                                                                 (zd::Scratch *)d->build, d->counter + 3, d->bp_elig, 2u);
-        SQ_LAUNCHED(ctx, 5);
+        SQ_LAUNCHED(ctx, 6);
         SQ_CUDA(ctx, cudaGetLastError());
         return SQ_OK;
     }

@@ -566,53 +566,55 @@ ZD_DEV int64_t decode_compressed_block(const uint8_t *src, uint32_t size, uint8_
     return (int64_t)pos + rest;
 }
 
-// ---- two passes over a frame whose blocks are self-contained (everything the K3 encoder writes) ------------------------------
-// A block is self-contained when (a) its literals are not Treeless and none of its three sequence tables is in Repeat_Mode
-// (block_is_independent answers that from the headers), (b) no sequence reads a repeat offset it has not set itself (found out
-// while decoding: the history is tracked with "known" flags), and (c) it starts where a frame of 128 KiB blocks puts it (every
-// block but the last regenerates exactly 128 KiB in all frames K3 and libzstd level <= 15 write; checked afterwards).
+// ---- two passes over a frame (block-parallel decoding) ---------------------------------------------------------------------
+// The blocks of a frame chain in three ways: Repeat_Mode / Treeless reuse the previous block's tables, repeat-offset codes read
+// the previous block's history, and matches read the previous blocks' output.  Only the last one needs the blocks in order:
+//   tables   a serial pre-pass per frame (snapshot_frame_tables) reads nothing but the table descriptions of every block and
+//            leaves each block a snapshot of the tables it decodes with;
+//   history  pass 1 tracks the three repeat offsets symbolically: a slot is either a number or "what slot s held when the block
+//            started, minus d"; the stored offsets and the block's final history are resolved in pass 2, in order;
+//   output   pass 1 assumes every block but the last regenerates 128 KiB (true for K3 and for libzstd below level 16, checked in
+//            pass 2), which tells it where its block starts.
 // Pass 1 (one warp per BLOCK, all blocks of all frames at once) does everything that does not read the output: Huffman literals,
-// the FSE chain, repeat-offset resolution, positions, and it PLACES THE LITERALS in the output.  What is left for pass 2 (one warp
-// per FRAME, in order, because matches reach back across blocks) is one {destination, length, offset} triple per match.
-// Anything that breaks an assumption sends the frame through the one-pass decoder afterwards.
-struct StoredSeq { uint32_t mpos, ml, off; };  // match destination (frame-relative), length, offset
-struct BlockState { int32_t status; uint32_t nseq, regen, self_contained; };
+// the FSE chain, repeat offsets, positions, and it PLACES THE LITERALS in the output.  What is left for pass 2 (one warp per
+// FRAME, in order) is one {destination, length, offset} triple per match.  Anything that breaks an assumption -- and every
+// malformed frame -- goes through the one-pass decoder afterwards, which also produces the error.
+struct StoredSeq { uint32_t mpos, ml, off; };  // match destination (frame-relative), length, offset (number or symbol)
+struct BlockState { int32_t status; uint32_t nseq, regen; uint32_t hist[3]; };  // hist: the history the block leaves (numbers or symbols)
 enum { NEED_ONE_PASS = -100 };
+constexpr uint32_t HIST_SYM = 0x80000000u;  // symbol: HIST_SYM | slot << 16 | delta  ==  (incoming slot) - delta
 
-ZD_DEV bool block_is_independent(const uint8_t *src, uint32_t size) {
+// Literals section of a compressed block: its type, header length and body length (for Compressed / Treeless the body is the
+// optional tree description followed by the streams).  false if the header is truncated.
+ZD_DEV bool literals_section_span(const uint8_t *src, uint32_t size, uint32_t *type_out, uint32_t *hl_out, uint32_t *body_out) {
     if (size < 1) return false;
     const uint32_t type = src[0] & 3, sf = (src[0] >> 2) & 3;
-    uint32_t used;
-    if (type == 3) return false;  // Treeless
+    uint32_t hl, body;
     if (type < 2) {
-        uint32_t hl, n;
+        uint32_t n;
         if (sf == 0 || sf == 2) { hl = 1; n = src[0] >> 3; }
         else if (sf == 1) { if (size < 2) return false; hl = 2; n = (src[0] | src[1] << 8) >> 4; }
         else { if (size < 3) return false; hl = 3; n = (src[0] | src[1] << 8 | (uint32_t)src[2] << 16) >> 4; }
-        used = type == 0 ? hl + n : hl + 1;
+        body = type == 0 ? n : 1;
     } else {
-        uint32_t hl, comp;
-        if (sf <= 1) { if (size < 3) return false; hl = 3; comp = (src[0] | src[1] << 8 | (uint32_t)src[2] << 16) >> 14; }
-        else if (sf == 2) { if (size < 4) return false; hl = 4; comp = (src[0] | src[1] << 8 | (uint32_t)src[2] << 16 | (uint32_t)src[3] << 24) >> 18; }
-        else { if (size < 5) return false; hl = 5; comp = (uint32_t)((src[0] | src[1] << 8 | (uint32_t)src[2] << 16 | (uint64_t)src[3] << 24 | (uint64_t)src[4] << 32) >> 22); }
-        used = hl + comp;
+        if (sf <= 1) { if (size < 3) return false; hl = 3; body = (src[0] | src[1] << 8 | (uint32_t)src[2] << 16) >> 14; }
+        else if (sf == 2) { if (size < 4) return false; hl = 4; body = (src[0] | src[1] << 8 | (uint32_t)src[2] << 16 | (uint32_t)src[3] << 24) >> 18; }
+        else { if (size < 5) return false; hl = 5; body = (uint32_t)((src[0] | src[1] << 8 | (uint32_t)src[2] << 16 | (uint64_t)src[3] << 24 | (uint64_t)src[4] << 32) >> 22); }
     }
-    if (used >= size) return false;  // malformed: let the one-pass decoder report it
-    const uint8_t *p = src + used;
-    uint32_t left = size - used, nseq = p[0];
-    if (nseq == 0) return true;
-    const uint32_t nh = nseq < 128 ? 1 : nseq < 255 ? 2 : 3;
-    if (left < nh + 1) return false;
-    const uint32_t modes = p[nh];
-    return (modes >> 6) != 3 && ((modes >> 4) & 3) != 3 && ((modes >> 2) & 3) != 3;
+    if (hl + body > size) return false;
+    *type_out = type; *hl_out = hl; *body_out = body;
+    return true;
 }
 
-// pass 1 of one compressed block whose output starts at out[out_start] (frame-relative; out is the frame's output, cap its size)
-ZD_DEV void decode_block_first_pass(const uint8_t *src, uint32_t size, Tables *T, Scratch *S, uint8_t *litbuf, uint8_t *out, uint32_t out_start, uint32_t cap,
+// pass 1 of one compressed block whose output starts at out[out_start] (frame-relative; out is the frame's output, cap its size);
+// *T holds the snapshot of the tables the block decodes with, or anything if the frame's blocks bring all their own (chained == false)
+ZD_DEV void decode_block_first_pass(const uint8_t *src, uint32_t size, bool chained, Tables *T, Scratch *S, uint8_t *litbuf, uint8_t *out, uint32_t out_start, uint32_t cap,
                                     bool first_block, StoredSeq *seqs, uint32_t seq_cap, BlockState *bs_out) {
     BlockState bs;
-    bs.status = 0; bs.nseq = 0; bs.regen = 0; bs.self_contained = 1;
-    T->have_huf = T->have_ll = T->have_ml = T->have_of = 0;  // an independent block brings all its tables
+    bs.status = 0; bs.nseq = 0; bs.regen = 0;
+    if (!chained) T->have_huf = T->have_ll = T->have_ml = T->have_of = 0;
+    // repeat offsets: the frame's first block starts from 1, 4, 8; any other from three symbols
+    uint32_t r0 = first_block ? 1u : HIST_SYM, r1 = first_block ? 4u : HIST_SYM | 1u << 16, r2 = first_block ? 8u : HIST_SYM | 2u << 16;
     Literals L;
     const int lused = decode_literals(src, size, T, litbuf, &L, S->weights, S->cells);
     int rc = lused < 0 ? lused : 0;
@@ -621,38 +623,34 @@ ZD_DEV void decode_block_first_pass(const uint8_t *src, uint32_t size, Tables *T
         const uint8_t *p = src + lused;
         uint32_t left = size - (uint32_t)lused;
         rc = read_sequences_header(&p, &left, &nseq, T, S);
-        if (!rc && nseq > seq_cap) rc = ERR_CORRUPT;
+        if (!rc && nseq > seq_cap) rc = ERR_CAPACITY;  // more sequences than the slot holds: the one-pass decoder takes the frame
         if (!rc && nseq) {
             BitReader b;
             if (br_init(&b, p, left) < 0) rc = ERR_CORRUPT;
             FseStates st;
             if (!rc) { st.ll = br_read(&b, T->ll_log); st.of = br_read(&b, T->of_log); st.ml = br_read(&b, T->ml_log); }
-            // repeat offsets with "known" flags: only the frame's first block knows 1, 4, 8
-            uint32_t r0 = first_block ? 1u : 0u, r1 = first_block ? 4u : 0u, r2 = first_block ? 8u : 0u;
-            bool k0 = first_block, k1 = first_block, k2 = first_block, foreign = false;
-            for (uint32_t i0 = 0; i0 < nseq && !rc && !foreign; i0 += ZD_WARP) {
+            for (uint32_t i0 = 0; i0 < nseq && !rc; i0 += ZD_WARP) {
                 const uint32_t nbatch = nseq - i0 < ZD_WARP ? nseq - i0 : ZD_WARP;
                 uint32_t my_ll = 0, my_ml = 0, my_off = 1;
                 int err = 0;
                 for (uint32_t k = 0; k < nbatch; k++) {
                     uint32_t ll, ml, ofv, off;
                     fse_step(&b, T, &st, i0 + k + 1 >= nseq, &ll, &ml, &ofv);
-                    if (ofv > 3) { off = ofv - 3; r2 = r1; k2 = k1; r1 = r0; k1 = k0; r0 = off; k0 = true; }
+                    if (ofv > 3) { off = ofv - 3; r2 = r1; r1 = r0; r0 = off; }
                     else {
                         const uint32_t idx = ofv - 1 + (ll == 0 ? 1 : 0);
-                        if (idx == 0) { off = r0; foreign = foreign || !k0; }
+                        if (idx == 0) off = r0;
                         else {
-                            const bool ks = idx == 1 ? k1 : idx == 2 ? k2 : k0;
-                            off = idx == 1 ? r1 : idx == 2 ? r2 : r0 - 1;
-                            foreign = foreign || !ks;
-                            if (ks && off == 0) err = 1;
-                            if (idx >= 2) { r2 = r1; k2 = k1; }
-                            r1 = r0; k1 = k0; r0 = off; k0 = ks;
+                            if (idx == 3) {  // r0 - 1: a number, or one more on a symbol's delta
+                                if (r0 & HIST_SYM) { off = r0 + 1; if ((off & 0xFFFFu) == 0) err = 1; }
+                                else { off = r0 - 1; if (off == 0) err = 1; }
+                            } else off = idx == 1 ? r1 : r2;
+                            if (idx >= 2) r2 = r1;
+                            r1 = r0; r0 = off;
                         }
                     }
                     if (k == ZD_LANE()) { my_ll = ll; my_ml = ml; my_off = off; }
                 }
-                if (foreign) break;  // a sequence reads history from before the block: the one-pass decoder takes the frame
                 if (err || b.pos < 0) { rc = ERR_CORRUPT; break; }
                 // positions
                 uint32_t lit_excl, out_excl, lit_tot, out_tot;
@@ -674,7 +672,7 @@ ZD_DEV void decode_block_first_pass(const uint8_t *src, uint32_t size, Tables *T
                 if ((uint64_t)pos + out_tot > cap) { rc = ERR_CAPACITY; break; }
                 const uint32_t my_lit_out = pos + out_excl, my_match = my_lit_out + my_ll;
                 const bool mine = ZD_LANE() < nbatch;
-                int bad = mine && my_off > my_match;
+                int bad = mine && !(my_off & HIST_SYM) && my_off > my_match;  // symbols are checked when pass 2 resolves them
 #if defined(__CUDA_ARCH__)
                 bad = __any_sync(0xffffffffu, bad);
 #endif
@@ -689,10 +687,9 @@ ZD_DEV void decode_block_first_pass(const uint8_t *src, uint32_t size, Tables *T
                 lit_pos += lit_tot;
                 pos += out_tot;
             }
-            if (!rc && !foreign && b.pos != 0) rc = ERR_CORRUPT;
-            if (foreign) bs.self_contained = 0;
+            if (!rc && b.pos != 0) rc = ERR_CORRUPT;
         } else if (!rc && left != 0) rc = ERR_CORRUPT;
-        if (!rc && bs.self_contained) {
+        if (!rc) {
             const uint32_t rest = L.size - lit_pos;
             if ((uint64_t)pos + rest > cap) rc = ERR_CAPACITY;
             else {
@@ -702,6 +699,7 @@ ZD_DEV void decode_block_first_pass(const uint8_t *src, uint32_t size, Tables *T
         }
     }
     bs.status = rc; bs.nseq = nseq; bs.regen = pos - out_start;
+    bs.hist[0] = r0; bs.hist[1] = r1; bs.hist[2] = r2;
     ZD_SYNC();
     if (ZD_LANE() == 0) *bs_out = bs;
 }
@@ -782,12 +780,12 @@ ZD_DEV int64_t decode_payload(const uint8_t *src, uint32_t size, uint8_t *out, u
     return pos;
 }
 
-// Two-pass eligibility of a payload: exactly one zstd frame, at most max_blocks blocks, every compressed block independent
-// (block_is_independent).  Anything else -- several frames, skippable frames, malformed headers -- is left to decode_payload,
-// which also produces the error.  Fills tasks[] (with the output start of every block under the 128 KiB assumption) and returns
-// the number of blocks, or 0 if not eligible.
+// Two-pass eligibility of a payload: exactly one zstd frame of 2 .. max_blocks well-formed blocks, at least one of them
+// compressed.  Anything else -- several frames, skippable frames, malformed headers, a single block (nothing to gain) -- is left
+// to decode_payload, which also produces the error.  Fills tasks[] (with the output start of every block under the 128 KiB
+// assumption) and returns the number of blocks, or 0 if not eligible.
 struct BlockTask { uint32_t src_off, size, type, out_start; };
-struct FrameInfo { uint32_t nblocks, has_fcs; uint64_t fcs; };
+struct FrameInfo { uint32_t nblocks, has_fcs; uint64_t fcs; uint32_t chained, reserved; };  // chained: some block inherits tables (snapshots needed)
 ZD_DEV uint32_t scan_frame(const uint8_t *src, uint32_t size, uint32_t max_blocks, BlockTask *tasks, FrameInfo *fi) {
     if (size < 6) return 0;
     const uint32_t magic = src[0] | src[1] << 8 | (uint32_t)src[2] << 16 | (uint32_t)src[3] << 24;
@@ -803,6 +801,7 @@ ZD_DEV uint32_t scan_frame(const uint8_t *src, uint32_t size, uint32_t max_block
     for (uint32_t i = 0; i < fcs_bytes; i++) fcs |= (uint64_t)src[h + i] << (8 * i);
     if (fcs_flag == 1) fcs += 256;
     uint32_t ip = h + fcs_bytes, nb = 0, start = 0;
+    bool any = false, chained = false;
     for (;;) {
         if (size - ip < 3 || nb >= max_blocks) return 0;
         const uint32_t bh = src[ip] | src[ip + 1] << 8 | (uint32_t)src[ip + 2] << 16;
@@ -811,24 +810,71 @@ ZD_DEV uint32_t scan_frame(const uint8_t *src, uint32_t size, uint32_t max_block
         if (type == 3 || bsz > Z_BLOCK_MAX) return 0;
         const uint32_t body = type == 1 ? 1u : bsz;
         if (body > size - ip) return 0;
-        if (type == 2 && !block_is_independent(src + ip, bsz)) return 0;
         tasks[nb].src_off = ip; tasks[nb].size = bsz; tasks[nb].type = type; tasks[nb].out_start = start;
         start += type == 2 ? Z_BLOCK_MAX : bsz;
+        any = any || type == 2;
+        if (type == 2) {  // Treeless literals or a Repeat_Mode table: the block decodes with tables of an earlier one
+            uint32_t lt, hl, body;
+            if (!literals_section_span(src + ip, bsz, &lt, &hl, &body) || hl + body >= bsz) chained = true;  // (or malformed: the snapshot pass finds out)
+            else {
+                const uint8_t *q = src + ip + hl + body;
+                const uint32_t left = bsz - hl - body, ns = q[0], nh = ns < 128 ? 1 : ns < 255 ? 2 : 3;
+                if (lt == 3) chained = true;
+                else if (ns) {
+                    if (left < nh + 1) chained = true;
+                    else { const uint32_t m = q[nh]; if ((m >> 6) == 3 || ((m >> 4) & 3) == 3 || ((m >> 2) & 3) == 3) chained = true; }
+                }
+            }
+        }
         nb++;
         ip += body;
         if (last) break;
     }
     if (has_checksum) { if (size - ip < 4) return 0; ip += 4; }
-    if (ip != size) return 0;
-    fi->nblocks = nb; fi->has_fcs = fcs_bytes != 0; fi->fcs = fcs;
+    if (ip != size || nb < 2 || !any) return 0;
+    fi->nblocks = nb; fi->has_fcs = fcs_bytes != 0; fi->fcs = fcs; fi->chained = chained ? 1u : 0u; fi->reserved = 0;
     return nb;
 }
 
+// Serial over the blocks of one frame, but reading only their table descriptions: after it, snaps[b] holds the tables compressed
+// block b decodes with (its own, or what Repeat_Mode / Treeless make it inherit).  false = malformed (one-pass decoder).
+ZD_DEV bool snapshot_frame_tables(const uint8_t *src, const BlockTask *tasks, uint32_t nblocks, Tables *T, Scratch *S, Tables *snaps) {
+    T->have_huf = T->have_ll = T->have_ml = T->have_of = 0;
+    for (uint32_t b = 0; b < nblocks; b++) {
+        if (tasks[b].type != 2) continue;
+        const uint8_t *bp = src + tasks[b].src_off;
+        const uint32_t size = tasks[b].size;
+        uint32_t type, hl, body;
+        if (!literals_section_span(bp, size, &type, &hl, &body)) return false;
+        if (type == 2) { if (read_huf_tree(bp + hl, body, T, S->weights, S->cells) < 0) return false; }
+        else if (type == 3 && !T->have_huf) return false;
+        const uint8_t *p = bp + hl + body;
+        uint32_t left = size - hl - body, nseq = 0;
+        if (read_sequences_header(&p, &left, &nseq, T, S) < 0) return false;
+        ZD_SYNC();
+        {   // all lanes copy the table state
+            const uint32_t *from = reinterpret_cast<const uint32_t *>(T);
+            uint32_t *to = reinterpret_cast<uint32_t *>(snaps + b);
+            for (uint32_t i = ZD_LANE(); i < sizeof(Tables) / 4; i += ZD_WARP) to[i] = from[i];
+        }
+        ZD_SYNC();
+    }
+    return true;
+}
+
+// number or symbol -> number, given the history at the block's start; 0 = not a valid offset
+ZD_DEV uint32_t resolve_hist(uint32_t h, const uint32_t R[3]) {
+    if (!(h & HIST_SYM)) return h;
+    const uint32_t base = R[(h >> 16) & 3u], d = h & 0xFFFFu;
+    return base > d ? base - d : 0u;
+}
+
 // pass 2 of a whole frame: raw / RLE blocks and the matches of the compressed ones, in order.  Returns the decoded size, or
-// NEED_ONE_PASS when pass 1 found a block that is not self-contained, failed, or does not start where it was assumed to.
+// NEED_ONE_PASS when pass 1 failed on a block, a block does not start where it was assumed to, or an offset is not valid.
 ZD_DEV int64_t execute_frame_matches(const uint8_t *src, const BlockTask *tasks, const FrameInfo *fi, const BlockState *states, const StoredSeq *seqs,
                                      size_t seq_stride, uint8_t *out, uint32_t cap) {
     uint32_t pos = 0;
+    uint32_t R[3] = {1, 4, 8};
     for (uint32_t b = 0; b < fi->nblocks; b++) {
         const BlockTask t = tasks[b];
         if (pos != t.out_start) return NEED_ONE_PASS;
@@ -844,13 +890,19 @@ ZD_DEV int64_t execute_frame_matches(const uint8_t *src, const BlockTask *tasks,
             pos += t.size;
         } else {
             const BlockState bs = states[b];
-            if (bs.status < 0 || !bs.self_contained || bs.regen > Z_BLOCK_MAX) return NEED_ONE_PASS;
+            if (bs.status < 0 || bs.regen > Z_BLOCK_MAX) return NEED_ONE_PASS;
             const StoredSeq *sq = seqs + (size_t)b * seq_stride;
             for (uint32_t i0 = 0; i0 < bs.nseq; i0 += ZD_WARP) {
                 const uint32_t nbatch = bs.nseq - i0 < ZD_WARP ? bs.nseq - i0 : ZD_WARP;
                 StoredSeq mine;
-                mine.mpos = 0; mine.ml = 0; mine.off = 1;
+                mine.mpos = 1; mine.ml = 0; mine.off = 1;
                 if (ZD_LANE() < nbatch) mine = sq[i0 + ZD_LANE()];
+                mine.off = resolve_hist(mine.off, R);
+                int bad = mine.off == 0 || mine.off > mine.mpos;
+#if defined(__CUDA_ARCH__)
+                bad = __any_sync(0xffffffffu, bad);
+#endif
+                if (bad) return NEED_ONE_PASS;
 #if defined(__CUDA_ARCH__)
                 const uint32_t src_end = mine.mpos - mine.off + (mine.off < mine.ml ? mine.off : mine.ml);
                 run_match_waves(out, mine.mpos, mine.ml, mine.off, src_end, nbatch >= 32 ? 0xffffffffu : (1u << nbatch) - 1u);
@@ -858,6 +910,9 @@ ZD_DEV int64_t execute_frame_matches(const uint8_t *src, const BlockTask *tasks,
                 copy_match(out, mine.mpos, mine.off, mine.ml);
 #endif
             }
+            const uint32_t n0 = resolve_hist(bs.hist[0], R), n1 = resolve_hist(bs.hist[1], R), n2 = resolve_hist(bs.hist[2], R);
+            if (bs.nseq && (n0 == 0 || n1 == 0 || n2 == 0)) return NEED_ONE_PASS;
+            if (bs.nseq) { R[0] = n0; R[1] = n1; R[2] = n2; }
             pos += bs.regen;
         }
     }

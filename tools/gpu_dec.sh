@@ -6,5 +6,7 @@ for n in 64 256 512; do
   timeout 300 python tools/dec_bench.py $n 2>&1 | tail -1
   SQ_NO_BLOCK_PARALLEL=1 timeout 300 python tools/dec_bench.py $n 2>&1 | tail -1 | sed 's/^/[one-pass] /'
 done | tee gpurun_out/dec_bench.log
-timeout 300 python tools/dec_bench.py 128 ref 2>&1 | tail -1 | tee -a gpurun_out/dec_bench.log
-SQ_NO_BLOCK_PARALLEL=1 timeout 300 python tools/dec_bench.py 128 ref 2>&1 | tail -1 | sed 's/^/[one-pass] /' | tee -a gpurun_out/dec_bench.log
+for n in 128 512 1536; do
+  timeout 400 python tools/dec_bench.py $n ref 2>&1 | tail -1
+  SQ_NO_BLOCK_PARALLEL=1 timeout 400 python tools/dec_bench.py $n ref 2>&1 | tail -1 | sed 's/^/[one-pass] /'
+done | tee -a gpurun_out/dec_bench.log
