@@ -632,3 +632,19 @@ def test_dense_search_flag_is_accepted(sq, oracle):
         sizes[dense] = sum(len(f) for _, f in res)
         c.close()
     assert abs(sizes[True] - sizes[False]) <= 0.002 * sizes[False], sizes
+
+
+def test_release_scratch_and_reuse(sq, oracle):
+    """sq_release_scratch hands the cached device scratch back; the next calls allocate it again and give the same answers"""
+    rng = random.Random(31)
+    c = sq.Context()
+    chunks = [rng.randbytes(5000) + bytes(200000), (b"squish " * 40000)[:262144 + 77]]
+    first = c.pack_batch(chunks)
+    c.check(c.lib.sq_release_scratch(c.h))
+    c.dedup_reset()
+    again = c.pack_batch(chunks)
+    assert [d for d, _ in first] == [d for d, _ in again]
+    for data, (_, f) in zip(chunks, again):
+        assert f is not None and oracle.decompress(f, 2 * MiB) == data
+    c.check(c.lib.sq_release_scratch(c.h))
+    assert c.unpack_batch([f for _, f in again], [2 * MiB] * 2) == chunks
