@@ -554,9 +554,9 @@ def run_ours(args):
         from squishrs_b200.sharded import DeviceOps, ShardedDedup
         sd = ShardedDedup(DeviceOps(ctx, sp), world, B, "cuda")
 
-    # Two streams alternate between steps: the long encode of step k+1 starts while the last chunks of step k are still in
-    # flight (one chunk occupies one search CTA for ~0.1 s, so a step's tail would otherwise leave most SMs idle).  The
-    # library gives each stream its own encoder scratch; digest + dedup of consecutive steps are ordered with events.
+    # Two streams alternate between steps: the encode of step k+1 starts while the tail of step k (parse, entropy coding, frame
+    # emission of its last blocks) is still in flight.  The library gives each stream its own encoder scratch; digest + dedup of
+    # consecutive steps are ordered with events.
     stream_b = torch.cuda.Stream()
     streams = [stream, stream_b] if not args.single_stream else [stream, stream]
     sps = [C.c_void_p(x.cuda_stream) for x in streams]
@@ -569,8 +569,8 @@ def run_ours(args):
     last_dedup = [None]
     # Multi-GPU: digest + digest exchange ("front") of step i+2 run on their own stream while steps i and i+1 encode, so a rank
     # never waits for its peers inside a step: the all-to-all it needs next was finished one step ago.  Three small
-    # (digest, verdict) sets rotate; the search kernel leaves a few CTA slots free (SQ_LZ_CTAS_TOTAL) so the front kernels and
-    # NCCL's copy kernels can run beside it.
+    # (digest, verdict) sets rotate.  The search kernel is launched per sub-batch of 256 chunks (~40 ms), so the front kernels and
+    # NCCL's copy kernels get SMs between two launches at the latest -- two steps ahead of where their result is needed.
     ahead = sd is not None and not args.single_stream
     front_stream = torch.cuda.Stream() if ahead else None
     fsp = C.c_void_p(front_stream.cuda_stream) if ahead else None
