@@ -268,7 +268,8 @@ int32_t sq_archive_unpack(sq_ctx *ctx, const char *archive_path, const char *out
 /* The building block of the multi-device pack: from now on `ctx` decides "new or duplicate" in `owner`'s index (the owner shares
  * with itself).  K1 runs where the batch is; 16 digest bytes per chunk travel to the owner's device, K2 runs there on one stream
  * in submission order, one verdict byte per chunk travels back; K3 runs where the batch is.  One host thread submits the batches
- * of all sharing contexts in chunk order. */
+ * of all sharing contexts in chunk order.  owner == NULL ends the sharing (the context uses its own index again); the owner must
+ * outlive every context that shares with it. */
 int32_t sq_share_dedup(sq_ctx *ctx, sq_ctx *owner);
 int32_t sq_archive_pack_multi(sq_ctx **ctxs, uint32_t n_ctx, const char *input_dir, const char *output_path,
                               int32_t threads, sq_pack_report *report);

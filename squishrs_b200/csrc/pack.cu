@@ -103,7 +103,8 @@ extern "C" int32_t sq_pack_device(sq_ctx *ctx, const void *d_data, const sq_span
 // `owner`'s index.  The owner shares with itself so that all contexts go through the same ordered stream.  One host thread must
 // submit the batches of all sharing contexts, in chunk order.
 extern "C" int32_t sq_share_dedup(sq_ctx *ctx, sq_ctx *owner) {
-    if (!ctx || !owner) return SQ_ERR_INVALID_ARG;
+    if (!ctx) return SQ_ERR_INVALID_ARG;
+    if (!owner) { ctx->dedup_owner = nullptr; return SQ_OK; }  // back to the context's own index
     SQ_CUDA(owner, cudaSetDevice(owner->device));
     if (!owner->dedup_stream) SQ_CUDA(owner, cudaStreamCreateWithFlags(&owner->dedup_stream, cudaStreamNonBlocking));
     for (int i = 0; i < 2; i++) if (!ctx->verdict_done[i]) SQ_CUDA(owner, cudaEventCreateWithFlags(&ctx->verdict_done[i], cudaEventDisableTiming));

@@ -338,6 +338,7 @@ static int32_t pack_impl(sq_ctx **ctxs, uint32_t D, const char *input_dir, const
     std::vector<Staging> in_stage(S), out_stage(S), res_stage(S);
     auto bail = [&](int32_t code) {  // early exit: give the staging back and do not leave a truncated archive behind
         for (uint32_t i = 0; i < S; i++) { sq_ctx *c = on(i % D); in_stage[i].release(c); out_stage[i].release(c); res_stage[i].release(c); }
+        for (uint32_t d = 0; d < D && D > 1; d++) sq_share_dedup(ctxs[d], nullptr);
         on(0);
         fclose(out);
         remove(output_path);
@@ -465,6 +466,7 @@ static int32_t pack_impl(sq_ctx **ctxs, uint32_t D, const char *input_dir, const
     if (!rc) { fseek(out, 0, SEEK_END); asize = (uint64_t)ftell(out); }
     fclose(out);
     for (uint32_t i = 0; i < S; i++) { sq_ctx *c = on(i % D); in_stage[i].release(c); out_stage[i].release(c); res_stage[i].release(c); }
+    for (uint32_t d = 0; d < D && D > 1; d++) sq_share_dedup(ctxs[d], nullptr);  // the sharing lasts for this pack only
     on(0);
     if (!rc && report) {
         memset(report, 0, sizeof *report);

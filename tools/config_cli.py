@@ -80,6 +80,14 @@ def config5(nfiles=20000):
     out["gpu_unpack_second_run_s"] = run([CLI, "unpack", str(BASE / "c5" / "ref.squish"), "-o", str(BASE / "c5" / "gpu_out3")])
     out["cpu_unpack_parallel_decode_s"] = run([REF, "-j", threads, "--parallel-decode", "unpack", str(BASE / "c5" / "ref.squish"), "-o", str(BASE / "c5" / "cpu_out2")]) if os.environ.get("SQ_REF_PD") else None
     out["gpu_unpack_gbs"] = nbytes / out["gpu_unpack_s"] / 1e9; out["cpu_unpack_gbs"] = nbytes / out["cpu_unpack_s"] / 1e9
+    if os.environ.get("SQ_C5_GPU_PACK"):  # not a BASELINE config: the same tree of small files packed by the GPU path
+        for d in ("gpu_out", "cpu_out", "gpu_out2", "gpu_out3", "cpu_out2"): shutil.rmtree(BASE / "c5" / d, ignore_errors=True)
+        out["gpu_pack_s"] = run([CLI, *DEV, "pack", str(src), "-o", str(BASE / "c5" / "gpu.squish")])
+        out["gpu_pack_second_run_s"] = run([CLI, *DEV, "pack", str(src), "-o", str(BASE / "c5" / "gpu2.squish")])
+        out["gpu_pack_phases"] = phases([CLI, *DEV, "pack", str(src), "-o", str(BASE / "c5" / "gpu3.squish")])
+        run([REF, "-j", threads, "unpack", str(BASE / "c5" / "gpu.squish"), "-o", str(BASE / "c5" / "x1")])
+        out["gpu_pack_identical_after_ref_unpack"] = same_tree(src, BASE / "c5" / "x1")
+        out["gpu_archive_bytes"] = (BASE / "c5" / "gpu.squish").stat().st_size; out["ref_archive_bytes"] = (BASE / "c5" / "ref.squish").stat().st_size
     return out
 
 
