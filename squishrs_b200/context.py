@@ -97,8 +97,9 @@ class Context:
             ret.append((bytes(res[i].digest), frame))
         return ret
 
-    def unpack_batch(self, payloads: Sequence[bytes], capacities: Sequence[int]):
-        """read_chunks for a batch: returns [bytes] or raises SquishError(ReaderError) like the reference."""
+    def unpack_batch(self, payloads: Sequence[bytes], capacities: Sequence[int], raise_on_error: bool = True):
+        """read_chunks for a batch: returns [bytes] or raises SquishError(ReaderError) like the reference; with
+        raise_on_error=False a payload that fails to decode yields None instead (errors are per payload, not per call)."""
         n = len(payloads)
         if n == 0:
             return []
@@ -118,7 +119,10 @@ class Context:
         ret = []
         for i in range(n):
             if res[i].status != L.SQ_OK:
-                raise L.SquishError(res[i].status, f"Error reading from squish: frame {i} failed to decode")
+                if raise_on_error:
+                    raise L.SquishError(res[i].status, f"Error reading from squish: frame {i} failed to decode")
+                ret.append(None)
+                continue
             ret.append(bytes(mv[frames[i].dst_off:frames[i].dst_off + res[i].out_len]))
         return ret
 

@@ -648,3 +648,31 @@ def test_release_scratch_and_reuse(sq, oracle):
         assert f is not None and oracle.decompress(f, 2 * MiB) == data
     c.check(c.lib.sq_release_scratch(c.h))
     assert c.unpack_batch([f for _, f in again], [2 * MiB] * 2) == chunks
+
+
+def test_block_parallel_decode_of_damaged_frames(sq, oracle):
+    """multi-block frames (K3-written and libzstd-written, so the block-parallel passes take them) with bits flipped, a few
+    hundred per call next to intact ones: a payload the GPU accepts must decode to what stock libzstd makes of it, a damaged
+    neighbour must not disturb an intact frame, and nothing may crash"""
+    rng = random.Random(77)
+    c = sq.Context()
+    lib = sq.load()
+    b = C.create_string_buffer(600000)
+    lib.sq_corpus_fill_host(b, 600000, 9, 4, 2)
+    data = b.raw
+    own = c.pack_batch([data])[0][1]
+    ref = oracle.compress(data, 12)
+    payloads, want = [], []
+    for base in (own, ref):
+        payloads.append(base); want.append(data)
+        for _ in range(150):
+            g = bytearray(base)
+            for _ in range(rng.randrange(1, 4)):
+                g[rng.randrange(4, len(g))] ^= 1 << rng.randrange(8)
+            payloads.append(bytes(g)); want.append(oracle.decompress(bytes(g), len(data)))
+        payloads.append(base[:len(base) // 2]); want.append(None)
+    got = c.unpack_batch(payloads, [len(data)] * len(payloads), raise_on_error=False)
+    assert got[0] == data and got[152] == data
+    for g, w in zip(got, want):
+        if g is not None:
+            assert g == w
