@@ -172,7 +172,9 @@ int32_t sq_unroute_verdicts_device(sq_ctx *ctx, const uint8_t *d_verdict_back, c
 /* Buffer slack for the *_device entry points: the kernels read whole aligned words around the bytes they are given.  d_data
  * (encode / digest) and d_comp (decode) must be readable for 16 bytes past the last span / payload and d_comp for 8 bytes
  * before the first payload that does not start at offset 0; a buffer from cudaMalloc with 64 spare bytes at the end, payloads
- * at 16-byte aligned offsets, always satisfies this (what the *_host entry points do). */
+ * at 16-byte aligned offsets, always satisfies this (what the *_host entry points do).  d_out of a decode: frame outputs at 16-byte
+ * aligned dst_off; the decoder reads back whole aligned 32-bit words of what it has written, so the buffer must be readable up to
+ * the next multiple of 4 after the last frame's capacity. */
 
 /* ---- K3: encode  == zstd::bulk::compress(chunk, 12) (src/util/chunk.rs:89-90) */
 /* worst-case frame bytes for a chunk of `len` bytes (raw-block fallback) */
