@@ -81,6 +81,11 @@ typedef struct {
 /* Record CUDA events between the encoder's kernels so sq_encode_stage_ms can report per-kernel durations (bench.py's
  * roofline line).  Costs four event records per encode call. */
 #define SQ_FLAG_STAGE_TIMING 2u
+/* Reproducible frames: the same chunk always compresses to the same bytes.  By default the match finder lets the entries of one
+ * hash row that fall into the same 512-position tile land in the order of their shared-memory atomics, which can move a few
+ * candidates in or out of a search window from run to run (a few hundred bytes in a gigabyte differ; every frame is valid either
+ * way).  With this flag the index kernel orders them exactly; the match search stage takes about 10 % longer. */
+#define SQ_FLAG_DETERMINISTIC 4u
 
 /* One chunk of a batch: bytes [off, off+len) of the batch buffer.
  * Chunk rule (reference src/archive/writer.rs:240-246): chunk i of a file is

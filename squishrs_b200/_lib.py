@@ -27,6 +27,7 @@ SQ_ERR_INVALID_ARG = -102
 SQ_ERR_CAPACITY = -103
 SQ_FLAG_DENSE_SEARCH = 1
 SQ_FLAG_STAGE_TIMING = 2
+SQ_FLAG_DETERMINISTIC = 4
 
 
 class SqConfig(C.Structure):

@@ -23,12 +23,14 @@ class Context:
     """Owns one sq_ctx (one GPU).  Raises SquishError(SQ_ERR_NO_DEVICE) without a CUDA device."""
 
     def __init__(self, device: int = 0, dedup_capacity: int = 1 << 20, max_batch_chunks: int = 4096, dense_search: bool = False,
-                 stage_timing: bool = False):
+                 stage_timing: bool = False, deterministic: bool = False):
         """dense_search: SQ_FLAG_DENSE_SEARCH, accepted and without effect since round 2 (every position is searched by default).
-        stage_timing: SQ_FLAG_STAGE_TIMING, per-kernel durations of the encoder through sq_encode_stage_ms."""
+        stage_timing: SQ_FLAG_STAGE_TIMING, per-kernel durations of the encoder through sq_encode_stage_ms.
+        deterministic: SQ_FLAG_DETERMINISTIC, the same chunk always compresses to the same bytes (slower index kernel)."""
         self.lib = L.load()
         cfg = L.SqConfig(device, 0, dedup_capacity, max_batch_chunks,
-                         (L.SQ_FLAG_DENSE_SEARCH if dense_search else 0) | (L.SQ_FLAG_STAGE_TIMING if stage_timing else 0))
+                         (L.SQ_FLAG_DENSE_SEARCH if dense_search else 0) | (L.SQ_FLAG_STAGE_TIMING if stage_timing else 0) |
+                         (L.SQ_FLAG_DETERMINISTIC if deterministic else 0))
         h = C.c_void_p()
         rc = self.lib.sq_create(C.byref(cfg), C.byref(h))
         if rc != L.SQ_OK:

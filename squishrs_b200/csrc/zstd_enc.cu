@@ -312,7 +312,7 @@ int32_t sq_encode_device_set(sq_ctx *ctx, int set, const void *d_data, const sq_
                 cfg.attrs = attr;
                 cfg.numAttrs = 1;
                 SQ_CUDA(ctx, cudaLaunchKernelEx(&cfg, lz2::index_kernel<LZ_INDEX_THREADS, LZ_INDEX_PARTS>, (const uint8_t *)d_data, d_spans, d_select, first, count,
-                                                e->list, e->words, e->rec));
+                                                e->list, e->words, e->rec, (uint32_t)((ctx->flags & SQ_FLAG_DETERMINISTIC) != 0)));
             }
             lz2::search_kernel<LZ_SEARCH_THREADS, LZ_SEARCH_MINB, LZ_SEARCH_TLOG><<<e->search_ctas, LZ_SEARCH_THREADS, SEARCH_SMEM, st>>>((const uint8_t *)d_data, d_spans, first, count,
                                                                                                                                     e->span_start, e->list, e->rec, e->status + 1, dbg);

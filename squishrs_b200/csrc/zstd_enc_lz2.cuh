@@ -150,10 +150,11 @@ __device__ __forceinline__ uint32_t index_word(uint64_t v, uint32_t prev, uint32
 template <int THREADS, int PARTS>
 __global__ void __launch_bounds__(THREADS, 2048 / THREADS > 2 ? 2 : 2048 / THREADS) index_kernel(const uint8_t *__restrict__ data, const sq_span *__restrict__ spans,
                                                             const uint8_t *__restrict__ select, uint32_t first, uint32_t count,
-                                                            uint32_t *__restrict__ list_all, uint32_t *__restrict__ words_all, uint32_t *__restrict__ rec_all) {
+                                                            uint32_t *__restrict__ list_all, uint32_t *__restrict__ words_all, uint32_t *__restrict__ rec_all,
+                                                            uint32_t ordered) {
     namespace cg = cooperative_groups;
     extern __shared__ __align__(16) uint32_t s_cnt[];  // ROWS counters: this CTA's histogram, then (own part only) running list indices
-    __shared__ uint32_t s_warp[THREADS / 32], s_part_total;
+    __shared__ uint32_t s_warp[THREADS / 32], s_part_total, s_turn;
     constexpr uint32_t PART_ROWS = ROWS / PARTS, PER = PART_ROWS / THREADS, PART_SHIFT = ROW_LOG - (PARTS == 4 ? 2 : PARTS == 2 ? 1 : 0);
     static_assert(PARTS == 1 || PARTS == 2 || PARTS == 4, "cluster size");
     static_assert(PART_ROWS % THREADS == 0, "row counters per thread");
@@ -235,6 +236,7 @@ __global__ void __launch_bounds__(THREADS, 2048 / THREADS > 2 ? 2 : 2048 / THREA
 #pragma unroll
             for (uint32_t k = 0; k < PER; k++) { s_cnt[part * PART_ROWS + tid * PER + k] = run; run += c[k]; }
         }
+        if (tid == 0) s_turn = 0;
         __syncthreads();
         // pass 2 (every CTA walks all positions and keeps the rows of its part): scatter, tile by tile; the words of the next
         // DEPTH tiles are requested before this round's tiles are worked on
@@ -256,11 +258,38 @@ __global__ void __launch_bounds__(THREADS, 2048 / THREADS > 2 ? 2 : 2048 / THREA
                 if (t0 + k * THREADS >= np) break;  // uniform over the CTA
                 const uint32_t row = (wv >> PTAG_BITS) & (ROWS - 1);
                 const bool mine = p < np && (row >> PART_SHIFT) == part;
-                if (mine && (wv & IDX_INS))
-                    list[atomicAdd(&s_cnt[row], 1u)] = p | (wv & ((1u << PTAG_BITS) - 1)) << POS_BITS | (wv >> (ROW_LOG + PTAG_BITS) & 63u) << (POS_BITS + PTAG_BITS);
+                const bool ins = mine && (wv & IDX_INS);
+                const uint32_t entry = p | (wv & ((1u << PTAG_BITS) - 1)) << POS_BITS | (wv >> (ROW_LOG + PTAG_BITS) & 63u) << (POS_BITS + PTAG_BITS);
+                if (!ordered) {
+                    if (ins) list[atomicAdd(&s_cnt[row], 1u)] = entry;
+                } else {
+                    // SQ_FLAG_DETERMINISTIC: a row's entries land in exact position order.  Lanes of one row rank themselves inside
+                    // the warp, one of them adds the group's count, and the warps of a tile take turns at the counters.
+                    const uint32_t peers = __match_any_sync(0xffffffffu, ins ? row : 0x80000000u | lane);
+                    const uint32_t leader = (uint32_t)__ffs((int)peers) - 1, rank = __popc(peers & ((1u << lane) - 1u));
+                    const uint32_t my_turn = ((t0 / THREADS) + k) * (THREADS / 32) + w;
+                    if (lane == 0) while (*reinterpret_cast<volatile uint32_t *>(&s_turn) != my_turn) __nanosleep(20);
+                    __syncwarp();
+                    uint32_t base = 0;
+                    if (ins && lane == leader) base = atomicAdd(&s_cnt[row], (uint32_t)__popc(peers));
+                    base = __shfl_sync(0xffffffffu, base, leader);
+                    __threadfence_block();
+                    __syncwarp();
+                    if (lane == 0) *reinterpret_cast<volatile uint32_t *>(&s_turn) = my_turn + 1;
+                    if (ins) list[base + rank] = entry;
+                }
                 __syncthreads();
                 if (mine) rec[p] = s_cnt[row];  // read while faster warps already scatter the next tile: E may come out a few entries later, which only moves the window
+                if (ordered) __syncthreads();   // ... unless the bytes have to be reproducible
             }
+        }
+        // What a window can see beside real entries is EMPTY, not whatever the memory held before: the pad in front of the first row
+        // (windows of the first positions start there) and the entries right behind the end of the list (a window is rounded up
+        // to 16 bytes).  Left-over bits could pass the 5-bit prefix test and displace a position's true nearest short candidate.
+        if (part == 0 && tid < LIST_PAD) list[(int32_t)tid - (int32_t)LIST_PAD] = EMPTY;
+        if (part == PARTS - 1) {
+            __syncthreads();
+            if (tid < 8) list[s_cnt[ROWS - 1] + tid] = EMPTY;
         }
         // no CTA of the cluster leaves (or reuses s_part_total) while another may still read its shared memory
         if (PARTS > 1) cluster.sync(); else __syncthreads();
@@ -315,6 +344,10 @@ __global__ void __launch_bounds__(THREADS, MINB) search_kernel(const uint8_t *__
         const uint32_t MIN_MATCH = n <= SMALL_CHUNK ? 4u : 5u, hshift = n <= SMALL_CHUNK ? 32u : 24u;
         const uint32_t t1 = min(n, t0 + SPAN);
         __syncwarp();
+        // the continuation table starts empty for every span (16 bytes per lane and store): what it answers then depends on this
+        // span alone, not on what the warp -- or a kernel before it -- left in shared memory
+        for (uint32_t i = lane; i < (2u << TLOG) / 8; i += 32) reinterpret_cast<uint4 *>(T)[i] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+        epoch = 0;
         for (uint32_t i = lane; i < WIN_WORDS; i += 32) reinterpret_cast<uint32_t *>(s_in)[i] = lz::stage_word(in, t0 + i * 4, n, aligned);
         // every position's window end, for the whole span (the index kernel left it in the record array)
         uint32_t jv[GROUPS];

@@ -140,7 +140,7 @@ int main(int argc, char **argv) {
         setenv("CUDA_VISIBLE_DEVICES", vis.c_str(), 1);
         device = 0;
     }
-    sq_config cfg = {device, 0, 1ull << 22, 4096, 0};
+    sq_config cfg = {device, 0, 1ull << 22, 4096, getenv("SQ_DETERMINISTIC") ? SQ_FLAG_DETERMINISTIC : 0u};  // SQ_DETERMINISTIC=1: byte-reproducible archives
     sq_ctx *ctx = nullptr;
     int32_t rc = sq_create(&cfg, &ctx);
     tmark("sq_create done", t_start);

@@ -676,3 +676,20 @@ def test_block_parallel_decode_of_damaged_frames(sq, oracle):
     for g, w in zip(got, want):
         if g is not None:
             assert g == w
+
+
+def test_deterministic_flag_gives_reproducible_frames(sq, oracle):
+    """SQ_FLAG_DETERMINISTIC: packing the same chunks twice (two contexts) gives byte-identical frames, and they decode"""
+    lib = sq.load()
+    chunks = []
+    for klass, n in ((0, 2 * MiB), (1, 2 * MiB), (2, 2 * MiB), (3, 2 * MiB), (0, 70000), (2, 300000)):
+        b = C.create_string_buffer(n)
+        lib.sq_corpus_fill_host(b, n, 5, klass + 11, klass)
+        chunks.append(b.raw)
+    runs = []
+    for _ in range(3):
+        c = sq.Context(deterministic=True)
+        runs.append([f for _, f in c.pack_batch(chunks)])
+    assert runs[0] == runs[1] == runs[2]
+    for data, f in zip(chunks, runs[0]):
+        assert oracle.decompress(f, 2 * MiB) == data
