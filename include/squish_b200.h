@@ -84,7 +84,7 @@ typedef struct {
 /* Reproducible frames: the same chunk always compresses to the same bytes.  By default the match finder lets the entries of one
  * hash row that fall into the same 512-position tile land in the order of their shared-memory atomics, which can move a few
  * candidates in or out of a search window from run to run (a few hundred bytes in a gigabyte differ; every frame is valid either
- * way).  With this flag the index kernel orders them exactly; the match search stage takes about 10 % longer. */
+ * way).  With this flag the index kernel orders them exactly; a pack then takes about twice as long. */
 #define SQ_FLAG_DETERMINISTIC 4u
 
 /* One chunk of a batch: bytes [off, off+len) of the batch buffer.

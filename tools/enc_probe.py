@@ -5,7 +5,8 @@ sys.path.insert(0, "/root/repo")
 import numpy as np, torch
 import squishrs_b200 as sq
 from bench import corpus_plan, CHUNK, SEED
-lib = sq.load(); ctx = sq.Context(max_batch_chunks=2048)
+import os
+lib = sq.load(); ctx = sq.Context(max_batch_chunks=2048, deterministic=bool(os.environ.get("SQ_DETERMINISTIC")))
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
 ids, kl = corpus_plan(n)
 corpus = torch.empty(n * CHUNK, dtype=torch.uint8, device="cuda")
